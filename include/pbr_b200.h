@@ -1,0 +1,132 @@
+/*
+ * pbr_b200.h -- C ABI of libpbr_b200.so: the B200 (sm_100a) replacement for the pixel path of
+ * dolphin-in-a-coma/pybatchrender.
+ *
+ * The reference has no FFI seam of its own (it is pure Python on top of Panda3D + OpenGL).  Its
+ * de-facto seam is the *buffer contract* between the host classes and the two GLSL programs
+ * (SURVEY.md section 8b): per node `matbuf` (4 RGBA32F texels per instance = the columns of the
+ * model matrix) and `colbuf` (1 texel per instance), per camera `viewbuf` (4 texels per scene = the
+ * columns of VP) and the light uniforms.  Every entry point below consumes exactly those buffers,
+ * as plain device pointers, and replaces the reference calls cited next to it.
+ *
+ * Conventions
+ *   - plain C, no torch types; every function returns PBR_OK (0) or a negative pbr_status and
+ *     never throws; pbr_last_error() returns a thread-local description of the last failure.
+ *   - all device work is enqueued on the caller's CUDA stream (`stream` is a cudaStream_t passed
+ *     as void*; NULL = the legacy default stream); no hidden synchronisation, no allocation on the
+ *     per-frame path.  The caller keeps every buffer alive until the stream work completes.
+ *   - matrices are "column packed": 16 floats, element [4*j + i] = row i, column j (what
+ *     reference shader_context.py:42-45 `_pack_columns` + `tobytes()` produce).
+ */
+#ifndef PBR_B200_H
+#define PBR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBR_B200_VERSION 100            /* major*10000 + minor*100 + patch */
+#define PBR_MAX_NODES 24                /* nodes per frame (kernel parameter space) */
+#define PBR_MAX_TILE 2048               /* max tile width / height in pixels */
+
+typedef enum {
+    PBR_OK = 0,
+    PBR_EINVAL = -1,        /* bad argument (null pointer, misaligned buffer, bad size) */
+    PBR_ECUDA = -2,         /* a CUDA runtime call failed; see pbr_last_error() */
+    PBR_ENOMEM = -3,
+    PBR_EUNSUPPORTED = -4   /* valid request outside what this build implements */
+} pbr_status;
+
+#define PBR_MESH_TWO_SIDED 1u           /* do not cull back faces of this mesh */
+
+typedef struct pbr_mesh_s *pbr_mesh_t;  /* device-resident static geometry */
+
+/* One PBRNode: replaces the `matbuf` / `colbuf` / `instancesPerScene` / `shareAcrossScenes`
+ * shader inputs of reference node.py:85-91 and the instanced draw of node.py:68. */
+typedef struct {
+    pbr_mesh_t mesh;
+    const float *mats;          /* device [B,16] column packed  (== matbuf) */
+    const float *cols;          /* device [B,4] RGBA            (== colbuf) */
+    int32_t instances_per_scene;/* I */
+    int32_t shared;             /* 1: B = I (same instances in every scene), 0: B = num_scenes*I,
+                                   row = scene*I + inst   (reference basic.vert:25-28) */
+    float use_texture;          /* must be 0 (textures: PBR_EUNSUPPORTED for now) */
+} pbr_node_desc;
+
+/* One frame: replaces taskMgr.step() + grab_pixels() + _rearrange_img() of reference
+ * renderer.py:377-389, i.e. basic.vert + GL rasterisation + basic.frag + readback + flip +
+ * un-tiling, for scenes [scene_begin, scene_begin+scene_count). */
+typedef struct {
+    int32_t num_scenes;         /* K: rows of vp / per-scene node buffers / out */
+    int32_t scene_begin;        /* shard / chunk window */
+    int32_t scene_count;
+    int32_t tile_w, tile_h;     /* per-scene resolution */
+    int32_t channels;           /* 3 (RGB) or 4 (RGBA) */
+    const float *vp;            /* device [K,16] column packed (== viewbuf, reference camera.py:146-148) */
+    float bg[4];                /* clear colour (reference renderer.py:262-264) */
+    float ambient[3];           /* reference light.py:11-14 / basic.frag:15-18 */
+    float dir_dir[3];
+    float dir_col[3];
+    float strength;
+    int32_t n_nodes;
+    const pbr_node_desc *nodes; /* host array, copied during the call */
+    uint8_t *out;               /* device [K,C,H,W] contiguous uint8; row 0 = top of the image */
+    uint32_t flags;             /* PBR_FRAME_* */
+} pbr_frame_desc;
+
+#define PBR_FRAME_FORCE_GENERAL 1u      /* skip the small-scene fast kernel (testing / debugging) */
+
+int pbr_version(void);
+const char *pbr_last_error(void);
+
+/* Upload static geometry.  pos/nrm: host [n_verts,3] float32 (object space, already baked the way
+ * reference node.py:61-72 flattens scale/HPR/pivot into vertices); uv may be NULL; idx: host
+ * [n_tris,3].  Replaces loader.loadModel + flattenStrong's vertex data living in GL buffers. */
+int pbr_mesh_create(const float *pos_xyz, const float *nrm_xyz, const float *uv, int32_t n_verts,
+                    const uint32_t *idx, int32_t n_tris, int32_t device, uint32_t flags, pbr_mesh_t *out);
+int pbr_mesh_destroy(pbr_mesh_t mesh);
+int pbr_mesh_info(pbr_mesh_t mesh, int32_t *n_tris, int32_t *all_flat, int32_t *device);
+
+/* Render one frame (asynchronous on `stream`). */
+int pbr_render(const pbr_frame_desc *frame, void *stream);
+
+/* Instance-transform kernel: out_mats[b] = column-packed [ R_b * s_b | t_b ; 0 0 0 1 ] and the
+ * 3x3 block of transforms_b44 is refreshed in place -- the device version of reference
+ * node.py:116-126 `_upload_current_transforms` (transforms[:, :3, :3] = rot * scale; pack; upload).
+ *   transforms: device [B,4,4] row-major (translation read from [:, :3, 3])
+ *   rot: device [B,3,3]; scale: device [B] ; out_mats: device [B,16]. */
+int pbr_pack_transforms(float *transforms_b44, const float *rot_b33, const float *scale_b,
+                        float *out_mats, int32_t n_instances, void *stream);
+
+/* Pose channels for pbr_compose_transforms: value = ptr ? ptr[b*stride] : constant. */
+typedef struct {
+    const float *ptr;           /* device pointer or NULL */
+    int32_t stride;             /* in floats */
+    float constant;
+} pbr_channel;
+
+/* One node's pose: position xyz, Euler H/P/R in radians (R = Rz(H) Ry(P) Rx(R), reference
+ * shader_context.py:47-84) and uniform scale -> column-packed matrices.  Fuses what the reference
+ * does in set_positions + set_hprs + set_scales + upload (node.py:128-154) into one pass; several
+ * nodes are batched into one launch. */
+typedef struct {
+    pbr_channel pos[3];
+    pbr_channel hpr[3];
+    pbr_channel scale;
+    float *out_mats;            /* device [n_instances,16] */
+    int32_t n_instances;
+} pbr_pose_desc;
+
+int pbr_compose_transforms(const pbr_pose_desc *poses, int32_t n_poses, void *stream);
+
+/* Host-buffer entry point (the end-to-end path): state and pixels live in (ideally pinned) host
+ * memory.  For each chunk of scenes: H2D of the per-scene inputs, pose kernel, raster kernel, D2H
+ * of the pixels, double-buffered over two internal streams.  See INTEGRATION.md. */
+typedef struct pbr_pipeline_s *pbr_pipeline_t;
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBR_B200_H */

@@ -1,0 +1,237 @@
+"""ctypes binding of ``csrc/libpbr_b200.so`` (C ABI declared in ``include/pbr_b200.h``).
+
+There is no CPU or PyTorch fallback behind this module: if the shared library is missing or the
+tensors are not CUDA tensors the calls raise.  The library is built in-tree by
+``__graft_entry__.build()`` / ``pybatchrender_b200.build.build_native()``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpbr_b200.so")
+
+PBR_MAX_NODES = 24
+PBR_MESH_TWO_SIDED = 1
+PBR_FRAME_FORCE_GENERAL = 1
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class _NodeDesc(ctypes.Structure):
+    _fields_ = [
+        ("mesh", ctypes.c_void_p),
+        ("mats", ctypes.c_void_p),
+        ("cols", ctypes.c_void_p),
+        ("instances_per_scene", ctypes.c_int32),
+        ("shared", ctypes.c_int32),
+        ("use_texture", ctypes.c_float),
+    ]
+
+
+class _FrameDesc(ctypes.Structure):
+    _fields_ = [
+        ("num_scenes", ctypes.c_int32),
+        ("scene_begin", ctypes.c_int32),
+        ("scene_count", ctypes.c_int32),
+        ("tile_w", ctypes.c_int32),
+        ("tile_h", ctypes.c_int32),
+        ("channels", ctypes.c_int32),
+        ("vp", ctypes.c_void_p),
+        ("bg", ctypes.c_float * 4),
+        ("ambient", ctypes.c_float * 3),
+        ("dir_dir", ctypes.c_float * 3),
+        ("dir_col", ctypes.c_float * 3),
+        ("strength", ctypes.c_float),
+        ("n_nodes", ctypes.c_int32),
+        ("nodes", ctypes.POINTER(_NodeDesc)),
+        ("out", ctypes.c_void_p),
+        ("flags", ctypes.c_uint32),
+    ]
+
+
+class _Channel(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_void_p), ("stride", ctypes.c_int32), ("constant", ctypes.c_float)]
+
+
+class _PoseDesc(ctypes.Structure):
+    _fields_ = [
+        ("pos", _Channel * 3),
+        ("hpr", _Channel * 3),
+        ("scale", _Channel),
+        ("out_mats", ctypes.c_void_p),
+        ("n_instances", ctypes.c_int32),
+    ]
+
+
+_EXPORTS = {
+    "pbr_version": (ctypes.c_int, []),
+    "pbr_last_error": (ctypes.c_char_p, []),
+    "pbr_mesh_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                       ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32,
+                                       ctypes.POINTER(ctypes.c_void_p)]),
+    "pbr_mesh_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "pbr_mesh_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32),
+                                     ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
+    "pbr_render": (ctypes.c_int, [ctypes.POINTER(_FrameDesc), ctypes.c_void_p]),
+    "pbr_pack_transforms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_int32, ctypes.c_void_p]),
+    "pbr_compose_transforms": (ctypes.c_int, [ctypes.POINTER(_PoseDesc), ctypes.c_int32, ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+def exported_symbols() -> list[str]:
+    return sorted(_EXPORTS)
+
+
+def load():
+    """dlopen the library (raises NativeError with a build hint if it is missing)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _EXPORTS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().pbr_last_error()
+        raise NativeError(f"{what} failed ({rc}): {msg.decode(errors='replace') if msg else ''}")
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _cuda_f32(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise NativeError(f"{what} must be a CUDA tensor: the B200 renderer has no CPU fallback")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise NativeError(f"{what} must be contiguous float32")
+    return t
+
+
+class NativeMesh:
+    """Device-resident static geometry (``pbr_mesh_t``)."""
+
+    def __init__(self, pos, nrm, idx, device: torch.device, two_sided: bool = False) -> None:
+        import numpy as np
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(nrm, dtype=np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 3)
+        dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        handle = ctypes.c_void_p()
+        rc = load().pbr_mesh_create(pos.ctypes.data, nrm.ctypes.data, None, pos.shape[0], idx.ctypes.data,
+                                    idx.shape[0], dev_index, PBR_MESH_TWO_SIDED if two_sided else 0,
+                                    ctypes.byref(handle))
+        _check(rc, "pbr_mesh_create")
+        self.handle = handle
+        self.n_tris = int(idx.shape[0])
+        self.device_index = dev_index
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            load().pbr_mesh_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Native:
+    """Thin object the renderer holds; every method enqueues work on torch's current stream."""
+
+    def __init__(self) -> None:
+        self.lib = load()
+
+    def version(self) -> int:
+        return int(self.lib.pbr_version())
+
+    def pack_transforms(self, transforms_b44, rot_b33, scale_b11, matbuf) -> None:
+        n = int(matbuf.shape[0])
+        for t, w in ((transforms_b44, "transforms_b44"), (rot_b33, "rot3_b33"), (scale_b11, "scale_b11"),
+                     (matbuf, "matbuf")):
+            _cuda_f32(t, w)
+        with torch.cuda.device(matbuf.device):
+            rc = self.lib.pbr_pack_transforms(transforms_b44.data_ptr(), rot_b33.data_ptr(), scale_b11.data_ptr(),
+                                              matbuf.data_ptr(), n, _stream_ptr(matbuf.device))
+        _check(rc, "pbr_pack_transforms")
+
+    def compose(self, poses: list[dict], device: torch.device) -> None:
+        """poses: [{pos: (c,c,c), hpr: (c,c,c), scale: c, out: tensor[B,16]}], c = float | (tensor1d_view)."""
+        arr = (_PoseDesc * len(poses))()
+        keep = []
+
+        def chan(dst, v):
+            if isinstance(v, torch.Tensor):
+                if not v.is_cuda or v.dtype != torch.float32 or v.dim() != 1:
+                    raise NativeError("pose channel tensors must be 1-D float32 CUDA views")
+                dst.ptr, dst.stride, dst.constant = v.data_ptr(), int(v.stride(0)), 0.0
+                keep.append(v)
+            else:
+                dst.ptr, dst.stride, dst.constant = None, 0, float(v)
+
+        for i, p in enumerate(poses):
+            for k in range(3):
+                chan(arr[i].pos[k], p["pos"][k])
+                chan(arr[i].hpr[k], p["hpr"][k])
+            chan(arr[i].scale, p.get("scale", 1.0))
+            out = _cuda_f32(p["out"], "pose out")
+            arr[i].out_mats = out.data_ptr()
+            arr[i].n_instances = int(out.shape[0])
+        with torch.cuda.device(device):
+            rc = self.lib.pbr_compose_transforms(arr, len(poses), _stream_ptr(device))
+        _check(rc, "pbr_compose_transforms")
+
+    def render(self, *, num_scenes, tile_w, tile_h, channels, vp, nodes, out, bg, ambient, dir_dir, dir_col,
+               strength, scene_begin=0, scene_count=None, flags=0) -> None:
+        """nodes: list of (NativeMesh, matbuf, colbuf, instances_per_scene, shared)."""
+        _cuda_f32(vp, "viewbuf")
+        if not out.is_cuda or out.dtype != torch.uint8 or not out.is_contiguous():
+            raise NativeError("out must be a contiguous uint8 CUDA tensor")
+        nd = (_NodeDesc * max(1, len(nodes)))()
+        for i, (mesh, mats, cols, inst, shared) in enumerate(nodes):
+            _cuda_f32(mats, "matbuf")
+            _cuda_f32(cols, "colbuf")
+            nd[i].mesh = mesh.handle
+            nd[i].mats = mats.data_ptr()
+            nd[i].cols = cols.data_ptr()
+            nd[i].instances_per_scene = int(inst)
+            nd[i].shared = 1 if shared else 0
+            nd[i].use_texture = 0.0
+        f = _FrameDesc()
+        f.num_scenes = int(num_scenes)
+        f.scene_begin = int(scene_begin)
+        f.scene_count = int(num_scenes - scene_begin if scene_count is None else scene_count)
+        f.tile_w, f.tile_h, f.channels = int(tile_w), int(tile_h), int(channels)
+        f.vp = vp.data_ptr()
+        f.bg = (ctypes.c_float * 4)(*[float(x) for x in bg])
+        f.ambient = (ctypes.c_float * 3)(*[float(x) for x in ambient])
+        f.dir_dir = (ctypes.c_float * 3)(*[float(x) for x in dir_dir])
+        f.dir_col = (ctypes.c_float * 3)(*[float(x) for x in dir_col])
+        f.strength = float(strength)
+        f.n_nodes = len(nodes)
+        f.nodes = ctypes.cast(nd, ctypes.POINTER(_NodeDesc))
+        f.out = out.data_ptr()
+        f.flags = int(flags)
+        with torch.cuda.device(out.device):
+            rc = self.lib.pbr_render(ctypes.byref(f), _stream_ptr(out.device))
+        _check(rc, "pbr_render")

@@ -1,0 +1,242 @@
+"""``PBRNode`` -- one instanced mesh: baked geometry + per-instance model matrices and colours.
+
+Reference: ``pybatchrender/renderer/node.py:12-342``.  Kept semantics:
+
+* ``total_instances = num_scenes * instances_per_scene``; ``buf_instances`` is
+  ``instances_per_scene`` for ``shared_across_scenes`` nodes, else ``total_instances`` (node.py:42-46)
+* host mirrors ``transforms_b44`` / ``rot3_b33`` / ``scale_b11``; an "upload" recomputes
+  ``transforms[:, :3, :3] = rot * scale`` and writes the column-packed matrices into ``matbuf``
+  (node.py:110-126); ``lazy=True`` defers that upload to the next non-lazy setter (node.py:133,142,153)
+* inputs of any leading shape flatten row-major to ``[B, k]`` -- instance index = scene * I + inst --
+  and are truncated to ``buf_instances`` (node.py:131,139,151,159)
+* constructor arguments ``positions/hprs/scales/colors`` are ignored with a warning (node.py:36-40);
+  ``model_path=None`` makes a geometry-less node whose setters do nothing (node.py:73-77)
+
+What changed: ``matbuf`` / ``colbuf`` are float32 tensors on the renderer's device ([B,16] and [B,4],
+the exact byte layout of the reference's RGBA32F buffer textures) that the CUDA rasteriser reads in
+place; nothing is serialised or re-uploaded per step.  On CUDA the upload is one fused kernel
+(``pbr_pack_transforms``) instead of a chain of torch ops.
+"""
+from __future__ import annotations
+
+import warnings
+from collections.abc import Sequence
+from typing import Literal
+
+import torch
+
+from .. import meshes as _meshes
+from .shader_context import PBRShaderContext
+
+
+class _NodeHandle:
+    """Stand-in for the Panda3D ``NodePath`` the reference exposes as ``node.np``."""
+
+    def __init__(self, owner: "PBRNode", name: str) -> None:
+        self._owner = owner
+        self._name = name
+        self._removed = False
+
+    def removeNode(self) -> None:
+        self._removed = True
+        self._owner._detach()
+
+    remove_node = removeNode
+
+    def isEmpty(self) -> bool:
+        return self._removed
+
+    is_empty = isEmpty
+
+    def getName(self) -> str:
+        return self._name
+
+
+class PBRNode(PBRShaderContext):
+    def __init__(self,
+                 showbase,
+                 model_path,
+                 num_scenes: int = 1,
+                 instances_per_scene: int = 1,
+                 texture=None,
+                 model_pivot_relative_point: tuple[float, float, float] | None = None,
+                 model_scale: float | Sequence[float] | None = None,
+                 model_hpr: Sequence[float] | None = None,
+                 model_scale_units: Literal["relative", "absolute"] = "relative",
+                 positions: torch.Tensor | None = None,
+                 hprs: torch.Tensor | None = None,
+                 scales: torch.Tensor | None = None,
+                 colors: torch.Tensor | None = None,
+                 backend: Literal["loop", "instanced"] = "instanced",
+                 shared_across_scenes: bool = False,
+                 parent=None,
+                 name: str | None = None) -> None:
+        if positions is not None or colors is not None or scales is not None or hprs is not None:
+            warnings.warn("initializing positions, colors, scales, hprs through the constructor is not "
+                          "implemented (as in the reference); they are ignored", stacklevel=3)
+        super().__init__(showbase, backend=backend)
+        self.num_scenes = int(num_scenes)
+        self.instances_per_scene = int(instances_per_scene)
+        self.shared_across = bool(shared_across_scenes)
+        self.total_instances = self.num_scenes * self.instances_per_scene
+        self.buf_instances = self.instances_per_scene if self.shared_across else self.total_instances
+        self.model_pivot_relative_point = model_pivot_relative_point
+        self.model_scale = model_scale
+        self.model_hpr = model_hpr
+        self.model_scale_units = model_scale_units
+        self.shader_inputs: dict = {}
+        self.name = name or (str(model_path) if isinstance(model_path, str) else "pbr_node")
+        self.np = _NodeHandle(self, self.name)
+        self._native_mesh = None          # device copy, created by the renderer on first use
+
+        if model_path is not None and not (isinstance(model_path, str) and model_path == ""):
+            self.mesh = _meshes.bake(_meshes.load_mesh(model_path), model_scale=model_scale,
+                                     model_hpr=model_hpr, model_scale_units=model_scale_units,
+                                     pivot_rel=model_pivot_relative_point)
+            self.has_geometry = True
+        else:
+            self.mesh = None
+            self.has_geometry = False
+
+        self._register_self()
+        self._attempt_camera_connect()
+        self._attempt_light_connect()
+
+        self.set_texture(texture)
+
+        if self.has_geometry:
+            dev, B = self.device, self.buf_instances
+            self.matbuf = torch.zeros((B, 16), dtype=torch.float32, device=dev)
+            self.colbuf = torch.ones((B, 4), dtype=torch.float32, device=dev)
+            self._set_shader_input("instancesPerScene", self.instances_per_scene)
+            self._set_shader_input("shareAcrossScenes", 1 if self.shared_across else 0)
+            self.transforms_b44 = torch.eye(4, dtype=torch.float32, device=dev).repeat(B, 1, 1)
+            self.rot3_b33 = torch.eye(3, dtype=torch.float32, device=dev).repeat(B, 1, 1)
+            self.scale_b11 = torch.ones((B, 1, 1), dtype=torch.float32, device=dev)
+            self._upload_current_transforms()
+
+    # ------------------------------------------------------------------ uploads
+    def _as_rows(self, value, width: int) -> torch.Tensor:
+        t = torch.as_tensor(value, dtype=torch.float32)
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=True)
+        return t.reshape(-1, width)[: self.buf_instances]
+
+    def _upload_mat(self, mats: torch.Tensor) -> None:
+        if not self.has_geometry:
+            return
+        self.matbuf.view(-1, 4, 4).copy_(mats.transpose(1, 2))
+        self._touch()
+
+    def _upload_current_transforms(self) -> None:
+        if not self.has_geometry:
+            return
+        native = getattr(self.base, "_native", None)
+        if native is not None and self.matbuf.is_cuda:
+            native.pack_transforms(self.transforms_b44, self.rot3_b33, self.scale_b11, self.matbuf)
+        else:
+            self.transforms_b44[:, 0:3, 0:3] = self.rot3_b33 * self.scale_b11
+            self.matbuf.view(-1, 4, 4).copy_(self.transforms_b44.transpose(1, 2))
+        self._touch()
+
+    def _touch(self) -> None:
+        self._version = getattr(self, "_version", 0) + 1
+
+    # ------------------------------------------------------------------ public setters
+    def set_positions(self, pos_si3, lazy: bool = False) -> None:
+        if not self.has_geometry:
+            return
+        self.transforms_b44[:, 0:3, 3] = self._as_rows(pos_si3, 3)
+        if not lazy:
+            self._upload_current_transforms()
+
+    def set_hprs(self, hpr_si3, lazy: bool = False) -> None:
+        if not self.has_geometry:
+            return
+        self.rot3_b33[:, :, :] = type(self)._rotation_mats_from_hpr(self._as_rows(hpr_si3, 3))
+        if not lazy:
+            self._upload_current_transforms()
+
+    def set_scales(self, scale_si1, lazy: bool = False) -> None:
+        if not self.has_geometry:
+            return
+        if isinstance(scale_si1, (float, int)):
+            self.scale_b11 = torch.full((self.buf_instances, 1, 1), float(scale_si1),
+                                        dtype=torch.float32, device=self.device)
+        else:
+            self.scale_b11 = self._as_rows(scale_si1, 1).reshape(-1, 1, 1).clone()
+        if not lazy:
+            self._upload_current_transforms()
+
+    def set_colors(self, col_si4) -> None:
+        if not self.has_geometry:
+            return
+        self.colbuf.copy_(self._as_rows(col_si4, 4))
+        self._touch()
+
+    def set_transforms(self, mats_b44) -> None:
+        """Full per-instance matrices; split into rotation and mean-column-norm scale (node.py:163-178)."""
+        if not self.has_geometry:
+            return
+        m = torch.as_tensor(mats_b44, dtype=torch.float32).to(self.device).reshape(-1, 4, 4)
+        self.transforms_b44 = m.clone()
+        r = self.transforms_b44[:, 0:3, 0:3].clone()
+        s = torch.linalg.norm(r, dim=2).mean(dim=1).clamp_min(1e-8)
+        self.scale_b11 = s.reshape(-1, 1, 1)
+        self.rot3_b33 = r / self.scale_b11
+        self._upload_current_transforms()
+
+    # ------------------------------------------------------------------ misc API
+    def set_texture(self, texture=None) -> None:
+        if texture is not None:
+            raise NotImplementedError(
+                "textured nodes are not supported by the B200 rasteriser yet (SURVEY.md 8f-4); "
+                "pass texture=None")
+        self._set_shader_input("useTexture", 0.0)
+
+    def reparent_to(self, parent) -> None:
+        raise NotImplementedError("PBRNode.reparent_to is not implemented yet")
+
+    def pivot_to_rel(self, relative_point: tuple[float, float, float] | None = None) -> None:
+        """Re-centre the baked geometry so the bounds-relative point becomes the origin (node.py:313-341)."""
+        if relative_point is None or not self.has_geometry:
+            return
+        _meshes.bake(self.mesh, pivot_rel=relative_point)
+        self._native_mesh = None
+        self._touch()
+
+    def _set_lighting_strength(self, strength: float, overwrite: bool = False) -> None:
+        if overwrite or not hasattr(self.base, "_pbr_light"):
+            self._set_shader_input("lightingStrength", float(strength))
+
+    def _set_lighting(self, dir_dir, dir_col, amb_col, overwrite: bool = False) -> None:
+        if overwrite or not hasattr(self.base, "_pbr_light"):
+            self._set_shader_input("dirLightDir", tuple(float(x) for x in dir_dir))
+            self._set_shader_input("dirLightCol", tuple(float(x) for x in dir_col))
+            self._set_shader_input("ambientCol", tuple(float(x) for x in amb_col))
+
+    def _register_self(self) -> None:
+        if not hasattr(self.base, "_pbr_nodes"):
+            self.base._pbr_nodes = []
+        if self not in self.base._pbr_nodes:
+            self.base._pbr_nodes.append(self)
+            if hasattr(self.base, "_scene_changed"):
+                self.base._scene_changed()
+
+    def _detach(self) -> None:
+        """``node.np.removeNode()``: stop drawing this node (Steering rebuilds obstacles this way)."""
+        nodes = getattr(self.base, "_pbr_nodes", [])
+        if self in nodes:
+            nodes.remove(self)
+            if hasattr(self.base, "_scene_changed"):
+                self.base._scene_changed()
+
+    def _attempt_camera_connect(self) -> None:
+        cam = getattr(self.base, "_pbr_cam", None)
+        if cam:
+            cam.attach(self)
+
+    def _attempt_light_connect(self) -> None:
+        light = getattr(self.base, "_pbr_light", None)
+        if light:
+            light.attach(self)

@@ -1,0 +1,263 @@
+"""``PBRRenderer`` -- registry of nodes / camera / light and the ``step()`` that produces pixels.
+
+Reference: ``pybatchrender/renderer/renderer.py:33-406`` (a Panda3D ``ShowBase`` subclass).  The
+public surface is kept: ``PBRRenderer(cfg | dict | None, **overrides)``, ``add_node``,
+``add_camera``, ``add_light``, ``set_background_color``, ``setup_environment``,
+``step(*args, return_pixels=True)`` / ``__call__`` returning a contiguous uint8 ``[N,C,H,W]`` tensor,
+the overridable ``_step`` hook, ``grab_pixels`` and ``_rearrange_img``.
+
+What ``step`` does instead of ``taskMgr.step()`` + frame grab + flip + un-tile (renderer.py:377-389,
+326-363): one call into ``libpbr_b200.so`` (``pbr_render``) that rasterises every scene straight
+into its slice of the output tensor on torch's current CUDA stream.  No window, no framebuffer, no
+readback, no host synchronisation.  Failures raise -- the reference's "return an all-zero frame on
+any exception" (renderer.py:347-350) is deliberately not reproduced.
+"""
+from __future__ import annotations
+
+from collections.abc import Sequence
+from typing import Literal
+
+import torch
+
+from ..config import PBRConfig
+from .camera import PBRCam
+from .light import PBRLight
+from .node import PBRNode
+
+
+class _Win:
+    """The reference reads the window size for the projection aspect (camera.py:154)."""
+
+    def __init__(self, cfg: PBRConfig) -> None:
+        self._cfg = cfg
+
+    def getXSize(self) -> int:
+        return int(self._cfg.window_resolution[0])
+
+    def getYSize(self) -> int:
+        return int(self._cfg.window_resolution[1])
+
+    get_x_size, get_y_size = getXSize, getYSize
+
+
+class _TaskMgr:
+    """Minimal stand-in for Panda3D's task manager: subclasses call ``taskMgr.step()`` / ``add``."""
+
+    def __init__(self) -> None:
+        self._tasks: list = []
+
+    def add(self, fn, name: str = "", **_kw) -> None:
+        self._tasks.append((name, fn))
+
+    def doMethodLater(self, _delay, fn, name: str = "", **_kw) -> None:
+        self._tasks.append((name, fn))
+
+    def remove(self, name: str) -> None:
+        self._tasks = [t for t in self._tasks if t[0] != name]
+
+    def step(self) -> None:
+        return None
+
+
+class PBRRenderer:
+    def __init__(self, cfg: PBRConfig | dict | None = None, **cfg_overrides) -> None:
+        self.cfg = PBRConfig.from_config(cfg, **cfg_overrides)
+        if self.cfg.device == "cuda":
+            self.device = torch.device("cuda", torch.cuda.current_device())
+            from .. import _native
+            self._native = _native.Native()        # raises if libpbr_b200.so is missing
+        else:
+            # host-side state can be built and inspected on CPU, but rendering needs the GPU
+            self.device = torch.device("cpu")
+            self._native = None
+        self.win = _Win(self.cfg)
+        self.taskMgr = _TaskMgr()
+        self.task_mgr = self.taskMgr
+        self._pbr_nodes: list[PBRNode] = []
+        self._pbr_cam: PBRCam | None = None
+        self._pbr_light: PBRLight | None = None
+        self.num_scenes = int(self.cfg.num_scenes)
+        self._background_color = (0.0, 0.0, 0.0, 1.0)      # renderer.py:262-264 default clear colour
+        self._scene_version = 0
+        self._node_cache = None
+        self._environment_ready = False
+
+    # ------------------------------------------------------------------ scene construction
+    def set_background_color(self, r: float, g: float, b: float, a: float = 1.0) -> None:
+        self._background_color = (float(r), float(g), float(b), float(a))
+
+    setBackgroundColor = set_background_color
+
+    def add_node(self,
+                 model_path,
+                 instances_per_scene: int,
+                 texture=None,
+                 model_pivot_relative_point: tuple[float, float, float] | None = None,
+                 model_scale: float | Sequence[float] | None = None,
+                 model_hpr: tuple[float, float, float] | None = None,
+                 model_scale_units: Literal["relative", "absolute"] = "relative",
+                 positions: torch.Tensor | None = None,
+                 hprs: torch.Tensor | None = None,
+                 scales: torch.Tensor | None = None,
+                 colors: torch.Tensor | None = None,
+                 backend: Literal["loop", "instanced"] = "instanced",
+                 shared_across_scenes: bool = False,
+                 parent: PBRNode | None = None,
+                 name: str | None = None) -> PBRNode:
+        return PBRNode(self, model_path=model_path,
+                       num_scenes=self.num_scenes,
+                       instances_per_scene=int(instances_per_scene),
+                       texture=texture,
+                       model_pivot_relative_point=model_pivot_relative_point,
+                       model_scale=model_scale,
+                       model_hpr=model_hpr,
+                       model_scale_units=model_scale_units,
+                       positions=positions, hprs=hprs, scales=scales, colors=colors,
+                       backend=backend,
+                       shared_across_scenes=shared_across_scenes,
+                       parent=parent,
+                       name=name)
+
+    def add_camera(self, fov_y_deg: float = 55.0, z_near: float = 0.05, z_far: float = 100.0,
+                   fixed_projection: bool = True) -> PBRCam:
+        self._pbr_cam = PBRCam(self, num_scenes=self.cfg.num_scenes,
+                               cols=self.cfg.tiles[0], rows=self.cfg.tiles[1],
+                               fov_y_deg=fov_y_deg, z_near=z_near, z_far=z_far,
+                               fixed_projection=fixed_projection)
+        return self._pbr_cam
+
+    def _set_tiles_auto(self) -> None:
+        if self._pbr_cam is None:
+            self.add_camera()
+        self._pbr_cam._set_tiles()
+
+    def add_light(self,
+                  ambient: tuple[float, float, float] = (0.2, 0.2, 0.25),
+                  dir_dir: tuple[float, float, float] = (0.4, -0.6, -0.7),
+                  dir_col: tuple[float, float, float] = (1.0, 1.0, 1.0),
+                  strength: float = 1.0) -> PBRLight:
+        self._pbr_light = PBRLight(self, ambient=ambient, dir_dir=dir_dir, dir_col=dir_col, strength=strength)
+        return self._pbr_light
+
+    def setup_environment(self) -> None:
+        if self._pbr_cam is None:
+            self.add_camera()
+        self._environment_ready = True
+
+    def _scene_changed(self) -> None:
+        self._scene_version += 1
+        self._node_cache = None
+
+    # ------------------------------------------------------------------ frame description
+    def _light_params(self):
+        L = self._pbr_light
+        if L is None:
+            # nodes without an add_light() have unset lighting uniforms in the reference
+            # (node.py:295-303 never applies its defaults); treated as unlit, SURVEY 8 a17
+            return (0.2, 0.2, 0.25), (0.4, -0.6, -0.7), (1.0, 1.0, 1.0), 0.0
+        return L.ambient, L.dir_dir, L.dir_col, L.strength
+
+    def _drawable_nodes(self) -> list[PBRNode]:
+        return [n for n in self._pbr_nodes if n.has_geometry and n.instances_per_scene > 0]
+
+    def frame_arrays(self) -> dict:
+        """Host copy of everything one frame consumes (numpy) -- used by tests to feed the oracle."""
+        if self._pbr_cam is None:
+            self.add_camera()
+        amb, ddir, dcol, strength = self._light_params()
+        nodes = []
+        for n in self._drawable_nodes():
+            nodes.append(dict(pos=n.mesh.pos.copy(), nrm=n.mesh.nrm.copy(), idx=n.mesh.idx.copy(),
+                              mats=n.matbuf.detach().cpu().numpy().copy(),
+                              cols=n.colbuf.detach().cpu().numpy().copy(),
+                              instances_per_scene=n.instances_per_scene, shared=n.shared_across,
+                              flags=1 if n.mesh.two_sided else 0))
+        return dict(num_scenes=self.num_scenes,
+                    tile_w=int(self.cfg.tile_resolution[0]), tile_h=int(self.cfg.tile_resolution[1]),
+                    channels=int(self.cfg.num_channels),
+                    vp=self._pbr_cam.viewbuf[: self.num_scenes].detach().cpu().numpy().copy(),
+                    bg=self._background_color, ambient=amb, dir_dir=ddir, dir_col=dcol, strength=strength,
+                    nodes=nodes)
+
+    def _native_nodes(self):
+        if self._node_cache is None:
+            self._node_cache = self._drawable_nodes()
+        for n in self._node_cache:
+            if n._native_mesh is None:
+                from .. import _native
+                n._native_mesh = _native.NativeMesh(n.mesh.pos, n.mesh.nrm, n.mesh.idx, self.device,
+                                                    two_sided=n.mesh.two_sided)
+        return [(n._native_mesh, n.matbuf, n.colbuf, n.instances_per_scene, n.shared_across)
+                for n in self._node_cache]
+
+    # ------------------------------------------------------------------ rendering
+    def render(self, out: torch.Tensor | None = None, scene_begin: int = 0, scene_count: int | None = None,
+               flags: int = 0) -> torch.Tensor:
+        """Rasterise the current scene state into ``out`` (allocated if None) and return it."""
+        if self._native is None:
+            raise RuntimeError(
+                "PBRRenderer: rendering needs a CUDA device and libpbr_b200.so (cfg.device is "
+                f"{self.cfg.device!r}); there is no CPU fallback")
+        if self._pbr_cam is None:
+            self.add_camera()
+        W, H = int(self.cfg.tile_resolution[0]), int(self.cfg.tile_resolution[1])
+        C, N = int(self.cfg.num_channels), self.num_scenes
+        if out is None:
+            out = torch.empty((N, C, H, W), dtype=torch.uint8, device=self.device)
+        elif tuple(out.shape) != (N, C, H, W):
+            raise ValueError(f"out must have shape {(N, C, H, W)}, got {tuple(out.shape)}")
+        amb, ddir, dcol, strength = self._light_params()
+        self._native.render(num_scenes=N, tile_w=W, tile_h=H, channels=C, vp=self._pbr_cam.viewbuf,
+                            nodes=self._native_nodes(), out=out, bg=self._background_color,
+                            ambient=amb, dir_dir=ddir, dir_col=dcol, strength=strength,
+                            scene_begin=scene_begin, scene_count=scene_count, flags=flags)
+        return out
+
+    def _step(self, *args, **kwargs):
+        """Hook: subclasses translate simulation state into node / camera setters."""
+        return None
+
+    def _interactive_step(self):
+        return None
+
+    def step(self, *args, return_pixels: bool = True, out: torch.Tensor | None = None, **kwargs):
+        if not getattr(self.cfg, "interactive", False):
+            self._step(*args, **kwargs)
+        if return_pixels:
+            return self.render(out=out)
+        return None
+
+    def __call__(self, *args, return_pixels: bool = True, **kwargs):
+        return self.step(*args, return_pixels=return_pixels, **kwargs)
+
+    # ------------------------------------------------------------------ reference-compat helpers
+    def grab_pixels(self) -> torch.Tensor:
+        """The reference's intermediate: the whole tiled window ``[rows*H, cols*W, C]`` (row 0 = top)."""
+        px = self.render()
+        cols, rows = self.cfg.tiles
+        N, C, H, W = px.shape
+        if N < cols * rows:
+            pad = torch.zeros((cols * rows - N, C, H, W), dtype=px.dtype, device=px.device)
+            px = torch.cat([px, pad], dim=0)
+        img = px.view(rows, cols, C, H, W).permute(0, 3, 1, 4, 2).reshape(rows * H, cols * W, C)
+        return img
+
+    def _rearrange_img(self, img: torch.Tensor) -> torch.Tensor:
+        """``(rows*H, cols*W, C)`` window image -> ``[num_scenes, C, H, W]`` (renderer.py:352-363)."""
+        C = self.cfg.num_channels
+        cols, rows = self.cfg.tiles
+        W, H = self.cfg.tile_resolution
+        t = img.permute(2, 0, 1).reshape(C, rows, H, cols, W)
+        t = t.permute(1, 3, 0, 2, 4).reshape(-1, C, H, W)
+        return t[: self.cfg.num_scenes]
+
+    # Panda3D ShowBase methods that reference subclasses / scripts may call
+    def disableMouse(self) -> None:
+        return None
+
+    def destroy(self) -> None:
+        for n in list(self._pbr_nodes):
+            if getattr(n, "_native_mesh", None) is not None:
+                n._native_mesh.close()
+                n._native_mesh = None
+        self._node_cache = None

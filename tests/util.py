@@ -1,0 +1,65 @@
+"""Shared helpers for the parity tests: renderer state -> oracle frame, synthetic scenes."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+import oracle
+
+
+def oracle_frame(renderer) -> oracle.OracleFrame:
+    fa = renderer.frame_arrays()
+    return oracle.OracleFrame(
+        num_scenes=fa["num_scenes"], tile_w=fa["tile_w"], tile_h=fa["tile_h"], channels=fa["channels"],
+        vp=fa["vp"], bg=fa["bg"], ambient=fa["ambient"], dir_dir=fa["dir_dir"], dir_col=fa["dir_col"],
+        strength=fa["strength"], nodes=[oracle.OracleNode(**n) for n in fa["nodes"]])
+
+
+def oracle_render(renderer, n_threads: int = 8, **kw) -> np.ndarray:
+    return oracle.render(oracle_frame(renderer), n_threads=n_threads, **kw)
+
+
+def cartpole_states(n: int, seed: int = 0, device="cpu") -> torch.Tensor:
+    """x ~ U(-2,2), theta ~ U(-30deg,30deg) (reference envs/cartpole/config.py:57-62)."""
+    g = torch.Generator().manual_seed(seed)
+    s = torch.zeros(n, 4)
+    s[:, 0] = torch.rand(n, generator=g) * 4.0 - 2.0
+    s[:, 1] = torch.rand(n, generator=g) * 2.0 - 1.0
+    s[:, 2] = (torch.rand(n, generator=g) * 60.0 - 30.0) * (np.pi / 180.0)
+    s[:, 3] = (torch.rand(n, generator=g) * 30.0 - 15.0) * (np.pi / 180.0)
+    return s.to(device)
+
+
+def many_cubes_renderer(num_scenes=8, instances=16, tile=(64, 64), seed=123, device=None, channels=3,
+                        spread=15.0, eye=(0.0, -12.0, 0.0), shared=False, two_sided=False, light=True):
+    """Scene shaped like reference demo_many_cubes.py:34-54: random boxes around the default camera
+    (positions U(-spread,spread)^3, HPR U(-pi,pi)^3, scale U(0.5,1.8), colours U(0,1)^3)."""
+    from pybatchrender_b200 import PBRRenderer
+    from pybatchrender_b200 import meshes
+    cfg = dict(num_scenes=num_scenes, tile_resolution=tile, num_channels=channels)
+    if device is not None:
+        cfg["device"] = device
+    r = PBRRenderer(cfg)
+    model = "models/box"
+    if two_sided:
+        m = meshes.box()
+        m.two_sided = True
+        # open box: drop the +z face so that inside faces become visible
+        m.idx = m.idx[:8].copy()
+        meshes.register_mesh("test/open_box", m)
+        model = "test/open_box"
+    node = r.add_node(model, instances_per_scene=instances, model_pivot_relative_point=(0.5, 0.5, 0.5),
+                      shared_across_scenes=shared)
+    rng = np.random.default_rng(seed)
+    B = node.buf_instances
+    node.set_positions(torch.tensor(rng.uniform(-spread, spread, (B, 3)), dtype=torch.float32), lazy=True)
+    node.set_hprs(torch.tensor(rng.uniform(-np.pi, np.pi, (B, 3)), dtype=torch.float32), lazy=True)
+    node.set_scales(torch.tensor(rng.uniform(0.5, 1.8, (B, 1)), dtype=torch.float32))
+    col = np.concatenate([rng.uniform(0, 1, (B, 3)), np.ones((B, 1))], axis=1)
+    node.set_colors(torch.tensor(col, dtype=torch.float32))
+    cam = r.add_camera()
+    cam.set_positions(torch.tensor(eye, dtype=torch.float32))
+    if light:
+        r.add_light()
+    r.setup_environment()
+    return r
