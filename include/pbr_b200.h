@@ -121,10 +121,9 @@ typedef struct {
 
 int pbr_compose_transforms(const pbr_pose_desc *poses, int32_t n_poses, void *stream);
 
-/* Host-buffer entry point (the end-to-end path): state and pixels live in (ideally pinned) host
- * memory.  For each chunk of scenes: H2D of the per-scene inputs, pose kernel, raster kernel, D2H
- * of the pixels, double-buffered over two internal streams.  See INTEGRATION.md. */
-typedef struct pbr_pipeline_s *pbr_pipeline_t;
+/* Sticky per-device status bits written by the kernels (diagnostics; synchronises the device).
+ * bit 0: the small-scene kernel ran out of record slots for clipped triangles in some scene. */
+int pbr_device_status(int32_t device, int32_t *status_bits, int32_t clear);
 
 #ifdef __cplusplus
 }

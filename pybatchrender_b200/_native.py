@@ -79,6 +79,7 @@ _EXPORTS = {
     "pbr_mesh_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32),
                                      ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     "pbr_render": (ctypes.c_int, [ctypes.POINTER(_FrameDesc), ctypes.c_void_p]),
+    "pbr_device_status": (ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]),
     "pbr_pack_transforms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_int32, ctypes.c_void_p]),
     "pbr_compose_transforms": (ctypes.c_int, [ctypes.POINTER(_PoseDesc), ctypes.c_int32, ctypes.c_void_p]),
@@ -164,6 +165,12 @@ class Native:
 
     def version(self) -> int:
         return int(self.lib.pbr_version())
+
+    def device_status(self, device_index: int, clear: bool = True) -> int:
+        """Sticky diagnostic bits written by the kernels (synchronises the device)."""
+        v = ctypes.c_int32(0)
+        _check(self.lib.pbr_device_status(int(device_index), ctypes.byref(v), 1 if clear else 0), "pbr_device_status")
+        return int(v.value)
 
     def pack_transforms(self, transforms_b44, rot_b33, scale_b11, matbuf) -> None:
         n = int(matbuf.shape[0])

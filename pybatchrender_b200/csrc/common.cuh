@@ -1,0 +1,398 @@
+// common.cuh -- frame description, triangle records and the fp32 / integer math shared by the
+// raster kernels.  Every float operation here mirrors oracle/pbr_oracle.c one to one (same order,
+// explicit fmaf only; the library is compiled with -fmad=false so nothing else fuses).
+#pragma once
+#include "../../include/pbr_b200.h"
+
+#include <cuda_runtime.h>
+
+namespace pbr {
+
+constexpr int MAX_POLY = 10;         // vertices of a clipped polygon (3 + 5 planes, with slack)
+constexpr int FAN = 8;               // max fan triangles of a clipped polygon
+
+// ------------------------------------------------------------------------------------------------
+// device-side frame description (kernel parameter, < 4 KB)
+// ------------------------------------------------------------------------------------------------
+struct NodeDev {
+    const float4 *tp;     // [T*3] triangle soup: xyz = position, w of corner 0 = flat flag (int bits)
+    const float4 *tn;     // [T*3] xyz = corner normal
+    const float4 *vpos;   // [V]   unique positions (de-duplicated)
+    const uint4 *tidx;    // [T]   (i0, i1, i2, flat) into vpos
+    const float *mats;    // [B,16] column packed
+    const float *cols;    // [B,4]
+    int n_tris;
+    int n_verts;          // unique positions
+    int inst;             // instances per scene
+    int shared;
+    int slot_begin;       // first triangle slot of this node inside a scene
+    int vert_begin;       // first (instance, vertex) pair of this node inside a scene
+    unsigned flags;
+    int pad;
+};
+
+struct FrameDev {
+    const float *vp;
+    unsigned char *out;
+    int *status;            // device word: sticky PBR_DEVSTAT_* bits
+    int scene_begin, scene_count;
+    int W, H, C;
+    int n_nodes, total_slots, total_verts;
+    int BH, nbands;         // band height (multiple of 8) and bands per tile
+    int nbx, nby;           // 8x8 blocks per band
+    int plane_stride;       // bytes between colour planes in shared memory (multiple of 16)
+    int linear;             // 1: the shared colour tile is a byte image of out[scene]
+    float hw, hh;
+    unsigned bg;            // packed RGBA8 clear colour
+    float amb[3], dcol[3], ldir[3];
+    float s, oms;           // clamp(strength), 1 - clamp(strength)
+    NodeDev nodes[PBR_MAX_NODES];
+};
+
+constexpr int DEVSTAT_WARP_OVERFLOW = 1;   // small-scene kernel ran out of record slots
+
+// record meta bits
+constexpr unsigned M_VALID = 1u << 16, M_SLOW = 1u << 17, M_SMOOTH = 1u << 18;
+constexpr unsigned M_NB0 = 1u << 19, M_NB1 = 1u << 20, M_NB2 = 1u << 21;
+
+struct __align__(16) Rec {
+    int e[9];        // fast: Eo[3], A[3], B[3]        slow: X0,Y0,X1,Y1,X2,Y2,-,-,-
+    float z0, dz1, dz2;
+    float invA;
+    unsigned col;    // packed RGBA8 (flat shading)
+    unsigned id;     // 1 + draw index
+    unsigned meta;   // anchor block x (8) | anchor block y (8) | flags
+};
+static_assert(sizeof(Rec) == 64, "Rec must be 64 bytes");
+
+struct CV {
+    float c[4];      // clip-space position
+    float n[3];      // world-space unit normal
+};
+
+struct BBox {
+    int bx0, by0, bx1, by1;   // 8x8-pixel blocks, inclusive
+};
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// ------------------------------------------------------------------------------------------------
+// math shared with the oracle (same operation order)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mat_vec4(const float *m, float x, float y, float z, float w, float *r) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = fmaf(m[i], x, fmaf(m[4 + i], y, fmaf(m[8 + i], z, m[12 + i] * w)));
+}
+
+__device__ __forceinline__ void xform_normal(const float *m, float nx, float ny, float nz, float *r) {
+    float t[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t[i] = fmaf(m[i], nx, fmaf(m[4 + i], ny, m[8 + i] * nz));
+    float l2 = fmaf(t[2], t[2], fmaf(t[1], t[1], t[0] * t[0]));
+    float inv = 1.0f / sqrtf(l2);
+    r[0] = t[0] * inv; r[1] = t[1] * inv; r[2] = t[2] * inv;
+}
+
+__device__ __forceinline__ unsigned unorm8(float c) {
+    c = fminf(fmaxf(c, 0.0f), 1.0f);
+    return (unsigned)__float2int_rz(c * 255.0f + 0.5f);
+}
+
+// ambient + Lambert with the strength blend (reference basic.frag:33-37), n unit length
+__device__ __forceinline__ unsigned shade(const FrameDev &f, const float *n, const float4 col) {
+    float ndl = fmaxf(fmaf(n[2], f.ldir[2], fmaf(n[1], f.ldir[1], n[0] * f.ldir[0])), 0.0f);
+    float cc[3] = {col.x, col.y, col.z};
+    unsigned out = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float light = fmaf(ndl, f.dcol[c], f.amb[c]);
+        float l = fmaf(light, f.s, f.oms);
+        out |= unorm8(cc[c] * l) << (8 * c);
+    }
+    out |= unorm8(col.w) << 24;
+    return out;
+}
+
+__device__ __forceinline__ float plane_dist4(const float *c, int p) {
+    const float G = 1024.0f;
+    switch (p) {
+    case 0: return c[2] + c[3];
+    case 1: return G * c[3] + c[0];
+    case 2: return G * c[3] - c[0];
+    case 3: return G * c[3] + c[1];
+    default: return G * c[3] - c[1];
+    }
+}
+__device__ __forceinline__ float plane_dist(const CV &v, int p) { return plane_dist4(v.c, p); }
+
+// all three vertices outside one plane of the tile frustum?
+__device__ __forceinline__ bool trivially_outside(const float *c0, const float *c1, const float *c2) {
+    bool rej = false;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+        const int a = p >> 1;
+        const bool o0 = (p & 1) ? (c0[a] > c0[3]) : (c0[a] < -c0[3]);
+        const bool o1 = (p & 1) ? (c1[a] > c1[3]) : (c1[a] < -c1[3]);
+        const bool o2 = (p & 1) ? (c2[a] > c2[3]) : (c2[a] < -c2[3]);
+        rej |= (o0 && o1 && o2);
+    }
+    return rej;
+}
+
+__device__ __forceinline__ bool needs_clip(const float *c) {
+    bool need = false;
+#pragma unroll
+    for (int p = 0; p < 5; ++p) need |= plane_dist4(c, p) < 0.0f;
+    return need;
+}
+
+// Sutherland-Hodgman against near + guard band; returns vertex count (0 = nothing left).
+__device__ __noinline__ int clip_poly(const CV *in3, CV *a) {
+    CV b[MAX_POLY];
+    int n = 3;
+    for (int i = 0; i < 3; ++i) a[i] = in3[i];
+    for (int p = 0; p < 5 && n >= 3; ++p) {
+        bool any_out = false;
+        for (int i = 0; i < n; ++i) any_out |= plane_dist(a[i], p) < 0.0f;
+        if (!any_out) continue;
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const CV &u = a[i];
+            const CV &v = a[(i + 1) % n];
+            float du = plane_dist(u, p), dv = plane_dist(v, p);
+            bool iu = !(du < 0.0f), iv = !(dv < 0.0f);
+            if (iu) b[m++] = u;
+            if (iu != iv) {
+                const CV &vi = iu ? u : v;
+                const CV &vo = iu ? v : u;
+                float di = iu ? du : dv, dout = iu ? dv : du;
+                float t = di / (di - dout);
+                CV w;
+                for (int k = 0; k < 4; ++k) w.c[k] = fmaf(t, vo.c[k] - vi.c[k], vi.c[k]);
+                for (int k = 0; k < 3; ++k) w.n[k] = fmaf(t, vo.n[k] - vi.n[k], vi.n[k]);
+                b[m++] = w;
+            }
+        }
+        n = m;
+        for (int i = 0; i < n; ++i) a[i] = b[i];
+    }
+    return n < 3 ? 0 : n;
+}
+
+// perspective divide + viewport (image orientation, y down) + snap to 1/256 px
+__device__ __forceinline__ bool project_vertex(const FrameDev &f, const float *c, int &X, int &Y, float &z) {
+    if (!(c[3] > 0.0f)) return false;
+    const float rw = 1.0f / c[3];
+    const float xs = fmaf(c[0] * rw, f.hw, f.hw);
+    const float ys = fmaf(-(c[1] * rw), f.hh, f.hh);
+    z = fmaf(0.5f, c[2] * rw, 0.5f);
+    const float fx = xs * 256.0f, fy = ys * 256.0f;
+    if (!(fabsf(fx) < 1073741824.0f) || !(fabsf(fy) < 1073741824.0f)) return false;
+    X = __float2int_rn(fx);
+    Y = __float2int_rn(fy);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// triangle setup from snapped vertices: cull, edge equations, depth plane -> record + block bbox.
+// r.col is left for the caller (flat colour is only worth computing for surviving triangles).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool setup_snapped(const FrameDev &f, int *X, int *Y, float *z, bool two_sided,
+                                              unsigned id, int band_y0, int band_h, Rec &r, BBox &bb) {
+    long long area2 = (long long)(X[1] - X[0]) * (Y[2] - Y[0]) - (long long)(X[2] - X[0]) * (Y[1] - Y[0]);
+    if (area2 == 0) return false;
+    if (area2 > 0) {                 // clockwise in GL's y-up window space: back face
+        if (!two_sided) return false;
+        int t = X[1]; X[1] = X[2]; X[2] = t;
+        t = Y[1]; Y[1] = Y[2]; Y[2] = t;
+        float q = z[1]; z[1] = z[2]; z[2] = q;
+        area2 = -area2;
+    }
+    const long long A2 = -area2;
+
+    // band-local coordinates (edge functions are translation invariant)
+    const int yshift = band_y0 * 256;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) Y[i] -= yshift;
+
+    const int xmin = min(X[0], min(X[1], X[2])), xmax = max(X[0], max(X[1], X[2]));
+    const int ymin = min(Y[0], min(Y[1], Y[2])), ymax = max(Y[0], max(Y[1], Y[2]));
+    const int i0 = max(0, (xmin - 128 + 255) >> 8), i1 = min(f.W - 1, (xmax - 128) >> 8);
+    const int j0 = max(0, (ymin - 128 + 255) >> 8), j1 = min(band_h - 1, (ymax - 128) >> 8);
+    if (i0 > i1 || j0 > j1) return false;
+    bb.bx0 = i0 >> 3; bb.bx1 = i1 >> 3; bb.by0 = j0 >> 3; bb.by1 = j1 >> 3;
+
+    r.invA = 1.0f / (float)A2;
+    r.z0 = z[0];
+    r.dz1 = z[1] - z[0];
+    r.dz2 = z[2] - z[0];
+    r.id = id;
+    r.col = 0;
+
+    unsigned meta = M_VALID | (unsigned)bb.bx0 | ((unsigned)bb.by0 << 8);
+    int dx[3], dy[3], bias[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int a = (i + 1) % 3, b = (i + 2) % 3;
+        dx[i] = X[b] - X[a];
+        dy[i] = Y[b] - Y[a];
+        // top-left rule in image space: samples exactly on an edge belong to left / top edges only
+        bias[i] = (dy[i] > 0 || (dy[i] == 0 && dx[i] < 0)) ? 0 : -1;
+    }
+    if (bias[0]) meta |= M_NB0;
+    if (bias[1]) meta |= M_NB1;
+    if (bias[2]) meta |= M_NB2;
+
+    // int32 fast path iff every |F| over hull(triangle, touched blocks) stays below 2^30
+    const long long rx0 = (long long)bb.bx0 * 2048 + 128, rx1 = (long long)bb.bx1 * 2048 + 7 * 256 + 128;
+    const long long ry0 = (long long)bb.by0 * 2048 + 128, ry1 = (long long)bb.by1 * 2048 + 7 * 256 + 128;
+    const long long spanx = max((long long)xmax, rx1) - min((long long)xmin, rx0);
+    const long long spany = max((long long)ymax, ry1) - min((long long)ymin, ry0);
+    const bool fast = spanx < (1ll << 30) && spany < (1ll << 30) && spanx * spany < (1ll << 29);
+    if (fast) {
+        const int pax = bb.bx0 * 2048 + 128, pay = bb.by0 * 2048 + 128;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int a = (i + 1) % 3;
+            r.e[i] = dy[i] * (pax - X[a]) - dx[i] * (pay - Y[a]) + bias[i];
+            r.e[3 + i] = dy[i] * 256;
+            r.e[6 + i] = -dx[i] * 256;
+        }
+    } else {
+        meta |= M_SLOW;
+        r.e[0] = X[0]; r.e[1] = Y[0]; r.e[2] = X[1]; r.e[3] = Y[1]; r.e[4] = X[2]; r.e[5] = Y[2];
+        r.e[6] = r.e[7] = r.e[8] = 0;
+    }
+    r.meta = meta;
+    return true;
+}
+
+// exact (biased) edge value of a slow-path record at sample (px,py) in 1/256 px units
+__device__ __forceinline__ long long slow_edge(const Rec &r, int i, int px, int py) {
+    const int a = (i + 1) % 3, b = (i + 2) % 3;
+    const int xa = r.e[2 * a], ya = r.e[2 * a + 1], xb = r.e[2 * b], yb = r.e[2 * b + 1];
+    const long long F = (long long)(yb - ya) * (px - xa) - (long long)(xb - xa) * (py - ya);
+    const unsigned nb = (r.meta >> (19 + i)) & 1u;
+    return F - (long long)nb;
+}
+
+// can the triangle of this record touch block (bx,by)?  (conservative: max of each edge function
+// over the block's pixel centres must be non-negative)
+__device__ __forceinline__ bool block_hit(const Rec &r, const BBox &bb, int bx, int by) {
+    bool hit = true;
+    if (!(r.meta & M_SLOW)) {
+        const int ox = (bx - bb.bx0) * 8, oy = (by - bb.by0) * 8;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int A = r.e[3 + i], B = r.e[6 + i];
+            const unsigned cx = (unsigned)(ox + (A > 0 ? 7 : 0)), cy = (unsigned)(oy + (B > 0 ? 7 : 0));
+            const int fmax = (int)((unsigned)r.e[i] + (unsigned)A * cx + (unsigned)B * cy);
+            hit &= fmax >= 0;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int a = (i + 1) % 3, b = (i + 2) % 3;
+            const int ddx = r.e[2 * b] - r.e[2 * a], ddy = r.e[2 * b + 1] - r.e[2 * a + 1];
+            const int cx = (bx * 8 + (ddy > 0 ? 7 : 0)) * 256 + 128;      // dF/dpx = ddy
+            const int cy = (by * 8 + (ddx < 0 ? 7 : 0)) * 256 + 128;      // dF/dpy = -ddx
+            hit &= slow_edge(r, i, cx, cy) >= 0;
+        }
+    }
+    return hit;
+}
+
+// set record t's bit in every block its triangle can touch.  masks: [nblk][MWORDS]
+template <int MWORDS>
+__device__ __forceinline__ void bin_record(const Rec &r, const BBox &bb, int t, int nbx, unsigned *masks) {
+    const unsigned bit = 1u << (t & 31);
+    const int word = t >> 5;
+    const bool small = (bb.bx1 - bb.bx0) + (bb.by1 - bb.by0) <= 1;       // <= 2 blocks: no reject test
+    for (int by = bb.by0; by <= bb.by1; ++by)
+        for (int bx = bb.bx0; bx <= bb.bx1; ++bx)
+            if (small || block_hit(r, bb, bx, by)) atomicOr(&masks[(by * nbx + bx) * MWORDS + word], bit);
+}
+
+// ------------------------------------------------------------------------------------------------
+// one 8x8 block: every lane owns pixels (lx, ly) and (lx, ly+4); loop over the block's records
+// ------------------------------------------------------------------------------------------------
+struct PixelState {
+    unsigned zb0, zb1, id0, id1, c0, c1;
+    bool ch0, ch1;
+};
+
+template <int MWORDS>
+__device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bmask, int px, int py0, bool ok0,
+                                             bool ok1, PixelState &ps) {
+    const int py1 = py0 + 4;
+#pragma unroll 1
+    for (int w = 0; w < MWORDS; ++w) {
+        unsigned m = bmask[w];
+#pragma unroll 1
+        while (m) {
+            const int t = w * 32 + __ffs(m) - 1;
+            m &= m - 1;
+            const Rec &r = recs[t];
+            const unsigned meta = r.meta;
+            bool cov0, cov1;
+            if (!(meta & M_SLOW)) {
+                const unsigned rx = (unsigned)(px - (int)(meta & 255u) * 8);
+                const unsigned ry = (unsigned)(py0 - (int)((meta >> 8) & 255u) * 8);
+                const int4 ea = *reinterpret_cast<const int4 *>(&r.e[0]);     // Eo0 Eo1 Eo2 A0
+                const int4 eb = *reinterpret_cast<const int4 *>(&r.e[4]);     // A1 A2 B0 B1
+                const int B2 = r.e[8];
+                const int F0 = (int)((unsigned)ea.x + (unsigned)ea.w * rx + (unsigned)eb.z * ry);
+                const int F1 = (int)((unsigned)ea.y + (unsigned)eb.x * rx + (unsigned)eb.w * ry);
+                const int F2 = (int)((unsigned)ea.z + (unsigned)eb.y * rx + (unsigned)B2 * ry);
+                const int G0 = (int)((unsigned)F0 + 4u * (unsigned)eb.z);
+                const int G1 = (int)((unsigned)F1 + 4u * (unsigned)eb.w);
+                const int G2 = (int)((unsigned)F2 + 4u * (unsigned)B2);
+                cov0 = ok0 && ((F0 | F1 | F2) >= 0);
+                cov1 = ok1 && ((G0 | G1 | G2) >= 0);
+                if (__any_sync(0xffffffffu, cov0 || cov1)) {
+                    const int nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
+                    const float invA = r.invA, z0 = r.z0, dz1 = r.dz1, dz2 = r.dz2;
+                    const unsigned id = r.id, col = r.col;
+                    const float za = fmaf((float)(F2 + nb2) * invA, dz2, fmaf((float)(F1 + nb1) * invA, dz1, z0));
+                    const float zc = fmaf((float)(G2 + nb2) * invA, dz2, fmaf((float)(G1 + nb1) * invA, dz1, z0));
+                    const unsigned za_b = __float_as_uint(za), zc_b = __float_as_uint(zc);
+                    const bool w0 = cov0 && (za_b < ps.zb0 || (za_b == ps.zb0 && id < ps.id0));
+                    const bool w1 = cov1 && (zc_b < ps.zb1 || (zc_b == ps.zb1 && id < ps.id1));
+                    if (w0) { ps.zb0 = za_b; ps.id0 = id; ps.c0 = col; ps.ch0 = true; }
+                    if (w1) { ps.zb1 = zc_b; ps.id1 = id; ps.c1 = col; ps.ch1 = true; }
+                }
+            } else {
+                const int spx = px * 256 + 128, spy0 = py0 * 256 + 128, spy1 = py1 * 256 + 128;
+                const long long F0 = slow_edge(r, 0, spx, spy0), F1 = slow_edge(r, 1, spx, spy0),
+                                F2 = slow_edge(r, 2, spx, spy0);
+                const long long G0 = slow_edge(r, 0, spx, spy1), G1 = slow_edge(r, 1, spx, spy1),
+                                G2 = slow_edge(r, 2, spx, spy1);
+                cov0 = ok0 && ((F0 | F1 | F2) >= 0);
+                cov1 = ok1 && ((G0 | G1 | G2) >= 0);
+                if (__any_sync(0xffffffffu, cov0 || cov1)) {
+                    const long long nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
+                    const float invA = r.invA, z0 = r.z0, dz1 = r.dz1, dz2 = r.dz2;
+                    const unsigned id = r.id, col = r.col;
+                    const float za = fmaf((float)(F2 + nb2) * invA, dz2, fmaf((float)(F1 + nb1) * invA, dz1, z0));
+                    const float zc = fmaf((float)(G2 + nb2) * invA, dz2, fmaf((float)(G1 + nb1) * invA, dz1, z0));
+                    const unsigned za_b = __float_as_uint(za), zc_b = __float_as_uint(zc);
+                    const bool w0 = cov0 && (za_b < ps.zb0 || (za_b == ps.zb0 && id < ps.id0));
+                    const bool w1 = cov1 && (zc_b < ps.zb1 || (zc_b == ps.zb1 && id < ps.id1));
+                    if (w0) { ps.zb0 = za_b; ps.id0 = id; ps.c0 = col; ps.ch0 = true; }
+                    if (w1) { ps.zb1 = zc_b; ps.id1 = id; ps.c1 = col; ps.ch1 = true; }
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void put_pixel(unsigned char *color, int plane_stride, int C, int W, int px, int py,
+                                          unsigned c) {
+    unsigned char *p = color + py * W + px;
+    p[0] = (unsigned char)(c & 255u);
+    p[plane_stride] = (unsigned char)((c >> 8) & 255u);
+    p[2 * plane_stride] = (unsigned char)((c >> 16) & 255u);
+    if (C == 4) p[3 * plane_stride] = (unsigned char)(c >> 24);
+}
+
+}  // namespace pbr

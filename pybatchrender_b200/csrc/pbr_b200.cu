@@ -1,28 +1,20 @@
-// pbr_b200.cu -- sm_100a kernels + C ABI (include/pbr_b200.h) for the PyBatchRender pixel path.
+// pbr_b200.cu -- C ABI (include/pbr_b200.h) and host-side launch logic of libpbr_b200.so.
 //
-// What this file replaces in the reference (dolphin-in-a-coma/pybatchrender):
+// What the library replaces in the reference (dolphin-in-a-coma/pybatchrender):
 //   pybatchrender/shaders/basic.vert:24-56   instance decode, clip = VP*(M*v), normal, colour
 //   OpenGL fixed function  near clip, divide, viewport, coverage, depth LESS
 //   pybatchrender/shaders/basic.frag:20-38   tile scissor, ambient + Lambert
 //   renderer/frame_grabber.py:85-106, renderer/renderer.py:352-363   readback, flip, un-tiling
 //   renderer/node.py:116-154                 transform composition + upload
 //
-// Arithmetic contract (shared with oracle/pbr_oracle.c, which is what tests compare against bit
-// for bit): all float math is IEEE fp32 with round-to-nearest, built with -fmad=false so that only
-// the explicit fmaf() calls fuse; coverage is exact integer arithmetic on coordinates snapped to
-// 1/256 pixel with a top-left fill rule; depth is interpolated from the integer edge functions.
+// Kernels (sm_100a only):
+//   raster_warp.cuh      raster_warp_kernel      one warp per scene, small flat-shaded scenes
+//   raster_general.cuh   raster_general_kernel   one CTA per (scene, band), everything else
+//   transforms.cuh       pack_transforms_kernel / compose_kernel   instance transforms
 //
-// Kernel map
-//   raster_kernel<KEY>   one CTA per (scene, band of rows).  Per pass over <=128 triangle slots:
-//                        (1) per-thread transform + cull + setup into shared-memory records,
-//                        (2) per-thread binning into per-8x8-block bitmasks (with an edge-function
-//                            block reject), (3) warps sweep the non-empty blocks, depth/id/colour
-//                            of their two pixels per lane in registers, (4) the finished band is
-//                            written with 128-bit stores straight into out[scene].
-//                        KEY=true keeps depth+id tiles in shared memory so that several passes
-//                        (scenes with >128 triangle slots, clipped triangles) compose;
-//                        KEY=false is the single-pass small-scene variant.
-//   pack_transforms_kernel / compose_kernel   the instance-transform kernels.
+// Arithmetic contract (shared with oracle/pbr_oracle.c, which tests compare against bit for bit):
+// IEEE fp32, round-to-nearest, -fmad=false so that only explicit fmaf() calls fuse; coverage is
+// exact integer arithmetic on coordinates snapped to 1/256 pixel with a top-left fill rule.
 #include "../../include/pbr_b200.h"
 
 #include <cuda_runtime.h>
@@ -30,15 +22,20 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <new>
 #include <vector>
 
+#include "common.cuh"
+#include "raster_general.cuh"
+#include "raster_warp.cuh"
+#include "transforms.cuh"
+
+using namespace pbr;
+
 namespace {
 
-// ------------------------------------------------------------------------------------------------
-// errors
-// ------------------------------------------------------------------------------------------------
 thread_local char g_err[512] = "";
 
 int fail(int code, const char *fmt, ...) {
@@ -56,720 +53,48 @@ int fail(int code, const char *fmt, ...) {
             return fail(PBR_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-// ------------------------------------------------------------------------------------------------
-// device-side frame description
-// ------------------------------------------------------------------------------------------------
-constexpr int THREADS = 128;
-constexpr int NWARPS = THREADS / 32;
-constexpr int CH = 128;              // triangle records per pass (one per thread)
-constexpr int MW = CH / 32;          // mask words per 8x8 block
-constexpr int MAX_POLY = 10;
-constexpr int FAN = 8;               // max fan triangles of a clipped polygon
-
-struct NodeDev {
-    const float4 *tp;   // [T*3] xyz = position, w of vertex 0 = flat flag
-    const float4 *tn;   // [T*3] xyz = normal
-    const float *mats;
-    const float *cols;
-    int n_tris;
-    int inst;
-    int shared;
-    int slot_begin;
-    unsigned flags;
-    int pad;
-};
-
-struct FrameDev {
-    const float *vp;
-    unsigned char *out;
-    int scene_begin, scene_count;
-    int W, H, C;
-    int n_nodes, total_slots;
-    int BH, nbands;         // band height (multiple of 8) and bands per tile
-    int nbx, nby;           // 8x8 blocks per band
-    int plane_stride;       // bytes between colour planes in shared memory (multiple of 16)
-    int linear;             // 1: the shared colour tile is a byte image of out[scene]
-    float hw, hh;
-    unsigned bg;            // packed RGBA8 clear colour
-    float amb[3], dcol[3], ldir[3];
-    float s, oms;           // clamp(strength), 1 - clamp(strength)
-    NodeDev nodes[PBR_MAX_NODES];
-};
-
-// record meta bits
-constexpr unsigned M_VALID = 1u << 16, M_SLOW = 1u << 17, M_SMOOTH = 1u << 18;
-constexpr unsigned M_NB0 = 1u << 19, M_NB1 = 1u << 20, M_NB2 = 1u << 21;
-
-struct __align__(16) Rec {
-    int e[9];        // fast: Eo[3], A[3], B[3]        slow: X0,Y0,X1,Y1,X2,Y2,-,-,-
-    float z0, dz1, dz2, invA;
-    unsigned col;    // packed RGBA8 (flat shading)
-    unsigned id;     // 1 + draw index
-    unsigned meta;   // anchor block x (8) | anchor block y (8) | flags
-};
-static_assert(sizeof(Rec) == 64, "Rec must be 64 bytes");
-
-struct CV {
-    float c[4];
-    float n[3];
-};
-
-// ------------------------------------------------------------------------------------------------
-// math shared with the oracle (same operation order)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mat_vec4(const float *m, float x, float y, float z, float w, float *r) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) r[i] = fmaf(m[i], x, fmaf(m[4 + i], y, fmaf(m[8 + i], z, m[12 + i] * w)));
-}
-
-__device__ __forceinline__ void xform_normal(const float *m, float nx, float ny, float nz, float *r) {
-    float t[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) t[i] = fmaf(m[i], nx, fmaf(m[4 + i], ny, m[8 + i] * nz));
-    float l2 = fmaf(t[2], t[2], fmaf(t[1], t[1], t[0] * t[0]));
-    float inv = 1.0f / sqrtf(l2);
-    r[0] = t[0] * inv; r[1] = t[1] * inv; r[2] = t[2] * inv;
-}
-
-__device__ __forceinline__ unsigned unorm8(float c) {
-    c = fminf(fmaxf(c, 0.0f), 1.0f);
-    return (unsigned)__float2int_rz(c * 255.0f + 0.5f);
-}
-
-__device__ __forceinline__ unsigned shade(const FrameDev &f, const float *n, const float4 col) {
-    float ndl = fmaxf(fmaf(n[2], f.ldir[2], fmaf(n[1], f.ldir[1], n[0] * f.ldir[0])), 0.0f);
-    float cc[3] = {col.x, col.y, col.z};
-    unsigned out = 0;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float light = fmaf(ndl, f.dcol[c], f.amb[c]);
-        float l = fmaf(light, f.s, f.oms);
-        out |= unorm8(cc[c] * l) << (8 * c);
-    }
-    out |= unorm8(col.w) << 24;
-    return out;
-}
-
-__device__ __forceinline__ float plane_dist(const CV &v, int p) {
-    const float G = 1024.0f;
-    switch (p) {
-    case 0: return v.c[2] + v.c[3];
-    case 1: return G * v.c[3] + v.c[0];
-    case 2: return G * v.c[3] - v.c[0];
-    case 3: return G * v.c[3] + v.c[1];
-    default: return G * v.c[3] - v.c[1];
-    }
-}
-
-// Sutherland-Hodgman against near + guard band; returns vertex count (0 = nothing left).
-__device__ __noinline__ int clip_poly(const CV *in3, CV *a) {
-    CV b[MAX_POLY];
-    int n = 3;
-    for (int i = 0; i < 3; ++i) a[i] = in3[i];
-    for (int p = 0; p < 5 && n >= 3; ++p) {
-        bool any_out = false;
-        for (int i = 0; i < n; ++i) any_out |= plane_dist(a[i], p) < 0.0f;
-        if (!any_out) continue;
-        int m = 0;
-        for (int i = 0; i < n; ++i) {
-            const CV &u = a[i];
-            const CV &v = a[(i + 1) % n];
-            float du = plane_dist(u, p), dv = plane_dist(v, p);
-            bool iu = !(du < 0.0f), iv = !(dv < 0.0f);
-            if (iu) b[m++] = u;
-            if (iu != iv) {
-                const CV &vi = iu ? u : v;
-                const CV &vo = iu ? v : u;
-                float di = iu ? du : dv, dout = iu ? dv : du;
-                float t = di / (di - dout);
-                CV w;
-                for (int k = 0; k < 4; ++k) w.c[k] = fmaf(t, vo.c[k] - vi.c[k], vi.c[k]);
-                for (int k = 0; k < 3; ++k) w.n[k] = fmaf(t, vo.n[k] - vi.n[k], vi.n[k]);
-                b[m++] = w;
-            }
-        }
-        n = m;
-        for (int i = 0; i < n; ++i) a[i] = b[i];
-    }
-    return n < 3 ? 0 : n;
-}
-
-// ------------------------------------------------------------------------------------------------
-// per-slot geometry: transform the triangle of (scene, slot) into clip space
-// ------------------------------------------------------------------------------------------------
-enum { SLOT_SKIP = 0, SLOT_OK = 1, SLOT_CLIP = 2 };
-
-struct SlotGeom {
-    CV v[3];
-    float4 col;
-    bool flat;
-    bool two_sided;
-};
-
-__device__ __forceinline__ int load_slot(const FrameDev &f, int scene, int slot, SlotGeom &g) {
-    int ni = 0;
-#pragma unroll 1
-    for (int i = 1; i < f.n_nodes; ++i)
-        if (slot >= f.nodes[i].slot_begin) ni = i;
-    const NodeDev &nd = f.nodes[ni];
-    const int local = slot - nd.slot_begin;
-    const int inst = local / nd.n_tris;
-    const int tri = local - inst * nd.n_tris;
-    const size_t b = nd.shared ? (size_t)inst : (size_t)scene * nd.inst + inst;
-
-    float M[16], VP[16];
-    const float4 *m4 = reinterpret_cast<const float4 *>(nd.mats + b * 16);
-    const float4 *v4 = reinterpret_cast<const float4 *>(f.vp + (size_t)scene * 16);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float4 a = __ldg(m4 + j), c = __ldg(v4 + j);
-        M[4 * j] = a.x; M[4 * j + 1] = a.y; M[4 * j + 2] = a.z; M[4 * j + 3] = a.w;
-        VP[4 * j] = c.x; VP[4 * j + 1] = c.y; VP[4 * j + 2] = c.z; VP[4 * j + 3] = c.w;
-    }
-    g.col = __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4));
-    g.two_sided = (nd.flags & PBR_MESH_TWO_SIDED) != 0;
-
-    const float4 p0 = __ldg(nd.tp + 3 * tri);
-    g.flat = __float_as_int(p0.w) != 0;
-    float4 n0 = __ldg(nd.tn + 3 * tri);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        float4 p = (k == 0) ? p0 : __ldg(nd.tp + 3 * tri + k);
-        float world[4];
-        mat_vec4(M, p.x, p.y, p.z, 1.0f, world);
-        mat_vec4(VP, world[0], world[1], world[2], world[3], g.v[k].c);
-        float4 n = (k == 0 || g.flat) ? n0 : __ldg(nd.tn + 3 * tri + k);
-        xform_normal(M, n.x, n.y, n.z, g.v[k].n);
-    }
-    // trivial reject against the tile frustum
-#pragma unroll
-    for (int p = 0; p < 6; ++p) {
-        bool all_out = true;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            float a = g.v[k].c[p >> 1], w = g.v[k].c[3];
-            bool out = (p & 1) ? (a > w) : (a < -w);
-            all_out &= out;
-        }
-        if (all_out) return SLOT_SKIP;
-    }
-    bool need_clip = false;
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-#pragma unroll
-        for (int p = 0; p < 5; ++p) need_clip |= plane_dist(g.v[k], p) < 0.0f;
-    return need_clip ? SLOT_CLIP : SLOT_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// triangle setup: project, snap, cull, edge equations, shading -> record + block bbox
-// ------------------------------------------------------------------------------------------------
-struct BBox {
-    int bx0, by0, bx1, by1;
-};
-
-__device__ __forceinline__ bool setup_tri(const FrameDev &f, const CV *vin, const float4 col, bool flat,
-                                          bool two_sided, unsigned id, int band_y0, int band_h, Rec &r,
-                                          BBox &bb) {
-    int X[3], Y[3];
-    float z[3];
-    int ord1 = 1, ord2 = 2;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        if (!(vin[i].c[3] > 0.0f)) return false;
-        float rw = 1.0f / vin[i].c[3];
-        float xs = fmaf(vin[i].c[0] * rw, f.hw, f.hw);
-        float ys = fmaf(-(vin[i].c[1] * rw), f.hh, f.hh);
-        z[i] = fmaf(0.5f, vin[i].c[2] * rw, 0.5f);
-        float fx = xs * 256.0f, fy = ys * 256.0f;
-        if (!(fabsf(fx) < 1073741824.0f) || !(fabsf(fy) < 1073741824.0f)) return false;
-        X[i] = __float2int_rn(fx);
-        Y[i] = __float2int_rn(fy);
-    }
-    long long area2 = (long long)(X[1] - X[0]) * (Y[2] - Y[0]) - (long long)(X[2] - X[0]) * (Y[1] - Y[0]);
-    if (area2 == 0) return false;
-    if (area2 > 0) {
-        if (!two_sided) return false;
-        int t = X[1]; X[1] = X[2]; X[2] = t;
-        t = Y[1]; Y[1] = Y[2]; Y[2] = t;
-        float q = z[1]; z[1] = z[2]; z[2] = q;
-        ord1 = 2; ord2 = 1;
-        area2 = -area2;
-    }
-    (void)ord1; (void)ord2;
-    const long long A2 = -area2;
-
-    // band-local coordinates (edge functions are translation invariant)
-    const int yshift = band_y0 * 256;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) Y[i] -= yshift;
-
-    int xmin = min(X[0], min(X[1], X[2])), xmax = max(X[0], max(X[1], X[2]));
-    int ymin = min(Y[0], min(Y[1], Y[2])), ymax = max(Y[0], max(Y[1], Y[2]));
-    int i0 = max(0, (xmin - 128 + 255) >> 8), i1 = min(f.W - 1, (xmax - 128) >> 8);
-    int j0 = max(0, (ymin - 128 + 255) >> 8), j1 = min(band_h - 1, (ymax - 128) >> 8);
-    if (i0 > i1 || j0 > j1) return false;
-    bb.bx0 = i0 >> 3; bb.bx1 = i1 >> 3; bb.by0 = j0 >> 3; bb.by1 = j1 >> 3;
-
-    r.invA = 1.0f / (float)A2;
-    r.z0 = z[0];
-    r.dz1 = z[1] - z[0];
-    r.dz2 = z[2] - z[0];
-    r.id = id;
-    r.col = 0;
-    if (flat) r.col = shade(f, vin[0].n, col);
-
-    unsigned meta = M_VALID | (unsigned)bb.bx0 | ((unsigned)bb.by0 << 8);
-    int dx[3], dy[3], bias[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const int a = (i + 1) % 3, b = (i + 2) % 3;
-        dx[i] = X[b] - X[a];
-        dy[i] = Y[b] - Y[a];
-        bias[i] = (dy[i] > 0 || (dy[i] == 0 && dx[i] < 0)) ? 0 : -1;
-    }
-    if (bias[0]) meta |= M_NB0;
-    if (bias[1]) meta |= M_NB1;
-    if (bias[2]) meta |= M_NB2;
-
-    // int32 fast path iff every |F| over hull(triangle, touched blocks) stays below 2^30
-    const long long rx0 = (long long)bb.bx0 * 2048 + 128, rx1 = (long long)bb.bx1 * 2048 + 7 * 256 + 128;
-    const long long ry0 = (long long)bb.by0 * 2048 + 128, ry1 = (long long)bb.by1 * 2048 + 7 * 256 + 128;
-    const long long spanx = max((long long)xmax, rx1) - min((long long)xmin, rx0);
-    const long long spany = max((long long)ymax, ry1) - min((long long)ymin, ry0);
-    const bool fast = spanx < (1ll << 30) && spany < (1ll << 30) && spanx * spany < (1ll << 29);
-    if (fast) {
-        const int pax = bb.bx0 * 2048 + 128, pay = bb.by0 * 2048 + 128;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int a = (i + 1) % 3;
-            r.e[i] = dy[i] * (pax - X[a]) - dx[i] * (pay - Y[a]) + bias[i];
-            r.e[3 + i] = dy[i] * 256;
-            r.e[6 + i] = -dx[i] * 256;
-        }
-    } else {
-        meta |= M_SLOW;
-        r.e[0] = X[0]; r.e[1] = Y[0]; r.e[2] = X[1]; r.e[3] = Y[1]; r.e[4] = X[2]; r.e[5] = Y[2];
-        r.e[6] = r.e[7] = r.e[8] = 0;
-    }
-    r.meta = meta;
-    return true;
-}
-
-// exact (biased) edge value of a slow-path record at sample (px,py) in 1/256 px units
-__device__ __forceinline__ long long slow_edge(const Rec &r, int i, int px, int py) {
-    const int a = (i + 1) % 3, b = (i + 2) % 3;
-    const int xa = r.e[2 * a], ya = r.e[2 * a + 1], xb = r.e[2 * b], yb = r.e[2 * b + 1];
-    const long long F = (long long)(yb - ya) * (px - xa) - (long long)(xb - xa) * (py - ya);
-    const unsigned nb = (r.meta >> (19 + i)) & 1u;
-    return F - (long long)nb;
-}
-
-// set this record's bit in every block its triangle can touch
-__device__ __forceinline__ void bin_record(const Rec &r, const BBox &bb, int t, int nbx, unsigned *masks) {
-    const unsigned bit = 1u << (t & 31);
-    const int word = t >> 5;
-    const bool slow = (r.meta & M_SLOW) != 0;
-    for (int by = bb.by0; by <= bb.by1; ++by) {
-        for (int bx = bb.bx0; bx <= bb.bx1; ++bx) {
-            bool hit = true;
-            if (!slow) {
-                const int ox = (bx - bb.bx0) * 8, oy = (by - bb.by0) * 8;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int A = r.e[3 + i], B = r.e[6 + i];
-                    const unsigned cx = (unsigned)(ox + (A > 0 ? 7 : 0)), cy = (unsigned)(oy + (B > 0 ? 7 : 0));
-                    const int fmax = (int)((unsigned)r.e[i] + (unsigned)A * cx + (unsigned)B * cy);
-                    hit &= fmax >= 0;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int a = (i + 1) % 3, b = (i + 2) % 3;
-                    const int ddx = r.e[2 * b] - r.e[2 * a], ddy = r.e[2 * b + 1] - r.e[2 * a + 1];
-                    // dF/dpx = ddy, dF/dpy = -ddx
-                    const int cx = (bx * 8 + (ddy > 0 ? 7 : 0)) * 256 + 128;
-                    const int cy = (by * 8 + (ddx < 0 ? 7 : 0)) * 256 + 128;
-                    hit &= slow_edge(r, i, cx, cy) >= 0;
-                }
-            }
-            if (hit) atomicOr(&masks[(by * nbx + bx) * MW + word], bit);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// shared-memory layout
-// ------------------------------------------------------------------------------------------------
-struct Smem {
-    unsigned char *color;   // [C][plane_stride]
-    float *ztile;           // [nblk*64]  (KEY only) block-major
-    unsigned *itile;        // [nblk*64]  (KEY only)
-    Rec *recs;              // [CH]
-    unsigned *masks;        // [nblk*MW]
-    unsigned short *blist;  // [nblk]
-    unsigned short *cliplist;  // [CH]
-    int *ctr;               // [4]: nlist, next, nclip
-};
-
-__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
-
-__host__ __device__ inline size_t smem_bytes(int C, int plane_stride, int nblk, bool key) {
-    size_t n = 0;
-    n += align16((size_t)C * plane_stride);
-    if (key) n += 2 * (size_t)nblk * 64 * 4;
-    n += (size_t)CH * sizeof(Rec);
-    n += align16((size_t)nblk * MW * 4);
-    n += align16((size_t)nblk * 2);
-    n += align16((size_t)CH * 2);
-    n += 16;
-    return n;
-}
-
-template <bool KEY>
-__device__ __forceinline__ Smem carve(unsigned char *base, int C, int plane_stride, int nblk) {
-    Smem s;
-    s.color = base; base += align16((size_t)C * plane_stride);
-    s.ztile = nullptr; s.itile = nullptr;
-    if (KEY) {
-        s.ztile = reinterpret_cast<float *>(base); base += (size_t)nblk * 64 * 4;
-        s.itile = reinterpret_cast<unsigned *>(base); base += (size_t)nblk * 64 * 4;
-    }
-    s.recs = reinterpret_cast<Rec *>(base); base += (size_t)CH * sizeof(Rec);
-    s.masks = reinterpret_cast<unsigned *>(base); base += align16((size_t)nblk * MW * 4);
-    s.blist = reinterpret_cast<unsigned short *>(base); base += align16((size_t)nblk * 2);
-    s.cliplist = reinterpret_cast<unsigned short *>(base); base += align16((size_t)CH * 2);
-    s.ctr = reinterpret_cast<int *>(base);
-    return s;
-}
-
-// ------------------------------------------------------------------------------------------------
-// raster pass: sweep the non-empty blocks of this band
-// ------------------------------------------------------------------------------------------------
-template <bool KEY>
-__device__ __forceinline__ void process_block(const FrameDev &f, const Smem &s, int b, int band_h, int lane) {
-    const int bx = b % f.nbx, by = b / f.nbx;
-    const int px = bx * 8 + (lane & 7);
-    const int py0 = by * 8 + (lane >> 3), py1 = py0 + 4;
-    const bool ok0 = px < f.W && py0 < band_h, ok1 = px < f.W && py1 < band_h;
-
-    unsigned zb0 = 0x3F800000u, zb1 = 0x3F800000u, id0 = 0, id1 = 0, c0 = 0, c1 = 0;
-    bool ch0 = false, ch1 = false;
-    if (KEY) {
-        zb0 = __float_as_uint(s.ztile[b * 64 + lane]);
-        zb1 = __float_as_uint(s.ztile[b * 64 + 32 + lane]);
-        id0 = s.itile[b * 64 + lane];
-        id1 = s.itile[b * 64 + 32 + lane];
-    }
-    const int spx = px * 256 + 128, spy0 = py0 * 256 + 128, spy1 = py1 * 256 + 128;
-
-#pragma unroll 1
-    for (int w = 0; w < MW; ++w) {
-        unsigned m = s.masks[b * MW + w];
-#pragma unroll 1
-        while (m) {
-            const int t = w * 32 + __ffs(m) - 1;
-            m &= m - 1;
-            const Rec &r = s.recs[t];
-            const unsigned meta = r.meta;
-            bool cov0, cov1;
-            float f1a, f2a, f1b, f2b;   // unbiased F1, F2 as floats for both pixels
-            if (!(meta & M_SLOW)) {
-                const unsigned rx = (unsigned)(px - (int)(meta & 255u) * 8);
-                const unsigned ry = (unsigned)(py0 - (int)((meta >> 8) & 255u) * 8);
-                const int A0 = r.e[3], A1 = r.e[4], A2 = r.e[5], B0 = r.e[6], B1 = r.e[7], B2 = r.e[8];
-                const int F0 = (int)((unsigned)r.e[0] + (unsigned)A0 * rx + (unsigned)B0 * ry);
-                const int F1 = (int)((unsigned)r.e[1] + (unsigned)A1 * rx + (unsigned)B1 * ry);
-                const int F2 = (int)((unsigned)r.e[2] + (unsigned)A2 * rx + (unsigned)B2 * ry);
-                const int G0 = (int)((unsigned)F0 + 4u * (unsigned)B0);
-                const int G1 = (int)((unsigned)F1 + 4u * (unsigned)B1);
-                const int G2 = (int)((unsigned)F2 + 4u * (unsigned)B2);
-                cov0 = ok0 && ((F0 | F1 | F2) >= 0);
-                cov1 = ok1 && ((G0 | G1 | G2) >= 0);
-                const int nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
-                f1a = (float)(F1 + nb1); f2a = (float)(F2 + nb2);
-                f1b = (float)(G1 + nb1); f2b = (float)(G2 + nb2);
-            } else {
-                const long long F0 = slow_edge(r, 0, spx, spy0), F1 = slow_edge(r, 1, spx, spy0),
-                                F2 = slow_edge(r, 2, spx, spy0);
-                const long long G0 = slow_edge(r, 0, spx, spy1), G1 = slow_edge(r, 1, spx, spy1),
-                                G2 = slow_edge(r, 2, spx, spy1);
-                cov0 = ok0 && ((F0 | F1 | F2) >= 0);
-                cov1 = ok1 && ((G0 | G1 | G2) >= 0);
-                const long long nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
-                f1a = (float)(F1 + nb1); f2a = (float)(F2 + nb2);
-                f1b = (float)(G1 + nb1); f2b = (float)(G2 + nb2);
-            }
-            if (__any_sync(0xffffffffu, cov0 || cov1)) {
-                const float invA = r.invA, z0 = r.z0, dz1 = r.dz1, dz2 = r.dz2;
-                const unsigned id = r.id, col = r.col;
-                if (cov0) {
-                    const float za = fmaf(f2a * invA, dz2, fmaf(f1a * invA, dz1, z0));
-                    const unsigned zb = __float_as_uint(za);
-                    if (zb < zb0 || (zb == zb0 && id < id0)) { zb0 = zb; id0 = id; c0 = col; ch0 = true; }
-                }
-                if (cov1) {
-                    const float zc = fmaf(f2b * invA, dz2, fmaf(f1b * invA, dz1, z0));
-                    const unsigned zb = __float_as_uint(zc);
-                    if (zb < zb1 || (zb == zb1 && id < id1)) { zb1 = zb; id1 = id; c1 = col; ch1 = true; }
-                }
-            }
-        }
-    }
-    if (ch0) {
-        if (KEY) { s.ztile[b * 64 + lane] = __uint_as_float(zb0); s.itile[b * 64 + lane] = id0; }
-        unsigned char *p = s.color + py0 * f.W + px;
-        p[0] = (unsigned char)(c0 & 255u);
-        p[f.plane_stride] = (unsigned char)((c0 >> 8) & 255u);
-        p[2 * f.plane_stride] = (unsigned char)((c0 >> 16) & 255u);
-        if (f.C == 4) p[3 * f.plane_stride] = (unsigned char)(c0 >> 24);
-    }
-    if (ch1) {
-        if (KEY) { s.ztile[b * 64 + 32 + lane] = __uint_as_float(zb1); s.itile[b * 64 + 32 + lane] = id1; }
-        unsigned char *p = s.color + py1 * f.W + px;
-        p[0] = (unsigned char)(c1 & 255u);
-        p[f.plane_stride] = (unsigned char)((c1 >> 8) & 255u);
-        p[2 * f.plane_stride] = (unsigned char)((c1 >> 16) & 255u);
-        if (f.C == 4) p[3 * f.plane_stride] = (unsigned char)(c1 >> 24);
-    }
-}
-
-// Called by all threads after records + masks of this pass are complete (and synchronised).
-template <bool KEY>
-__device__ __forceinline__ void raster_pass(const FrameDev &f, const Smem &s, int nblk, int band_h) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (tid == 0) { s.ctr[0] = 0; s.ctr[1] = 0; }
-    __syncthreads();
-    for (int b = tid; b < nblk; b += THREADS) {
-        unsigned any = 0;
-#pragma unroll
-        for (int w = 0; w < MW; ++w) any |= s.masks[b * MW + w];
-        if (any) s.blist[atomicAdd(&s.ctr[0], 1)] = (unsigned short)b;
-    }
-    __syncthreads();
-    const int nlist = s.ctr[0];
-    while (true) {
-        int i = 0;
-        if (lane == 0) i = atomicAdd(&s.ctr[1], 1);
-        i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= nlist) break;
-        process_block<KEY>(f, s, s.blist[i], band_h, lane);
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ void zero_masks(const Smem &s, int nblk) {
-    for (int i = threadIdx.x; i < nblk * MW; i += THREADS) s.masks[i] = 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// the raster kernel
-// ------------------------------------------------------------------------------------------------
-template <bool KEY>
-__global__ void __launch_bounds__(THREADS) raster_kernel(const __grid_constant__ FrameDev f) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x;
-    const int scene = f.scene_begin + (int)(blockIdx.x / f.nbands);
-    const int band = (int)(blockIdx.x % f.nbands);
-    const int band_y0 = band * f.BH;
-    const int band_h = min(f.BH, f.H - band_y0);
-    const int nblk = f.nbx * f.nby;
-    const Smem s = carve<KEY>(smem_raw, f.C, f.plane_stride, nblk);
-
-    // clear: colour planes to the background, depth to 1.0, id to 0
-    {
-        const int words = f.plane_stride / 4;
-        for (int c = 0; c < f.C; ++c) {
-            const unsigned v = ((f.bg >> (8 * c)) & 255u) * 0x01010101u;
-            unsigned *p = reinterpret_cast<unsigned *>(s.color + (size_t)c * f.plane_stride);
-            for (int i = tid; i < words; i += THREADS) p[i] = v;
-        }
-        if (KEY) {
-            for (int i = tid; i < nblk * 64; i += THREADS) { s.ztile[i] = 1.0f; s.itile[i] = 0u; }
-        }
-    }
-
-    const int S = f.total_slots;
-#pragma unroll 1
-    for (int chunk = 0; chunk < S; chunk += CH) {
-        zero_masks(s, nblk);
-        if (tid == 0) s.ctr[2] = 0;
-        __syncthreads();
-
-        // (1) + (2): one triangle slot per thread
-        {
-            Rec r;
-            r.meta = 0;
-            const int slot = chunk + tid;
-            if (slot < S) {
-                SlotGeom g;
-                const int st = load_slot(f, scene, slot, g);
-                if (st == SLOT_OK) {
-                    BBox bb;
-                    if (setup_tri(f, g.v, g.col, g.flat, g.two_sided, (unsigned)slot + 1u, band_y0, band_h, r, bb))
-                        bin_record(r, bb, tid, f.nbx, s.masks);
-                    else
-                        r.meta = 0;
-                } else if (st == SLOT_CLIP) {
-                    s.cliplist[atomicAdd(&s.ctr[2], 1)] = (unsigned short)tid;
-                }
-            }
-            s.recs[tid] = r;
-        }
-        __syncthreads();
-        const int nclip = s.ctr[2];
-        if (!KEY && nclip > 0) {
-            // the single-pass variant cannot compose passes: host never selects it when this can
-            // matter (see pbr_render); flag by painting nothing extra.  (unreachable by contract)
-        }
-        raster_pass<KEY>(f, s, nblk, band_h);
-
-        // (1') clipped triangles: 16 slots x 8 fan triangles per pass
-        if (KEY) {
-#pragma unroll 1
-            for (int q0 = 0; q0 < nclip; q0 += CH / FAN) {
-                zero_masks(s, nblk);
-                __syncthreads();
-                Rec r;
-                r.meta = 0;
-                const int q = q0 + tid / FAN, k = tid % FAN;
-                if (q < nclip) {
-                    const int slot = chunk + s.cliplist[q];
-                    SlotGeom g;
-                    load_slot(f, scene, slot, g);
-                    CV poly[MAX_POLY];
-                    const int n = clip_poly(g.v, poly);
-                    if (k + 2 < n) {
-                        CV tri[3] = {poly[0], poly[k + 1], poly[k + 2]};
-                        BBox bb;
-                        if (setup_tri(f, tri, g.col, g.flat, g.two_sided, (unsigned)slot + 1u, band_y0, band_h, r, bb))
-                            bin_record(r, bb, tid, f.nbx, s.masks);
-                        else
-                            r.meta = 0;
-                    }
-                }
-                s.recs[tid] = r;
-                __syncthreads();
-                raster_pass<KEY>(f, s, nblk, band_h);
-            }
-        }
-    }
-    __syncthreads();
-
-    // (4) write the band: 128-bit stores straight into the caller's tensor
-    const size_t scene_bytes = (size_t)f.C * f.H * f.W;
-    unsigned char *dst_scene = f.out + (size_t)scene * scene_bytes;
-    if (f.linear) {
-        const int n16 = (int)(scene_bytes / 16);
-        const uint4 *src = reinterpret_cast<const uint4 *>(s.color);
-        uint4 *dst = reinterpret_cast<uint4 *>(dst_scene);
-        for (int i = tid; i < n16; i += THREADS) __stcs(dst + i, src[i]);
-        for (int i = n16 * 16 + tid; i < (int)scene_bytes; i += THREADS) dst_scene[i] = s.color[i];
-    } else {
-        const int nbytes = band_h * f.W;
-        for (int c = 0; c < f.C; ++c) {
-            unsigned char *dst = dst_scene + ((size_t)c * f.H + band_y0) * f.W;
-            const unsigned char *src = s.color + (size_t)c * f.plane_stride;
-            if ((reinterpret_cast<size_t>(dst) & 15) == 0) {
-                const int n16 = nbytes / 16;
-                for (int i = tid; i < n16; i += THREADS)
-                    __stcs(reinterpret_cast<uint4 *>(dst) + i, reinterpret_cast<const uint4 *>(src)[i]);
-                for (int i = n16 * 16 + tid; i < nbytes; i += THREADS) dst[i] = src[i];
-            } else {
-                for (int i = tid; i < nbytes; i += THREADS) dst[i] = src[i];
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// instance-transform kernels
-// ------------------------------------------------------------------------------------------------
-__global__ void pack_transforms_kernel(float *__restrict__ tr, const float *__restrict__ rot,
-                                       const float *__restrict__ scale, float *__restrict__ out, int n) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n) return;
-    float *T = tr + (size_t)b * 16;
-    const float *R = rot + (size_t)b * 9;
-    const float s = scale[b];
-    float m[16];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            m[4 * i + j] = R[3 * i + j] * s;
-            T[4 * i + j] = m[4 * i + j];
-        }
-        m[4 * i + 3] = T[4 * i + 3];
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) m[12 + j] = T[12 + j];
-    float4 *o = reinterpret_cast<float4 *>(out + (size_t)b * 16);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = make_float4(m[j], m[4 + j], m[8 + j], m[12 + j]);   // column j
-}
-
-constexpr int MAX_POSES = 8;
-struct PoseBatch {
-    pbr_pose_desc p[MAX_POSES];
-    int n;
-};
-
-__device__ __forceinline__ float chan(const pbr_channel &c, int b) {
-    return c.ptr ? __ldg(c.ptr + (size_t)b * c.stride) : c.constant;
-}
-
-__global__ void compose_kernel(const __grid_constant__ PoseBatch pb) {
-    const pbr_pose_desc &d = pb.p[blockIdx.y];
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= d.n_instances) return;
-    const float x = chan(d.pos[0], b), y = chan(d.pos[1], b), z = chan(d.pos[2], b);
-    const float h = chan(d.hpr[0], b), p = chan(d.hpr[1], b), r = chan(d.hpr[2], b);
-    const float s = chan(d.scale, b);
-    float sh, ch, sp, cp, sr, cr;
-    sincosf(h, &sh, &ch);
-    sincosf(p, &sp, &cp);
-    sincosf(r, &sr, &cr);
-    // R = Rz(h) Ry(p) Rx(r)   (reference shader_context.py:47-84)
-    const float r00 = ch * cp, r01 = ch * sp * sr - sh * cr, r02 = ch * sp * cr + sh * sr;
-    const float r10 = sh * cp, r11 = sh * sp * sr + ch * cr, r12 = sh * sp * cr - ch * sr;
-    const float r20 = -sp, r21 = cp * sr, r22 = cp * cr;
-    float4 *o = reinterpret_cast<float4 *>(d.out_mats + (size_t)b * 16);
-    o[0] = make_float4(r00 * s, r10 * s, r20 * s, 0.0f);
-    o[1] = make_float4(r01 * s, r11 * s, r21 * s, 0.0f);
-    o[2] = make_float4(r02 * s, r12 * s, r22 * s, 0.0f);
-    o[3] = make_float4(x, y, z, 1.0f);
-}
-
-// ------------------------------------------------------------------------------------------------
-// host side
-// ------------------------------------------------------------------------------------------------
 unsigned host_unorm8(float c) {
-    c = c < 0.0f ? 0.0f : c;       // fmaxf(NaN,0)=0 semantics: NaN < 0 is false, handled below
-    if (!(c == c)) c = 0.0f;
+    if (!(c == c)) c = 0.0f;         // fmaxf(NaN, 0) = 0
+    c = c < 0.0f ? 0.0f : c;
     c = c > 1.0f ? 1.0f : c;
     volatile float v = c * 255.0f;
     volatile float w = v + 0.5f;
     return (unsigned)(int)w;
 }
 
-struct DeviceLimits {
+struct DeviceState {
     int max_smem_optin = 0;
-    bool attr_set[2] = {false, false};
-    int attr_bytes[2] = {0, 0};
+    int sm_count = 0;
+    bool attr_general = false, attr_warp = false;
+    int *status = nullptr;           // device word with sticky DEVSTAT_* bits
 };
 std::mutex g_mu;
-DeviceLimits g_dev[64];
+DeviceState g_dev[64];
+
+int device_state(int device, DeviceState **out) {
+    DeviceState &st = g_dev[device & 63];
+    if (st.max_smem_optin == 0) {
+        CUDA_TRY(cudaDeviceGetAttribute(&st.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        CUDA_TRY(cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, device));
+        CUDA_TRY(cudaMalloc(&st.status, sizeof(int)));
+        CUDA_TRY(cudaMemset(st.status, 0, sizeof(int)));
+    }
+    *out = &st;
+    return PBR_OK;
+}
 
 }  // namespace
 
 struct pbr_mesh_s {
     int device;
     int n_tris;
+    int n_verts;        // unique positions
     int all_flat;
     unsigned flags;
-    float4 *tp;
-    float4 *tn;
+    float4 *tp;         // [T*3]
+    float4 *tn;         // [T*3]
+    float4 *vpos;       // [V]
+    uint4 *tidx;        // [T]
 };
 
 extern "C" {
@@ -785,36 +110,57 @@ int pbr_mesh_create(const float *pos, const float *nrm, const float *uv, int32_t
     *out = nullptr;
     if (!pos || !nrm || !idx || n_verts <= 0 || n_tris <= 0)
         return fail(PBR_EINVAL, "pbr_mesh_create: empty or NULL geometry (n_verts=%d n_tris=%d)", n_verts, n_tris);
-    std::vector<float4> tp((size_t)n_tris * 3), tn((size_t)n_tris * 3);
+    std::vector<float4> tp((size_t)n_tris * 3), tn((size_t)n_tris * 3), vpos;
+    std::vector<uint4> tidx((size_t)n_tris);
+    struct Key {
+        uint32_t a, b, c;
+        bool operator<(const Key &o) const { return a != o.a ? a < o.a : (b != o.b ? b < o.b : c < o.c); }
+    };
+    std::map<Key, uint32_t> uniq;
     int all_flat = 1;
     for (int t = 0; t < n_tris; ++t) {
         bool flat = true;
+        uint32_t ui[3];
         for (int k = 0; k < 3; ++k) {
-            uint32_t v = idx[3 * t + k];
+            const uint32_t v = idx[3 * t + k];
             if (v >= (uint32_t)n_verts) return fail(PBR_EINVAL, "pbr_mesh_create: index %u out of range", v);
             tp[3 * t + k] = make_float4(pos[3 * v], pos[3 * v + 1], pos[3 * v + 2], 0.0f);
             tn[3 * t + k] = make_float4(nrm[3 * v], nrm[3 * v + 1], nrm[3 * v + 2], 0.0f);
             if (memcmp(nrm + 3 * (size_t)v, nrm + 3 * (size_t)idx[3 * t], 12) != 0) flat = false;
+            Key key;
+            memcpy(&key, pos + 3 * (size_t)v, 12);
+            auto it = uniq.find(key);
+            if (it == uniq.end()) {
+                it = uniq.emplace(key, (uint32_t)vpos.size()).first;
+                vpos.push_back(make_float4(pos[3 * v], pos[3 * v + 1], pos[3 * v + 2], 1.0f));
+            }
+            ui[k] = it->second;
         }
-        int flag = flat ? 1 : 0;
+        const int flag = flat ? 1 : 0;
         memcpy(&tp[3 * t].w, &flag, 4);
+        tidx[t] = make_uint4(ui[0], ui[1], ui[2], (unsigned)flag);
         if (!flat) all_flat = 0;
     }
     int prev = 0;
     CUDA_TRY(cudaGetDevice(&prev));
     CUDA_TRY(cudaSetDevice(device));
     pbr_mesh_s *m = new (std::nothrow) pbr_mesh_s();
-    if (!m) return fail(PBR_ENOMEM, "pbr_mesh_create: host allocation failed");
-    m->device = device; m->n_tris = n_tris; m->all_flat = all_flat; m->flags = flags;
-    m->tp = nullptr; m->tn = nullptr;
-    size_t bytes = (size_t)n_tris * 3 * sizeof(float4);
-    cudaError_t e = cudaMalloc(&m->tp, bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&m->tn, bytes);
-    if (e == cudaSuccess) e = cudaMemcpy(m->tp, tp.data(), bytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(m->tn, tn.data(), bytes, cudaMemcpyHostToDevice);
+    if (!m) { cudaSetDevice(prev); return fail(PBR_ENOMEM, "pbr_mesh_create: host allocation failed"); }
+    memset(m, 0, sizeof(*m));
+    m->device = device; m->n_tris = n_tris; m->n_verts = (int)vpos.size(); m->all_flat = all_flat; m->flags = flags;
+    const size_t tb = (size_t)n_tris * 3 * sizeof(float4), vb = vpos.size() * sizeof(float4), ib = (size_t)n_tris * sizeof(uint4);
+    cudaError_t e = cudaMalloc(&m->tp, tb);
+    if (e == cudaSuccess) e = cudaMalloc(&m->tn, tb);
+    if (e == cudaSuccess) e = cudaMalloc(&m->vpos, vb);
+    if (e == cudaSuccess) e = cudaMalloc(&m->tidx, ib);
+    if (e == cudaSuccess) e = cudaMemcpy(m->tp, tp.data(), tb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(m->tn, tn.data(), tb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(m->vpos, vpos.data(), vb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(m->tidx, tidx.data(), ib, cudaMemcpyHostToDevice);
     cudaSetDevice(prev);
     if (e != cudaSuccess) {
-        cudaFree(m->tp); cudaFree(m->tn); delete m;
+        cudaFree(m->tp); cudaFree(m->tn); cudaFree(m->vpos); cudaFree(m->tidx);
+        delete m;
         return fail(e == cudaErrorMemoryAllocation ? PBR_ENOMEM : PBR_ECUDA, "pbr_mesh_create: %s", cudaGetErrorString(e));
     }
     *out = m;
@@ -823,8 +169,7 @@ int pbr_mesh_create(const float *pos, const float *nrm, const float *uv, int32_t
 
 int pbr_mesh_destroy(pbr_mesh_t m) {
     if (!m) return PBR_OK;
-    cudaFree(m->tp);
-    cudaFree(m->tn);
+    cudaFree(m->tp); cudaFree(m->tn); cudaFree(m->vpos); cudaFree(m->tidx);
     delete m;
     return PBR_OK;
 }
@@ -868,12 +213,14 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         float inv = 1.0f / sqrtf(l2);
         f.ldir[0] = x * inv; f.ldir[1] = y * inv; f.ldir[2] = z * inv;
         float s = d->strength;
-        s = s < 0.0f ? 0.0f : s; if (!(s == s)) s = 0.0f; s = s > 1.0f ? 1.0f : s;
+        if (!(s == s)) s = 0.0f;
+        s = s < 0.0f ? 0.0f : s;
+        s = s > 1.0f ? 1.0f : s;
         f.s = s; f.oms = 1.0f - s;
         for (int c = 0; c < 3; ++c) { f.amb[c] = d->ambient[c]; f.dcol[c] = d->dir_col[c]; }
     }
-    long long slots = 0;
-    bool any_smooth = false;
+    long long slots = 0, verts = 0;
+    bool any_smooth = false, warp_ok = true;
     f.n_nodes = 0;
     for (int i = 0; i < d->n_nodes; ++i) {
         const pbr_node_desc &n = d->nodes[i];
@@ -886,60 +233,98 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         if (n.use_texture != 0.0f) return fail(PBR_EUNSUPPORTED, "pbr_render: node %d: textures are not implemented", i);
         if (n.instances_per_scene == 0) continue;
         NodeDev &nd = f.nodes[f.n_nodes++];
-        nd.tp = n.mesh->tp; nd.tn = n.mesh->tn; nd.mats = n.mats; nd.cols = n.cols;
-        nd.n_tris = n.mesh->n_tris; nd.inst = n.instances_per_scene; nd.shared = n.shared ? 1 : 0;
-        nd.slot_begin = (int)slots; nd.flags = n.mesh->flags;
+        nd.tp = n.mesh->tp; nd.tn = n.mesh->tn; nd.vpos = n.mesh->vpos; nd.tidx = n.mesh->tidx;
+        nd.mats = n.mats; nd.cols = n.cols;
+        nd.n_tris = n.mesh->n_tris; nd.n_verts = n.mesh->n_verts;
+        nd.inst = n.instances_per_scene; nd.shared = n.shared ? 1 : 0;
+        nd.slot_begin = (int)slots; nd.vert_begin = (int)verts; nd.flags = n.mesh->flags;
         slots += (long long)n.instances_per_scene * n.mesh->n_tris;
+        verts += (long long)n.instances_per_scene * n.mesh->n_verts;
         if (!n.mesh->all_flat) any_smooth = true;
+        if (n.instances_per_scene >= 8192 || n.mesh->n_tris >= 8192) warp_ok = false;
         if (slots > (1ll << 30)) return fail(PBR_EUNSUPPORTED, "pbr_render: more than 2^30 triangles per scene");
     }
     if (any_smooth) return fail(PBR_EUNSUPPORTED, "pbr_render: smooth-normal meshes are not implemented yet");
     f.total_slots = (int)slots;
+    f.total_verts = (int)(verts > 0x7fffffff ? 0x7fffffff : verts);
 
-    // band height: full tile when the per-CTA shared memory stays moderate, else bands of rows
     std::lock_guard<std::mutex> lock(g_mu);
-    DeviceLimits &lim = g_dev[device & 63];
-    if (lim.max_smem_optin == 0)
-        CUDA_TRY(cudaDeviceGetAttribute(&lim.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    DeviceState *st = nullptr;
+    if (int rc = device_state(device, &st)) return rc;
+    f.status = st->status;
 
-    const bool key = true;   // single-pass variant is selected below when safe
-    (void)key;
     const int W = f.W, H = f.H;
     const int nbx = (W + 7) / 8;
-    auto bytes_for = [&](int BH, bool k) {
-        int nby = (BH + 7) / 8;
-        int ps = (int)align16((size_t)BH * W);
-        return smem_bytes(f.C, ps, nbx * nby, k);
+    const int H8 = ((H + 7) / 8) * 8;
+
+    // ---- small-scene kernel: one warp per scene
+    warp_ok = warp_ok && !(d->flags & PBR_FRAME_FORCE_GENERAL) && slots <= W_MAXSLOT && verts <= W_MAXVERT &&
+              nbx <= 256 && H8 / 8 <= 256;
+    if (warp_ok) {
+        const int ps = (int)align16((size_t)H8 * W);
+        const size_t smem = warp_smem_bytes(f.C, ps, nbx * (H8 / 8));
+        if (smem <= 40 * 1024 && smem <= (size_t)st->max_smem_optin) {
+            f.BH = H8; f.nbands = 1; f.nbx = nbx; f.nby = H8 / 8;
+            f.plane_stride = (H8 == H && ((H * W) % 16) == 0) ? H * W : ps;
+            f.linear = (f.plane_stride == H * W) ? 1 : 0;
+            if (!st->attr_warp) {
+                CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+                CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                st->attr_warp = true;
+            }
+            raster_warp_kernel<<<(unsigned)f.scene_count, 32, smem, (cudaStream_t)stream>>>(f);
+            CUDA_TRY(cudaGetLastError());
+            return PBR_OK;
+        }
+    }
+
+    // ---- general kernel: one CTA per (scene, band of rows)
+    auto bytes_for = [&](int BH) {
+        const int nby = (BH + 7) / 8;
+        const int ps = (int)align16((size_t)BH * W);
+        return general_smem_bytes(f.C, ps, nbx * nby);
     };
     const size_t budget = 56 * 1024;
-    int BH = ((H + 7) / 8) * 8;
-    while (BH > 8 && bytes_for(BH, true) > budget) BH -= 8;
-    if (bytes_for(BH, true) > (size_t)lim.max_smem_optin)
-        return fail(PBR_EUNSUPPORTED, "pbr_render: tile width %d needs %zu bytes of shared memory per 8-row band", W, bytes_for(BH, true));
-    if (BH > H) BH = ((H + 7) / 8) * 8;
+    int BH = H8;
+    while (BH > 8 && bytes_for(BH) > budget) BH -= 8;
+    if (bytes_for(BH) > (size_t)st->max_smem_optin)
+        return fail(PBR_EUNSUPPORTED, "pbr_render: tile width %d needs %zu bytes of shared memory per 8-row band", W, bytes_for(BH));
     f.BH = BH;
     f.nbands = (H + BH - 1) / BH;
     f.nbx = nbx;
     f.nby = BH / 8;
-    if (f.nby < 1) f.nby = 1;
     if (f.nbx > 256 || f.nby > 256) return fail(PBR_EUNSUPPORTED, "pbr_render: more than 256 blocks per band side");
     f.plane_stride = (int)align16((size_t)BH * W);
     f.linear = (f.nbands == 1 && f.plane_stride == H * W) ? 1 : 0;
-    if (f.nbands == 1 && !f.linear) {
-        // full tile but H*W not a multiple of 16: keep planes separate (per-plane stores)
-    }
-    const size_t smem = bytes_for(BH, true);
-    const int which = 1;
-    if (!lim.attr_set[which] || lim.attr_bytes[which] < (int)smem) {
-        CUDA_TRY(cudaFuncSetAttribute(raster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim.max_smem_optin));
-        lim.attr_set[which] = true;
-        lim.attr_bytes[which] = lim.max_smem_optin;
+    const size_t smem = bytes_for(BH);
+    if (!st->attr_general) {
+        CUDA_TRY(cudaFuncSetAttribute(raster_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem_optin));
+        st->attr_general = true;
     }
     const long long grid = (long long)f.scene_count * f.nbands;
     if (grid > 0x7fffffffll) return fail(PBR_EUNSUPPORTED, "pbr_render: grid too large");
-    raster_kernel<true><<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(f);
+    raster_general_kernel<<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(f);
     CUDA_TRY(cudaGetLastError());
     return PBR_OK;
+}
+
+int pbr_device_status(int32_t device, int32_t *status_bits, int32_t clear) {
+    if (!status_bits) return fail(PBR_EINVAL, "pbr_device_status: NULL output");
+    std::lock_guard<std::mutex> lock(g_mu);
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    CUDA_TRY(cudaSetDevice(device));
+    DeviceState *st = nullptr;
+    int rc = device_state(device, &st);
+    if (rc == PBR_OK) {
+        int v = 0;
+        cudaError_t e = cudaMemcpy(&v, st->status, sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && clear) e = cudaMemset(st->status, 0, sizeof(int));
+        if (e != cudaSuccess) rc = fail(PBR_ECUDA, "pbr_device_status: %s", cudaGetErrorString(e));
+        *status_bits = v;
+    }
+    cudaSetDevice(prev);
+    return rc;
 }
 
 int pbr_pack_transforms(float *transforms_b44, const float *rot_b33, const float *scale_b, float *out_mats,

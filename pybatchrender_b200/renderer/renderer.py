@@ -81,6 +81,7 @@ class PBRRenderer:
         self._scene_version = 0
         self._node_cache = None
         self._environment_ready = False
+        self.render_flags = 0          # PBR_FRAME_* bits OR-ed into every pbr_render call
 
     # ------------------------------------------------------------------ scene construction
     def set_background_color(self, r: float, g: float, b: float, a: float = 1.0) -> None:
@@ -210,7 +211,7 @@ class PBRRenderer:
         self._native.render(num_scenes=N, tile_w=W, tile_h=H, channels=C, vp=self._pbr_cam.viewbuf,
                             nodes=self._native_nodes(), out=out, bg=self._background_color,
                             ambient=amb, dir_dir=ddir, dir_col=dcol, strength=strength,
-                            scene_begin=scene_begin, scene_count=scene_count, flags=flags)
+                            scene_begin=scene_begin, scene_count=scene_count, flags=flags | self.render_flags)
         return out
 
     def _step(self, *args, **kwargs):

@@ -23,9 +23,12 @@ def _assert_same(gpu: torch.Tensor, ref: np.ndarray, what: str = ""):
                              f"(first at {np.argwhere(diff)[0].tolist()})")
 
 
-def _cartpole(n, tile=(64, 64), **kw):
+def _cartpole(n, tile=(64, 64), general=False, **kw):
     from pybatchrender_b200.envs.cartpole import CartPoleRenderer
-    return CartPoleRenderer(dict(num_scenes=n, tile_resolution=tile, device="cuda", **kw))
+    r = CartPoleRenderer(dict(num_scenes=n, tile_resolution=tile, device="cuda", **kw))
+    if general:
+        r.render_flags = 1          # PBR_FRAME_FORCE_GENERAL: skip the one-warp-per-scene kernel
+    return r
 
 
 def test_native_library_is_loaded():
@@ -61,10 +64,11 @@ def test_notebook_golden_tiles_on_gpu(golden):
     assert np.array_equal((px[1] != 105).any(0), (gold[1] != 105).any(0))
 
 
+@pytest.mark.parametrize("general", [False, True], ids=["warp", "general"])
 @pytest.mark.parametrize("n,tile", [(256, (64, 64)), (100, (84, 84)), (37, (128, 128)), (9, (50, 30)),
-                                    (5, (256, 256)), (3, (8, 8)), (2, (200, 40))])
-def test_cartpole_random_states_bit_exact(n, tile):
-    r = _cartpole(n, tile)
+                                    (5, (256, 256)), (3, (8, 8)), (2, (200, 40)), (33, (96, 64))])
+def test_cartpole_random_states_bit_exact(n, tile, general):
+    r = _cartpole(n, tile, general=general)
     px = r.step(cartpole_states(n, seed=n).cuda())
     _assert_same(px, oracle_render(r), f"cartpole {n}x{tile}")
 
@@ -106,6 +110,23 @@ def test_camera_inside_geometry_heavy_clipping():
     r = many_cubes_renderer(num_scenes=16, instances=12, tile=(64, 64), device="cuda", seed=11, spread=3.0,
                             eye=(0.0, -1.0, 0.0))
     _assert_same(r.step(), oracle_render(r), "heavy clipping")
+
+
+@pytest.mark.parametrize("general", [False, True], ids=["warp", "general"])
+@pytest.mark.parametrize("seed,eye,spread", [(21, (0.0, -1.0, 0.0), 2.0), (22, (0.0, -2.5, 0.3), 3.0),
+                                              (23, (0.2, 0.1, 0.0), 2.5), (24, (0.0, -6.0, 0.0), 6.0)])
+def test_small_scene_with_clipping(general, seed, eye, spread):
+    """3 boxes = 36 slots: eligible for the one-warp-per-scene kernel, camera close enough that
+    triangles cross the near plane (fan triangles go to the spare record slots)."""
+    r = many_cubes_renderer(num_scenes=64, instances=3, tile=(64, 64), device="cuda", seed=seed, spread=spread,
+                            eye=eye)
+    if general:
+        r.render_flags = 1
+    px = r.step()
+    ref = oracle_render(r)
+    assert (ref != 0).any()
+    _assert_same(px, ref, "small scene clipping")
+    assert r._native.device_status(torch.cuda.current_device()) == 0
 
 
 def test_shared_node_many_instances():
