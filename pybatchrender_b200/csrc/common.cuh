@@ -57,11 +57,10 @@ constexpr unsigned M_NB0 = 1u << 19, M_NB1 = 1u << 20, M_NB2 = 1u << 21;
 
 struct __align__(16) Rec {
     int e[9];        // fast: Eo[3], A[3], B[3]        slow: X0,Y0,X1,Y1,X2,Y2,-,-,-
-    float z0, dz1, dz2;
-    float invA;
     unsigned col;    // packed RGBA8 (flat shading)
     unsigned id;     // 1 + draw index
     unsigned meta;   // anchor block x (8) | anchor block y (8) | flags
+    float z0, dz1, dz2, invA;   // 16-byte aligned: one LDS.128
 };
 static_assert(sizeof(Rec) == 64, "Rec must be 64 bytes");
 
@@ -317,9 +316,16 @@ __device__ __forceinline__ void bin_record(const Rec &r, const BBox &bb, int t, 
 // one 8x8 block: every lane owns pixels (lx, ly) and (lx, ly+4); loop over the block's records
 // ------------------------------------------------------------------------------------------------
 struct PixelState {
-    unsigned zb0, zb1, id0, id1, c0, c1;
+    unsigned long long k0, k1;   // (depth bits << 32) | id   -- smaller wins (LESS, ties to the earlier draw)
+    unsigned c0, c1;             // packed RGBA8 of the current winner
     bool ch0, ch1;
 };
+
+constexpr unsigned long long KEY_CLEAR = 0x3F80000000000000ull;   // depth 1.0, id 0
+
+__device__ __forceinline__ unsigned long long make_key(float z, unsigned id) {
+    return ((unsigned long long)__float_as_uint(z) << 32) | id;
+}
 
 template <int MWORDS>
 __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bmask, int px, int py0, bool ok0,
@@ -333,14 +339,16 @@ __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bm
             const int t = w * 32 + __ffs(m) - 1;
             m &= m - 1;
             const Rec &r = recs[t];
-            const unsigned meta = r.meta;
+            const int4 ec = *reinterpret_cast<const int4 *>(&r.e[8]);         // B2 col id meta
+            const unsigned meta = (unsigned)ec.w;
             bool cov0, cov1;
+            float f1a, f2a, f1b, f2b;
             if (!(meta & M_SLOW)) {
-                const unsigned rx = (unsigned)(px - (int)(meta & 255u) * 8);
-                const unsigned ry = (unsigned)(py0 - (int)((meta >> 8) & 255u) * 8);
+                const unsigned rx = (unsigned)px - (meta & 255u) * 8u;
+                const unsigned ry = (unsigned)py0 - ((meta >> 8) & 255u) * 8u;
                 const int4 ea = *reinterpret_cast<const int4 *>(&r.e[0]);     // Eo0 Eo1 Eo2 A0
                 const int4 eb = *reinterpret_cast<const int4 *>(&r.e[4]);     // A1 A2 B0 B1
-                const int B2 = r.e[8];
+                const int B2 = ec.x;
                 const int F0 = (int)((unsigned)ea.x + (unsigned)ea.w * rx + (unsigned)eb.z * ry);
                 const int F1 = (int)((unsigned)ea.y + (unsigned)eb.x * rx + (unsigned)eb.w * ry);
                 const int F2 = (int)((unsigned)ea.z + (unsigned)eb.y * rx + (unsigned)B2 * ry);
@@ -349,18 +357,10 @@ __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bm
                 const int G2 = (int)((unsigned)F2 + 4u * (unsigned)B2);
                 cov0 = ok0 && ((F0 | F1 | F2) >= 0);
                 cov1 = ok1 && ((G0 | G1 | G2) >= 0);
-                if (__any_sync(0xffffffffu, cov0 || cov1)) {
-                    const int nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
-                    const float invA = r.invA, z0 = r.z0, dz1 = r.dz1, dz2 = r.dz2;
-                    const unsigned id = r.id, col = r.col;
-                    const float za = fmaf((float)(F2 + nb2) * invA, dz2, fmaf((float)(F1 + nb1) * invA, dz1, z0));
-                    const float zc = fmaf((float)(G2 + nb2) * invA, dz2, fmaf((float)(G1 + nb1) * invA, dz1, z0));
-                    const unsigned za_b = __float_as_uint(za), zc_b = __float_as_uint(zc);
-                    const bool w0 = cov0 && (za_b < ps.zb0 || (za_b == ps.zb0 && id < ps.id0));
-                    const bool w1 = cov1 && (zc_b < ps.zb1 || (zc_b == ps.zb1 && id < ps.id1));
-                    if (w0) { ps.zb0 = za_b; ps.id0 = id; ps.c0 = col; ps.ch0 = true; }
-                    if (w1) { ps.zb1 = zc_b; ps.id1 = id; ps.c1 = col; ps.ch1 = true; }
-                }
+                if (!__any_sync(0xffffffffu, cov0 || cov1)) continue;
+                const int nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
+                f1a = (float)(F1 + nb1); f2a = (float)(F2 + nb2);
+                f1b = (float)(G1 + nb1); f2b = (float)(G2 + nb2);
             } else {
                 const int spx = px * 256 + 128, spy0 = py0 * 256 + 128, spy1 = py1 * 256 + 128;
                 const long long F0 = slow_edge(r, 0, spx, spy0), F1 = slow_edge(r, 1, spx, spy0),
@@ -369,19 +369,19 @@ __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bm
                                 G2 = slow_edge(r, 2, spx, spy1);
                 cov0 = ok0 && ((F0 | F1 | F2) >= 0);
                 cov1 = ok1 && ((G0 | G1 | G2) >= 0);
-                if (__any_sync(0xffffffffu, cov0 || cov1)) {
-                    const long long nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
-                    const float invA = r.invA, z0 = r.z0, dz1 = r.dz1, dz2 = r.dz2;
-                    const unsigned id = r.id, col = r.col;
-                    const float za = fmaf((float)(F2 + nb2) * invA, dz2, fmaf((float)(F1 + nb1) * invA, dz1, z0));
-                    const float zc = fmaf((float)(G2 + nb2) * invA, dz2, fmaf((float)(G1 + nb1) * invA, dz1, z0));
-                    const unsigned za_b = __float_as_uint(za), zc_b = __float_as_uint(zc);
-                    const bool w0 = cov0 && (za_b < ps.zb0 || (za_b == ps.zb0 && id < ps.id0));
-                    const bool w1 = cov1 && (zc_b < ps.zb1 || (zc_b == ps.zb1 && id < ps.id1));
-                    if (w0) { ps.zb0 = za_b; ps.id0 = id; ps.c0 = col; ps.ch0 = true; }
-                    if (w1) { ps.zb1 = zc_b; ps.id1 = id; ps.c1 = col; ps.ch1 = true; }
-                }
+                if (!__any_sync(0xffffffffu, cov0 || cov1)) continue;
+                const long long nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
+                f1a = (float)(F1 + nb1); f2a = (float)(F2 + nb2);
+                f1b = (float)(G1 + nb1); f2b = (float)(G2 + nb2);
             }
+            const float4 zq = *reinterpret_cast<const float4 *>(&r.z0);      // z0 dz1 dz2 invA
+            const unsigned id = (unsigned)ec.z, col = (unsigned)ec.y;
+            const float za = fmaf(f2a * zq.w, zq.z, fmaf(f1a * zq.w, zq.y, zq.x));
+            const float zc = fmaf(f2b * zq.w, zq.z, fmaf(f1b * zq.w, zq.y, zq.x));
+            const unsigned long long ka = make_key(za, id), kc = make_key(zc, id);
+            const bool w0 = cov0 & (ka < ps.k0), w1 = cov1 & (kc < ps.k1);
+            ps.k0 = w0 ? ka : ps.k0; ps.c0 = w0 ? col : ps.c0; ps.ch0 |= w0;
+            ps.k1 = w1 ? kc : ps.k1; ps.c1 = w1 ? col : ps.c1; ps.ch1 |= w1;
         }
     }
 }

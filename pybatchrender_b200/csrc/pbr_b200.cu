@@ -261,14 +261,13 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
     warp_ok = warp_ok && !(d->flags & PBR_FRAME_FORCE_GENERAL) && slots <= W_MAXSLOT && verts <= W_MAXVERT &&
               nbx <= 256 && H8 / 8 <= 256;
     if (warp_ok) {
-        const int ps = (int)align16((size_t)H8 * W);
-        const size_t smem = warp_smem_bytes(f.C, ps, nbx * (H8 / 8));
+        const size_t smem = warp_smem_bytes(nbx * (H8 / 8));
         if (smem <= 40 * 1024 && smem <= (size_t)st->max_smem_optin) {
             f.BH = H8; f.nbands = 1; f.nbx = nbx; f.nby = H8 / 8;
-            f.plane_stride = (H8 == H && ((H * W) % 16) == 0) ? H * W : ps;
-            f.linear = (f.plane_stride == H * W) ? 1 : 0;
+            f.plane_stride = H * W;
+            f.linear = 1;
             if (!st->attr_warp) {
-                CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+                CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024));
                 CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
                 st->attr_warp = true;
             }

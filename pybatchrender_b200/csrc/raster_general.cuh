@@ -86,8 +86,7 @@ __device__ __forceinline__ bool setup_tri(const FrameDev &f, const CV *vin, cons
 // ------------------------------------------------------------------------------------------------
 struct Smem {
     unsigned char *color;      // [C][plane_stride]
-    float *ztile;              // [nblk*64] block-major
-    unsigned *itile;           // [nblk*64]
+    unsigned long long *ktile; // [nblk*64] block-major (depth bits << 32) | id
     Rec *recs;                 // [CH]
     unsigned *masks;           // [nblk*MW]
     unsigned short *blist;     // [nblk]
@@ -110,8 +109,7 @@ __host__ __device__ inline size_t general_smem_bytes(int C, int plane_stride, in
 __device__ __forceinline__ Smem carve(unsigned char *base, int C, int plane_stride, int nblk) {
     Smem s;
     s.color = base; base += align16((size_t)C * plane_stride);
-    s.ztile = reinterpret_cast<float *>(base); base += (size_t)nblk * 64 * 4;
-    s.itile = reinterpret_cast<unsigned *>(base); base += (size_t)nblk * 64 * 4;
+    s.ktile = reinterpret_cast<unsigned long long *>(base); base += (size_t)nblk * 64 * 8;
     s.recs = reinterpret_cast<Rec *>(base); base += (size_t)CH * sizeof(Rec);
     s.masks = reinterpret_cast<unsigned *>(base); base += align16((size_t)nblk * MW * 4);
     s.blist = reinterpret_cast<unsigned short *>(base); base += align16((size_t)nblk * 2);
@@ -126,21 +124,17 @@ __device__ __forceinline__ void general_block(const FrameDev &f, const Smem &s, 
     const int py0 = by * 8 + (lane >> 3), py1 = py0 + 4;
     const bool ok0 = px < f.W && py0 < band_h, ok1 = px < f.W && py1 < band_h;
     PixelState ps;
-    ps.zb0 = __float_as_uint(s.ztile[b * 64 + lane]);
-    ps.zb1 = __float_as_uint(s.ztile[b * 64 + 32 + lane]);
-    ps.id0 = s.itile[b * 64 + lane];
-    ps.id1 = s.itile[b * 64 + 32 + lane];
+    ps.k0 = s.ktile[b * 64 + lane];
+    ps.k1 = s.ktile[b * 64 + 32 + lane];
     ps.c0 = ps.c1 = 0;
     ps.ch0 = ps.ch1 = false;
     raster_block<MW>(s.recs, s.masks + b * MW, px, py0, ok0, ok1, ps);
     if (ps.ch0) {
-        s.ztile[b * 64 + lane] = __uint_as_float(ps.zb0);
-        s.itile[b * 64 + lane] = ps.id0;
+        s.ktile[b * 64 + lane] = ps.k0;
         put_pixel(s.color, f.plane_stride, f.C, f.W, px, py0, ps.c0);
     }
     if (ps.ch1) {
-        s.ztile[b * 64 + 32 + lane] = __uint_as_float(ps.zb1);
-        s.itile[b * 64 + 32 + lane] = ps.id1;
+        s.ktile[b * 64 + 32 + lane] = ps.k1;
         put_pixel(s.color, f.plane_stride, f.C, f.W, px, py1, ps.c1);
     }
 }
@@ -222,10 +216,9 @@ __global__ void __launch_bounds__(THREADS) raster_general_kernel(const __grid_co
 
     clear_color(f, s.color, tid, THREADS);
     {
-        uint4 *zt = reinterpret_cast<uint4 *>(s.ztile), *it = reinterpret_cast<uint4 *>(s.itile);
-        const uint4 one = make_uint4(0x3F800000u, 0x3F800000u, 0x3F800000u, 0x3F800000u);
-        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-        for (int i = tid; i < nblk * 16; i += THREADS) { zt[i] = one; it[i] = zero; }
+        uint4 *kt = reinterpret_cast<uint4 *>(s.ktile);
+        const uint4 clr = make_uint4(0u, 0x3F800000u, 0u, 0x3F800000u);
+        for (int i = tid; i < nblk * 32; i += THREADS) kt[i] = clr;
     }
 
     const int S = f.total_slots;

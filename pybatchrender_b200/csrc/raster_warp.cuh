@@ -1,39 +1,39 @@
-// raster_warp.cuh -- the small-scene raster kernel: ONE WARP per scene, no block-level barriers.
+// raster_warp.cuh -- the small-scene raster kernel: ONE WARP per scene, no block-level barriers and
+// no colour tile in shared memory.
 //
-// Target: CartPole-class scenes (a few instances of small flat-shaded meshes, <= 48 triangle slots,
-// tile up to ~128x128).  A scene costs only a few thousand warp instructions, so the design goal is
-// to keep every issue slot busy: a CTA is a single warp that owns its scene end to end, 10+ such
-// CTAs are resident per SM, and there is nothing to wait for except the warp's own memory traffic.
+// Target: CartPole-class scenes (a few instances of small flat-shaded meshes, <= 48 triangle slots).
+// A scene costs only a few thousand warp instructions and ~2 % of its pixels are covered, so the
+// design goals are (a) as many resident warps per SM as possible -- the per-scene shared-memory
+// footprint is ~7 KB (records, masks, parked vertices), which lets 24+ single-warp CTAs share an SM
+// -- and (b) no wasted memory traffic: the background goes straight to out[scene] as 128-bit
+// stores issued first (so HBM/L2 work overlaps the geometry phase), and only covered pixels are
+// patched afterwards (the lines are still dirty in L2, so DRAM sees each byte once).
 //
+//   0  background 128-bit stores of the clear colour over out[scene]           (renderer.py:262-264)
 //   A  vertices   lanes = (instance, unique vertex): clip = VP*(M*v), outcodes, project + snap,
-//                 parked in shared memory (aliasing the not-yet-cleared colour tile)
+//                 parked in shared memory                                        (basic.vert:24-43)
 //   B1 classify   lanes = triangle slots: trivial reject / needs-clip / back-face cull from the
 //                 parked vertices; survivors are compacted with ballots
-//   B2 setup      lanes = surviving triangles: integer edge equations, depth plane, flat shade ->
-//                 64-byte record in shared memory; binned into per-8x8-block 64-bit masks
+//   B2 setup      lanes = surviving triangles: integer edge equations, depth plane, flat shade
+//                 (basic.frag:31-38) -> 64-byte record; binned into per-8x8-block 64-bit masks
 //   B3 clip       lanes = triangles crossing the near plane / guard band: Sutherland-Hodgman, fan
 //                 triangles appended to the spare record slots
-//   C  clear      colour tile = background (128-bit shared stores)
-//   D  raster     non-empty blocks, one after the other; every lane owns 2 pixels of the block and
-//                 keeps their depth / id / colour in registers across the block's records
-//   E  store      the finished tile goes out with 128-bit streaming stores into out[scene]
+//   D  raster     non-empty blocks one after the other; every lane owns 2 pixels of the block and
+//                 keeps their (depth|id) key and colour in registers across the block's records;
+//                 winners are written straight to out[scene] (byte stores, merged in L2)
 #pragma once
 #include "common.cuh"
-#include "raster_general.cuh"   // store_band, clear_color
 
 namespace pbr {
 
 constexpr int W_MAXREC = 64;     // records per scene (triangle slots that survive + clipped fans)
 constexpr int W_MAXSLOT = 48;    // eligibility: leaves >= 16 spare records for clipped fans
-constexpr int W_MAXVERT = 96;    // (instance, vertex) pairs per scene
+constexpr int W_MAXVERT = 64;    // (instance, vertex) pairs per scene
 constexpr int W_MW = W_MAXREC / 32;
 
-__host__ __device__ inline size_t warp_smem_bytes(int C, int plane_stride, int nblk) {
-    size_t color = align16((size_t)C * plane_stride);
-    const size_t scratch = (size_t)W_MAXVERT * 32;
-    if (color < scratch) color = scratch;
-    return color + (size_t)W_MAXREC * sizeof(Rec) + align16((size_t)nblk * W_MW * 4) + align16((size_t)nblk * 2) +
-           2 * W_MAXREC * 4;
+__host__ __device__ inline size_t warp_smem_bytes(int nblk) {
+    return (size_t)W_MAXVERT * 32 + (size_t)W_MAXREC * sizeof(Rec) + align16((size_t)nblk * W_MW * 4) +
+           align16((size_t)nblk * 2) + 2 * W_MAXREC * 4;
 }
 
 struct WSlot {
@@ -61,20 +61,38 @@ __device__ __forceinline__ void load_mat(const float *m, float *M) {
 // vertex flags
 constexpr int VF_CLIP = 0x40, VF_PROJ = 0x80;
 
+// fill [dst, dst+n) with byte value v: 128-bit stores on the aligned body
+__device__ __forceinline__ void fill_bytes(unsigned char *dst, int n, unsigned v, int lane) {
+    const unsigned v4 = v * 0x01010101u;
+    const int head = min(n, (int)((16 - (reinterpret_cast<size_t>(dst) & 15)) & 15));
+    for (int i = lane; i < head; i += 32) dst[i] = (unsigned char)v;
+    const int n16 = (n - head) / 16;
+    uint4 *p = reinterpret_cast<uint4 *>(dst + head);
+    const uint4 q = make_uint4(v4, v4, v4, v4);
+    for (int i = lane; i < n16; i += 32) p[i] = q;
+    for (int i = head + n16 * 16 + lane; i < n; i += 32) dst[i] = (unsigned char)v;
+}
+
 __global__ void __launch_bounds__(32) raster_warp_kernel(const __grid_constant__ FrameDev f) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int scene = f.scene_begin + (int)blockIdx.x;
     const int nblk = f.nbx * f.nby;
+    const int HW = f.H * f.W;
+    unsigned char *out_scene = f.out + (size_t)scene * f.C * HW;
+
+    // ---- 0: background straight to global memory
+    if (((f.bg ^ (f.bg >> 8)) & (f.C == 4 ? 0xffffffu : 0xffffu)) == 0) {
+        fill_bytes(out_scene, f.C * HW, f.bg & 255u, lane);       // grey background: one run
+    } else {
+        for (int c = 0; c < f.C; ++c) fill_bytes(out_scene + (size_t)c * HW, HW, (f.bg >> (8 * c)) & 255u, lane);
+    }
 
     // ---- carve shared memory
-    size_t color_bytes = align16((size_t)f.C * f.plane_stride);
-    if (color_bytes < (size_t)W_MAXVERT * 32) color_bytes = (size_t)W_MAXVERT * 32;
-    unsigned char *color = smem_raw;
-    float4 *clipc = reinterpret_cast<float4 *>(smem_raw);                      // [W_MAXVERT] (aliases colour)
+    float4 *clipc = reinterpret_cast<float4 *>(smem_raw);                      // [W_MAXVERT]
     int4 *proj = reinterpret_cast<int4 *>(smem_raw + (size_t)W_MAXVERT * 16);  // [W_MAXVERT]
-    Rec *recs = reinterpret_cast<Rec *>(smem_raw + color_bytes);
+    Rec *recs = reinterpret_cast<Rec *>(smem_raw + (size_t)W_MAXVERT * 32);
     unsigned *masks = reinterpret_cast<unsigned *>(recs + W_MAXREC);
     unsigned short *blist = reinterpret_cast<unsigned short *>(masks + align16((size_t)nblk * W_MW * 4) / 4);
     unsigned *live = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(blist) + align16((size_t)nblk * 2));
@@ -191,73 +209,70 @@ __global__ void __launch_bounds__(32) raster_warp_kernel(const __grid_constant__
     int nrec = nlive;
 
     // ---- B3: clipped triangles -> fan triangles in the spare record slots
-    bool overflow = false;
+    if (nclip > 0) {
+        bool overflow = false;
 #pragma unroll 1
-    for (int base = 0; base < nclip; base += 32) {
-        const int j = base + lane;
-        int cnt = 0;
-        CV poly[MAX_POLY];
-        float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
-        unsigned id = 0;
-        bool two_sided = false;
-        if (j < nclip) {
-            const WSlot ws = unpack_slot(clipl[j]);
-            const NodeDev &nd = f.nodes[ws.ni];
-            const uint4 ti = __ldg(nd.tidx + ws.tri);
-            const int vb = nd.vert_begin + ws.inst * nd.n_verts;
-            const size_t b = nd.shared ? (size_t)ws.inst : (size_t)scene * nd.inst + ws.inst;
-            float M[16], n[3];
-            load_mat(nd.mats + b * 16, M);
-            const float4 n0 = __ldg(nd.tn + 3 * ws.tri);
-            xform_normal(M, n0.x, n0.y, n0.z, n);
-            col = __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4));
-            id = (unsigned)(nd.slot_begin + ws.inst * nd.n_tris + ws.tri) + 1u;
-            two_sided = (nd.flags & PBR_MESH_TWO_SIDED) != 0;
-            CV v[3];
-            const unsigned vi[3] = {ti.x, ti.y, ti.z};
+        for (int base = 0; base < nclip; base += 32) {
+            const int j = base + lane;
+            int cnt = 0;
+            CV poly[MAX_POLY];
+            float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned id = 0;
+            bool two_sided = false;
+            if (j < nclip) {
+                const WSlot ws = unpack_slot(clipl[j]);
+                const NodeDev &nd = f.nodes[ws.ni];
+                const uint4 ti = __ldg(nd.tidx + ws.tri);
+                const int vb = nd.vert_begin + ws.inst * nd.n_verts;
+                const size_t b = nd.shared ? (size_t)ws.inst : (size_t)scene * nd.inst + ws.inst;
+                float M[16], n[3];
+                load_mat(nd.mats + b * 16, M);
+                const float4 n0 = __ldg(nd.tn + 3 * ws.tri);
+                xform_normal(M, n0.x, n0.y, n0.z, n);
+                col = __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4));
+                id = (unsigned)(nd.slot_begin + ws.inst * nd.n_tris + ws.tri) + 1u;
+                two_sided = (nd.flags & PBR_MESH_TWO_SIDED) != 0;
+                CV v[3];
+                const unsigned vi[3] = {ti.x, ti.y, ti.z};
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float4 c = clipc[vb + vi[k]];
-                v[k].c[0] = c.x; v[k].c[1] = c.y; v[k].c[2] = c.z; v[k].c[3] = c.w;
-                v[k].n[0] = n[0]; v[k].n[1] = n[1]; v[k].n[2] = n[2];
+                for (int k = 0; k < 3; ++k) {
+                    const float4 c = clipc[vb + vi[k]];
+                    v[k].c[0] = c.x; v[k].c[1] = c.y; v[k].c[2] = c.z; v[k].c[3] = c.w;
+                    v[k].n[0] = n[0]; v[k].n[1] = n[1]; v[k].n[2] = n[2];
+                }
+                const int np = clip_poly(v, poly);
+                cnt = np >= 3 ? np - 2 : 0;
             }
-            const int np = clip_poly(v, poly);
-            cnt = np >= 3 ? np - 2 : 0;
-        }
-        // exclusive prefix sum of cnt over the warp
-        int incl = cnt;
+            int incl = cnt;                      // inclusive prefix sum over the warp
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        const int start = nrec + incl - cnt;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int start = nrec + incl - cnt;
 #pragma unroll 1
-        for (int k = 0; k < cnt; ++k) {
-            const int idx = start + k;
-            if (idx >= W_MAXREC) { overflow = true; break; }
-            int X[3], Y[3];
-            float z[3];
-            const bool ok = project_vertex(f, poly[0].c, X[0], Y[0], z[0]) &&
-                            project_vertex(f, poly[k + 1].c, X[1], Y[1], z[1]) &&
-                            project_vertex(f, poly[k + 2].c, X[2], Y[2], z[2]);
-            Rec r;
-            BBox bb;
-            if (ok && setup_snapped(f, X, Y, z, two_sided, id, 0, f.H, r, bb)) {
-                r.col = shade(f, poly[0].n, col);
-                recs[idx] = r;
-                bin_record<W_MW>(r, bb, idx, f.nbx, masks);
+            for (int k = 0; k < cnt; ++k) {
+                const int idx = start + k;
+                if (idx >= W_MAXREC) { overflow = true; break; }
+                int X[3], Y[3];
+                float z[3];
+                const bool ok = project_vertex(f, poly[0].c, X[0], Y[0], z[0]) &&
+                                project_vertex(f, poly[k + 1].c, X[1], Y[1], z[1]) &&
+                                project_vertex(f, poly[k + 2].c, X[2], Y[2], z[2]);
+                Rec r;
+                BBox bb;
+                if (ok && setup_snapped(f, X, Y, z, two_sided, id, 0, f.H, r, bb)) {
+                    r.col = shade(f, poly[0].n, col);
+                    recs[idx] = r;
+                    bin_record<W_MW>(r, bb, idx, f.nbx, masks);
+                }
             }
+            nrec = min(nrec + total, W_MAXREC);
         }
-        nrec = min(nrec + total, W_MAXREC);
+        if (__any_sync(0xffffffffu, overflow) && lane == 0) atomicOr(f.status, DEVSTAT_WARP_OVERFLOW);
     }
-    if (__any_sync(0xffffffffu, overflow) && lane == 0) atomicOr(f.status, DEVSTAT_WARP_OVERFLOW);
-    __syncwarp();
-
-    // ---- C: clear the colour tile (the vertex scratch is dead now)
-    clear_color(f, color, lane, 32);
-    __syncwarp();
+    __syncwarp();     // records + masks visible to the whole warp; background stores ordered before patches
 
     // ---- D: raster the non-empty blocks
     int nlist = 0;
@@ -265,32 +280,44 @@ __global__ void __launch_bounds__(32) raster_warp_kernel(const __grid_constant__
     for (int b0 = 0; b0 < nblk; b0 += 32) {
         const int b = b0 + lane;
         bool nz = false;
-        if (b < nblk) nz = (masks[b * W_MW] | masks[b * W_MW + 1]) != 0u;
+        int packed = 0;
+        if (b < nblk) {
+            nz = (masks[b * W_MW] | masks[b * W_MW + 1]) != 0u;
+            const int by = b / f.nbx;
+            packed = (by << 8) | (b - by * f.nbx);
+        }
         const unsigned bal = __ballot_sync(0xffffffffu, nz);
-        if (nz) blist[nlist + __popc(bal & lt_mask)] = (unsigned short)b;
+        if (nz) blist[nlist + __popc(bal & lt_mask)] = (unsigned short)packed;
         nlist += __popc(bal);
     }
     __syncwarp();
     const int lx = lane & 7, ly = lane >> 3;
 #pragma unroll 1
     for (int i = 0; i < nlist; ++i) {
-        const int b = blist[i];
-        const int by = b / f.nbx, bx = b - by * f.nbx;
+        const int pk = blist[i];
+        const int bx = pk & 255, by = pk >> 8;
         const int px = bx * 8 + lx, py0 = by * 8 + ly;
         const bool ok0 = px < f.W && py0 < f.H, ok1 = px < f.W && py0 + 4 < f.H;
         PixelState ps;
-        ps.zb0 = ps.zb1 = 0x3F800000u;
-        ps.id0 = ps.id1 = 0u;
+        ps.k0 = ps.k1 = KEY_CLEAR;
         ps.c0 = ps.c1 = 0u;
         ps.ch0 = ps.ch1 = false;
-        raster_block<W_MW>(recs, masks + b * W_MW, px, py0, ok0, ok1, ps);
-        if (ps.ch0) put_pixel(color, f.plane_stride, f.C, f.W, px, py0, ps.c0);
-        if (ps.ch1) put_pixel(color, f.plane_stride, f.C, f.W, px, py0 + 4, ps.c1);
+        raster_block<W_MW>(recs, masks + (by * f.nbx + bx) * W_MW, px, py0, ok0, ok1, ps);
+        unsigned char *p = out_scene + py0 * f.W + px;
+        if (ps.ch0) {
+            p[0] = (unsigned char)(ps.c0 & 255u);
+            p[HW] = (unsigned char)((ps.c0 >> 8) & 255u);
+            p[2 * HW] = (unsigned char)((ps.c0 >> 16) & 255u);
+            if (f.C == 4) p[3 * HW] = (unsigned char)(ps.c0 >> 24);
+        }
+        if (ps.ch1) {
+            p += 4 * f.W;
+            p[0] = (unsigned char)(ps.c1 & 255u);
+            p[HW] = (unsigned char)((ps.c1 >> 8) & 255u);
+            p[2 * HW] = (unsigned char)((ps.c1 >> 16) & 255u);
+            if (f.C == 4) p[3 * HW] = (unsigned char)(ps.c1 >> 24);
+        }
     }
-    __syncwarp();
-
-    // ---- E: store
-    store_band(f, color, scene, 0, f.H, lane, 32);
 }
 
 }  // namespace pbr
