@@ -83,6 +83,12 @@ class PBRConfig:
 
     num_workers: int = 1
 
+    # Scene sharding (not in the reference; see pybatchrender_b200/dist.py): this process renders
+    # scenes [scene_offset, scene_offset + num_scenes) of a global batch of global_num_scenes.
+    # `tiles` is then the *global* grid so that the projection aspect (quirk Q1) matches.
+    scene_offset: int = 0
+    global_num_scenes: int | None = None
+
     # ------------------------------------------------------------------ resolution
     def process_resolution(self) -> None:
         if self.tiles is None and self.num_scenes is not None:

@@ -1,3 +1,9 @@
+from .config import CartPoleConfig
 from .renderer import CartPoleRenderer
 
-__all__ = ["CartPoleRenderer"]
+try:
+    from .env import CartPoleEnv
+except Exception:  # pragma: no cover
+    CartPoleEnv = None
+
+__all__ = ["CartPoleConfig", "CartPoleRenderer", "CartPoleEnv"]
