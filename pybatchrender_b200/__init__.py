@@ -15,6 +15,7 @@ from .renderer.node import PBRNode
 from .renderer.camera import PBRCam
 from .renderer.light import PBRLight
 from .renderer.renderer import PBRRenderer
+from . import dist
 
 
 def native_available() -> bool:
@@ -35,4 +36,4 @@ except Exception:  # pragma: no cover
     envs = None
 
 __all__ = ["PBRConfig", "PBRShaderContext", "PBRNode", "PBRCam", "PBRLight", "PBRRenderer", "PBREnv",
-           "envs", "native_available", "__version__"]
+           "envs", "dist", "native_available", "__version__"]
