@@ -53,7 +53,18 @@ typedef struct {
     int32_t shared;             /* 1: B = I (same instances in every scene), 0: B = num_scenes*I,
                                    row = scene*I + inst   (reference basic.vert:25-28) */
     float use_texture;          /* must be 0 (textures: PBR_EUNSUPPORTED for now) */
+    uint32_t flags;             /* PBR_NODE_* */
 } pbr_node_desc;
+
+#define PBR_NODE_IN_BASE 1u             /* already rendered into frame->base: skipped by pbr_render,
+                                           but its triangles keep their draw indices */
+
+/* Static layer: the image (colour + depth|id keys) of nodes that are identical in every scene --
+ * `shared` nodes seen through a camera whose VP is the same for all scenes (CartPole's rail:
+ * reference envs/cartpole/renderer.py:33-39,91-93).  Rendered once by pbr_base_render, after which
+ * every scene of pbr_render starts from it instead of the clear colour.  Results are bit-identical
+ * to rendering those nodes in every scene. */
+typedef struct pbr_base_s *pbr_base_t;
 
 /* One frame: replaces taskMgr.step() + grab_pixels() + _rearrange_img() of reference
  * renderer.py:377-389, i.e. basic.vert + GL rasterisation + basic.frag + readback + flip +
@@ -74,6 +85,7 @@ typedef struct {
     const pbr_node_desc *nodes; /* host array, copied during the call */
     uint8_t *out;               /* device [K,C,H,W] contiguous uint8; row 0 = top of the image */
     uint32_t flags;             /* PBR_FRAME_* */
+    pbr_base_t base;            /* optional static layer (NULL: start from the clear colour) */
 } pbr_frame_desc;
 
 #define PBR_FRAME_FORCE_GENERAL 1u      /* skip the small-scene fast kernel (testing / debugging) */
@@ -91,6 +103,14 @@ int pbr_mesh_info(pbr_mesh_t mesh, int32_t *n_tris, int32_t *all_flat, int32_t *
 
 /* Render one frame (asynchronous on `stream`). */
 int pbr_render(const pbr_frame_desc *frame, void *stream);
+
+/* Static layer life cycle.  pbr_base_render draws the `shared` nodes of `frame` (all other nodes
+ * are skipped but keep their draw indices) for ONE scene using row `frame->scene_begin` of vp;
+ * frame->out is ignored.  The caller re-renders the base whenever those nodes, the camera, the
+ * light, the clear colour or the tile size change. */
+int pbr_base_create(int32_t device, pbr_base_t *out);
+int pbr_base_destroy(pbr_base_t base);
+int pbr_base_render(pbr_base_t base, const pbr_frame_desc *frame, void *stream);
 
 /* Instance-transform kernel: out_mats[b] = column-packed [ R_b * s_b | t_b ; 0 0 0 1 ] and the
  * 3x3 block of transforms_b44 is refreshed in place -- the device version of reference

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpbr_b200.so")
 PBR_MAX_NODES = 24
 PBR_MESH_TWO_SIDED = 1
 PBR_FRAME_FORCE_GENERAL = 1
+PBR_NODE_IN_BASE = 1
 
 
 class NativeError(RuntimeError):
@@ -31,6 +32,7 @@ class _NodeDesc(ctypes.Structure):
         ("instances_per_scene", ctypes.c_int32),
         ("shared", ctypes.c_int32),
         ("use_texture", ctypes.c_float),
+        ("flags", ctypes.c_uint32),
     ]
 
 
@@ -52,6 +54,7 @@ class _FrameDesc(ctypes.Structure):
         ("nodes", ctypes.POINTER(_NodeDesc)),
         ("out", ctypes.c_void_p),
         ("flags", ctypes.c_uint32),
+        ("base", ctypes.c_void_p),
     ]
 
 
@@ -79,6 +82,9 @@ _EXPORTS = {
     "pbr_mesh_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32),
                                      ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     "pbr_render": (ctypes.c_int, [ctypes.POINTER(_FrameDesc), ctypes.c_void_p]),
+    "pbr_base_create": (ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
+    "pbr_base_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "pbr_base_render": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(_FrameDesc), ctypes.c_void_p]),
     "pbr_device_status": (ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]),
     "pbr_pack_transforms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_int32, ctypes.c_void_p]),
@@ -157,6 +163,27 @@ class NativeMesh:
             pass
 
 
+class NativeBase:
+    """Static layer handle (``pbr_base_t``): shared nodes under a uniform camera, rendered once."""
+
+    def __init__(self, device: torch.device) -> None:
+        dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        handle = ctypes.c_void_p()
+        _check(load().pbr_base_create(dev_index, ctypes.byref(handle)), "pbr_base_create")
+        self.handle = handle
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            load().pbr_base_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Native:
     """Thin object the renderer holds; every method enqueues work on torch's current stream."""
 
@@ -208,14 +235,13 @@ class Native:
             rc = self.lib.pbr_compose_transforms(arr, len(poses), _stream_ptr(device))
         _check(rc, "pbr_compose_transforms")
 
-    def render(self, *, num_scenes, tile_w, tile_h, channels, vp, nodes, out, bg, ambient, dir_dir, dir_col,
-               strength, scene_begin=0, scene_count=None, flags=0) -> None:
-        """nodes: list of (NativeMesh, matbuf, colbuf, instances_per_scene, shared)."""
+    def _frame(self, *, num_scenes, tile_w, tile_h, channels, vp, nodes, out, bg, ambient, dir_dir, dir_col,
+               strength, scene_begin=0, scene_count=None, flags=0, base=None):
+        """nodes: list of (NativeMesh, matbuf, colbuf, instances_per_scene, shared[, in_base])."""
         _cuda_f32(vp, "viewbuf")
-        if not out.is_cuda or out.dtype != torch.uint8 or not out.is_contiguous():
-            raise NativeError("out must be a contiguous uint8 CUDA tensor")
         nd = (_NodeDesc * max(1, len(nodes)))()
-        for i, (mesh, mats, cols, inst, shared) in enumerate(nodes):
+        for i, item in enumerate(nodes):
+            mesh, mats, cols, inst, shared = item[:5]
             _cuda_f32(mats, "matbuf")
             _cuda_f32(cols, "colbuf")
             nd[i].mesh = mesh.handle
@@ -224,6 +250,7 @@ class Native:
             nd[i].instances_per_scene = int(inst)
             nd[i].shared = 1 if shared else 0
             nd[i].use_texture = 0.0
+            nd[i].flags = PBR_NODE_IN_BASE if (len(item) > 5 and item[5]) else 0
         f = _FrameDesc()
         f.num_scenes = int(num_scenes)
         f.scene_begin = int(scene_begin)
@@ -237,8 +264,24 @@ class Native:
         f.strength = float(strength)
         f.n_nodes = len(nodes)
         f.nodes = ctypes.cast(nd, ctypes.POINTER(_NodeDesc))
-        f.out = out.data_ptr()
+        f.out = out.data_ptr() if out is not None else None
         f.flags = int(flags)
+        f.base = base.handle if base is not None else None
+        return f, nd
+
+    def render(self, *, out, **kw) -> None:
+        if not out.is_cuda or out.dtype != torch.uint8 or not out.is_contiguous():
+            raise NativeError("out must be a contiguous uint8 CUDA tensor")
+        f, keep = self._frame(out=out, **kw)
         with torch.cuda.device(out.device):
             rc = self.lib.pbr_render(ctypes.byref(f), _stream_ptr(out.device))
         _check(rc, "pbr_render")
+        del keep
+
+    def base_render(self, base: NativeBase, *, vp, **kw) -> None:
+        """Render the static layer from the nodes flagged in_base (vp row ``scene_begin`` is used)."""
+        f, keep = self._frame(out=None, vp=vp, **kw)
+        with torch.cuda.device(vp.device):
+            rc = self.lib.pbr_base_render(base.handle, ctypes.byref(f), _stream_ptr(vp.device))
+        _check(rc, "pbr_base_render")
+        del keep

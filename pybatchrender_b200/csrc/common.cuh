@@ -25,16 +25,24 @@ struct NodeDev {
     int n_verts;          // unique positions
     int inst;             // instances per scene
     int shared;
-    int slot_begin;       // first triangle slot of this node inside a scene
+    int slot_begin;       // first triangle slot of this node inside a scene (compact, active nodes only)
     int vert_begin;       // first (instance, vertex) pair of this node inside a scene
     unsigned flags;
-    int pad;
+    int id_begin;         // draw index of this node's first triangle in the full frame (skipped nodes count)
 };
 
 struct FrameDev {
     const float *vp;
     unsigned char *out;
     int *status;            // device word: sticky PBR_DEVSTAT_* bits
+    // static layer (see pbr_base_t): inputs of a frame that starts from it ...
+    const unsigned char *base_color;         // [C,H,W]
+    const unsigned long long *base_keys;     // [nblk,64] block-major depth|id keys
+    const unsigned char *base_flags;         // [nblk] 1 = block has base coverage
+    // ... and outputs of the pass that renders it (general kernel, one scene)
+    unsigned long long *base_keys_out;
+    unsigned char *base_flags_out;
+    int vp_scene_override;  // >= 0: use this row of vp for every scene (base pass)
     int scene_begin, scene_count;
     int W, H, C;
     int n_nodes, total_slots, total_verts;

@@ -182,46 +182,20 @@ int pbr_mesh_info(pbr_mesh_t m, int32_t *n_tris, int32_t *all_flat, int32_t *dev
     return PBR_OK;
 }
 
-int pbr_render(const pbr_frame_desc *d, void *stream) {
-    if (!d) return fail(PBR_EINVAL, "pbr_render: NULL frame");
-    if (d->tile_w < 1 || d->tile_h < 1 || d->tile_w > PBR_MAX_TILE || d->tile_h > PBR_MAX_TILE)
-        return fail(PBR_EINVAL, "pbr_render: tile %dx%d outside [1,%d]", d->tile_w, d->tile_h, PBR_MAX_TILE);
-    if (d->channels != 3 && d->channels != 4) return fail(PBR_EINVAL, "pbr_render: channels must be 3 or 4, got %d", d->channels);
-    if (d->scene_begin < 0 || d->scene_count < 0 || (long long)d->scene_begin + d->scene_count > d->num_scenes)
-        return fail(PBR_EINVAL, "pbr_render: scene window [%d,+%d) outside [0,%d)", d->scene_begin, d->scene_count, d->num_scenes);
-    if (!d->out || !d->vp) return fail(PBR_EINVAL, "pbr_render: out / vp is NULL");
-    if ((reinterpret_cast<size_t>(d->out) & 15) || (reinterpret_cast<size_t>(d->vp) & 15))
-        return fail(PBR_EINVAL, "pbr_render: out and vp must be 16-byte aligned");
-    if (d->n_nodes < 0 || d->n_nodes > PBR_MAX_NODES) return fail(PBR_EUNSUPPORTED, "pbr_render: %d nodes (max %d)", d->n_nodes, PBR_MAX_NODES);
-    if (d->n_nodes > 0 && !d->nodes) return fail(PBR_EINVAL, "pbr_render: nodes is NULL");
-    if (d->scene_count == 0) return PBR_OK;
+enum NodeMode { NODES_ALL = 0, NODES_SKIP_BASE = 1, NODES_SHARED_ONLY = 2 };
 
-    int device = 0;
-    CUDA_TRY(cudaGetDevice(&device));
-
-    FrameDev f;
-    memset(&f, 0, sizeof(f));
-    f.vp = d->vp; f.out = d->out;
-    f.scene_begin = d->scene_begin; f.scene_count = d->scene_count;
-    f.W = d->tile_w; f.H = d->tile_h; f.C = d->channels;
-    f.hw = 0.5f * (float)d->tile_w; f.hh = 0.5f * (float)d->tile_h;
-    f.bg = host_unorm8(d->bg[0]) | (host_unorm8(d->bg[1]) << 8) | (host_unorm8(d->bg[2]) << 16) | (host_unorm8(d->bg[3]) << 24);
-    {
-        // normalize(dirLightDir) and clamp(strength): same fp32 operations as the oracle's make_light
-        volatile float x = d->dir_dir[0], y = d->dir_dir[1], z = d->dir_dir[2];
-        float l2 = fmaf(z, z, fmaf(y, y, x * x));
-        float inv = 1.0f / sqrtf(l2);
-        f.ldir[0] = x * inv; f.ldir[1] = y * inv; f.ldir[2] = z * inv;
-        float s = d->strength;
-        if (!(s == s)) s = 0.0f;
-        s = s < 0.0f ? 0.0f : s;
-        s = s > 1.0f ? 1.0f : s;
-        f.s = s; f.oms = 1.0f - s;
-        for (int c = 0; c < 3; ++c) { f.amb[c] = d->ambient[c]; f.dcol[c] = d->dir_col[c]; }
-    }
+struct NodeStats {
     long long slots = 0, verts = 0;
     bool any_smooth = false, warp_ok = true;
+    int skipped = 0;
+};
+
+// Fill f.nodes from the host descriptors.  Draw indices (id_begin) always count every node so
+// that a frame split into static layer + per-scene part numbers its triangles like the full frame.
+static int fill_nodes(const pbr_frame_desc *d, int device, NodeMode mode, FrameDev &f, NodeStats &st) {
+    long long ids = 0;
     f.n_nodes = 0;
+    st = NodeStats();
     for (int i = 0; i < d->n_nodes; ++i) {
         const pbr_node_desc &n = d->nodes[i];
         if (!n.mesh) return fail(PBR_EINVAL, "pbr_render: node %d has no mesh", i);
@@ -231,53 +205,84 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
             return fail(PBR_EINVAL, "pbr_render: node %d mats / cols must be 16-byte aligned", i);
         if (n.instances_per_scene < 0) return fail(PBR_EINVAL, "pbr_render: node %d instances_per_scene < 0", i);
         if (n.use_texture != 0.0f) return fail(PBR_EUNSUPPORTED, "pbr_render: node %d: textures are not implemented", i);
+        const long long ntri = (long long)n.instances_per_scene * n.mesh->n_tris;
+        const long long id_begin = ids;
+        ids += ntri;
+        if (ids > (1ll << 30)) return fail(PBR_EUNSUPPORTED, "pbr_render: more than 2^30 triangles per scene");
         if (n.instances_per_scene == 0) continue;
+        const bool in_base = (n.flags & PBR_NODE_IN_BASE) != 0;
+        if ((mode == NODES_SKIP_BASE && in_base) || (mode == NODES_SHARED_ONLY && !(n.shared && in_base))) {
+            st.skipped++;
+            continue;
+        }
         NodeDev &nd = f.nodes[f.n_nodes++];
         nd.tp = n.mesh->tp; nd.tn = n.mesh->tn; nd.vpos = n.mesh->vpos; nd.tidx = n.mesh->tidx;
         nd.mats = n.mats; nd.cols = n.cols;
         nd.n_tris = n.mesh->n_tris; nd.n_verts = n.mesh->n_verts;
         nd.inst = n.instances_per_scene; nd.shared = n.shared ? 1 : 0;
-        nd.slot_begin = (int)slots; nd.vert_begin = (int)verts; nd.flags = n.mesh->flags;
-        slots += (long long)n.instances_per_scene * n.mesh->n_tris;
-        verts += (long long)n.instances_per_scene * n.mesh->n_verts;
-        if (!n.mesh->all_flat) any_smooth = true;
-        if (n.instances_per_scene >= 8192 || n.mesh->n_tris >= 8192) warp_ok = false;
-        if (slots > (1ll << 30)) return fail(PBR_EUNSUPPORTED, "pbr_render: more than 2^30 triangles per scene");
+        nd.slot_begin = (int)st.slots; nd.vert_begin = (int)st.verts; nd.flags = n.mesh->flags;
+        nd.id_begin = (int)id_begin;
+        st.slots += ntri;
+        st.verts += (long long)n.instances_per_scene * n.mesh->n_verts;
+        if (!n.mesh->all_flat) st.any_smooth = true;
+        if (n.instances_per_scene >= 8192 || n.mesh->n_tris >= 8192) st.warp_ok = false;
     }
-    if (any_smooth) return fail(PBR_EUNSUPPORTED, "pbr_render: smooth-normal meshes are not implemented yet");
-    f.total_slots = (int)slots;
-    f.total_verts = (int)(verts > 0x7fffffff ? 0x7fffffff : verts);
+    if (st.any_smooth) return fail(PBR_EUNSUPPORTED, "pbr_render: smooth-normal meshes are not implemented yet");
+    f.total_slots = (int)st.slots;
+    f.total_verts = (int)(st.verts > 0x7fffffff ? 0x7fffffff : st.verts);
+    return PBR_OK;
+}
 
-    std::lock_guard<std::mutex> lock(g_mu);
-    DeviceState *st = nullptr;
-    if (int rc = device_state(device, &st)) return rc;
-    f.status = st->status;
+struct pbr_base_s {
+    int device;
+    int W, H, C;            // layout of the last successful pbr_base_render (0 = none yet)
+    size_t color_bytes, key_blocks;
+    unsigned char *color;
+    unsigned long long *keys;
+    unsigned char *flags;
+};
 
+static int check_frame(const pbr_frame_desc *d, const char *who, bool need_out) {
+    if (!d) return fail(PBR_EINVAL, "%s: NULL frame", who);
+    if (d->tile_w < 1 || d->tile_h < 1 || d->tile_w > PBR_MAX_TILE || d->tile_h > PBR_MAX_TILE)
+        return fail(PBR_EINVAL, "%s: tile %dx%d outside [1,%d]", who, d->tile_w, d->tile_h, PBR_MAX_TILE);
+    if (d->channels != 3 && d->channels != 4) return fail(PBR_EINVAL, "%s: channels must be 3 or 4, got %d", who, d->channels);
+    if (d->scene_begin < 0 || d->scene_count < 0 || (long long)d->scene_begin + d->scene_count > d->num_scenes)
+        return fail(PBR_EINVAL, "%s: scene window [%d,+%d) outside [0,%d)", who, d->scene_begin, d->scene_count, d->num_scenes);
+    if (!d->vp || (need_out && !d->out)) return fail(PBR_EINVAL, "%s: out / vp is NULL", who);
+    if ((need_out && (reinterpret_cast<size_t>(d->out) & 15)) || (reinterpret_cast<size_t>(d->vp) & 15))
+        return fail(PBR_EINVAL, "%s: out and vp must be 16-byte aligned", who);
+    if (d->n_nodes < 0 || d->n_nodes > PBR_MAX_NODES) return fail(PBR_EUNSUPPORTED, "%s: %d nodes (max %d)", who, d->n_nodes, PBR_MAX_NODES);
+    if (d->n_nodes > 0 && !d->nodes) return fail(PBR_EINVAL, "%s: nodes is NULL", who);
+    return PBR_OK;
+}
+
+static void fill_uniforms(const pbr_frame_desc *d, FrameDev &f) {
+    memset(&f, 0, sizeof(f));
+    f.vp = d->vp; f.out = d->out;
+    f.vp_scene_override = -1;
+    f.scene_begin = d->scene_begin; f.scene_count = d->scene_count;
+    f.W = d->tile_w; f.H = d->tile_h; f.C = d->channels;
+    f.hw = 0.5f * (float)d->tile_w; f.hh = 0.5f * (float)d->tile_h;
+    f.bg = host_unorm8(d->bg[0]) | (host_unorm8(d->bg[1]) << 8) | (host_unorm8(d->bg[2]) << 16) | (host_unorm8(d->bg[3]) << 24);
+    // normalize(dirLightDir) and clamp(strength): same fp32 operations as the oracle's make_light
+    volatile float x = d->dir_dir[0], y = d->dir_dir[1], z = d->dir_dir[2];
+    float l2 = fmaf(z, z, fmaf(y, y, x * x));
+    float inv = 1.0f / sqrtf(l2);
+    f.ldir[0] = x * inv; f.ldir[1] = y * inv; f.ldir[2] = z * inv;
+    float s = d->strength;
+    if (!(s == s)) s = 0.0f;
+    s = s < 0.0f ? 0.0f : s;
+    s = s > 1.0f ? 1.0f : s;
+    f.s = s; f.oms = 1.0f - s;
+    for (int c = 0; c < 3; ++c) { f.amb[c] = d->ambient[c]; f.dcol[c] = d->dir_col[c]; }
+}
+
+// general kernel: one CTA per (scene, band of rows).  plan = choose the band height.
+static int plan_general(FrameDev &f, DeviceState *st, size_t *smem_out) {
     const int W = f.W, H = f.H;
     const int nbx = (W + 7) / 8;
     const int H8 = ((H + 7) / 8) * 8;
-
-    // ---- small-scene kernel: one warp per scene
-    warp_ok = warp_ok && !(d->flags & PBR_FRAME_FORCE_GENERAL) && slots <= W_MAXSLOT && verts <= W_MAXVERT &&
-              nbx <= 256 && H8 / 8 <= 256;
-    if (warp_ok) {
-        const size_t smem = warp_smem_bytes(nbx * (H8 / 8));
-        if (smem <= 40 * 1024 && smem <= (size_t)st->max_smem_optin) {
-            f.BH = H8; f.nbands = 1; f.nbx = nbx; f.nby = H8 / 8;
-            f.plane_stride = H * W;
-            f.linear = 1;
-            if (!st->attr_warp) {
-                CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024));
-                CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-                st->attr_warp = true;
-            }
-            raster_warp_kernel<<<(unsigned)f.scene_count, 32, smem, (cudaStream_t)stream>>>(f);
-            CUDA_TRY(cudaGetLastError());
-            return PBR_OK;
-        }
-    }
-
-    // ---- general kernel: one CTA per (scene, band of rows)
     auto bytes_for = [&](int BH) {
         const int nby = (BH + 7) / 8;
         const int ps = (int)align16((size_t)BH * W);
@@ -295,7 +300,15 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
     if (f.nbx > 256 || f.nby > 256) return fail(PBR_EUNSUPPORTED, "pbr_render: more than 256 blocks per band side");
     f.plane_stride = (int)align16((size_t)BH * W);
     f.linear = (f.nbands == 1 && f.plane_stride == H * W) ? 1 : 0;
-    const size_t smem = bytes_for(BH);
+    *smem_out = bytes_for(BH);
+    return PBR_OK;
+}
+
+static int launch_general(FrameDev &f, DeviceState *st, void *stream) {
+    size_t smem = 0;
+    if (f.BH == 0)
+        if (int rc = plan_general(f, st, &smem)) return rc;
+    smem = general_smem_bytes(f.C, f.plane_stride, f.nbx * f.nby);
     if (!st->attr_general) {
         CUDA_TRY(cudaFuncSetAttribute(raster_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem_optin));
         st->attr_general = true;
@@ -304,6 +317,118 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
     if (grid > 0x7fffffffll) return fail(PBR_EUNSUPPORTED, "pbr_render: grid too large");
     raster_general_kernel<<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(f);
     CUDA_TRY(cudaGetLastError());
+    return PBR_OK;
+}
+
+int pbr_render(const pbr_frame_desc *d, void *stream) {
+    if (int rc = check_frame(d, "pbr_render", true)) return rc;
+    if (d->scene_count == 0) return PBR_OK;
+    int device = 0;
+    CUDA_TRY(cudaGetDevice(&device));
+
+    FrameDev f;
+    fill_uniforms(d, f);
+    std::lock_guard<std::mutex> lock(g_mu);
+    DeviceState *st = nullptr;
+    if (int rc = device_state(device, &st)) return rc;
+    f.status = st->status;
+
+    const int W = f.W, H = f.H;
+    const int nbx = (W + 7) / 8;
+    const int H8 = ((H + 7) / 8) * 8;
+    const size_t warp_smem = warp_smem_bytes(nbx * (H8 / 8));
+    auto warp_eligible = [&](const NodeStats &ns) {
+        return ns.warp_ok && !(d->flags & PBR_FRAME_FORCE_GENERAL) && ns.slots <= W_MAXSLOT && ns.verts <= W_MAXVERT &&
+               nbx <= 256 && H8 / 8 <= 256 && warp_smem <= 40 * 1024 && warp_smem <= (size_t)st->max_smem_optin;
+    };
+
+    // a usable static layer?  (same device and layout; only the small-scene kernel consumes it)
+    const pbr_base_s *base = d->base;
+    if (base && (base->device != device || base->W != W || base->H != H || base->C != f.C))
+        return fail(PBR_EINVAL, "pbr_render: base layer was rendered for %dx%dx%d on device %d", base->W, base->H, base->C, base->device);
+
+    NodeStats ns;
+    bool use_base = false;
+    if (base) {
+        if (int rc = fill_nodes(d, device, NODES_SKIP_BASE, f, ns)) return rc;
+        use_base = ns.skipped > 0 && warp_eligible(ns);
+    }
+    if (!use_base)
+        if (int rc = fill_nodes(d, device, NODES_ALL, f, ns)) return rc;
+
+    if (warp_eligible(ns)) {
+        f.BH = H8; f.nbands = 1; f.nbx = nbx; f.nby = H8 / 8;
+        f.plane_stride = H * W;
+        f.linear = 1;
+        if (use_base) { f.base_color = base->color; f.base_keys = base->keys; f.base_flags = base->flags; }
+        if (!st->attr_warp) {
+            CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            st->attr_warp = true;
+        }
+        raster_warp_kernel<<<(unsigned)f.scene_count, 32, warp_smem, (cudaStream_t)stream>>>(f);
+        CUDA_TRY(cudaGetLastError());
+        return PBR_OK;
+    }
+    return launch_general(f, st, stream);
+}
+
+int pbr_base_create(int32_t device, pbr_base_t *out) {
+    if (!out) return fail(PBR_EINVAL, "pbr_base_create: out is NULL");
+    pbr_base_s *b = new (std::nothrow) pbr_base_s();
+    if (!b) return fail(PBR_ENOMEM, "pbr_base_create: host allocation failed");
+    memset(b, 0, sizeof(*b));
+    b->device = device;
+    *out = b;
+    return PBR_OK;
+}
+
+int pbr_base_destroy(pbr_base_t b) {
+    if (!b) return PBR_OK;
+    cudaFree(b->color); cudaFree(b->keys); cudaFree(b->flags);
+    delete b;
+    return PBR_OK;
+}
+
+int pbr_base_render(pbr_base_t b, const pbr_frame_desc *d, void *stream) {
+    if (!b) return fail(PBR_EINVAL, "pbr_base_render: NULL base");
+    if (int rc = check_frame(d, "pbr_base_render", false)) return rc;
+    int device = 0;
+    CUDA_TRY(cudaGetDevice(&device));
+    if (device != b->device) return fail(PBR_EINVAL, "pbr_base_render: base belongs to device %d, current device is %d", b->device, device);
+    if (d->scene_begin >= d->num_scenes) return fail(PBR_EINVAL, "pbr_base_render: scene_begin outside vp");
+
+    FrameDev f;
+    fill_uniforms(d, f);
+    std::lock_guard<std::mutex> lock(g_mu);
+    DeviceState *st = nullptr;
+    if (int rc = device_state(device, &st)) return rc;
+    f.status = st->status;
+    NodeStats ns;
+    if (int rc = fill_nodes(d, device, NODES_SHARED_ONLY, f, ns)) return rc;
+
+    // (re)allocate the layer: colour image + keys for every 8x8 block of every band
+    size_t smem_unused = 0;
+    if (int rc = plan_general(f, st, &smem_unused)) return rc;
+    const size_t color_bytes = align16((size_t)f.C * f.H * f.W);
+    const size_t key_blocks = (size_t)f.nbx * f.nby * f.nbands;           // the last band may overhang the tile
+    if (color_bytes > b->color_bytes || key_blocks > b->key_blocks) {
+        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+        cudaFree(b->color); cudaFree(b->keys); cudaFree(b->flags);
+        b->color = nullptr; b->keys = nullptr; b->flags = nullptr; b->color_bytes = b->key_blocks = 0; b->W = 0;
+        CUDA_TRY(cudaMalloc(&b->color, color_bytes));
+        CUDA_TRY(cudaMalloc(&b->keys, key_blocks * 64 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMalloc(&b->flags, key_blocks));
+        b->color_bytes = color_bytes; b->key_blocks = key_blocks;
+    }
+    f.out = b->color;
+    f.base_keys_out = b->keys;
+    f.base_flags_out = b->flags;
+    f.vp_scene_override = d->scene_begin;
+    f.scene_begin = 0;
+    f.scene_count = 1;
+    if (int rc = launch_general(f, st, stream)) { b->W = 0; return rc; }
+    b->W = f.W; b->H = f.H; b->C = f.C;
     return PBR_OK;
 }
 

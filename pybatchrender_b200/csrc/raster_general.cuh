@@ -26,6 +26,7 @@ struct SlotGeom {
     float4 col;
     bool flat;
     bool two_sided;
+    unsigned id;          // 1 + draw index
 };
 
 __device__ __forceinline__ int load_slot(const FrameDev &f, int scene, int slot, SlotGeom &g) {
@@ -41,7 +42,8 @@ __device__ __forceinline__ int load_slot(const FrameDev &f, int scene, int slot,
 
     float M[16], VP[16];
     const float4 *m4 = reinterpret_cast<const float4 *>(nd.mats + b * 16);
-    const float4 *v4 = reinterpret_cast<const float4 *>(f.vp + (size_t)scene * 16);
+    const int vp_row = f.vp_scene_override >= 0 ? f.vp_scene_override : scene;
+    const float4 *v4 = reinterpret_cast<const float4 *>(f.vp + (size_t)vp_row * 16);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         float4 a = __ldg(m4 + j), c = __ldg(v4 + j);
@@ -50,6 +52,7 @@ __device__ __forceinline__ int load_slot(const FrameDev &f, int scene, int slot,
     }
     g.col = __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4));
     g.two_sided = (nd.flags & PBR_MESH_TWO_SIDED) != 0;
+    g.id = (unsigned)(nd.id_begin + local) + 1u;
 
     const float4 p0 = __ldg(nd.tp + 3 * tri);
     g.flat = __float_as_int(p0.w) != 0;
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(THREADS) raster_general_kernel(const __grid_co
                 const int st = load_slot(f, scene, slot, g);
                 if (st == SLOT_OK) {
                     BBox bb;
-                    if (setup_tri(f, g.v, g.col, g.flat, g.two_sided, (unsigned)slot + 1u, band_y0, band_h, r, bb))
+                    if (setup_tri(f, g.v, g.col, g.flat, g.two_sided, g.id, band_y0, band_h, r, bb))
                         bin_record<MW>(r, bb, tid, f.nbx, s.masks);
                     else
                         r.meta = 0;
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(THREADS) raster_general_kernel(const __grid_co
                 if (k + 2 < n) {
                     CV tri[3] = {poly[0], poly[k + 1], poly[k + 2]};
                     BBox bb;
-                    if (setup_tri(f, tri, g.col, g.flat, g.two_sided, (unsigned)slot + 1u, band_y0, band_h, r, bb))
+                    if (setup_tri(f, tri, g.col, g.flat, g.two_sided, g.id, band_y0, band_h, r, bb))
                         bin_record<MW>(r, bb, tid, f.nbx, s.masks);
                     else
                         r.meta = 0;
@@ -280,6 +283,17 @@ __global__ void __launch_bounds__(THREADS) raster_general_kernel(const __grid_co
     }
     __syncthreads();
     store_band(f, s.color, scene, band_y0, band_h, tid, THREADS);
+
+    // static-layer pass: also publish the depth|id keys and which blocks have any coverage
+    if (f.base_keys_out != nullptr) {
+        const size_t blk0 = (size_t)band * (f.BH / 8) * f.nbx;
+        for (int i = tid; i < nblk * 64; i += THREADS) f.base_keys_out[blk0 * 64 + i] = s.ktile[i];
+        for (int b = tid; b < nblk; b += THREADS) {
+            bool any = false;
+            for (int k = 0; k < 64; ++k) any |= s.ktile[b * 64 + k] != KEY_CLEAR;
+            f.base_flags_out[blk0 + b] = any ? 1 : 0;
+        }
+    }
 }
 
 }  // namespace pbr

@@ -82,8 +82,17 @@ __global__ void __launch_bounds__(32) raster_warp_kernel(const __grid_constant__
     const int HW = f.H * f.W;
     unsigned char *out_scene = f.out + (size_t)scene * f.C * HW;
 
-    // ---- 0: background straight to global memory
-    if (((f.bg ^ (f.bg >> 8)) & (f.C == 4 ? 0xffffffu : 0xffffu)) == 0) {
+    // ---- 0: background (or the pre-rendered static layer) straight to global memory
+    if (f.base_color != nullptr) {
+        const int n = f.C * HW;
+        if ((n & 15) == 0) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(f.base_color);
+            uint4 *dst = reinterpret_cast<uint4 *>(out_scene);
+            for (int i = lane; i < n / 16; i += 32) dst[i] = __ldg(src + i);
+        } else {
+            for (int i = lane; i < n; i += 32) out_scene[i] = __ldg(f.base_color + i);
+        }
+    } else if (((f.bg ^ (f.bg >> 8)) & (f.C == 4 ? 0xffffffu : 0xffffu)) == 0) {
         fill_bytes(out_scene, f.C * HW, f.bg & 255u, lane);       // grey background: one run
     } else {
         for (int c = 0; c < f.C; ++c) fill_bytes(out_scene + (size_t)c * HW, HW, (f.bg >> (8 * c)) & 255u, lane);
@@ -191,7 +200,7 @@ __global__ void __launch_bounds__(32) raster_warp_kernel(const __grid_constant__
             const int4 q0 = proj[vb + ti.x], q1 = proj[vb + ti.y], q2 = proj[vb + ti.z];
             int X[3] = {q0.x, q1.x, q2.x}, Y[3] = {q0.y, q1.y, q2.y};
             float z[3] = {__int_as_float(q0.z), __int_as_float(q1.z), __int_as_float(q2.z)};
-            const unsigned id = (unsigned)(nd.slot_begin + ws.inst * nd.n_tris + ws.tri) + 1u;
+            const unsigned id = (unsigned)(nd.id_begin + ws.inst * nd.n_tris + ws.tri) + 1u;
             Rec r;
             BBox bb;
             if (setup_snapped(f, X, Y, z, (nd.flags & PBR_MESH_TWO_SIDED) != 0, id, 0, f.H, r, bb)) {
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(32) raster_warp_kernel(const __grid_constant__
                 const float4 n0 = __ldg(nd.tn + 3 * ws.tri);
                 xform_normal(M, n0.x, n0.y, n0.z, n);
                 col = __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4));
-                id = (unsigned)(nd.slot_begin + ws.inst * nd.n_tris + ws.tri) + 1u;
+                id = (unsigned)(nd.id_begin + ws.inst * nd.n_tris + ws.tri) + 1u;
                 two_sided = (nd.flags & PBR_MESH_TWO_SIDED) != 0;
                 CV v[3];
                 const unsigned vi[3] = {ti.x, ti.y, ti.z};
@@ -300,6 +309,13 @@ __global__ void __launch_bounds__(32) raster_warp_kernel(const __grid_constant__
         const bool ok0 = px < f.W && py0 < f.H, ok1 = px < f.W && py0 + 4 < f.H;
         PixelState ps;
         ps.k0 = ps.k1 = KEY_CLEAR;
+        if (f.base_flags != nullptr) {
+            const int b = by * f.nbx + bx;
+            if (__ldg(f.base_flags + b)) {          // the static layer covers part of this block
+                ps.k0 = __ldg(f.base_keys + (size_t)b * 64 + lane);
+                ps.k1 = __ldg(f.base_keys + (size_t)b * 64 + 32 + lane);
+            }
+        }
         ps.c0 = ps.c1 = 0u;
         ps.ch0 = ps.ch1 = false;
         raster_block<W_MW>(recs, masks + (by * f.nbx + bx) * W_MW, px, py0, ok0, ok1, ps);

@@ -72,6 +72,9 @@ class PBRCam(PBRShaderContext):
                           up_k3=torch.tensor([0.0, 0.0, 1.0]))
         self._update_vp()
 
+        # True while every scene provably has the same view (all inputs so far were broadcast (3,)
+        # vectors): lets the renderer pre-render shared nodes once (static layer)
+        self._uni = {"eye": True, "fwd": True, "up": True}
         self.sync_from_base_cam = False
         if getattr(self.base, "_pbr_nodes", None):
             self.attach_all()
@@ -211,8 +214,18 @@ class PBRCam(PBRShaderContext):
     def get_vp(self) -> torch.Tensor:
         return self.VP_k44.clone()
 
+    @property
+    def uniform(self) -> bool:
+        """All scenes share one VP (known from how the camera was set, never from a device read)."""
+        return self.num_scenes == 1 or all(self._uni.values())
+
+    def _bcast(self, x) -> bool:
+        t = torch.as_tensor(x)
+        return self.num_scenes == 1 or t.ndim == 1 or t.shape[0] == 1
+
     # ------------------------------------------------------------------ public API
     def look_at(self, target_k3, lazy: bool = False) -> None:
+        self._uni["fwd"] = self._uni["eye"] and self._bcast(target_k3)
         self._update_view(forward_k3=self._fwd_from_lookat(target_k3))
         if not lazy:
             self._update_vp()
@@ -224,6 +237,8 @@ class PBRCam(PBRShaderContext):
         self.set_eye(eye_k3, lazy=lazy)
 
     def set_positions_and_lookat(self, eye_k3, target_k3, lazy: bool = False) -> None:
+        self._uni["eye"] = self._bcast(eye_k3)
+        self._uni["fwd"] = self._uni["eye"] and self._bcast(target_k3)
         eye = self._ensure_kx3(eye_k3, "eye_k3")
         target = self._ensure_kx3(target_k3, "target_k3")
         self._update_view(eye_k3=eye, forward_k3=self._fwd_from_lookat(target, eye))
@@ -235,27 +250,32 @@ class PBRCam(PBRShaderContext):
         return self._ensure_kx3(target_k3, "target_k3") - eye
 
     def set_hprs(self, hpr_k3, lazy: bool = False) -> None:
+        self._uni["fwd"] = self._uni["up"] = self._bcast(hpr_k3)
         fwd, up = self._fwd_up_from_hpr(self._ensure_kx3(hpr_k3, "hpr_k3"))
         self._update_view(forward_k3=fwd, up_k3=up)
         if not lazy:
             self._update_vp()
 
     def set_eye(self, eye_k3, lazy: bool = False) -> None:
+        self._uni["eye"] = self._bcast(eye_k3)
         self._update_view(eye_k3=eye_k3)
         if not lazy:
             self._update_vp()
 
     def set_forward(self, forward_k3, lazy: bool = False) -> None:
+        self._uni["fwd"] = self._bcast(forward_k3)
         self._update_view(forward_k3=forward_k3)
         if not lazy:
             self._update_vp()
 
     def set_up(self, up_k3, lazy: bool = False) -> None:
+        self._uni["up"] = self._bcast(up_k3)
         self._update_view(up_k3=up_k3)
         if not lazy:
             self._update_vp()
 
     def set_right(self, right_k3, lazy: bool = False) -> None:
+        self._uni["up"] = self._uni["fwd"] and self._bcast(right_k3)
         right = self._normalize(self._ensure_kx3(right_k3, "right_k3"))
         f = -self.V_k44[:, 2, 0:3]
         self._update_view(forward_k3=f, up_k3=torch.cross(right, f, dim=-1))

@@ -82,6 +82,11 @@ class PBRRenderer:
         self._node_cache = None
         self._environment_ready = False
         self.render_flags = 0          # PBR_FRAME_* bits OR-ed into every pbr_render call
+        # static layer: shared nodes seen through a scene-independent camera are rendered once and
+        # every scene starts from that image (bit-identical output, see include/pbr_b200.h)
+        self.static_layer = True
+        self._base = None
+        self._base_sig = None
 
     # ------------------------------------------------------------------ scene construction
     def set_background_color(self, r: float, g: float, b: float, a: float = 1.0) -> None:
@@ -180,7 +185,7 @@ class PBRRenderer:
                     bg=self._background_color, ambient=amb, dir_dir=ddir, dir_col=dcol, strength=strength,
                     nodes=nodes)
 
-    def _native_nodes(self):
+    def _native_nodes(self, in_base: bool = False):
         if self._node_cache is None:
             self._node_cache = self._drawable_nodes()
         for n in self._node_cache:
@@ -188,8 +193,26 @@ class PBRRenderer:
                 from .. import _native
                 n._native_mesh = _native.NativeMesh(n.mesh.pos, n.mesh.nrm, n.mesh.idx, self.device,
                                                     two_sided=n.mesh.two_sided)
-        return [(n._native_mesh, n.matbuf, n.colbuf, n.instances_per_scene, n.shared_across)
-                for n in self._node_cache]
+        return [(n._native_mesh, n.matbuf, n.colbuf, n.instances_per_scene, n.shared_across,
+                 in_base and n.shared_across) for n in self._node_cache]
+
+    def invalidate_static(self) -> None:
+        """Force the static layer to be re-rendered (needed only if matbuf / colbuf / viewbuf of a
+        shared node or the camera were written behind the API's back)."""
+        self._base_sig = None
+
+    def _static_signature(self):
+        cam = self._pbr_cam
+        if not (self.static_layer and cam is not None and cam.uniform):
+            return None
+        if self._node_cache is None:
+            self._node_cache = self._drawable_nodes()
+        shared = [n for n in self._node_cache if n.shared_across]
+        if not shared or len(shared) == len(self._node_cache) and self.num_scenes < 2:
+            return None
+        return (tuple((id(n), getattr(n, "_version", 0)) for n in shared), id(cam), getattr(cam, "_version", 0),
+                self._light_params(), self._background_color, tuple(self.cfg.tile_resolution),
+                int(self.cfg.num_channels), self._scene_version)
 
     # ------------------------------------------------------------------ rendering
     def render(self, out: torch.Tensor | None = None, scene_begin: int = 0, scene_count: int | None = None,
@@ -208,10 +231,21 @@ class PBRRenderer:
         elif tuple(out.shape) != (N, C, H, W):
             raise ValueError(f"out must have shape {(N, C, H, W)}, got {tuple(out.shape)}")
         amb, ddir, dcol, strength = self._light_params()
-        self._native.render(num_scenes=N, tile_w=W, tile_h=H, channels=C, vp=self._pbr_cam.viewbuf,
-                            nodes=self._native_nodes(), out=out, bg=self._background_color,
-                            ambient=amb, dir_dir=ddir, dir_col=dcol, strength=strength,
-                            scene_begin=scene_begin, scene_count=scene_count, flags=flags | self.render_flags)
+        common = dict(num_scenes=N, tile_w=W, tile_h=H, channels=C, vp=self._pbr_cam.viewbuf,
+                      bg=self._background_color, ambient=amb, dir_dir=ddir, dir_col=dcol, strength=strength)
+        sig = self._static_signature()
+        base = None
+        if sig is not None:
+            if self._base is None:
+                from .. import _native
+                self._base = _native.NativeBase(self.device)
+            if sig != self._base_sig:
+                self._native.base_render(self._base, nodes=self._native_nodes(in_base=True), scene_begin=0,
+                                         scene_count=1, **common)
+                self._base_sig = sig
+            base = self._base
+        self._native.render(nodes=self._native_nodes(in_base=base is not None), out=out, scene_begin=scene_begin,
+                            scene_count=scene_count, flags=flags | self.render_flags, base=base, **common)
         return out
 
     def _step(self, *args, **kwargs):

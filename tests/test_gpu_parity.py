@@ -200,3 +200,71 @@ def test_errors_are_loud():
         r._native.render(num_scenes=4, tile_w=64, tile_h=64, channels=3, vp=r._pbr_cam.viewbuf.cpu(),
                          nodes=r._native_nodes(), out=torch.empty((4, 3, 64, 64), dtype=torch.uint8, device="cuda"),
                          bg=(0, 0, 0, 1), ambient=(0, 0, 0), dir_dir=(0, 0, 1), dir_col=(1, 1, 1), strength=1.0)
+
+
+# ------------------------------------------------------------------ static layer (pbr_base_t)
+def _mixed_scene(num_scenes=32, seed=31, tile=(64, 64)):
+    """Shared boxes (static layer candidates) interpenetrating per-scene boxes."""
+    from pybatchrender_b200 import PBRRenderer
+    r = PBRRenderer(dict(num_scenes=num_scenes, tile_resolution=tile, device="cuda"))
+    rng = np.random.default_rng(seed)
+    shared = r.add_node("models/box", instances_per_scene=2, model_pivot_relative_point=(0.5, 0.5, 0.5),
+                        shared_across_scenes=True)
+    per = r.add_node("models/box", instances_per_scene=1, model_pivot_relative_point=(0.5, 0.5, 0.5))
+    for node in (shared, per):
+        B = node.buf_instances
+        node.set_positions(torch.tensor(rng.uniform(-2, 2, (B, 3)), dtype=torch.float32), lazy=True)
+        node.set_hprs(torch.tensor(rng.uniform(-np.pi, np.pi, (B, 3)), dtype=torch.float32), lazy=True)
+        node.set_scales(torch.tensor(rng.uniform(1.0, 3.0, (B, 1)), dtype=torch.float32))
+        node.set_colors(torch.tensor(np.concatenate([rng.uniform(0, 1, (B, 3)), np.ones((B, 1))], 1), dtype=torch.float32))
+    cam = r.add_camera()
+    cam.set_positions(torch.tensor([0.0, -9.0, 1.0]))
+    cam.look_at(torch.tensor([0.0, 0.0, 0.0]))
+    r.add_light()
+    r.setup_environment()
+    return r, shared, per
+
+
+def test_static_layer_is_bit_identical_and_tracks_changes():
+    r, shared, per = _mixed_scene()
+    assert r._pbr_cam.uniform
+    a = r.step()
+    assert r._base is not None and r._base_sig is not None          # the static layer was used
+    _assert_same(a, oracle_render(r), "static layer")
+    r.static_layer = False
+    b = r.step()
+    assert torch.equal(a, b)
+    r.static_layer = True
+    # moving a shared instance must re-render the layer
+    pos = torch.tensor([[0.5, 0.0, 0.3], [-1.0, 0.5, -0.2]])
+    shared.set_positions(pos)
+    c = r.step()
+    _assert_same(c, oracle_render(r), "static layer after shared update")
+    assert not torch.equal(a, c)
+    # light and background are part of the layer too
+    r._pbr_light.set_ambient((0.5, 0.1, 0.1))
+    r.set_background_color(0.2, 0.3, 0.4)
+    _assert_same(r.step(), oracle_render(r), "static layer after light/bg update")
+
+
+def test_static_layer_disabled_by_per_scene_camera():
+    r, shared, per = _mixed_scene(num_scenes=8)
+    eyes = torch.tensor(np.random.default_rng(2).uniform(-1, 1, (8, 3)), dtype=torch.float32) + torch.tensor([0., -9., 1.])
+    r._pbr_cam.set_positions(eyes)
+    assert not r._pbr_cam.uniform
+    px = r.step()
+    assert r._base_sig is None
+    _assert_same(px, oracle_render(r), "per-scene camera")
+    r._pbr_cam.set_positions(torch.tensor([0.0, -9.0, 1.0]))
+    r._pbr_cam.look_at(torch.tensor([0.0, 0.0, 0.0]))
+    assert r._pbr_cam.uniform
+    _assert_same(r.step(), oracle_render(r), "uniform again")
+
+
+def test_static_layer_non_square_tiles_and_rgba():
+    from pybatchrender_b200.envs.cartpole import CartPoleRenderer
+    for tile, ch in [((84, 84), 3), ((50, 30), 4), ((128, 96), 3)]:
+        r = CartPoleRenderer(dict(num_scenes=21, tile_resolution=tile, device="cuda", num_channels=ch))
+        px = r.step(cartpole_states(21, seed=5).cuda())
+        assert r._base_sig is not None
+        _assert_same(px, oracle_render(r), f"static layer {tile} C={ch}")
