@@ -29,6 +29,8 @@ struct NodeDev {
     int vert_begin;       // first (instance, vertex) pair of this node inside a scene
     unsigned flags;
     int id_begin;         // draw index of this node's first triangle in the full frame (skipped nodes count)
+    unsigned tri_magic;   // floor(2^32 / n_tris) + 1   (x / n_tris == __umulhi(x, magic) for x * n_tris < 2^32)
+    unsigned vert_magic;  // floor(2^32 / n_verts) + 1
 };
 
 struct FrameDev {
@@ -48,6 +50,7 @@ struct FrameDev {
     int n_nodes, total_slots, total_verts;
     int BH, nbands;         // band height (multiple of 8) and bands per tile
     int nbx, nby;           // 8x8 blocks per band
+    unsigned nbx_magic;     // floor(2^32 / nbx) + 1
     int plane_stride;       // bytes between colour planes in shared memory (multiple of 16)
     int linear;             // 1: the shared colour tile is a byte image of out[scene]
     float hw, hh;
@@ -82,6 +85,10 @@ struct BBox {
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// exact x / d for x * d < 2^32 (d >= 2), via a precomputed magic = floor(2^32 / d) + 1; d == 1 -> magic 0
+__host__ inline unsigned div_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)(0x100000000ull / d) + 1u; }
+__device__ __forceinline__ int fast_div(int x, unsigned magic) { return magic ? (int)__umulhi((unsigned)x, magic) : x; }
 
 // ------------------------------------------------------------------------------------------------
 // math shared with the oracle (same operation order)
@@ -335,10 +342,24 @@ __device__ __forceinline__ unsigned long long make_key(float z, unsigned id) {
     return ((unsigned long long)__float_as_uint(z) << 32) | id;
 }
 
+// exact int64 coverage of one slow-path record at this lane's two pixels (rare: huge triangles)
+__device__ __noinline__ bool slow_cover(const Rec &r, int px, int py0, bool ok0, bool ok1, bool &cov0, bool &cov1,
+                                        float &f1a, float &f2a, float &f1b, float &f2b) {
+    const unsigned meta = r.meta;
+    const int spx = px * 256 + 128, spy0 = py0 * 256 + 128, spy1 = (py0 + 4) * 256 + 128;
+    const long long F0 = slow_edge(r, 0, spx, spy0), F1 = slow_edge(r, 1, spx, spy0), F2 = slow_edge(r, 2, spx, spy0);
+    const long long G0 = slow_edge(r, 0, spx, spy1), G1 = slow_edge(r, 1, spx, spy1), G2 = slow_edge(r, 2, spx, spy1);
+    cov0 = ok0 && ((F0 | F1 | F2) >= 0);
+    cov1 = ok1 && ((G0 | G1 | G2) >= 0);
+    const long long nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
+    f1a = (float)(F1 + nb1); f2a = (float)(F2 + nb2);
+    f1b = (float)(G1 + nb1); f2b = (float)(G2 + nb2);
+    return cov0 || cov1;
+}
+
 template <int MWORDS>
 __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bmask, int px, int py0, bool ok0,
                                              bool ok1, PixelState &ps) {
-    const int py1 = py0 + 4;
 #pragma unroll 1
     for (int w = 0; w < MWORDS; ++w) {
         unsigned m = bmask[w];
@@ -347,15 +368,17 @@ __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bm
             const int t = w * 32 + __ffs(m) - 1;
             m &= m - 1;
             const Rec &r = recs[t];
+            // the whole record in four 128-bit shared loads, issued back to back
+            const int4 ea = *reinterpret_cast<const int4 *>(&r.e[0]);         // Eo0 Eo1 Eo2 A0
+            const int4 eb = *reinterpret_cast<const int4 *>(&r.e[4]);         // A1 A2 B0 B1
             const int4 ec = *reinterpret_cast<const int4 *>(&r.e[8]);         // B2 col id meta
+            const float4 zq = *reinterpret_cast<const float4 *>(&r.z0);       // z0 dz1 dz2 invA
             const unsigned meta = (unsigned)ec.w;
             bool cov0, cov1;
             float f1a, f2a, f1b, f2b;
             if (!(meta & M_SLOW)) {
                 const unsigned rx = (unsigned)px - (meta & 255u) * 8u;
                 const unsigned ry = (unsigned)py0 - ((meta >> 8) & 255u) * 8u;
-                const int4 ea = *reinterpret_cast<const int4 *>(&r.e[0]);     // Eo0 Eo1 Eo2 A0
-                const int4 eb = *reinterpret_cast<const int4 *>(&r.e[4]);     // A1 A2 B0 B1
                 const int B2 = ec.x;
                 const int F0 = (int)((unsigned)ea.x + (unsigned)ea.w * rx + (unsigned)eb.z * ry);
                 const int F1 = (int)((unsigned)ea.y + (unsigned)eb.x * rx + (unsigned)eb.w * ry);
@@ -370,19 +393,9 @@ __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bm
                 f1a = (float)(F1 + nb1); f2a = (float)(F2 + nb2);
                 f1b = (float)(G1 + nb1); f2b = (float)(G2 + nb2);
             } else {
-                const int spx = px * 256 + 128, spy0 = py0 * 256 + 128, spy1 = py1 * 256 + 128;
-                const long long F0 = slow_edge(r, 0, spx, spy0), F1 = slow_edge(r, 1, spx, spy0),
-                                F2 = slow_edge(r, 2, spx, spy0);
-                const long long G0 = slow_edge(r, 0, spx, spy1), G1 = slow_edge(r, 1, spx, spy1),
-                                G2 = slow_edge(r, 2, spx, spy1);
-                cov0 = ok0 && ((F0 | F1 | F2) >= 0);
-                cov1 = ok1 && ((G0 | G1 | G2) >= 0);
-                if (!__any_sync(0xffffffffu, cov0 || cov1)) continue;
-                const long long nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
-                f1a = (float)(F1 + nb1); f2a = (float)(F2 + nb2);
-                f1b = (float)(G1 + nb1); f2b = (float)(G2 + nb2);
+                const bool any = slow_cover(r, px, py0, ok0, ok1, cov0, cov1, f1a, f2a, f1b, f2b);
+                if (!__any_sync(0xffffffffu, any)) continue;
             }
-            const float4 zq = *reinterpret_cast<const float4 *>(&r.z0);      // z0 dz1 dz2 invA
             const unsigned id = (unsigned)ec.z, col = (unsigned)ec.y;
             const float za = fmaf(f2a * zq.w, zq.z, fmaf(f1a * zq.w, zq.y, zq.x));
             const float zc = fmaf(f2b * zq.w, zq.z, fmaf(f1b * zq.w, zq.y, zq.x));

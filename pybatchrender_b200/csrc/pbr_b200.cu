@@ -222,6 +222,8 @@ static int fill_nodes(const pbr_frame_desc *d, int device, NodeMode mode, FrameD
         nd.inst = n.instances_per_scene; nd.shared = n.shared ? 1 : 0;
         nd.slot_begin = (int)st.slots; nd.vert_begin = (int)st.verts; nd.flags = n.mesh->flags;
         nd.id_begin = (int)id_begin;
+        nd.tri_magic = div_magic((unsigned)n.mesh->n_tris);
+        nd.vert_magic = div_magic((unsigned)n.mesh->n_verts);
         st.slots += ntri;
         st.verts += (long long)n.instances_per_scene * n.mesh->n_verts;
         if (!n.mesh->all_flat) st.any_smooth = true;
@@ -358,6 +360,7 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
 
     if (warp_eligible(ns)) {
         f.BH = H8; f.nbands = 1; f.nbx = nbx; f.nby = H8 / 8;
+        f.nbx_magic = div_magic((unsigned)nbx);
         f.plane_stride = H * W;
         f.linear = 1;
         if (use_base) { f.base_color = base->color; f.base_keys = base->keys; f.base_flags = base->flags; }

@@ -73,7 +73,7 @@ __device__ __forceinline__ void fill_bytes(unsigned char *dst, int n, unsigned v
     for (int i = head + n16 * 16 + lane; i < n; i += 32) dst[i] = (unsigned char)v;
 }
 
-__global__ void __launch_bounds__(32) raster_warp_kernel(const __grid_constant__ FrameDev f) {
+__global__ void __launch_bounds__(32, 32) raster_warp_kernel(const __grid_constant__ FrameDev f) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -107,7 +107,18 @@ __global__ void __launch_bounds__(32) raster_warp_kernel(const __grid_constant__
     unsigned *live = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(blist) + align16((size_t)nblk * 2));
     unsigned *clipl = live + W_MAXREC;
 
-    for (int i = lane; i < nblk * W_MW; i += 32) masks[i] = 0u;
+    {   // masks are 8 bytes per block and the region is padded to 16 bytes: clear with 128-bit stores
+        uint4 *m4 = reinterpret_cast<uint4 *>(masks);
+        const int n16 = (int)(align16((size_t)nblk * W_MW * 4) / 16);
+        for (int i = lane; i < n16; i += 32) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    // which blocks does the static layer cover?  one bit per block, two words for up to 64 blocks
+    unsigned bf0 = 0u, bf1 = 0u;
+    const bool base_bits = f.base_flags != nullptr && nblk <= 64;
+    if (base_bits) {
+        bf0 = __ballot_sync(0xffffffffu, lane < nblk && __ldg(f.base_flags + lane) != 0);
+        bf1 = __ballot_sync(0xffffffffu, lane + 32 < nblk && __ldg(f.base_flags + lane + 32) != 0);
+    }
 
     // ---- A: vertices
     {
@@ -121,7 +132,7 @@ __global__ void __launch_bounds__(32) raster_warp_kernel(const __grid_constant__
                 if (v >= f.nodes[i].vert_begin) ni = i;
             const NodeDev &nd = f.nodes[ni];
             const int local = v - nd.vert_begin;
-            const int inst = local / nd.n_verts;
+            const int inst = fast_div(local, nd.vert_magic);
             const int vert = local - inst * nd.n_verts;
             const size_t b = nd.shared ? (size_t)inst : (size_t)scene * nd.inst + inst;
             float M[16];
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(32) raster_warp_kernel(const __grid_constant__
                 if (s >= f.nodes[i].slot_begin) ni = i;
             const NodeDev &nd = f.nodes[ni];
             const int local = s - nd.slot_begin;
-            const int inst = local / nd.n_tris;
+            const int inst = fast_div(local, nd.tri_magic);
             const int tri = local - inst * nd.n_tris;
             packed = pack_slot(ni, inst, tri);
             const uint4 ti = __ldg(nd.tidx + tri);
@@ -292,7 +303,7 @@ __global__ void __launch_bounds__(32) raster_warp_kernel(const __grid_constant__
         int packed = 0;
         if (b < nblk) {
             nz = (masks[b * W_MW] | masks[b * W_MW + 1]) != 0u;
-            const int by = b / f.nbx;
+            const int by = fast_div(b, f.nbx_magic);
             packed = (by << 8) | (b - by * f.nbx);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, nz);
@@ -311,7 +322,9 @@ __global__ void __launch_bounds__(32) raster_warp_kernel(const __grid_constant__
         ps.k0 = ps.k1 = KEY_CLEAR;
         if (f.base_flags != nullptr) {
             const int b = by * f.nbx + bx;
-            if (__ldg(f.base_flags + b)) {          // the static layer covers part of this block
+            const bool covered = base_bits ? (((b < 32 ? bf0 : bf1) >> (b & 31)) & 1u) != 0u
+                                           : __ldg(f.base_flags + b) != 0;
+            if (covered) {                          // the static layer covers part of this block
                 ps.k0 = __ldg(f.base_keys + (size_t)b * 64 + lane);
                 ps.k1 = __ldg(f.base_keys + (size_t)b * 64 + 32 + lane);
             }
