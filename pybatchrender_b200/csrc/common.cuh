@@ -53,6 +53,7 @@ struct FrameDev {
     unsigned nbx_magic;     // floor(2^32 / nbx) + 1
     int plane_stride;       // bytes between colour planes in shared memory (multiple of 16)
     int linear;             // 1: the shared colour tile is a byte image of out[scene]
+    int debug;              // profiling aid: 1 = stop after the background, 2 = stop after setup
     float hw, hh;
     unsigned bg;            // packed RGBA8 clear colour
     float amb[3], dcol[3], ldir[3];
@@ -357,6 +358,63 @@ __device__ __noinline__ bool slow_cover(const Rec &r, int px, int py0, bool ok0,
     return cov0 || cov1;
 }
 
+// int32 fast-path coverage of one record at this lane's two pixels; F1/F2 (G1/G2) are the unbiased
+// edge values used for the depth weights
+struct FastCov {
+    int F1, F2, G1, G2;
+    bool cov0, cov1;
+};
+
+__device__ __forceinline__ FastCov fast_cover(const int4 &ea, const int4 &eb, const int4 &ec, int px, int py0,
+                                              bool ok0, bool ok1) {
+    const unsigned meta = (unsigned)ec.w;
+    const unsigned rx = (unsigned)px - (meta & 255u) * 8u;
+    const unsigned ry = (unsigned)py0 - ((meta >> 8) & 255u) * 8u;
+    const int B2 = ec.x;
+    const int F0 = (int)((unsigned)ea.x + (unsigned)ea.w * rx + (unsigned)eb.z * ry);
+    const int F1 = (int)((unsigned)ea.y + (unsigned)eb.x * rx + (unsigned)eb.w * ry);
+    const int F2 = (int)((unsigned)ea.z + (unsigned)eb.y * rx + (unsigned)B2 * ry);
+    const int G0 = (int)((unsigned)F0 + 4u * (unsigned)eb.z);
+    const int G1 = (int)((unsigned)F1 + 4u * (unsigned)eb.w);
+    const int G2 = (int)((unsigned)F2 + 4u * (unsigned)B2);
+    FastCov c;
+    c.cov0 = ok0 && ((F0 | F1 | F2) >= 0);
+    c.cov1 = ok1 && ((G0 | G1 | G2) >= 0);
+    const int nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
+    c.F1 = F1 + nb1; c.F2 = F2 + nb2; c.G1 = G1 + nb1; c.G2 = G2 + nb2;
+    return c;
+}
+
+// depth from the edge values + LESS test (ties to the earlier draw) for both pixels of the lane
+__device__ __forceinline__ void depth_update(PixelState &ps, float f1a, float f2a, float f1b, float f2b, bool cov0,
+                                             bool cov1, const float4 &zq, unsigned id, unsigned col) {
+    const float za = fmaf(f2a * zq.w, zq.z, fmaf(f1a * zq.w, zq.y, zq.x));
+    const float zc = fmaf(f2b * zq.w, zq.z, fmaf(f1b * zq.w, zq.y, zq.x));
+    const unsigned long long ka = make_key(za, id), kc = make_key(zc, id);
+    const bool w0 = cov0 & (ka < ps.k0), w1 = cov1 & (kc < ps.k1);
+    ps.k0 = w0 ? ka : ps.k0; ps.c0 = w0 ? col : ps.c0; ps.ch0 |= w0;
+    ps.k1 = w1 ? kc : ps.k1; ps.c1 = w1 ? col : ps.c1; ps.ch1 |= w1;
+}
+
+// one record, any path
+__device__ __forceinline__ void raster_one(const Rec &r, const int4 &ea, const int4 &eb, const int4 &ec,
+                                           const float4 &zq, int px, int py0, bool ok0, bool ok1, PixelState &ps) {
+    if (!((unsigned)ec.w & M_SLOW)) {
+        const FastCov c = fast_cover(ea, eb, ec, px, py0, ok0, ok1);
+        if (!__any_sync(0xffffffffu, c.cov0 || c.cov1)) return;
+        depth_update(ps, (float)c.F1, (float)c.F2, (float)c.G1, (float)c.G2, c.cov0, c.cov1, zq, (unsigned)ec.z,
+                     (unsigned)ec.y);
+    } else {
+        bool cov0, cov1;
+        float f1a, f2a, f1b, f2b;
+        const bool any = slow_cover(r, px, py0, ok0, ok1, cov0, cov1, f1a, f2a, f1b, f2b);
+        if (!__any_sync(0xffffffffu, any)) return;
+        depth_update(ps, f1a, f2a, f1b, f2b, cov0, cov1, zq, (unsigned)ec.z, (unsigned)ec.y);
+    }
+}
+
+// All records of one block, in draw order.  (A two-records-per-iteration variant was measured:
+// slower -- register pressure and the wasted second evaluation on odd counts outweigh the ILP.)
 template <int MWORDS>
 __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bmask, int px, int py0, bool ok0,
                                              bool ok1, PixelState &ps) {
@@ -373,36 +431,7 @@ __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bm
             const int4 eb = *reinterpret_cast<const int4 *>(&r.e[4]);         // A1 A2 B0 B1
             const int4 ec = *reinterpret_cast<const int4 *>(&r.e[8]);         // B2 col id meta
             const float4 zq = *reinterpret_cast<const float4 *>(&r.z0);       // z0 dz1 dz2 invA
-            const unsigned meta = (unsigned)ec.w;
-            bool cov0, cov1;
-            float f1a, f2a, f1b, f2b;
-            if (!(meta & M_SLOW)) {
-                const unsigned rx = (unsigned)px - (meta & 255u) * 8u;
-                const unsigned ry = (unsigned)py0 - ((meta >> 8) & 255u) * 8u;
-                const int B2 = ec.x;
-                const int F0 = (int)((unsigned)ea.x + (unsigned)ea.w * rx + (unsigned)eb.z * ry);
-                const int F1 = (int)((unsigned)ea.y + (unsigned)eb.x * rx + (unsigned)eb.w * ry);
-                const int F2 = (int)((unsigned)ea.z + (unsigned)eb.y * rx + (unsigned)B2 * ry);
-                const int G0 = (int)((unsigned)F0 + 4u * (unsigned)eb.z);
-                const int G1 = (int)((unsigned)F1 + 4u * (unsigned)eb.w);
-                const int G2 = (int)((unsigned)F2 + 4u * (unsigned)B2);
-                cov0 = ok0 && ((F0 | F1 | F2) >= 0);
-                cov1 = ok1 && ((G0 | G1 | G2) >= 0);
-                if (!__any_sync(0xffffffffu, cov0 || cov1)) continue;
-                const int nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
-                f1a = (float)(F1 + nb1); f2a = (float)(F2 + nb2);
-                f1b = (float)(G1 + nb1); f2b = (float)(G2 + nb2);
-            } else {
-                const bool any = slow_cover(r, px, py0, ok0, ok1, cov0, cov1, f1a, f2a, f1b, f2b);
-                if (!__any_sync(0xffffffffu, any)) continue;
-            }
-            const unsigned id = (unsigned)ec.z, col = (unsigned)ec.y;
-            const float za = fmaf(f2a * zq.w, zq.z, fmaf(f1a * zq.w, zq.y, zq.x));
-            const float zc = fmaf(f2b * zq.w, zq.z, fmaf(f1b * zq.w, zq.y, zq.x));
-            const unsigned long long ka = make_key(za, id), kc = make_key(zc, id);
-            const bool w0 = cov0 & (ka < ps.k0), w1 = cov1 & (kc < ps.k1);
-            ps.k0 = w0 ? ka : ps.k0; ps.c0 = w0 ? col : ps.c0; ps.ch0 |= w0;
-            ps.k1 = w1 ? kc : ps.k1; ps.c1 = w1 ? col : ps.c1; ps.ch1 |= w1;
+            raster_one(r, ea, eb, ec, zq, px, py0, ok0, ok1, ps);
         }
     }
 }

@@ -21,6 +21,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -363,13 +364,15 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         f.nbx_magic = div_magic((unsigned)nbx);
         f.plane_stride = H * W;
         f.linear = 1;
+        f.debug = (int)((d->flags >> 8) & 3u);
         if (use_base) { f.base_color = base->color; f.base_keys = base->keys; f.base_flags = base->flags; }
         if (!st->attr_warp) {
             CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             st->attr_warp = true;
         }
-        raster_warp_kernel<<<(unsigned)f.scene_count, 32, warp_smem, (cudaStream_t)stream>>>(f);
+        static const size_t smem_pad = getenv("PBR_B200_WARP_SMEM_PAD") ? (size_t)atoi(getenv("PBR_B200_WARP_SMEM_PAD")) : 0;   // occupancy experiments
+        raster_warp_kernel<<<(unsigned)f.scene_count, 32, warp_smem + smem_pad, (cudaStream_t)stream>>>(f);
         CUDA_TRY(cudaGetLastError());
         return PBR_OK;
     }

@@ -26,10 +26,10 @@
 
 namespace pbr {
 
-constexpr int W_MAXREC = 64;     // records per scene (triangle slots that survive + clipped fans)
-constexpr int W_MAXSLOT = 48;    // eligibility: leaves >= 16 spare records for clipped fans
-constexpr int W_MAXVERT = 64;    // (instance, vertex) pairs per scene
-constexpr int W_MW = W_MAXREC / 32;
+constexpr int W_MAXREC = 48;     // records per scene (triangle slots that survive + clipped fans); < 64 (mask bits)
+constexpr int W_MAXSLOT = 36;    // eligibility: leaves >= 12 spare records for clipped fans
+constexpr int W_MAXVERT = 48;    // (instance, vertex) pairs per scene
+constexpr int W_MW = 2;            // mask words per block (64 record bits)
 
 __host__ __device__ inline size_t warp_smem_bytes(int nblk) {
     return (size_t)W_MAXVERT * 32 + (size_t)W_MAXREC * sizeof(Rec) + align16((size_t)nblk * W_MW * 4) +
@@ -73,7 +73,10 @@ __device__ __forceinline__ void fill_bytes(unsigned char *dst, int n, unsigned v
     for (int i = head + n16 * 16 + lane; i < n; i += 32) dst[i] = (unsigned char)v;
 }
 
-__global__ void __launch_bounds__(32, 32) raster_warp_kernel(const __grid_constant__ FrameDev f) {
+#ifndef W_MINB
+#define W_MINB 32
+#endif
+__global__ void __launch_bounds__(32, W_MINB) raster_warp_kernel(const __grid_constant__ FrameDev f) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -82,22 +85,51 @@ __global__ void __launch_bounds__(32, 32) raster_warp_kernel(const __grid_consta
     const int HW = f.H * f.W;
     unsigned char *out_scene = f.out + (size_t)scene * f.C * HW;
 
-    // ---- 0: background (or the pre-rendered static layer) straight to global memory
-    if (f.base_color != nullptr) {
-        const int n = f.C * HW;
-        if ((n & 15) == 0) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(f.base_color);
-            uint4 *dst = reinterpret_cast<uint4 *>(out_scene);
-            for (int i = lane; i < n / 16; i += 32) dst[i] = __ldg(src + i);
-        } else {
-            for (int i = lane; i < n; i += 32) out_scene[i] = __ldg(f.base_color + i);
+    // ---- prefetch this scene's (cold) rows before the output burst occupies the load/store queue
+    if (lane < f.n_nodes) {
+        const NodeDev &nd = f.nodes[lane];
+        const int ninst = min(nd.inst, 8);
+        for (int i = 0; i < ninst; ++i) {
+            const size_t b = nd.shared ? (size_t)i : (size_t)scene * nd.inst + i;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nd.mats + b * 16));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nd.cols + b * 4));
         }
-    } else if (((f.bg ^ (f.bg >> 8)) & (f.C == 4 ? 0xffffffu : 0xffffu)) == 0) {
-        fill_bytes(out_scene, f.C * HW, f.bg & 255u, lane);       // grey background: one run
-    } else {
-        for (int c = 0; c < f.C; ++c) fill_bytes(out_scene + (size_t)c * HW, HW, (f.bg >> (8 * c)) & 255u, lane);
+    } else if (lane == 31) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(f.vp + (size_t)scene * 16));
     }
 
+    // ---- background (or the pre-rendered static layer) straight to global memory.  Issued AFTER the
+    // raster phase: scenes finish their (variable amount of) raster work at different times, so the
+    // bandwidth-bound output bursts of some warps overlap the issue-bound raster loops of others;
+    // covered pixels wait in a small shared-memory patch list until the background is out.
+    auto write_background = [&]() {
+        if (f.base_color != nullptr) {
+            const int n = f.C * HW;
+            if ((n & 15) == 0) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(f.base_color);
+                uint4 *dst = reinterpret_cast<uint4 *>(out_scene);
+                // 8 independent 128-bit loads in flight per lane, then 8 stores (a plain copy loop
+                // serialises on the L2 latency of every load)
+                const int n16 = n / 16;
+                int i = lane;
+                for (; i + 7 * 32 < n16; i += 8 * 32) {
+                    uint4 v[8];
+    #pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = __ldg(src + i + k * 32);
+    #pragma unroll
+                    for (int k = 0; k < 8; ++k) dst[i + k * 32] = v[k];
+                }
+                for (; i < n16; i += 32) dst[i] = __ldg(src + i);
+            } else {
+                for (int i = lane; i < n; i += 32) out_scene[i] = __ldg(f.base_color + i);
+            }
+        } else if (((f.bg ^ (f.bg >> 8)) & (f.C == 4 ? 0xffffffu : 0xffffu)) == 0) {
+            fill_bytes(out_scene, f.C * HW, f.bg & 255u, lane);       // grey background: one run
+        } else {
+            for (int c = 0; c < f.C; ++c) fill_bytes(out_scene + (size_t)c * HW, HW, (f.bg >> (8 * c)) & 255u, lane);
+        }
+    };
+    if (f.debug == 1) { write_background(); return; }
     // ---- carve shared memory
     float4 *clipc = reinterpret_cast<float4 *>(smem_raw);                      // [W_MAXVERT]
     int4 *proj = reinterpret_cast<int4 *>(smem_raw + (size_t)W_MAXVERT * 16);  // [W_MAXVERT]
@@ -158,9 +190,31 @@ __global__ void __launch_bounds__(32, 32) raster_warp_kernel(const __grid_consta
     }
     __syncwarp();
 
-    // ---- B1: classify triangle slots
+    // setup + shade + bin one surviving triangle into record j
+    auto setup_live = [&](const NodeDev &nd, int inst, int tri, const int4 &q0, const int4 &q1, const int4 &q2, int j) {
+        int X[3] = {q0.x, q1.x, q2.x}, Y[3] = {q0.y, q1.y, q2.y};
+        float z[3] = {__int_as_float(q0.z), __int_as_float(q1.z), __int_as_float(q2.z)};
+        const unsigned id = (unsigned)(nd.id_begin + inst * nd.n_tris + tri) + 1u;
+        Rec r;
+        BBox bb;
+        if (setup_snapped(f, X, Y, z, (nd.flags & PBR_MESH_TWO_SIDED) != 0, id, 0, f.H, r, bb)) {
+            const size_t b = nd.shared ? (size_t)inst : (size_t)scene * nd.inst + inst;
+            float M[16], n[3];
+            load_mat(nd.mats + b * 16, M);
+            const float4 n0 = __ldg(nd.tn + 3 * tri);
+            xform_normal(M, n0.x, n0.y, n0.z, n);
+            r.col = shade(f, n, __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4)));
+            recs[j] = r;
+            bin_record<W_MW>(r, bb, j, f.nbx, masks);
+        }
+    };
+
+    // ---- B1: classify triangle slots.  With <= 32 slots every lane keeps its own slot and goes
+    // straight to setup (record index = slot); otherwise survivors are compacted first so that the
+    // expensive setup runs on full warps.
     int nlive = 0, nclip = 0;
     const int S = f.total_slots;
+    const bool direct = S <= 32;
 #pragma unroll 1
     for (int base = 0; base < S; base += 32) {
         const int s = base + lane;
@@ -189,42 +243,34 @@ __global__ void __launch_bounds__(32, 32) raster_warp_kernel(const __grid_consta
                 const bool two_sided = (nd.flags & PBR_MESH_TWO_SIDED) != 0;
                 cat = (area2 < 0 || (two_sided && area2 > 0)) ? 1 : 0;
             }
+            if (direct && cat == 1) setup_live(nd, inst, tri, q0, q1, q2, s);
         }
-        const unsigned bl = __ballot_sync(0xffffffffu, cat == 1);
         const unsigned bc = __ballot_sync(0xffffffffu, cat == 2);
-        if (cat == 1) live[nlive + __popc(bl & lt_mask)] = packed;
         if (cat == 2) clipl[nclip + __popc(bc & lt_mask)] = packed;
-        nlive += __popc(bl);
         nclip += __popc(bc);
+        if (!direct) {
+            const unsigned bl = __ballot_sync(0xffffffffu, cat == 1);
+            if (cat == 1) live[nlive + __popc(bl & lt_mask)] = packed;
+            nlive += __popc(bl);
+        }
     }
     __syncwarp();
 
-    // ---- B2: setup + bin the surviving triangles (record index = position in the live list)
+    // ---- B2 (only when slots were compacted): record index = position in the live list
+    if (!direct) {
 #pragma unroll 1
-    for (int base = 0; base < nlive; base += 32) {
-        const int j = base + lane;
-        if (j < nlive) {
-            const WSlot ws = unpack_slot(live[j]);
-            const NodeDev &nd = f.nodes[ws.ni];
-            const uint4 ti = __ldg(nd.tidx + ws.tri);
-            const int vb = nd.vert_begin + ws.inst * nd.n_verts;
-            const int4 q0 = proj[vb + ti.x], q1 = proj[vb + ti.y], q2 = proj[vb + ti.z];
-            int X[3] = {q0.x, q1.x, q2.x}, Y[3] = {q0.y, q1.y, q2.y};
-            float z[3] = {__int_as_float(q0.z), __int_as_float(q1.z), __int_as_float(q2.z)};
-            const unsigned id = (unsigned)(nd.id_begin + ws.inst * nd.n_tris + ws.tri) + 1u;
-            Rec r;
-            BBox bb;
-            if (setup_snapped(f, X, Y, z, (nd.flags & PBR_MESH_TWO_SIDED) != 0, id, 0, f.H, r, bb)) {
-                const size_t b = nd.shared ? (size_t)ws.inst : (size_t)scene * nd.inst + ws.inst;
-                float M[16], n[3];
-                load_mat(nd.mats + b * 16, M);
-                const float4 n0 = __ldg(nd.tn + 3 * ws.tri);
-                xform_normal(M, n0.x, n0.y, n0.z, n);
-                r.col = shade(f, n, __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4)));
-                recs[j] = r;
-                bin_record<W_MW>(r, bb, j, f.nbx, masks);
+        for (int base = 0; base < nlive; base += 32) {
+            const int j = base + lane;
+            if (j < nlive) {
+                const WSlot ws = unpack_slot(live[j]);
+                const NodeDev &nd = f.nodes[ws.ni];
+                const uint4 ti = __ldg(nd.tidx + ws.tri);
+                const int vb = nd.vert_begin + ws.inst * nd.n_verts;
+                setup_live(nd, ws.inst, ws.tri, proj[vb + ti.x], proj[vb + ti.y], proj[vb + ti.z], j);
             }
         }
+    } else {
+        nlive = S;
     }
     int nrec = nlive;
 
@@ -294,6 +340,7 @@ __global__ void __launch_bounds__(32, 32) raster_warp_kernel(const __grid_consta
     }
     __syncwarp();     // records + masks visible to the whole warp; background stores ordered before patches
 
+    if (f.debug == 2) return;
     // ---- D: raster the non-empty blocks
     int nlist = 0;
 #pragma unroll 1
@@ -312,6 +359,22 @@ __global__ void __launch_bounds__(32, 32) raster_warp_kernel(const __grid_consta
     }
     __syncwarp();
     const int lx = lane & 7, ly = lane >> 3;
+    uint2 *plist = reinterpret_cast<uint2 *>(smem_raw);          // (pixel offset, RGBA8): aliases the dead vertex scratch
+    constexpr int PCAP = W_MAXVERT * 32 / 8;
+    int npatch = 0;
+    bool bg_done = false;
+    auto put = [&](unsigned off, unsigned c) {
+        unsigned char *p = out_scene + off;
+        p[0] = (unsigned char)(c & 255u);
+        p[HW] = (unsigned char)((c >> 8) & 255u);
+        p[2 * HW] = (unsigned char)((c >> 16) & 255u);
+        if (f.C == 4) p[3 * HW] = (unsigned char)(c >> 24);
+    };
+    auto flush = [&]() {
+        __syncwarp();
+        for (int i = lane; i < npatch; i += 32) { const uint2 e = plist[i]; put(e.x, e.y); }
+        npatch = 0;
+    };
 #pragma unroll 1
     for (int i = 0; i < nlist; ++i) {
         const int pk = blist[i];
@@ -332,20 +395,28 @@ __global__ void __launch_bounds__(32, 32) raster_warp_kernel(const __grid_consta
         ps.c0 = ps.c1 = 0u;
         ps.ch0 = ps.ch1 = false;
         raster_block<W_MW>(recs, masks + (by * f.nbx + bx) * W_MW, px, py0, ok0, ok1, ps);
-        unsigned char *p = out_scene + py0 * f.W + px;
-        if (ps.ch0) {
-            p[0] = (unsigned char)(ps.c0 & 255u);
-            p[HW] = (unsigned char)((ps.c0 >> 8) & 255u);
-            p[2 * HW] = (unsigned char)((ps.c0 >> 16) & 255u);
-            if (f.C == 4) p[3 * HW] = (unsigned char)(ps.c0 >> 24);
+        if (f.debug == 3) continue;
+        const unsigned off0 = (unsigned)(py0 * f.W + px), off1 = off0 + 4u * (unsigned)f.W;
+        const unsigned b0 = __ballot_sync(0xffffffffu, ps.ch0), b1 = __ballot_sync(0xffffffffu, ps.ch1);
+        const int cnt = __popc(b0) + __popc(b1);
+        if (!bg_done && npatch + cnt > PCAP) {       // patch list full: background now, direct writes from here on
+            write_background();
+            flush();
+            __syncwarp();
+            bg_done = true;
         }
-        if (ps.ch1) {
-            p += 4 * f.W;
-            p[0] = (unsigned char)(ps.c1 & 255u);
-            p[HW] = (unsigned char)((ps.c1 >> 8) & 255u);
-            p[2 * HW] = (unsigned char)((ps.c1 >> 16) & 255u);
-            if (f.C == 4) p[3 * HW] = (unsigned char)(ps.c1 >> 24);
+        if (bg_done) {
+            if (ps.ch0) put(off0, ps.c0);
+            if (ps.ch1) put(off1, ps.c1);
+        } else {
+            if (ps.ch0) plist[npatch + __popc(b0 & lt_mask)] = make_uint2(off0, ps.c0);
+            if (ps.ch1) plist[npatch + __popc(b0) + __popc(b1 & lt_mask)] = make_uint2(off1, ps.c1);
+            npatch += cnt;
         }
+    }
+    if (!bg_done) {
+        write_background();
+        flush();
     }
 }
 
