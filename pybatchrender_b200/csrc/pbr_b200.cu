@@ -339,10 +339,10 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
     const int W = f.W, H = f.H;
     const int nbx = (W + 7) / 8;
     const int H8 = ((H + 7) / 8) * 8;
-    const size_t warp_smem = warp_smem_bytes(nbx * (H8 / 8));
+    const size_t warp_smem = warp_smem_bytes(nbx * (H8 / 8), W_WARPS);
     auto warp_eligible = [&](const NodeStats &ns) {
         return ns.warp_ok && !(d->flags & PBR_FRAME_FORCE_GENERAL) && ns.slots <= W_MAXSLOT && ns.verts <= W_MAXVERT &&
-               nbx <= 256 && H8 / 8 <= 256 && warp_smem <= 40 * 1024 && warp_smem <= (size_t)st->max_smem_optin;
+               nbx <= 256 && H8 / 8 <= 256 && warp_smem <= 100 * 1024 && warp_smem <= (size_t)st->max_smem_optin;
     };
 
     // a usable static layer?  (same device and layout; only the small-scene kernel consumes it)
@@ -367,12 +367,13 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         f.debug = (int)((d->flags >> 8) & 3u);
         if (use_base) { f.base_color = base->color; f.base_keys = base->keys; f.base_flags = base->flags; }
         if (!st->attr_warp) {
-            CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024));
-            CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             st->attr_warp = true;
         }
         static const size_t smem_pad = getenv("PBR_B200_WARP_SMEM_PAD") ? (size_t)atoi(getenv("PBR_B200_WARP_SMEM_PAD")) : 0;   // occupancy experiments
-        raster_warp_kernel<<<(unsigned)f.scene_count, 32, warp_smem + smem_pad, (cudaStream_t)stream>>>(f);
+        const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS - 1) / W_WARPS);
+        raster_warp_kernel<W_WARPS><<<wgrid, 32 * W_WARPS, warp_smem + smem_pad, (cudaStream_t)stream>>>(f);
         CUDA_TRY(cudaGetLastError());
         return PBR_OK;
     }
