@@ -37,6 +37,7 @@ TILE = (64, 64)
 ALGO_BYTES_PER_SCENE = 3 * 64 * 64 + 64 + 2 * (64 + 16)      # 12,512 B
 STATE_RING = 16
 OUT_RING = 4            # 4 x 50.3 MB of output > 126 MB L2, so pixel writes cannot stay cached
+NCU_DRAM_BYTES_PER_LAUNCH = 1000192 + 1414912      # ncu --set full, profiles/r01f_raster_warp_ncu.txt
 
 
 def parse():
@@ -345,7 +346,11 @@ def run_ours(args):
                              f"state ring of {STATE_RING}",
                        "launch": f"CUDA graphs of {STATE_RING} steps"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "raster_kernel",
+                         "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                         "traffic_note": "dram__bytes_read+write of one isolated launch under ncu (profiles/r01f_*): "
+                                         "the 50 MB of pixel writes are still dirty in the 126 MB L2 when the kernel "
+                                         "ends, so DRAM sees them later; no re-reads",
+                         "kernel": "raster_warp_kernel<4>",
                          "kernel_ms": raster_ms_max, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SCENE * N,
                          "peak_source": peak_src},
             "e2e": {"value": total_scenes * e2e_steps / (e2e_ms_max * 1e-3), "unit": "scene-frames/s",
