@@ -34,3 +34,26 @@ e0.record()
 for _ in range(50): g.replay()
 e1.record(); torch.cuda.synchronize()
 print('no static layer us/frame',e0.elapsed_time(e1)/800*1000)
+for dbg in (1, 2):
+    r.render_flags = dbg << 8
+    for i in range(5): r.step(st[i%16],out=outs[i%4])
+    torch.cuda.synchronize()
+    g=torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(16): r.render(out=outs[i%4])
+    for _ in range(3): g.replay()
+    torch.cuda.synchronize()
+    e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50): g.replay()
+    e1.record(); torch.cuda.synchronize()
+    print('no static layer, debug',dbg,'us/frame',e0.elapsed_time(e1)/800*1000)
+# pure device fill for reference
+x = outs[0]
+for _ in range(3): x.fill_(7)
+torch.cuda.synchronize()
+e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+e0.record()
+for i in range(200): outs[i%4].fill_(7)
+e1.record(); torch.cuda.synchronize()
+print('torch fill_ of one 50 MB frame us', e0.elapsed_time(e1)/200*1000)

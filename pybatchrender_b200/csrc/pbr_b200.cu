@@ -68,6 +68,11 @@ struct DeviceState {
     int sm_count = 0;
     bool attr_general = false, attr_warp = false;
     int *status = nullptr;           // device word with sticky DEVSTAT_* bits
+    // clear-colour image [C,H,W]: copy source of the small-scene kernel's background when there is
+    // no static layer (one code path for both; the 12 KB tile stays in L1/L2)
+    unsigned char *bgtile = nullptr;
+    size_t bgtile_bytes = 0;
+    unsigned bg_sig[4] = {0, 0, 0, 0};   // W, H, C, packed colour of the current contents
 };
 std::mutex g_mu;
 DeviceState g_dev[64];
@@ -365,7 +370,24 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         f.plane_stride = H * W;
         f.linear = 1;
         f.debug = (int)((d->flags >> 8) & 3u);
-        if (use_base) { f.base_color = base->color; f.base_keys = base->keys; f.base_flags = base->flags; }
+        if (use_base) {
+            f.base_color = base->color; f.base_keys = base->keys; f.base_flags = base->flags;
+        } else if ((((size_t)f.C * H * W) & 15) == 0) {
+            const size_t need = (size_t)f.C * H * W;
+            if (need > st->bgtile_bytes) {
+                CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+                cudaFree(st->bgtile);
+                st->bgtile = nullptr; st->bgtile_bytes = 0; st->bg_sig[0] = 0;
+                CUDA_TRY(cudaMalloc(&st->bgtile, need));
+                st->bgtile_bytes = need;
+            }
+            if (st->bg_sig[0] != (unsigned)W || st->bg_sig[1] != (unsigned)H || st->bg_sig[2] != (unsigned)f.C || st->bg_sig[3] != f.bg) {
+                fill_planes_kernel<<<(unsigned)((need + 255) / 256), 256, 0, (cudaStream_t)stream>>>(st->bgtile, H * W, f.C, f.bg);
+                CUDA_TRY(cudaGetLastError());
+                st->bg_sig[0] = (unsigned)W; st->bg_sig[1] = (unsigned)H; st->bg_sig[2] = (unsigned)f.C; st->bg_sig[3] = f.bg;
+            }
+            f.base_color = st->bgtile;
+        }
         if (!st->attr_warp) {
             CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));

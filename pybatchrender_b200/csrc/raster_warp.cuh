@@ -81,7 +81,9 @@ __device__ __forceinline__ void fill_bytes(unsigned char *dst, int n, unsigned v
     const int n16 = (n - head) / 16;
     uint4 *p = reinterpret_cast<uint4 *>(dst + head);
     const uint4 q = make_uint4(v4, v4, v4, v4);
-    for (int i = lane; i < n16; i += 32) p[i] = q;
+    // asm volatile keeps the 512-byte warp stores in ascending address order
+    for (int i = lane; i < n16; i += 32)
+        asm volatile("st.global.v4.u32 [%0], {%1, %1, %1, %1};" ::"l"(p + i), "r"(v4) : "memory");
     for (int i = head + n16 * 16 + lane; i < n; i += 32) dst[i] = (unsigned char)v;
 }
 
@@ -143,19 +145,6 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
     int nlist = 0;
     if (active) {
         unsigned char *out_scene = f.out + (size_t)scene * scene_bytes_out;
-
-        // ---- prefetch this scene's rows before the output burst occupies the load/store queue
-        if (lane < f.n_nodes) {
-            const NodeDev &nd = f.nodes[lane];
-            const int ninst = min(nd.inst, 8);
-            for (int i = 0; i < ninst; ++i) {
-                const size_t b = nd.shared ? (size_t)i : (size_t)scene * nd.inst + i;
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(nd.mats + b * 16));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(nd.cols + b * 4));
-            }
-        } else if (lane == 31) {
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(f.vp + (size_t)scene * 16));
-        }
 
         // ---- 0: background
         write_background(f, out_scene, HW, lane);

@@ -7,6 +7,12 @@ namespace pbr {
 // ------------------------------------------------------------------------------------------------
 // instance-transform kernels
 // ------------------------------------------------------------------------------------------------
+// plane c of a [C, hw] byte image = byte c of the packed colour
+__global__ void fill_planes_kernel(unsigned char *dst, int hw, int C, unsigned rgba) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < hw * C) dst[i] = (unsigned char)((rgba >> (8 * (i / hw))) & 255u);
+}
+
 __global__ void pack_transforms_kernel(float *__restrict__ tr, const float *__restrict__ rot,
                                        const float *__restrict__ scale, float *__restrict__ out, int n) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
