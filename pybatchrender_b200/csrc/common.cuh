@@ -37,6 +37,7 @@ struct FrameDev {
     const float *vp;
     unsigned char *out;
     int *status;            // device word: sticky PBR_DEVSTAT_* bits
+    volatile int *status_host;   // the same bits in host-mapped pinned memory (read by the host without a sync)
     // static layer (see pbr_base_t): inputs of a frame that starts from it ...
     const unsigned char *base_color;         // [C,H,W]
     const unsigned long long *base_keys;     // [nblk,64] block-major depth|id keys

@@ -68,6 +68,8 @@ struct DeviceState {
     int sm_count = 0;
     bool attr_general = false, attr_warp = false;
     int *status = nullptr;           // device word with sticky DEVSTAT_* bits
+    volatile int *status_host = nullptr;   // host-mapped copy (pinned, zero-copy): polled without a sync
+    int *status_host_dev = nullptr;        // device alias of status_host
     // clear-colour image [C,H,W]: copy source of the small-scene kernel's background when there is
     // no static layer (one code path for both; the 12 KB tile stays in L1/L2)
     unsigned char *bgtile = nullptr;
@@ -84,6 +86,11 @@ int device_state(int device, DeviceState **out) {
         CUDA_TRY(cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, device));
         CUDA_TRY(cudaMalloc(&st.status, sizeof(int)));
         CUDA_TRY(cudaMemset(st.status, 0, sizeof(int)));
+        int *hp = nullptr;
+        CUDA_TRY(cudaHostAlloc(&hp, sizeof(int), cudaHostAllocMapped));
+        *hp = 0;
+        CUDA_TRY(cudaHostGetDevicePointer(&st.status_host_dev, hp, 0));
+        st.status_host = hp;
     }
     *out = &st;
     return PBR_OK;
@@ -340,13 +347,16 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
     DeviceState *st = nullptr;
     if (int rc = device_state(device, &st)) return rc;
     f.status = st->status;
+    f.status_host = st->status_host_dev;
 
     const int W = f.W, H = f.H;
     const int nbx = (W + 7) / 8;
     const int H8 = ((H + 7) / 8) * 8;
     const size_t warp_smem = warp_smem_bytes(nbx * (H8 / 8), W_WARPS);
     auto warp_eligible = [&](const NodeStats &ns) {
-        return ns.warp_ok && !(d->flags & PBR_FRAME_FORCE_GENERAL) && ns.slots <= W_MAXSLOT && ns.verts <= W_MAXVERT &&
+        // once a scene overflowed the small-scene kernel's record slots (too many clipped fan
+        // triangles; sticky flag in host-mapped memory) this device keeps to the general kernel
+        return ns.warp_ok && *st->status_host == 0 && !(d->flags & PBR_FRAME_FORCE_GENERAL) && ns.slots <= W_MAXSLOT && ns.verts <= W_MAXVERT &&
                nbx <= 256 && H8 / 8 <= 256 && warp_smem <= 100 * 1024 && warp_smem <= (size_t)st->max_smem_optin;
     };
 
@@ -433,6 +443,7 @@ int pbr_base_render(pbr_base_t b, const pbr_frame_desc *d, void *stream) {
     DeviceState *st = nullptr;
     if (int rc = device_state(device, &st)) return rc;
     f.status = st->status;
+    f.status_host = st->status_host_dev;
     NodeStats ns;
     if (int rc = fill_nodes(d, device, NODES_SHARED_ONLY, f, ns)) return rc;
 
@@ -472,7 +483,7 @@ int pbr_device_status(int32_t device, int32_t *status_bits, int32_t clear) {
     if (rc == PBR_OK) {
         int v = 0;
         cudaError_t e = cudaMemcpy(&v, st->status, sizeof(int), cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess && clear) e = cudaMemset(st->status, 0, sizeof(int));
+        if (e == cudaSuccess && clear) { e = cudaMemset(st->status, 0, sizeof(int)); *st->status_host = 0; }
         if (e != cudaSuccess) rc = fail(PBR_ECUDA, "pbr_device_status: %s", cudaGetErrorString(e));
         *status_bits = v;
     }

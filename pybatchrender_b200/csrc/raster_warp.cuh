@@ -340,7 +340,10 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
                     }
                     nrec = min(nrec + total, W_MAXREC);
                 }
-                if (__any_sync(0xffffffffu, overflow) && lane == 0) atomicOr(f.status, DEVSTAT_WARP_OVERFLOW);
+                if (__any_sync(0xffffffffu, overflow) && lane == 0) {
+                    atomicOr(f.status, DEVSTAT_WARP_OVERFLOW);
+                    *f.status_host = DEVSTAT_WARP_OVERFLOW;      // host stops choosing this kernel
+                }
             }
             __syncwarp();     // records + masks complete; background stores ordered before patches
 
