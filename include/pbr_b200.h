@@ -89,6 +89,8 @@ typedef struct {
 } pbr_frame_desc;
 
 #define PBR_FRAME_FORCE_GENERAL 1u      /* skip the small-scene fast kernel (testing / debugging) */
+#define PBR_FRAME_FORCE_FUSED 2u        /* general path: keep geometry fused into the raster kernel
+                                           instead of the geometry pre-pass + TMA-staged raster */
 
 int pbr_version(void);
 const char *pbr_last_error(void);

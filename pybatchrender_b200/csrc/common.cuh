@@ -63,6 +63,7 @@ struct FrameDev {
 };
 
 constexpr int DEVSTAT_WARP_OVERFLOW = 1;   // small-scene kernel ran out of record slots
+constexpr int DEVSTAT_STAGED_OVERFLOW = 2; // geometry pre-pass ran out of per-scene record capacity
 
 // record meta bits
 constexpr unsigned M_VALID = 1u << 16, M_SLOW = 1u << 17, M_SMOOTH = 1u << 18;

@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "raster_general.cuh"
 #include "raster_warp.cuh"
+#include "raster_staged.cuh"
 #include "transforms.cuh"
 
 using namespace pbr;
@@ -66,7 +67,13 @@ unsigned host_unorm8(float c) {
 struct DeviceState {
     int max_smem_optin = 0;
     int sm_count = 0;
-    bool attr_general = false, attr_warp = false;
+    bool attr_general = false, attr_warp = false, attr_staged = false;
+    // scratch of the geometry pre-pass: per-scene record lists (grown on demand, reused per launch)
+    Rec *g_recs = nullptr;
+    unsigned *g_bbox = nullptr;
+    int *g_count = nullptr;
+    size_t g_rec_cap = 0;            // records allocated (all scenes of one launch)
+    size_t g_scene_cap = 0;          // scenes allocated in g_count
     int *status = nullptr;           // device word with sticky DEVSTAT_* bits
     volatile int *status_host = nullptr;   // host-mapped copy (pinned, zero-copy): polled without a sync
     int *status_host_dev = nullptr;        // device alias of status_host
@@ -335,6 +342,48 @@ static int launch_general(FrameDev &f, DeviceState *st, void *stream) {
     return PBR_OK;
 }
 
+// geometry pre-pass + TMA-staged raster, in launches of as many scenes as the scratch budget holds
+static int launch_staged(FrameDev &f, DeviceState *st, void *stream) {
+    const size_t cap = ((size_t)f.total_slots + (size_t)f.total_slots / 2 + 64 + 3) & ~(size_t)3;
+    static const size_t budget_mb = getenv("PBR_B200_SCRATCH_MB") ? (size_t)atoll(getenv("PBR_B200_SCRATCH_MB")) : 1024;
+    const size_t per_scene = cap * (sizeof(Rec) + 4);
+    size_t per_launch = (budget_mb << 20) / per_scene;
+    if (per_launch < 1) per_launch = 1;
+    if (per_launch > (size_t)f.scene_count) per_launch = (size_t)f.scene_count;
+    if (per_launch > 65535) per_launch = 65535;                     // gridDim.y of the geometry kernel
+    if (per_launch * cap > st->g_rec_cap || per_launch > st->g_scene_cap) {
+        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+        cudaFree(st->g_recs); cudaFree(st->g_bbox); cudaFree(st->g_count);
+        st->g_recs = nullptr; st->g_bbox = nullptr; st->g_count = nullptr; st->g_rec_cap = 0; st->g_scene_cap = 0;
+        CUDA_TRY(cudaMalloc(&st->g_recs, per_launch * cap * sizeof(Rec)));
+        CUDA_TRY(cudaMalloc(&st->g_bbox, per_launch * cap * 4 + 64));
+        CUDA_TRY(cudaMalloc(&st->g_count, per_launch * sizeof(int)));
+        st->g_rec_cap = per_launch * cap; st->g_scene_cap = per_launch;
+    }
+    const size_t smem = staged_smem_bytes(f.C, f.plane_stride, f.nbx * f.nby);
+    if (smem > (size_t)st->max_smem_optin) return launch_general(f, st, stream);
+    if (!st->attr_staged) {
+        CUDA_TRY(cudaFuncSetAttribute(raster_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem_optin));
+        st->attr_staged = true;
+    }
+    StagedDev g;
+    g.recs = st->g_recs; g.bbox = st->g_bbox; g.count = st->g_count; g.cap = (int)cap;
+    const int first = f.scene_begin, last = f.scene_begin + f.scene_count;
+    for (int s0 = first; s0 < last; s0 += (int)per_launch) {
+        const int n = (int)((size_t)(last - s0) < per_launch ? (size_t)(last - s0) : per_launch);
+        g.scene0 = s0;
+        CUDA_TRY(cudaMemsetAsync(st->g_count, 0, (size_t)n * sizeof(int), (cudaStream_t)stream));
+        dim3 ggrid((unsigned)((f.total_slots + G_THREADS - 1) / G_THREADS), (unsigned)n);
+        geom_kernel<<<ggrid, G_THREADS, 0, (cudaStream_t)stream>>>(f, g);
+        CUDA_TRY(cudaGetLastError());
+        const long long grid = (long long)n * f.nbands;
+        if (grid > 0x7fffffffll) return fail(PBR_EUNSUPPORTED, "pbr_render: grid too large");
+        raster_staged_kernel<<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(f, g);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return PBR_OK;
+}
+
 int pbr_render(const pbr_frame_desc *d, void *stream) {
     if (int rc = check_frame(d, "pbr_render", true)) return rc;
     if (d->scene_count == 0) return PBR_OK;
@@ -409,6 +458,11 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         CUDA_TRY(cudaGetLastError());
         return PBR_OK;
     }
+    // large scenes: geometry once per frame into per-scene record lists, then TMA-staged raster
+    size_t smem_fused = 0;
+    if (int rc = plan_general(f, st, &smem_fused)) return rc;
+    if (!(d->flags & PBR_FRAME_FORCE_FUSED) && (ns.slots > CH || f.nbands > 1))
+        return launch_staged(f, st, stream);
     return launch_general(f, st, stream);
 }
 

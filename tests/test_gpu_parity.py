@@ -90,20 +90,31 @@ def test_cartpole_generic_setters_match_fused_pose():
     torch.testing.assert_close(r.pole.matbuf, fused_pole, atol=1e-6, rtol=0)
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["staged", "fused"])
 @pytest.mark.parametrize("channels", [3, 4])
-def test_many_cubes_clipping_and_multipass(channels):
+def test_many_cubes_clipping_and_multipass(channels, fused):
     """16 boxes/scene = 192 triangle slots (> one 128-slot pass), camera inside the cloud so that
     triangles cross the near plane (clip path) and the guard band."""
     r = many_cubes_renderer(num_scenes=24, instances=16, tile=(64, 64), device="cuda", channels=channels)
+    if fused:
+        r.render_flags = 2          # PBR_FRAME_FORCE_FUSED: geometry inside the raster kernel
     px = r.step()
     ref = oracle_render(r)
     assert (ref != 0).any()
     _assert_same(px, ref, "many cubes")
 
 
-def test_many_cubes_large_tile_bands():
-    r = many_cubes_renderer(num_scenes=6, instances=40, tile=(128, 128), device="cuda", seed=7)
-    _assert_same(r.step(), oracle_render(r), "many cubes 128")
+@pytest.mark.parametrize("fused", [False, True], ids=["staged", "fused"])
+@pytest.mark.parametrize("n,inst,tile,seed", [(6, 40, (128, 128), 7), (3, 150, (256, 256), 8), (5, 300, (84, 84), 9),
+                                              (2, 64, (200, 120), 10)])
+def test_many_cubes_large_tile_bands(n, inst, tile, seed, fused):
+    """Several bands per tile and several 128-record chunks per scene: geometry pre-pass + TMA-staged
+    raster against the fused kernel and the oracle."""
+    r = many_cubes_renderer(num_scenes=n, instances=inst, tile=tile, device="cuda", seed=seed)
+    if fused:
+        r.render_flags = 2
+    _assert_same(r.step(), oracle_render(r), f"many cubes {tile} x{inst}")
+    assert r._native.device_status(torch.cuda.current_device()) == 0
 
 
 def test_camera_inside_geometry_heavy_clipping():
