@@ -38,56 +38,52 @@ def grid_for(n: int) -> tuple[int, int]:
     return cols, rows
 
 
+_PANDA_PRC_EXTRAS = "audio-library-name null\ntextures-power-2 none\nsync-video 0\n"
+
+
 @dataclass
 class PBRConfig:
-    offscreen: bool = True
-
+    # ---- batch geometry: how many scenes, how big each tile is.  `tiles` / `window_resolution`
+    # describe the reference's single tiled window; they survive because the *window* aspect enters
+    # the projection (quirk Q1).
     num_scenes: int | None = None
-    tiles: tuple[int, int] | int | None = None
     tile_resolution: tuple[int, int] | None = None
+    tiles: tuple[int, int] | int | None = None
     window_resolution: tuple[int, int] | None = None
-
-    num_channels: int = 3
     batch_inner_dim: int | None = None
-
-    clip_camera: tuple[float, float] = (3.0, 500.0)
-    min_objects: int = 50
-    max_objects: int = 100
+    num_channels: int = 3
     device: str | None = None
-    panda3d_backend: str | None = "arm"
-    log_level: int = logging.DEBUG
-    extra_prc_file_data: str = (
-        "audio-library-name null\n"
-        "textures-power-2 none\n"
-        "sync-video 0\n"
-    )
 
-    render_mode: str = "rgb_array"
-    dt: float = 1 / 60
-    warmup_steps: int = 5
+    # ---- scene sharding (not in the reference; see pybatchrender_b200/dist.py): this process renders
+    # scenes [scene_offset, scene_offset + num_scenes) of a batch of global_num_scenes, and `tiles`
+    # is then the *global* grid so that the projection aspect matches the unsharded render
+    scene_offset: int = 0
+    global_num_scenes: int | None = None
 
-    report_fps: bool = True
-    report_fps_interval: float = 1.0
-
-    manual_camera_control: bool = False
-    cuda_gl_interop: bool = True
-
-    interactive: bool = False
-
-    # TorchRL env-related
+    # ---- env layer (TorchRL)
     direct_obs_dim: int | None = None
     action_n: int | None = None
     action_type: str = "discrete"
     max_steps: int = 500
     auto_reset: bool = True
-
     num_workers: int = 1
 
-    # Scene sharding (not in the reference; see pybatchrender_b200/dist.py): this process renders
-    # scenes [scene_offset, scene_offset + num_scenes) of a global batch of global_num_scenes.
-    # `tiles` is then the *global* grid so that the projection aspect (quirk Q1) matches.
-    scene_offset: int = 0
-    global_num_scenes: int | None = None
+    # ---- accepted for compatibility with existing configs; no effect on the CUDA rasteriser
+    offscreen: bool = True
+    interactive: bool = False
+    manual_camera_control: bool = False
+    cuda_gl_interop: bool = True
+    panda3d_backend: str | None = "arm"
+    extra_prc_file_data: str = _PANDA_PRC_EXTRAS
+    render_mode: str = "rgb_array"
+    warmup_steps: int = 5
+    dt: float = 1 / 60
+    report_fps: bool = True
+    report_fps_interval: float = 1.0
+    log_level: int = logging.DEBUG
+    clip_camera: tuple[float, float] = (3.0, 500.0)
+    min_objects: int = 50
+    max_objects: int = 100
 
     # ------------------------------------------------------------------ resolution
     def process_resolution(self) -> None:

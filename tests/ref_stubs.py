@@ -129,14 +129,23 @@ def install():
                           "direct.showbase.ShowBase": sb, "direct.showbase.ShowBaseGlobal": sbg,
                           "direct.task": task, "direct.gui": gui, "direct.gui.OnscreenText": ost}.items():
             sys.modules[name] = mod
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
+    # load the reference package under a private name: this repo ships its own ``pybatchrender``
+    # alias package, which must not shadow (or be shadowed by) the reference checkout
     import importlib
-    cfg_mod = importlib.import_module("pybatchrender.config")
-    sc = importlib.import_module("pybatchrender.renderer.shader_context")
-    node = importlib.import_module("pybatchrender.renderer.node")
-    cam = importlib.import_module("pybatchrender.renderer.camera")
-    light = importlib.import_module("pybatchrender.renderer.light")
-    rend = importlib.import_module("pybatchrender.renderer.renderer")
+    import importlib.util
+    name = "_reference_pybatchrender"
+    if name not in sys.modules:
+        pkg_dir = os.path.join(REF_ROOT, "pybatchrender")
+        spec = importlib.util.spec_from_file_location(name, os.path.join(pkg_dir, "__init__.py"),
+                                                      submodule_search_locations=[pkg_dir])
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+    cfg_mod = importlib.import_module(name + ".config")
+    sc = importlib.import_module(name + ".renderer.shader_context")
+    node = importlib.import_module(name + ".renderer.node")
+    cam = importlib.import_module(name + ".renderer.camera")
+    light = importlib.import_module(name + ".renderer.light")
+    rend = importlib.import_module(name + ".renderer.renderer")
     return dict(PBRConfig=cfg_mod.PBRConfig, PBRShaderContext=sc.PBRShaderContext, PBRNode=node.PBRNode,
                 PBRCam=cam.PBRCam, PBRLight=light.PBRLight, rearrange=rend.PBRRenderer._rearrange_img)

@@ -119,3 +119,14 @@ def test_sphere_is_closed_and_outward():
         p0, p1, p2 = s.pos[t]
         n = np.cross(p1 - p0, p2 - p0)
         assert np.dot(n, (p0 + p1 + p2) / 3) > 0
+
+
+def test_drop_in_import_name():
+    """``import pybatchrender`` (the reference's package name) resolves to this implementation."""
+    import pybatchrender as ref_name
+    from pybatchrender.renderer.renderer import PBRRenderer as R1
+    from pybatchrender.envs.cartpole.renderer import CartPoleRenderer as C1
+    from pybatchrender import PBRConfig, PBRRenderer, PBREnv  # noqa: F401  (Steering's import line)
+    assert R1 is pbr.PBRRenderer and ref_name.PBRConfig is pbr.PBRConfig
+    assert "CartPole-v0" in ref_name.envs.list_envs()
+    assert C1(dict(num_scenes=2, device="cpu")).num_scenes == 2
