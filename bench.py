@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer loop (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", action="store_true",
+                    help="N>1: also time the optional NCCL gather of all frames onto rank 0 (reported separately)")
     return ap.parse_args()
 
 
@@ -321,6 +323,21 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    # ---- optional: frames of all ranks onto rank 0 (NCCL gather over NVLink); never part of step()
+    gather_ms = None
+    if distributed and args.gather:
+        from pybatchrender_b200.dist import gather_frames
+        for _ in range(2):
+            gather_frames(outs[0], dst=0)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(10):
+            gather_frames(outs[0], dst=0)
+        g1.record()
+        barrier()
+        gather_ms = g0.elapsed_time(g1) / 10
+
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
@@ -358,6 +375,10 @@ def run_ours(args):
                     "steps": e2e_steps},
             "gpu_launches": launches_per_step * K,
             "clocks": sampler.summary(),
+            "gather": None if gather_ms is None else {
+                "ms": gather_ms, "bytes_into_rank0": (world - 1) * N * 3 * TILE[0] * TILE[1],
+                "GBps_into_rank0": (world - 1) * N * 3 * TILE[0] * TILE[1] / (gather_ms * 1e-3) / 1e9,
+                "note": "optional collective, timed separately, not part of value / e2e"},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
