@@ -302,3 +302,59 @@ def test_record_overflow_falls_back_to_the_general_kernel():
         _assert_same(first, ref, f"no overflow, seed {seed}")
     r._native.device_status(dev, clear=True)   # do not leave the device in general-only mode
     assert found, "no seed produced a record overflow (test scene needs adjusting)"
+
+
+# ------------------------------------------------------------------ BASELINE configs at full size
+def _sampled_equal(r, px, scenes):
+    """Oracle on a sample of scenes of a big batch (the oracle renders single scenes cheaply)."""
+    from util import oracle_frame
+    import oracle
+    fr = oracle_frame(r)
+    got = px.cpu().numpy()
+    for s in scenes:
+        ref = oracle.render(fr, scene_begin=int(s), scene_count=1)[int(s)]
+        assert np.array_equal(got[int(s)], ref), f"scene {s} differs from the oracle"
+
+
+def test_config4_full_size_65536_scenes_84x84():
+    """BASELINE config 4 on one GPU (the multi-GPU run shards the same batch): 65,536 CartPole scenes
+    at 84x84.  Sampled scenes are checked against the oracle; every tile must contain the shared rail
+    pixels that no cart / pole can occlude and mostly background."""
+    n = 65536
+    r = _cartpole(n, (84, 84))
+    assert r.cfg.tiles == (256, 256)
+    px = r.step(cartpole_states(n, seed=4).cuda())
+    assert px.shape == (n, 3, 84, 84)
+    rng = np.random.default_rng(0)
+    _sampled_equal(r, px, list(rng.integers(0, n, 24)) + [0, n - 1])
+    nonbg = (px != 0).any(1).flatten(1).sum(1)
+    assert int(nonbg.min()) > 30 and int(nonbg.max()) < 1200
+    # idempotence: rendering the same state again gives the same bytes
+    assert torch.equal(px, r.render())
+
+
+def test_config3_full_size_many_cubes_1024x256_128x128():
+    """BASELINE config 3: 1024 scenes x 256 boxes at 128x128 (geometry pre-pass + TMA-staged raster,
+    4 bands per tile, ~12 record chunks per scene, near-plane clipping)."""
+    r = many_cubes_renderer(num_scenes=1024, instances=256, tile=(128, 128), device="cuda")
+    px = r.step()
+    assert px.shape == (1024, 3, 128, 128)
+    _sampled_equal(r, px, [0, 1, 511, 1023] + list(np.random.default_rng(1).integers(0, 1024, 8)))
+    assert r._native.device_status(torch.cuda.current_device()) == 0
+    assert torch.equal(px, r.render())
+
+
+def test_sharded_render_equals_single_process_render():
+    """Two shard renderers on one GPU (scene_offset / global grid from dist.shard_config) produce the
+    same frames as the unsharded renderer."""
+    from pybatchrender_b200.dist import shard_config
+    from pybatchrender_b200.envs.cartpole import CartPoleConfig, CartPoleRenderer
+    n = 300
+    st = cartpole_states(n, seed=8).cuda()
+    g = CartPoleConfig(num_scenes=n, tile_resolution=(64, 64), device="cuda")
+    full = CartPoleRenderer(g).step(st)
+    parts = []
+    for rank in range(3):
+        cfg = shard_config(g, rank, 3)
+        parts.append(CartPoleRenderer(cfg).step(st[cfg.scene_offset:cfg.scene_offset + cfg.num_scenes]))
+    assert torch.equal(torch.cat(parts), full)
