@@ -54,6 +54,7 @@ struct FrameDev {
     unsigned nbx_magic;     // floor(2^32 / nbx) + 1
     int plane_stride;       // bytes between colour planes in shared memory (multiple of 16)
     int linear;             // 1: the shared colour tile is a byte image of out[scene]
+    int smooth;             // 1: some mesh has per-vertex normals (SMOOTH kernel instantiations)
     int debug;              // profiling aid: 1 = stop after the background, 2 = stop after setup
     float hw, hh;
     unsigned bg;            // packed RGBA8 clear colour
@@ -77,6 +78,15 @@ struct __align__(16) Rec {
     float z0, dz1, dz2, invA;   // 16-byte aligned: one LDS.128
 };
 static_assert(sizeof(Rec) == 64, "Rec must be 64 bytes");
+
+// companion of a Rec for triangles with per-vertex normals (smooth shading): what the fragment
+// shader interpolates (reference basic.vert:53-54 -> basic.frag:33-38)
+struct __align__(16) SRec {
+    float n[3][3];   // world-space unit normals of the three vertices (after a two-sided swap)
+    float rw[3];     // 1 / w_clip of the three vertices (perspective-correct weights)
+    float col[4];    // instance RGBA
+};
+static_assert(sizeof(SRec) == 64, "SRec must be 64 bytes");
 
 struct CV {
     float c[4];      // clip-space position
@@ -197,9 +207,9 @@ __device__ __noinline__ int clip_poly(const CV *in3, CV *a) {
 }
 
 // perspective divide + viewport (image orientation, y down) + snap to 1/256 px
-__device__ __forceinline__ bool project_vertex(const FrameDev &f, const float *c, int &X, int &Y, float &z) {
+__device__ __forceinline__ bool project_vertex(const FrameDev &f, const float *c, int &X, int &Y, float &z, float &rw) {
     if (!(c[3] > 0.0f)) return false;
-    const float rw = 1.0f / c[3];
+    rw = 1.0f / c[3];
     const float xs = fmaf(c[0] * rw, f.hw, f.hw);
     const float ys = fmaf(-(c[1] * rw), f.hh, f.hh);
     z = fmaf(0.5f, c[2] * rw, 0.5f);
@@ -209,13 +219,19 @@ __device__ __forceinline__ bool project_vertex(const FrameDev &f, const float *c
     Y = __float2int_rn(fy);
     return true;
 }
+__device__ __forceinline__ bool project_vertex(const FrameDev &f, const float *c, int &X, int &Y, float &z) {
+    float rw;
+    return project_vertex(f, c, X, Y, z, rw);
+}
 
 // ------------------------------------------------------------------------------------------------
 // triangle setup from snapped vertices: cull, edge equations, depth plane -> record + block bbox.
 // r.col is left for the caller (flat colour is only worth computing for surviving triangles).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool setup_snapped(const FrameDev &f, int *X, int *Y, float *z, bool two_sided,
-                                              unsigned id, int band_y0, int band_h, Rec &r, BBox &bb) {
+                                              unsigned id, int band_y0, int band_h, Rec &r, BBox &bb,
+                                              bool *swapped = nullptr) {
+    if (swapped) *swapped = false;
     long long area2 = (long long)(X[1] - X[0]) * (Y[2] - Y[0]) - (long long)(X[2] - X[0]) * (Y[1] - Y[0]);
     if (area2 == 0) return false;
     if (area2 > 0) {                 // clockwise in GL's y-up window space: back face
@@ -224,6 +240,7 @@ __device__ __forceinline__ bool setup_snapped(const FrameDev &f, int *X, int *Y,
         t = Y[1]; Y[1] = Y[2]; Y[2] = t;
         float q = z[1]; z[1] = z[2]; z[2] = q;
         area2 = -area2;
+        if (swapped) *swapped = true;
     }
     const long long A2 = -area2;
 
@@ -347,23 +364,24 @@ __device__ __forceinline__ unsigned long long make_key(float z, unsigned id) {
 
 // exact int64 coverage of one slow-path record at this lane's two pixels (rare: huge triangles)
 __device__ __noinline__ bool slow_cover(const Rec &r, int px, int py0, bool ok0, bool ok1, bool &cov0, bool &cov1,
-                                        float &f1a, float &f2a, float &f1b, float &f2b) {
+                                        float &f1a, float &f2a, float &f1b, float &f2b, float &f0a, float &f0b) {
     const unsigned meta = r.meta;
     const int spx = px * 256 + 128, spy0 = py0 * 256 + 128, spy1 = (py0 + 4) * 256 + 128;
     const long long F0 = slow_edge(r, 0, spx, spy0), F1 = slow_edge(r, 1, spx, spy0), F2 = slow_edge(r, 2, spx, spy0);
     const long long G0 = slow_edge(r, 0, spx, spy1), G1 = slow_edge(r, 1, spx, spy1), G2 = slow_edge(r, 2, spx, spy1);
     cov0 = ok0 && ((F0 | F1 | F2) >= 0);
     cov1 = ok1 && ((G0 | G1 | G2) >= 0);
-    const long long nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
+    const long long nb0 = (meta >> 19) & 1, nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
     f1a = (float)(F1 + nb1); f2a = (float)(F2 + nb2);
     f1b = (float)(G1 + nb1); f2b = (float)(G2 + nb2);
+    f0a = (float)(F0 + nb0); f0b = (float)(G0 + nb0);
     return cov0 || cov1;
 }
 
-// int32 fast-path coverage of one record at this lane's two pixels; F1/F2 (G1/G2) are the unbiased
-// edge values used for the depth weights
+// int32 fast-path coverage of one record at this lane's two pixels; F* (G*) are the unbiased edge
+// values of pixel 0 (pixel 1): F1, F2 weight the depth, F0 is only needed for smooth shading
 struct FastCov {
-    int F1, F2, G1, G2;
+    int F0, F1, F2, G0, G1, G2;
     bool cov0, cov1;
 };
 
@@ -382,44 +400,74 @@ __device__ __forceinline__ FastCov fast_cover(const int4 &ea, const int4 &eb, co
     FastCov c;
     c.cov0 = ok0 && ((F0 | F1 | F2) >= 0);
     c.cov1 = ok1 && ((G0 | G1 | G2) >= 0);
-    const int nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
-    c.F1 = F1 + nb1; c.F2 = F2 + nb2; c.G1 = G1 + nb1; c.G2 = G2 + nb2;
+    const int nb0 = (meta >> 19) & 1, nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
+    c.F0 = F0 + nb0; c.F1 = F1 + nb1; c.F2 = F2 + nb2;
+    c.G0 = G0 + nb0; c.G1 = G1 + nb1; c.G2 = G2 + nb2;
     return c;
 }
 
 // depth from the edge values + LESS test (ties to the earlier draw) for both pixels of the lane
 __device__ __forceinline__ void depth_update(PixelState &ps, float f1a, float f2a, float f1b, float f2b, bool cov0,
-                                             bool cov1, const float4 &zq, unsigned id, unsigned col) {
+                                             bool cov1, const float4 &zq, unsigned id, unsigned col, bool &w0,
+                                             bool &w1) {
     const float za = fmaf(f2a * zq.w, zq.z, fmaf(f1a * zq.w, zq.y, zq.x));
     const float zc = fmaf(f2b * zq.w, zq.z, fmaf(f1b * zq.w, zq.y, zq.x));
     const unsigned long long ka = make_key(za, id), kc = make_key(zc, id);
-    const bool w0 = cov0 & (ka < ps.k0), w1 = cov1 & (kc < ps.k1);
+    w0 = cov0 & (ka < ps.k0);
+    w1 = cov1 & (kc < ps.k1);
     ps.k0 = w0 ? ka : ps.k0; ps.c0 = w0 ? col : ps.c0; ps.ch0 |= w0;
     ps.k1 = w1 ? kc : ps.k1; ps.c1 = w1 ? col : ps.c1; ps.ch1 |= w1;
 }
 
-// one record, any path
-__device__ __forceinline__ void raster_one(const Rec &r, const int4 &ea, const int4 &eb, const int4 &ec,
-                                           const float4 &zq, int px, int py0, bool ok0, bool ok1, PixelState &ps) {
+// fragment shader for a smooth triangle at one pixel: perspective-correct normal (weights b_i / w_i;
+// their normalisation is dropped because the normal is re-normalised), ambient + Lambert
+__device__ __forceinline__ unsigned shade_pixel(const FrameDev &f, const SRec &sr, float f0, float f1, float f2,
+                                                float invA) {
+    const float p0 = (f0 * invA) * sr.rw[0], p1 = (f1 * invA) * sr.rw[1], p2 = (f2 * invA) * sr.rw[2];
+    float n[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) n[k] = fmaf(p2, sr.n[2][k], fmaf(p1, sr.n[1][k], p0 * sr.n[0][k]));
+    const float l2 = fmaf(n[2], n[2], fmaf(n[1], n[1], n[0] * n[0]));
+    const float inv = 1.0f / sqrtf(l2);
+    n[0] *= inv; n[1] *= inv; n[2] *= inv;
+    return shade(f, n, make_float4(sr.col[0], sr.col[1], sr.col[2], sr.col[3]));
+}
+
+// one record, any path.  SMOOTH: records flagged M_SMOOTH shade the pixels they win per pixel.
+template <bool SMOOTH>
+__device__ __forceinline__ void raster_one(const FrameDev &f, const Rec &r, const SRec *sr, const int4 &ea,
+                                           const int4 &eb, const int4 &ec, const float4 &zq, int px, int py0,
+                                           bool ok0, bool ok1, PixelState &ps) {
+    bool w0, w1;
+    float f0a = 0.f, f1a, f2a, f0b = 0.f, f1b, f2b;
     if (!((unsigned)ec.w & M_SLOW)) {
         const FastCov c = fast_cover(ea, eb, ec, px, py0, ok0, ok1);
         if (!__any_sync(0xffffffffu, c.cov0 || c.cov1)) return;
-        depth_update(ps, (float)c.F1, (float)c.F2, (float)c.G1, (float)c.G2, c.cov0, c.cov1, zq, (unsigned)ec.z,
-                     (unsigned)ec.y);
+        f1a = (float)c.F1; f2a = (float)c.F2; f1b = (float)c.G1; f2b = (float)c.G2;
+        if (SMOOTH) { f0a = (float)c.F0; f0b = (float)c.G0; }
+        depth_update(ps, f1a, f2a, f1b, f2b, c.cov0, c.cov1, zq, (unsigned)ec.z, (unsigned)ec.y, w0, w1);
     } else {
         bool cov0, cov1;
-        float f1a, f2a, f1b, f2b;
-        const bool any = slow_cover(r, px, py0, ok0, ok1, cov0, cov1, f1a, f2a, f1b, f2b);
+        const bool any = slow_cover(r, px, py0, ok0, ok1, cov0, cov1, f1a, f2a, f1b, f2b, f0a, f0b);
         if (!__any_sync(0xffffffffu, any)) return;
-        depth_update(ps, f1a, f2a, f1b, f2b, cov0, cov1, zq, (unsigned)ec.z, (unsigned)ec.y);
+        depth_update(ps, f1a, f2a, f1b, f2b, cov0, cov1, zq, (unsigned)ec.z, (unsigned)ec.y, w0, w1);
+    }
+    if (SMOOTH) {
+        if (((unsigned)ec.w & M_SMOOTH) && __any_sync(0xffffffffu, w0 || w1)) {
+            const unsigned ca = shade_pixel(f, *sr, f0a, f1a, f2a, zq.w);
+            const unsigned cb = shade_pixel(f, *sr, f0b, f1b, f2b, zq.w);
+            ps.c0 = w0 ? ca : ps.c0;
+            ps.c1 = w1 ? cb : ps.c1;
+        }
     }
 }
 
 // All records of one block, in draw order.  (A two-records-per-iteration variant was measured:
 // slower -- register pressure and the wasted second evaluation on odd counts outweigh the ILP.)
-template <int MWORDS>
+template <int MWORDS, bool SMOOTH = false>
 __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bmask, int px, int py0, bool ok0,
-                                             bool ok1, PixelState &ps) {
+                                             bool ok1, PixelState &ps, const FrameDev *f = nullptr,
+                                             const SRec *srecs = nullptr) {
 #pragma unroll 1
     for (int w = 0; w < MWORDS; ++w) {
         unsigned m = bmask[w];
@@ -433,7 +481,7 @@ __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bm
             const int4 eb = *reinterpret_cast<const int4 *>(&r.e[4]);         // A1 A2 B0 B1
             const int4 ec = *reinterpret_cast<const int4 *>(&r.e[8]);         // B2 col id meta
             const float4 zq = *reinterpret_cast<const float4 *>(&r.z0);       // z0 dz1 dz2 invA
-            raster_one(r, ea, eb, ec, zq, px, py0, ok0, ok1, ps);
+            raster_one<SMOOTH>(*f, r, SMOOTH ? srecs + t : nullptr, ea, eb, ec, zq, px, py0, ok0, ok1, ps);
         }
     }
 }

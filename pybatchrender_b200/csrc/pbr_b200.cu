@@ -70,6 +70,8 @@ struct DeviceState {
     bool attr_general = false, attr_warp = false, attr_staged = false;
     // scratch of the geometry pre-pass: per-scene record lists (grown on demand, reused per launch)
     Rec *g_recs = nullptr;
+    SRec *g_srecs = nullptr;
+    size_t g_srec_cap = 0;
     unsigned *g_bbox = nullptr;
     int *g_count = nullptr;
     size_t g_rec_cap = 0;            // records allocated (all scenes of one launch)
@@ -249,7 +251,7 @@ static int fill_nodes(const pbr_frame_desc *d, int device, NodeMode mode, FrameD
         if (!n.mesh->all_flat) st.any_smooth = true;
         if (n.instances_per_scene >= 8192 || n.mesh->n_tris >= 8192) st.warp_ok = false;
     }
-    if (st.any_smooth) return fail(PBR_EUNSUPPORTED, "pbr_render: smooth-normal meshes are not implemented yet");
+    f.smooth = st.any_smooth ? 1 : 0;
     f.total_slots = (int)st.slots;
     f.total_verts = (int)(st.verts > 0x7fffffff ? 0x7fffffff : st.verts);
     return PBR_OK;
@@ -308,7 +310,7 @@ static int plan_general(FrameDev &f, DeviceState *st, size_t *smem_out) {
     auto bytes_for = [&](int BH) {
         const int nby = (BH + 7) / 8;
         const int ps = (int)align16((size_t)BH * W);
-        return general_smem_bytes(f.C, ps, nbx * nby);
+        return general_smem_bytes(f.C, ps, nbx * nby, f.smooth != 0);
     };
     const size_t budget = 56 * 1024;
     int BH = H8;
@@ -330,14 +332,18 @@ static int launch_general(FrameDev &f, DeviceState *st, void *stream) {
     size_t smem = 0;
     if (f.BH == 0)
         if (int rc = plan_general(f, st, &smem)) return rc;
-    smem = general_smem_bytes(f.C, f.plane_stride, f.nbx * f.nby);
+    smem = general_smem_bytes(f.C, f.plane_stride, f.nbx * f.nby, f.smooth != 0);
     if (!st->attr_general) {
-        CUDA_TRY(cudaFuncSetAttribute(raster_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(raster_general_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(raster_general_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem_optin));
         st->attr_general = true;
     }
     const long long grid = (long long)f.scene_count * f.nbands;
     if (grid > 0x7fffffffll) return fail(PBR_EUNSUPPORTED, "pbr_render: grid too large");
-    raster_general_kernel<<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(f);
+    if (f.smooth)
+        raster_general_kernel<true><<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(f);
+    else
+        raster_general_kernel<false><<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(f);
     CUDA_TRY(cudaGetLastError());
     return PBR_OK;
 }
@@ -346,28 +352,35 @@ static int launch_general(FrameDev &f, DeviceState *st, void *stream) {
 static int launch_staged(FrameDev &f, DeviceState *st, void *stream) {
     const size_t cap = ((size_t)f.total_slots + (size_t)f.total_slots / 2 + 64 + 3) & ~(size_t)3;
     static const size_t budget_mb = getenv("PBR_B200_SCRATCH_MB") ? (size_t)atoll(getenv("PBR_B200_SCRATCH_MB")) : 1024;
-    const size_t per_scene = cap * (sizeof(Rec) + 4);
+    const bool smooth = f.smooth != 0;
+    const size_t per_scene = cap * (sizeof(Rec) + 4 + (smooth ? sizeof(SRec) : 0));
     size_t per_launch = (budget_mb << 20) / per_scene;
     if (per_launch < 1) per_launch = 1;
     if (per_launch > (size_t)f.scene_count) per_launch = (size_t)f.scene_count;
     if (per_launch > 65535) per_launch = 65535;                     // gridDim.y of the geometry kernel
-    if (per_launch * cap > st->g_rec_cap || per_launch > st->g_scene_cap) {
+    if (per_launch * cap > st->g_rec_cap || per_launch > st->g_scene_cap || (smooth && per_launch * cap > st->g_srec_cap)) {
         CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-        cudaFree(st->g_recs); cudaFree(st->g_bbox); cudaFree(st->g_count);
-        st->g_recs = nullptr; st->g_bbox = nullptr; st->g_count = nullptr; st->g_rec_cap = 0; st->g_scene_cap = 0;
+        cudaFree(st->g_recs); cudaFree(st->g_bbox); cudaFree(st->g_count); cudaFree(st->g_srecs);
+        st->g_recs = nullptr; st->g_bbox = nullptr; st->g_count = nullptr; st->g_srecs = nullptr;
+        st->g_rec_cap = 0; st->g_scene_cap = 0; st->g_srec_cap = 0;
         CUDA_TRY(cudaMalloc(&st->g_recs, per_launch * cap * sizeof(Rec)));
         CUDA_TRY(cudaMalloc(&st->g_bbox, per_launch * cap * 4 + 64));
         CUDA_TRY(cudaMalloc(&st->g_count, per_launch * sizeof(int)));
         st->g_rec_cap = per_launch * cap; st->g_scene_cap = per_launch;
+        if (smooth) {
+            CUDA_TRY(cudaMalloc(&st->g_srecs, per_launch * cap * sizeof(SRec)));
+            st->g_srec_cap = per_launch * cap;
+        }
     }
-    const size_t smem = staged_smem_bytes(f.C, f.plane_stride, f.nbx * f.nby);
+    const size_t smem = staged_smem_bytes(f.C, f.plane_stride, f.nbx * f.nby, smooth);
     if (smem > (size_t)st->max_smem_optin) return launch_general(f, st, stream);
     if (!st->attr_staged) {
-        CUDA_TRY(cudaFuncSetAttribute(raster_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(raster_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem_optin));
+        CUDA_TRY(cudaFuncSetAttribute(raster_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem_optin));
         st->attr_staged = true;
     }
     StagedDev g;
-    g.recs = st->g_recs; g.bbox = st->g_bbox; g.count = st->g_count; g.cap = (int)cap;
+    g.recs = st->g_recs; g.srecs = smooth ? st->g_srecs : nullptr; g.bbox = st->g_bbox; g.count = st->g_count; g.cap = (int)cap;
     const int first = f.scene_begin, last = f.scene_begin + f.scene_count;
     for (int s0 = first; s0 < last; s0 += (int)per_launch) {
         const int n = (int)((size_t)(last - s0) < per_launch ? (size_t)(last - s0) : per_launch);
@@ -378,7 +391,10 @@ static int launch_staged(FrameDev &f, DeviceState *st, void *stream) {
         CUDA_TRY(cudaGetLastError());
         const long long grid = (long long)n * f.nbands;
         if (grid > 0x7fffffffll) return fail(PBR_EUNSUPPORTED, "pbr_render: grid too large");
-        raster_staged_kernel<<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(f, g);
+        if (smooth)
+            raster_staged_kernel<true><<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(f, g);
+        else
+            raster_staged_kernel<false><<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(f, g);
         CUDA_TRY(cudaGetLastError());
     }
     return PBR_OK;
@@ -405,7 +421,7 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
     auto warp_eligible = [&](const NodeStats &ns) {
         // once a scene overflowed the small-scene kernel's record slots (too many clipped fan
         // triangles; sticky flag in host-mapped memory) this device keeps to the general kernel
-        return ns.warp_ok && *st->status_host == 0 && !(d->flags & PBR_FRAME_FORCE_GENERAL) && ns.slots <= W_MAXSLOT && ns.verts <= W_MAXVERT &&
+        return ns.warp_ok && !ns.any_smooth && *st->status_host == 0 && !(d->flags & PBR_FRAME_FORCE_GENERAL) && ns.slots <= W_MAXSLOT && ns.verts <= W_MAXVERT &&
                nbx <= 256 && H8 / 8 <= 256 && warp_smem <= 100 * 1024 && warp_smem <= (size_t)st->max_smem_optin;
     };
 

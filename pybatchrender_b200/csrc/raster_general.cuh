@@ -2,7 +2,8 @@
 //
 // Any number of triangle slots (128 per pass), near-plane / guard-band clipping, depth + id tiles in
 // shared memory so that passes compose.  Used for scenes the small-scene kernel (raster_warp.cuh)
-// does not take: many instances, large tiles, smooth meshes.
+// does not take: many instances, large tiles, smooth meshes (SMOOTH instantiation: per-pixel
+// normal interpolation, basic.frag:33-38, from a second 64-byte record per triangle).
 //
 // Per pass: (1) one triangle slot per thread: transform (reference basic.vert:24-56), trivial
 // reject, project, snap, cull, edge setup, flat shade (basic.frag:31-38) -> shared-memory record;
@@ -71,16 +72,33 @@ __device__ __forceinline__ int load_slot(const FrameDev &f, int scene, int slot,
     return clip ? SLOT_CLIP : SLOT_OK;
 }
 
+// sr: where the smooth-shading companion of the record goes (may be shared or global memory);
+// only written for non-flat triangles
 __device__ __forceinline__ bool setup_tri(const FrameDev &f, const CV *vin, const float4 col, bool flat,
                                           bool two_sided, unsigned id, int band_y0, int band_h, Rec &r,
-                                          BBox &bb) {
+                                          BBox &bb, SRec *sr = nullptr) {
     int X[3], Y[3];
-    float z[3];
+    float z[3], rw[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
-        if (!project_vertex(f, vin[i].c, X[i], Y[i], z[i])) return false;
-    if (!setup_snapped(f, X, Y, z, two_sided, id, band_y0, band_h, r, bb)) return false;
-    if (flat) r.col = shade(f, vin[0].n, col);
+        if (!project_vertex(f, vin[i].c, X[i], Y[i], z[i], rw[i])) return false;
+    bool swapped;
+    if (!setup_snapped(f, X, Y, z, two_sided, id, band_y0, band_h, r, bb, &swapped)) return false;
+    if (flat) {
+        r.col = shade(f, vin[0].n, col);
+    } else {
+        r.col = 0;
+        r.meta |= M_SMOOTH;
+        const int i1 = swapped ? 2 : 1, i2 = swapped ? 1 : 2;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            sr->n[0][k] = vin[0].n[k];
+            sr->n[1][k] = vin[i1].n[k];
+            sr->n[2][k] = vin[i2].n[k];
+        }
+        sr->rw[0] = rw[0]; sr->rw[1] = rw[i1]; sr->rw[2] = rw[i2];
+        sr->col[0] = col.x; sr->col[1] = col.y; sr->col[2] = col.z; sr->col[3] = col.w;
+    }
     return true;
 }
 
@@ -91,14 +109,15 @@ struct Smem {
     unsigned char *color;      // [C][plane_stride]
     unsigned long long *ktile; // [nblk*64] block-major (depth bits << 32) | id
     Rec *recs;                 // [CH]
+    SRec *srecs;               // [CH] when the frame has smooth meshes, else unused
     unsigned *masks;           // [nblk*MW]
     unsigned short *blist;     // [nblk]
     unsigned short *cliplist;  // [CH]
     int *ctr;                  // nlist, next, nclip
 };
 
-__host__ __device__ inline size_t general_smem_bytes(int C, int plane_stride, int nblk) {
-    size_t n = 0;
+__host__ __device__ inline size_t general_smem_bytes(int C, int plane_stride, int nblk, bool smooth) {
+    size_t n = smooth ? (size_t)CH * sizeof(SRec) : 0;
     n += align16((size_t)C * plane_stride);
     n += 2 * (size_t)nblk * 64 * 4;
     n += (size_t)CH * sizeof(Rec);
@@ -109,11 +128,12 @@ __host__ __device__ inline size_t general_smem_bytes(int C, int plane_stride, in
     return n;
 }
 
-__device__ __forceinline__ Smem carve(unsigned char *base, int C, int plane_stride, int nblk) {
+__device__ __forceinline__ Smem carve(unsigned char *base, int C, int plane_stride, int nblk, bool smooth) {
     Smem s;
     s.color = base; base += align16((size_t)C * plane_stride);
     s.ktile = reinterpret_cast<unsigned long long *>(base); base += (size_t)nblk * 64 * 8;
     s.recs = reinterpret_cast<Rec *>(base); base += (size_t)CH * sizeof(Rec);
+    s.srecs = reinterpret_cast<SRec *>(base); base += smooth ? (size_t)CH * sizeof(SRec) : 0;
     s.masks = reinterpret_cast<unsigned *>(base); base += align16((size_t)nblk * MW * 4);
     s.blist = reinterpret_cast<unsigned short *>(base); base += align16((size_t)nblk * 2);
     s.cliplist = reinterpret_cast<unsigned short *>(base); base += align16((size_t)CH * 2);
@@ -121,6 +141,7 @@ __device__ __forceinline__ Smem carve(unsigned char *base, int C, int plane_stri
     return s;
 }
 
+template <bool SMOOTH>
 __device__ __forceinline__ void general_block(const FrameDev &f, const Smem &s, int b, int band_h, int lane) {
     const int bx = b % f.nbx, by = b / f.nbx;
     const int px = bx * 8 + (lane & 7);
@@ -131,7 +152,7 @@ __device__ __forceinline__ void general_block(const FrameDev &f, const Smem &s, 
     ps.k1 = s.ktile[b * 64 + 32 + lane];
     ps.c0 = ps.c1 = 0;
     ps.ch0 = ps.ch1 = false;
-    raster_block<MW>(s.recs, s.masks + b * MW, px, py0, ok0, ok1, ps);
+    raster_block<MW, SMOOTH>(s.recs, s.masks + b * MW, px, py0, ok0, ok1, ps, &f, s.srecs);
     if (ps.ch0) {
         s.ktile[b * 64 + lane] = ps.k0;
         put_pixel(s.color, f.plane_stride, f.C, f.W, px, py0, ps.c0);
@@ -143,6 +164,7 @@ __device__ __forceinline__ void general_block(const FrameDev &f, const Smem &s, 
 }
 
 // Called by all threads after records + masks of this pass are complete (and synchronised).
+template <bool SMOOTH>
 __device__ __forceinline__ void raster_pass(const FrameDev &f, const Smem &s, int nblk, int band_h) {
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) { s.ctr[0] = 0; s.ctr[1] = 0; }
@@ -160,7 +182,7 @@ __device__ __forceinline__ void raster_pass(const FrameDev &f, const Smem &s, in
         if (lane == 0) i = atomicAdd(&s.ctr[1], 1);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= nlist) break;
-        general_block(f, s, s.blist[i], band_h, lane);
+        general_block<SMOOTH>(f, s, s.blist[i], band_h, lane);
     }
     __syncthreads();
 }
@@ -207,6 +229,7 @@ __device__ __forceinline__ void clear_color(const FrameDev &f, unsigned char *co
     }
 }
 
+template <bool SMOOTH>
 __global__ void __launch_bounds__(THREADS) raster_general_kernel(const __grid_constant__ FrameDev f) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
@@ -215,7 +238,7 @@ __global__ void __launch_bounds__(THREADS) raster_general_kernel(const __grid_co
     const int band_y0 = band * f.BH;
     const int band_h = min(f.BH, f.H - band_y0);
     const int nblk = f.nbx * f.nby;
-    const Smem s = carve(smem_raw, f.C, f.plane_stride, nblk);
+    const Smem s = carve(smem_raw, f.C, f.plane_stride, nblk, SMOOTH);
 
     clear_color(f, s.color, tid, THREADS);
     {
@@ -239,7 +262,7 @@ __global__ void __launch_bounds__(THREADS) raster_general_kernel(const __grid_co
                 const int st = load_slot(f, scene, slot, g);
                 if (st == SLOT_OK) {
                     BBox bb;
-                    if (setup_tri(f, g.v, g.col, g.flat, g.two_sided, g.id, band_y0, band_h, r, bb))
+                    if (setup_tri(f, g.v, g.col, g.flat, g.two_sided, g.id, band_y0, band_h, r, bb, s.srecs + tid))
                         bin_record<MW>(r, bb, tid, f.nbx, s.masks);
                     else
                         r.meta = 0;
@@ -251,7 +274,7 @@ __global__ void __launch_bounds__(THREADS) raster_general_kernel(const __grid_co
         }
         __syncthreads();
         const int nclip = s.ctr[2];
-        raster_pass(f, s, nblk, band_h);
+        raster_pass<SMOOTH>(f, s, nblk, band_h);
 
         // clipped triangles: 16 slots x 8 fan triangles per pass
 #pragma unroll 1
@@ -270,7 +293,7 @@ __global__ void __launch_bounds__(THREADS) raster_general_kernel(const __grid_co
                 if (k + 2 < n) {
                     CV tri[3] = {poly[0], poly[k + 1], poly[k + 2]};
                     BBox bb;
-                    if (setup_tri(f, tri, g.col, g.flat, g.two_sided, g.id, band_y0, band_h, r, bb))
+                    if (setup_tri(f, tri, g.col, g.flat, g.two_sided, g.id, band_y0, band_h, r, bb, s.srecs + tid))
                         bin_record<MW>(r, bb, tid, f.nbx, s.masks);
                     else
                         r.meta = 0;
@@ -278,7 +301,7 @@ __global__ void __launch_bounds__(THREADS) raster_general_kernel(const __grid_co
             }
             s.recs[tid] = r;
             __syncthreads();
-            raster_pass(f, s, nblk, band_h);
+            raster_pass<SMOOTH>(f, s, nblk, band_h);
         }
     }
     __syncthreads();

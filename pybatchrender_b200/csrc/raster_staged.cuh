@@ -27,6 +27,7 @@ constexpr int G_THREADS = 256;
 
 struct StagedDev {
     Rec *recs;               // [scenes_in_launch][cap]
+    SRec *srecs;             // [scenes_in_launch][cap] smooth-shading companions, or NULL (all meshes flat)
     unsigned *bbox;          // [scenes_in_launch][cap]  bx0 | by0 << 8 | bx1 << 16 | by1 << 24 (tile blocks)
     int *count;              // [scenes_in_launch]
     int cap;                 // records per scene (multiple of 4)
@@ -37,7 +38,7 @@ struct StagedDev {
 // geometry
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void append_record(const StagedDev &g, const FrameDev &f, int local_scene, const Rec &r,
-                                              const BBox &bb) {
+                                              const BBox &bb, const SRec &sr) {
     const int idx = atomicAdd(&g.count[local_scene], 1);
     if (idx >= g.cap) {
         atomicOr(f.status, DEVSTAT_STAGED_OVERFLOW);
@@ -48,6 +49,11 @@ __device__ __forceinline__ void append_record(const StagedDev &g, const FrameDev
     const uint4 *src = reinterpret_cast<const uint4 *>(&r);
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
     g.bbox[o] = (unsigned)bb.bx0 | ((unsigned)bb.by0 << 8) | ((unsigned)bb.bx1 << 16) | ((unsigned)bb.by1 << 24);
+    if (g.srecs != nullptr && (r.meta & M_SMOOTH)) {
+        uint4 *sd = reinterpret_cast<uint4 *>(g.srecs + o);
+        const uint4 *ss = reinterpret_cast<const uint4 *>(&sr);
+        sd[0] = ss[0]; sd[1] = ss[1]; sd[2] = ss[2]; sd[3] = ss[3];
+    }
 }
 
 __global__ void __launch_bounds__(G_THREADS) geom_kernel(const __grid_constant__ FrameDev f,
@@ -60,16 +66,17 @@ __global__ void __launch_bounds__(G_THREADS) geom_kernel(const __grid_constant__
     const int st = load_slot(f, scene, slot, sg);
     if (st == SLOT_SKIP) return;
     Rec r;
+    SRec sr;
     BBox bb;
     if (st == SLOT_OK) {
-        if (setup_tri(f, sg.v, sg.col, sg.flat, sg.two_sided, sg.id, 0, f.H, r, bb)) append_record(g, f, local_scene, r, bb);
+        if (setup_tri(f, sg.v, sg.col, sg.flat, sg.two_sided, sg.id, 0, f.H, r, bb, &sr)) append_record(g, f, local_scene, r, bb, sr);
         return;
     }
     CV poly[MAX_POLY];
     const int n = clip_poly(sg.v, poly);
     for (int k = 0; k + 2 < n; ++k) {
         CV tri[3] = {poly[0], poly[k + 1], poly[k + 2]};
-        if (setup_tri(f, tri, sg.col, sg.flat, sg.two_sided, sg.id, 0, f.H, r, bb)) append_record(g, f, local_scene, r, bb);
+        if (setup_tri(f, tri, sg.col, sg.flat, sg.two_sided, sg.id, 0, f.H, r, bb, &sr)) append_record(g, f, local_scene, r, bb, sr);
     }
 }
 
@@ -114,6 +121,7 @@ struct StagedSmem {
     unsigned char *color;          // [C][plane_stride]
     unsigned long long *ktile;     // [nblk*64]
     Rec *recs[2];                  // 2 x [CH]
+    SRec *srecs[2];                // 2 x [CH] (smooth frames only)
     unsigned *bbox[2];             // 2 x [CH]
     unsigned *masks;               // [nblk*MW]
     unsigned short *blist;         // [nblk]
@@ -121,17 +129,19 @@ struct StagedSmem {
     unsigned long long *bar;       // 2 mbarriers
 };
 
-__host__ __device__ inline size_t staged_smem_bytes(int C, int plane_stride, int nblk) {
-    return align16((size_t)C * plane_stride) + (size_t)nblk * 64 * 8 + 2 * (size_t)CH * sizeof(Rec) + 2 * (size_t)CH * 4 +
+__host__ __device__ inline size_t staged_smem_bytes(int C, int plane_stride, int nblk, bool smooth) {
+    return (smooth ? 2 * (size_t)CH * sizeof(SRec) : 0) + align16((size_t)C * plane_stride) + (size_t)nblk * 64 * 8 + 2 * (size_t)CH * sizeof(Rec) + 2 * (size_t)CH * 4 +
            align16((size_t)nblk * MW * 4) + align16((size_t)nblk * 2) + 16 + 16;
 }
 
-__device__ __forceinline__ StagedSmem staged_carve(unsigned char *base, int C, int plane_stride, int nblk) {
+__device__ __forceinline__ StagedSmem staged_carve(unsigned char *base, int C, int plane_stride, int nblk, bool smooth) {
     StagedSmem s;
     s.color = base; base += align16((size_t)C * plane_stride);
     s.ktile = reinterpret_cast<unsigned long long *>(base); base += (size_t)nblk * 64 * 8;
     s.recs[0] = reinterpret_cast<Rec *>(base); base += (size_t)CH * sizeof(Rec);
     s.recs[1] = reinterpret_cast<Rec *>(base); base += (size_t)CH * sizeof(Rec);
+    s.srecs[0] = reinterpret_cast<SRec *>(base); base += smooth ? (size_t)CH * sizeof(SRec) : 0;
+    s.srecs[1] = reinterpret_cast<SRec *>(base); base += smooth ? (size_t)CH * sizeof(SRec) : 0;
     s.bbox[0] = reinterpret_cast<unsigned *>(base); base += (size_t)CH * 4;
     s.bbox[1] = reinterpret_cast<unsigned *>(base); base += (size_t)CH * 4;
     s.masks = reinterpret_cast<unsigned *>(base); base += align16((size_t)nblk * MW * 4);
@@ -141,6 +151,7 @@ __device__ __forceinline__ StagedSmem staged_carve(unsigned char *base, int C, i
     return s;
 }
 
+template <bool SMOOTH>
 __global__ void __launch_bounds__(THREADS) raster_staged_kernel(const __grid_constant__ FrameDev f,
                                                                 const __grid_constant__ StagedDev g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(THREADS) raster_staged_kernel(const __grid_con
     const int band_h = min(f.BH, f.H - band_y0);
     const int band_by0 = band_y0 / 8;
     const int nblk = f.nbx * f.nby;
-    const StagedSmem s = staged_carve(smem_raw, f.C, f.plane_stride, nblk);
+    const StagedSmem s = staged_carve(smem_raw, f.C, f.plane_stride, nblk, SMOOTH);
 
     const int total = min(g.count[local_scene], g.cap);
     const Rec *grecs = g.recs + (size_t)local_scene * g.cap;
@@ -168,8 +179,9 @@ __global__ void __launch_bounds__(THREADS) raster_staged_kernel(const __grid_con
     auto issue = [&](int c) {       // thread 0: stage chunk c into buffer c & 1
         const int cnt = min(CH, total - c * CH);
         const unsigned rb = (unsigned)cnt * (unsigned)sizeof(Rec), bb = (unsigned)align16((size_t)cnt * 4);
-        mbar_expect_tx(&s.bar[c & 1], rb + bb);
+        mbar_expect_tx(&s.bar[c & 1], (SMOOTH ? 2 * rb : rb) + bb);
         tma_load(s.recs[c & 1], grecs + (size_t)c * CH, rb, &s.bar[c & 1]);
+        if (SMOOTH) tma_load(s.srecs[c & 1], g.srecs + (size_t)local_scene * g.cap + (size_t)c * CH, rb, &s.bar[c & 1]);
         tma_load(s.bbox[c & 1], gbbox + (size_t)c * CH, bb, &s.bar[c & 1]);
     };
     if (tid == 0 && nchunks > 0) issue(0);
@@ -240,7 +252,7 @@ __global__ void __launch_bounds__(THREADS) raster_staged_kernel(const __grid_con
             ps.k1 = s.ktile[b * 64 + 32 + lane];
             ps.c0 = ps.c1 = 0;
             ps.ch0 = ps.ch1 = false;
-            raster_block<MW>(recs, s.masks + b * MW, px, py0, ok0, ok1, ps);
+            raster_block<MW, SMOOTH>(recs, s.masks + b * MW, px, py0, ok0, ok1, ps, &f, s.srecs[buf]);
             if (ps.ch0) {
                 s.ktile[b * 64 + lane] = ps.k0;
                 put_pixel(s.color, f.plane_stride, f.C, f.W, px, py0 - band_y0, ps.c0);

@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
         }
         ps.c0 = ps.c1 = 0u;
         ps.ch0 = ps.ch1 = false;
-        raster_block<W_MW>(srecs, smasks + b * W_MW, px, py0, ok0, ok1, ps);
+        raster_block<W_MW, false>(srecs, smasks + b * W_MW, px, py0, ok0, ok1, ps, &f);
         if (f.debug == 3) continue;
         unsigned char *p = out_scene + py0 * f.W + px;
         if (ps.ch0) {

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import cartpole_states, many_cubes_renderer, oracle_render
+from util import cartpole_states, many_cubes_renderer, mixed_mesh_renderer, oracle_render
 
 pytestmark = pytest.mark.gpu
 
@@ -358,3 +358,22 @@ def test_sharded_render_equals_single_process_render():
         cfg = shard_config(g, rank, 3)
         parts.append(CartPoleRenderer(cfg).step(st[cfg.scene_offset:cfg.scene_offset + cfg.num_scenes]))
     assert torch.equal(torch.cat(parts), full)
+
+
+# ------------------------------------------------------------------ smooth shading
+@pytest.mark.parametrize("kw", [
+    dict(num_scenes=6, boxes=0, spheres=1, segments=8, rings=4),                       # fused general kernel
+    dict(num_scenes=6, boxes=4, spheres=3),                                            # staged (TMA) path
+    dict(num_scenes=4, boxes=4, spheres=3, channels=4, tile=(96, 80)),
+    dict(num_scenes=3, boxes=6, spheres=6, tile=(200, 136), segments=16, rings=12),   # several bands
+    dict(num_scenes=4, boxes=2, spheres=4, two_sided=True),
+    dict(num_scenes=4, boxes=3, spheres=3, shared_spheres=True),
+    dict(num_scenes=4, boxes=2, spheres=6, spread=3.0, eye=(0.0, -2.0, 0.0)),          # heavy near-plane clipping
+    dict(num_scenes=4, boxes=0, spheres=3, spread=1.5, eye=(0.2, -0.3, 0.1), two_sided=True),   # camera inside
+])
+@pytest.mark.parametrize("fused", [False, True])
+def test_smooth_normals_bit_exact(kw, fused):
+    r = mixed_mesh_renderer(device="cuda", **kw)
+    r.render_flags = 2 if fused else 0          # PBR_FRAME_FORCE_FUSED
+    _assert_same(r.render(), oracle_render(r), f"smooth {kw} fused={fused}")
+    assert r._native.device_status(torch.cuda.current_device()) == 0

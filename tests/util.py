@@ -63,3 +63,41 @@ def many_cubes_renderer(num_scenes=8, instances=16, tile=(64, 64), seed=123, dev
         r.add_light()
     r.setup_environment()
     return r
+
+
+def mixed_mesh_renderer(num_scenes=8, boxes=6, spheres=5, tile=(64, 64), seed=7, device=None, channels=3,
+                        spread=6.0, eye=(0.0, -12.0, 0.0), segments=10, rings=6, two_sided=False,
+                        shared_spheres=False):
+    """Flat boxes + smooth-shaded UV spheres (per-vertex normals, non-uniform scales) in one frame:
+    the shape of reference demo_mixed_meshes.py (BASELINE config 5) without its model files."""
+    from pybatchrender_b200 import PBRRenderer
+    from pybatchrender_b200 import meshes
+    cfg = dict(num_scenes=num_scenes, tile_resolution=tile, num_channels=channels)
+    if device is not None:
+        cfg["device"] = device
+    r = PBRRenderer(cfg)
+    sph = meshes.uv_sphere(1.0, segments, rings)
+    if two_sided:
+        sph.two_sided = True
+        sph.idx = sph.idx[: (2 * sph.idx.shape[0]) // 3].copy()       # open bowl: inside faces show
+    name = f"test/sphere_{segments}_{rings}_{int(two_sided)}"
+    meshes.register_mesh(name, sph)
+    rng = np.random.default_rng(seed)
+    nodes = []
+    if boxes:
+        nodes.append((r.add_node("models/box", instances_per_scene=boxes, model_pivot_relative_point=(0.5, 0.5, 0.5)), 1))
+    if spheres:
+        nodes.append((r.add_node(name, instances_per_scene=spheres, shared_across_scenes=shared_spheres,
+                                 model_scale=(1.0, 0.7, 1.3)), 1))
+    for node, k in nodes:
+        B = node.buf_instances
+        node.set_positions(torch.tensor(rng.uniform(-spread, spread, (B, 3)), dtype=torch.float32), lazy=True)
+        node.set_hprs(torch.tensor(rng.uniform(-np.pi, np.pi, (B, 3)), dtype=torch.float32), lazy=True)
+        node.set_scales(torch.tensor(rng.uniform(0.6, 2.2, (B, k)), dtype=torch.float32))
+        col = np.concatenate([rng.uniform(0, 1, (B, 3)), np.ones((B, 1))], axis=1)
+        node.set_colors(torch.tensor(col, dtype=torch.float32))
+    cam = r.add_camera()
+    cam.set_positions(torch.tensor(eye, dtype=torch.float32))
+    r.add_light()
+    r.setup_environment()
+    return r
