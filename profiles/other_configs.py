@@ -13,7 +13,7 @@ import bench  # noqa: E402
 from pybatchrender_b200.envs.cartpole import CartPoleRenderer  # noqa: E402
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-from util import many_cubes_renderer  # noqa: E402
+from util import config5_renderer, many_cubes_renderer  # noqa: E402
 
 PEAK = bench.measured_peak()[0]
 
@@ -47,6 +47,11 @@ def main():
     n = 1024
     r = many_cubes_renderer(num_scenes=n, instances=256, tile=(128, 128), device="cuda")
     report("config3: many cubes 1024 x 256 boxes, 128^2", n, time_render(r, 5), 3 * 128 * 128 + 64 + 256 * 80)
+    del r
+    torch.cuda.empty_cache()
+    n = 16384
+    r = config5_renderer(num_scenes=n, device="cuda")
+    report("config5: mixed meshes 16384 x 64 instances, 256^2 (1 GPU)", n, time_render(r, 2), 3 * 256 * 256 + 64 + 64 * 80)
 
 
 if __name__ == "__main__":

@@ -94,6 +94,60 @@ def uv_sphere(radius: float = 1.0, segments: int = 16, rings: int = 12) -> MeshD
                     np.array(uv, np.float32))
 
 
+def cone(segments: int = 32) -> MeshData:
+    """Cone in the frame of the reference's ``models/cone.egg``: base circle of radius 1 in the
+    plane y = -1 (flat cap, normal -y), apex at (0, 1, 0), smooth side normals.  The apex gets one
+    vertex per side triangle carrying the side normal at the triangle's mid angle."""
+    pos, nrm, tris = [], [], []
+    slope = 1.0 / math.sqrt(5.0)                      # side normal = (2 cos, 1, 2 sin) / sqrt(5)
+    ring = [(math.sin(2.0 * math.pi * k / segments), -math.cos(2.0 * math.pi * k / segments)) for k in range(segments)]
+    for x, z in ring:                                 # cap ring: vertices 0 .. segments-1
+        pos.append((x, -1.0, z))
+        nrm.append((0.0, -1.0, 0.0))
+    for x, z in ring:                                 # side ring: segments .. 2*segments-1
+        pos.append((x, -1.0, z))
+        nrm.append((2.0 * slope * x, slope, 2.0 * slope * z))
+    for k in range(segments):                         # apex copies: 2*segments .. 3*segments-1
+        a = 2.0 * math.pi * (k + 0.5) / segments
+        pos.append((0.0, 1.0, 0.0))
+        nrm.append((2.0 * slope * math.sin(a), slope, -2.0 * slope * math.cos(a)))
+    for k in range(1, segments - 1):                  # cap fan (what a loader makes of the n-gon)
+        tris.append((0, k, k + 1))
+    for k in range(segments):
+        tris.append((segments + k, 2 * segments + k, segments + (k + 1) % segments))
+    return MeshData(np.array(pos, np.float32), np.array(nrm, np.float32), np.array(tris, np.uint32))
+
+
+def cylinder(radius: float = 50.0, half_height: float = 100.0, segments: int = 32, stacks: int = 4) -> MeshData:
+    """Capped cylinder about the +Z axis (the shape of the reference's ``models/cylinder/scene.gltf``
+    once loaded into a Z-up world: radius 50, z in [-100, 100], 32 segments x 4 stacks, flat caps,
+    smooth side): 2 + segments * (stacks + 3) vertices, segments * (2 * stacks + 2) triangles."""
+    pos, nrm, tris = [], [], []
+    pos += [(0.0, 0.0, -half_height), (0.0, 0.0, half_height)]
+    nrm += [(0.0, 0.0, -1.0), (0.0, 0.0, 1.0)]
+    col = stacks + 3                                  # per segment: bottom cap, stacks+1 side, top cap
+    for k in range(segments):
+        a = 2.0 * math.pi * k / segments
+        c, s_ = math.cos(a), math.sin(a)
+        pos.append((radius * c, radius * s_, -half_height)); nrm.append((0.0, 0.0, -1.0))
+        for j in range(stacks + 1):
+            pos.append((radius * c, radius * s_, -half_height + 2.0 * half_height * j / stacks)); nrm.append((c, s_, 0.0))
+        pos.append((radius * c, radius * s_, half_height)); nrm.append((0.0, 0.0, 1.0))
+    for k in range(segments):
+        a0, a1 = 2 + k * col, 2 + ((k + 1) % segments) * col
+        tris.append((0, a1, a0))                                            # bottom cap (faces -z)
+        for j in range(stacks):
+            p00, p01, p10, p11 = a0 + 1 + j, a0 + 2 + j, a1 + 1 + j, a1 + 2 + j
+            tris.append((p10, p11, p01))
+            tris.append((p10, p01, p00))
+        tris.append((1, a0 + col - 1, a1 + col - 1))                        # top cap (faces +z)
+    m = MeshData(np.array(pos, np.float32), np.array(nrm, np.float32), np.array(tris, np.uint32))
+    m.two_sided = True                                # the asset's material is doubleSided
+    return m
+
+
+MODELS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "models")
+
 _BUILTINS = {
     "models/box": box,
     "box": box,
@@ -120,9 +174,13 @@ def load_mesh(model_path) -> MeshData:
     stem = key[:-4] if key.endswith((".egg", ".bam")) and key[:-4] in _BUILTINS else key
     if stem in _BUILTINS:
         return _BUILTINS[stem]()
-    if os.path.exists(key):
-        from . import mesh_io
+    from . import mesh_io
+    if os.path.isfile(key):
         return mesh_io.load_file(key)
+    # "models/<file>" resolves into the package's models directory the way the reference's Steering
+    # renderer resolves it (envs/steering/renderer.py:90-107)
+    if key.startswith("models/") and os.path.isfile(os.path.join(MODELS_DIR, key[7:])):
+        return mesh_io.load_file(os.path.join(MODELS_DIR, key[7:]))
     raise FileNotFoundError(
         f"model {model_path!r}: not a built-in ({sorted(set(_BUILTINS))}), not registered and not a file")
 

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import cartpole_states, many_cubes_renderer, mixed_mesh_renderer, oracle_render
+from util import cartpole_states, config5_renderer, many_cubes_renderer, mixed_mesh_renderer, oracle_render
 
 pytestmark = pytest.mark.gpu
 
@@ -377,3 +377,26 @@ def test_smooth_normals_bit_exact(kw, fused):
     r.render_flags = 2 if fused else 0          # PBR_FRAME_FORCE_FUSED
     _assert_same(r.render(), oracle_render(r), f"smooth {kw} fused={fused}")
     assert r._native.device_status(torch.cuda.current_device()) == 0
+
+
+def test_config5_mixed_mesh_files_small():
+    """Box + models/cone.egg + models/cylinder/scene.gltf + sphere through the file readers, all four
+    kinds of normals (flat, smooth, n-gon cap, two-sided glTF material), every byte vs the oracle."""
+    r = config5_renderer(num_scenes=3, per_node=16, tile=(256, 256), device="cuda")
+    assert [n.mesh.n_tris for n in r._drawable_nodes()][1:3] == [62, 320]
+    _assert_same(r.render(), oracle_render(r), "config 5, 3 scenes")
+    assert r._native.device_status(torch.cuda.current_device()) == 0
+
+
+def test_config5_full_size_16384_scenes_256x256():
+    """BASELINE config 5 at full size on one GPU: 16,384 scenes x 64 instances at 256x256 (3.2 GB of
+    frames, ~12k triangle slots per scene, several staged launches).  Sampled scenes vs the oracle,
+    idempotence, no overflow."""
+    n = 16384
+    r = config5_renderer(num_scenes=n, device="cuda")
+    px = r.step()
+    assert px.shape == (n, 3, 256, 256)
+    _sampled_equal(r, px, [0, 1, n // 2, n - 1] + list(np.random.default_rng(5).integers(0, n, 4)))
+    assert r._native.device_status(torch.cuda.current_device()) == 0
+    again = r.render()
+    assert torch.equal(px, again)

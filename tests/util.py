@@ -101,3 +101,35 @@ def mixed_mesh_renderer(num_scenes=8, boxes=6, spheres=5, tile=(64, 64), seed=7,
     r.add_light()
     r.setup_environment()
     return r
+
+
+def config5_renderer(num_scenes=16384, per_node=16, tile=(256, 256), seed=123, device=None, spread=15.0):
+    """BASELINE config 5 ("mixed-mesh"): four per-scene nodes x ``per_node`` instances --
+    procedural box, models/cone.egg, models/cylinder/scene.gltf, UV sphere (stand-in for the
+    un-vendored models/smiley) -- camera eye (0,-40,10) looking at the origin, instances drawn like
+    config 3 (positions U(-spread,spread)^3, HPR U(-pi,pi)^3, scales U(0.5,1.8), colours U(0,1)^3)."""
+    from pybatchrender_b200 import PBRRenderer
+    cfg = dict(num_scenes=num_scenes, tile_resolution=tile)
+    if device is not None:
+        cfg["device"] = device
+    r = PBRRenderer(cfg)
+    nodes = [
+        r.add_node("models/box", instances_per_scene=per_node, model_pivot_relative_point=(0.5, 0.5, 0.5)),
+        r.add_node("models/cone.egg", instances_per_scene=per_node, model_pivot_relative_point=(0.5, 0.5, 0.5)),
+        r.add_node("models/cylinder/scene.gltf", instances_per_scene=per_node, model_scale=2.0,
+                   model_scale_units="absolute", model_pivot_relative_point=(0.5, 0.5, 0.5)),
+        r.add_node("models/smiley", instances_per_scene=per_node),
+    ]
+    g = torch.Generator().manual_seed(seed)
+    for node in nodes:
+        B = node.buf_instances
+        node.set_positions((torch.rand(B, 3, generator=g) * 2 - 1) * spread, lazy=True)
+        node.set_hprs((torch.rand(B, 3, generator=g) * 2 - 1) * float(np.pi), lazy=True)
+        node.set_scales(torch.rand(B, 1, generator=g) * 1.3 + 0.5)
+        node.set_colors(torch.cat([torch.rand(B, 3, generator=g), torch.ones(B, 1)], 1))
+    cam = r.add_camera()
+    cam.set_positions(torch.tensor([0.0, -40.0, 10.0]))
+    cam.look_at(torch.tensor([0.0, 0.0, 0.0]))
+    r.add_light()
+    r.setup_environment()
+    return r
