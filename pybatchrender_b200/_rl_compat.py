@@ -14,7 +14,7 @@ import torch
 
 try:  # pragma: no cover - not available in the build image
     from tensordict import TensorDict
-    from torchrl.data.tensor_specs import Categorical, Composite, Unbounded
+    from torchrl.data.tensor_specs import Bounded, Categorical, Composite, Unbounded
     from torchrl.envs import EnvBase, ParallelEnv
     HAVE_TORCHRL = True
 except Exception:
@@ -91,6 +91,15 @@ except Exception:
     class Unbounded(_Spec):
         def __init__(self, shape, dtype=torch.float32, device=None):
             super().__init__(shape, dtype, device)
+
+    class Bounded(_Spec):
+        def __init__(self, low, high, shape, dtype=torch.float32, device=None):
+            super().__init__(shape, dtype, device)
+            self.low, self.high = float(low), float(high)
+
+        def rand(self):
+            u = torch.rand(self.shape, dtype=self.dtype, device=self.device)
+            return u * (self.high - self.low) + self.low
 
     class Categorical(_Spec):
         def __init__(self, n, shape, dtype=torch.long, device=None):

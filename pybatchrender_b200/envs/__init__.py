@@ -53,6 +53,9 @@ def _register_builtin_envs() -> None:
     from .cartpole import CartPoleConfig, CartPoleEnv, CartPoleRenderer
     if CartPoleEnv is not None and "CartPole-v0" not in _ENV_REGISTRY:
         register("CartPole-v0", CartPoleEnv, CartPoleRenderer, CartPoleConfig)
+    from .steering import SteeringConfig, SteeringEnv, SteeringRenderer
+    if SteeringEnv is not None and "Steering-v0" not in _ENV_REGISTRY:
+        register("Steering-v0", SteeringEnv, SteeringRenderer, SteeringConfig)
 
 
 def _discover_entry_points() -> None:
