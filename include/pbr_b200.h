@@ -42,6 +42,7 @@ typedef enum {
 #define PBR_MESH_TWO_SIDED 1u           /* do not cull back faces of this mesh */
 
 typedef struct pbr_mesh_s *pbr_mesh_t;  /* device-resident static geometry */
+typedef struct pbr_texture_s *pbr_texture_t;   /* device-resident RGBA8 image (p3d_Texture0) */
 
 /* One PBRNode: replaces the `matbuf` / `colbuf` / `instancesPerScene` / `shareAcrossScenes`
  * shader inputs of reference node.py:85-91 and the instanced draw of node.py:68. */
@@ -52,8 +53,10 @@ typedef struct {
     int32_t instances_per_scene;/* I */
     int32_t shared;             /* 1: B = I (same instances in every scene), 0: B = num_scenes*I,
                                    row = scene*I + inst   (reference basic.vert:25-28) */
-    float use_texture;          /* must be 0 (textures: PBR_EUNSUPPORTED for now) */
+    float use_texture;          /* the `useTexture` shader input (reference node.py:285-287, basic.frag:31-32):
+                                   base = mix(1, texture(uv).rgb, clamp(use_texture, 0, 1)) */
     uint32_t flags;             /* PBR_NODE_* */
+    pbr_texture_t texture;      /* image sampled when use_texture > 0; NULL = white (node stays untextured) */
 } pbr_node_desc;
 
 #define PBR_NODE_IN_BASE 1u             /* already rendered into frame->base: skipped by pbr_render,
@@ -96,11 +99,17 @@ int pbr_version(void);
 const char *pbr_last_error(void);
 
 /* Upload static geometry.  pos/nrm: host [n_verts,3] float32 (object space, already baked the way
- * reference node.py:61-72 flattens scale/HPR/pivot into vertices); uv may be NULL; idx: host
+ * reference node.py:61-72 flattens scale/HPR/pivot into vertices); uv: host [n_verts,2] or NULL; idx: host
  * [n_tris,3].  Replaces loader.loadModel + flattenStrong's vertex data living in GL buffers. */
 int pbr_mesh_create(const float *pos_xyz, const float *nrm_xyz, const float *uv, int32_t n_verts,
                     const uint32_t *idx, int32_t n_tris, int32_t device, uint32_t flags, pbr_mesh_t *out);
 int pbr_mesh_destroy(pbr_mesh_t mesh);
+
+/* Upload an image for `use_texture` nodes.  rgba: host [height, width, 4] uint8, row 0 = v 0 (the
+ * bottom row of the picture, as GL stores it).  Sampling: GL_REPEAT, GL_LINEAR, fp32.  Replaces
+ * loader.loadTexture + NodePath.setTexture of reference node.py:277-287. */
+int pbr_texture_create(const uint8_t *rgba, int32_t width, int32_t height, int32_t device, pbr_texture_t *out);
+int pbr_texture_destroy(pbr_texture_t texture);
 int pbr_mesh_info(pbr_mesh_t mesh, int32_t *n_tris, int32_t *all_flat, int32_t *device);
 
 /* Render one frame (asynchronous on `stream`). */

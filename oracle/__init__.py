@@ -32,6 +32,7 @@ class _Mesh(ctypes.Structure):
         ("n_verts", ctypes.c_int),
         ("n_tris", ctypes.c_int),
         ("flags", ctypes.c_uint32),
+        ("uv", ctypes.c_void_p),
     ]
 
 
@@ -42,6 +43,10 @@ class _Node(ctypes.Structure):
         ("cols", ctypes.c_void_p),
         ("instances_per_scene", ctypes.c_int),
         ("shared", ctypes.c_int),
+        ("use_texture", ctypes.c_float),
+        ("tex", ctypes.c_void_p),
+        ("tex_w", ctypes.c_int),
+        ("tex_h", ctypes.c_int),
     ]
 
 
@@ -110,6 +115,9 @@ class OracleNode:
     instances_per_scene: int = 1
     shared: bool = False
     flags: int = 0
+    uv: np.ndarray | None = None        # [V,2]
+    texture: np.ndarray | None = None   # [h,w,4] uint8, row 0 = v 0
+    use_texture: float = 0.0
 
 
 @dataclass
@@ -144,8 +152,17 @@ def _pack(frame: OracleFrame, out: np.ndarray, scene_begin: int, scene_count: in
         if idx.size and int(idx.max()) >= pos.shape[0]:
             raise ValueError("index out of range")
         keep += [pos, nrm, idx, mats, cols]
+        uv = None if n.uv is None else _f32(n.uv, (-1, 2))
+        tex = None if n.texture is None else np.ascontiguousarray(np.asarray(n.texture, dtype=np.uint8))
+        if tex is not None and (tex.ndim != 3 or tex.shape[2] != 4):
+            raise ValueError(f"node {i}: texture must be [h,w,4] uint8")
+        keep += [uv, tex]
         nodes[i].mesh = _Mesh(pos.ctypes.data, nrm.ctypes.data, idx.ctypes.data,
-                              pos.shape[0], idx.shape[0], int(n.flags))
+                              pos.shape[0], idx.shape[0], int(n.flags), None if uv is None else uv.ctypes.data)
+        nodes[i].use_texture = float(n.use_texture)
+        nodes[i].tex = None if tex is None else tex.ctypes.data
+        nodes[i].tex_w = 0 if tex is None else int(tex.shape[1])
+        nodes[i].tex_h = 0 if tex is None else int(tex.shape[0])
         nodes[i].mats = mats.ctypes.data
         nodes[i].cols = cols.ctypes.data
         nodes[i].instances_per_scene = int(n.instances_per_scene)

@@ -29,7 +29,37 @@ int orc_version(void) { return ORC_VERSION; }
 typedef struct {
     float c[4];   /* clip-space x y z w */
     float n[3];   /* world-space unit normal (v_normal of basic.vert:53) */
+    float uv[2];  /* v_uv */
 } cvert;
+
+/* what a textured draw samples */
+typedef struct {
+    const uint8_t *tex;   /* NULL = untextured */
+    int w, h;
+    float use;            /* clamp(useTexture, 0, 1) */
+} texture_t;
+
+/* texture(p3d_Texture0, uv).rgb with GL_REPEAT / GL_LINEAR, fp32, texel centres at (i + 0.5) / size */
+static void sample_bilinear(const texture_t *T, float u, float v, float rgb[3]) {
+    u -= floorf(u);
+    v -= floorf(v);
+    const float x = fmaf(u, (float)T->w, -0.5f), y = fmaf(v, (float)T->h, -0.5f);
+    const float xf = floorf(x), yf = floorf(y);
+    const float fx = x - xf, fy = y - yf;
+    int x0 = (int)xf, y0 = (int)yf;
+    x0 = x0 < 0 ? x0 + T->w : (x0 >= T->w ? x0 - T->w : x0);
+    y0 = y0 < 0 ? y0 + T->h : (y0 >= T->h ? y0 - T->h : y0);
+    const int x1 = x0 + 1 >= T->w ? 0 : x0 + 1, y1 = y0 + 1 >= T->h ? 0 : y0 + 1;
+    const uint8_t *c00 = T->tex + 4 * ((size_t)y0 * T->w + x0), *c10 = T->tex + 4 * ((size_t)y0 * T->w + x1);
+    const uint8_t *c01 = T->tex + 4 * ((size_t)y1 * T->w + x0), *c11 = T->tex + 4 * ((size_t)y1 * T->w + x1);
+    for (int c = 0; c < 3; ++c) {
+        const float a00 = (float)c00[c] / 255.0f, a10 = (float)c10[c] / 255.0f;
+        const float a01 = (float)c01[c] / 255.0f, a11 = (float)c11[c] / 255.0f;
+        const float lo = fmaf(fx, a10 - a00, a00);
+        const float hi = fmaf(fx, a11 - a01, a01);
+        rgb[c] = fmaf(fy, hi - lo, lo);
+    }
+}
 
 /* r = Mcols * v, Mcols = 16 floats, texel j = column j  [ref: basic.vert:30-43, GLSL mat4*vec4] */
 static inline void mat_vec4(const float *m, const float v[4], float r[4]) {
@@ -108,6 +138,7 @@ static int clip_poly(const cvert *in3, cvert *poly) {
                 cvert w;
                 for (int k = 0; k < 4; ++k) w.c[k] = fmaf(t, vo->c[k] - vi->c[k], vi->c[k]);
                 for (int k = 0; k < 3; ++k) w.n[k] = fmaf(t, vo->n[k] - vi->n[k], vi->n[k]);
+                for (int k = 0; k < 2; ++k) w.uv[k] = fmaf(t, vo->uv[k] - vi->uv[k], vi->uv[k]);
                 b[m++] = w;
             }
         }
@@ -121,7 +152,8 @@ static int clip_poly(const cvert *in3, cvert *poly) {
 
 /* Rasterise one (already clipped) triangle. */
 static void raster_tri(const target_t *T, const light_t *L, const cvert v_in[3], const float col[4],
-                       int flat, int two_sided, uint32_t id) {
+                       int flat, int two_sided, uint32_t id, const texture_t *tx) {
+    if (tx->tex) flat = 0;                 /* textured triangles are shaded per pixel */
     cvert v[3];
     memcpy(v, v_in, sizeof(v));
     const float hw = 0.5f * (float)T->W, hh = 0.5f * (float)T->H;
@@ -218,7 +250,18 @@ static void raster_tri(const target_t *T, const light_t *L, const cvert v_in[3],
                 float l2 = fmaf(n[2], n[2], fmaf(n[1], n[1], n[0] * n[0]));
                 float inv = 1.0f / sqrtf(l2);
                 n[0] *= inv; n[1] *= inv; n[2] *= inv;
-                shade(L, n, col, rgba);
+                float pc[4] = {col[0], col[1], col[2], col[3]};
+                if (tx->tex) {
+                    /* [ref: basic.frag:31-32,37] base = mix(1, texel, useTexture); col = base * v_color * l */
+                    const float sum = (p0 + p1) + p2;
+                    const float tu = fmaf(p2, v[2].uv[0], fmaf(p1, v[1].uv[0], p0 * v[0].uv[0])) / sum;
+                    const float tv = fmaf(p2, v[2].uv[1], fmaf(p1, v[1].uv[1], p0 * v[0].uv[1])) / sum;
+                    float t3[3];
+                    sample_bilinear(tx, tu, tv, t3);
+                    const float a = tx->use, oma = 1.0f - tx->use;
+                    for (int c = 0; c < 3; ++c) pc[c] *= fmaf(t3[c], a, oma);
+                }
+                shade(L, n, pc, rgba);
             }
             for (int c = 0; c < T->C; ++c) T->out[(size_t)c * T->H * T->W + o] = rgba[c];
         }
@@ -239,6 +282,12 @@ static void render_scene(const orc_frame *f, int scene, const light_t *L, target
         const orc_mesh *me = &nd->mesh;
         const int I = nd->instances_per_scene;
         const int two_sided = (me->flags & ORC_MESH_TWO_SIDED) != 0;
+        texture_t tx = {NULL, 0, 0, 0.0f};
+        {
+            float ut = nd->use_texture;
+            ut = !(ut == ut) || ut < 0.0f ? 0.0f : (ut > 1.0f ? 1.0f : ut);
+            if (nd->tex && ut > 0.0f) { tx.tex = nd->tex; tx.w = nd->tex_w; tx.h = nd->tex_h; tx.use = ut; }
+        }
         for (int inst = 0; inst < I; ++inst) {
             /* [ref: basic.vert:25-28]  id = shared ? inst : scene*I + inst   (evident intent) */
             size_t b = nd->shared ? (size_t)inst : (size_t)scene * I + inst;
@@ -255,6 +304,8 @@ static void render_scene(const orc_frame *f, int scene, const light_t *L, target
                     mat_vec4(M, obj, world);
                     mat_vec4(VP, world, v[k].c);                 /* clip = VP * (M * v) */
                     xform_normal(M, n, v[k].n);
+                    v[k].uv[0] = (tx.tex && me->uv) ? me->uv[2 * (size_t)vi] : 0.0f;
+                    v[k].uv[1] = (tx.tex && me->uv) ? me->uv[2 * (size_t)vi + 1] : 0.0f;
                     if (memcmp(n, n0, 12) != 0) flat = 0;
                 }
                 /* trivial reject against the tile frustum (fragments outside the tile are
@@ -276,13 +327,13 @@ static void render_scene(const orc_frame *f, int scene, const light_t *L, target
                         if (plane_dist(&v[k], p) < 0.0f) need_clip = 1;
                 const uint32_t id = slot + 1;
                 if (!need_clip) {
-                    raster_tri(T, L, v, col, flat, two_sided, id);
+                    raster_tri(T, L, v, col, flat, two_sided, id, &tx);
                 } else {
                     cvert poly[MAX_POLY];
                     int n = clip_poly(v, poly);
                     for (int k = 1; k + 1 < n; ++k) {
                         cvert tri[3] = {poly[0], poly[k], poly[k + 1]};
-                        raster_tri(T, L, tri, col, flat, two_sided, id);
+                        raster_tri(T, L, tri, col, flat, two_sided, id, &tx);
                     }
                 }
             }

@@ -18,7 +18,8 @@
  * in examples/notebooks/cartpole_benchmark.ipynb (raw line 473) and the three printed states
  * (raw lines 422-424); see tests/test_oracle_golden.py and tests/golden/make_golden.py.
  * Unpinned corners (no reference output exists in the tree): tie-break orientation of the
- * top-left rule, exact depth ties, smooth-normal meshes, near-plane clipping, C=4.
+ * top-left rule, exact depth ties, smooth-normal meshes, near-plane clipping, C=4,
+ * texture filtering (GL leaves the filter arithmetic to the implementation; here: GL_REPEAT, GL_LINEAR, fp32).
  */
 #ifndef PBR_ORACLE_H
 #define PBR_ORACLE_H
@@ -38,6 +39,7 @@ typedef struct {
     int n_verts;
     int n_tris;
     uint32_t flags;
+    const float *uv;       /* [n_verts,2] texture coordinates, or NULL (basic.vert v_uv) */
 } orc_mesh;
 
 typedef struct {
@@ -46,6 +48,9 @@ typedef struct {
     const float *cols;     /* [B,4] RGBA                                       (== colbuf, node.py:156-161) */
     int instances_per_scene;
     int shared;            /* shareAcrossScenes: B = I when set, else B = K*I  (node.py:42-46) */
+    float use_texture;     /* useTexture shader input (node.py:285-287) */
+    const uint8_t *tex;    /* [tex_h, tex_w, 4] RGBA8, row 0 = v 0; NULL = untextured */
+    int tex_w, tex_h;
 } orc_node;
 
 typedef struct {

@@ -33,6 +33,7 @@ class _NodeDesc(ctypes.Structure):
         ("shared", ctypes.c_int32),
         ("use_texture", ctypes.c_float),
         ("flags", ctypes.c_uint32),
+        ("texture", ctypes.c_void_p),
     ]
 
 
@@ -79,6 +80,9 @@ _EXPORTS = {
                                        ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32,
                                        ctypes.POINTER(ctypes.c_void_p)]),
     "pbr_mesh_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "pbr_texture_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                          ctypes.POINTER(ctypes.c_void_p)]),
+    "pbr_texture_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "pbr_mesh_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32),
                                      ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     "pbr_render": (ctypes.c_int, [ctypes.POINTER(_FrameDesc), ctypes.c_void_p]),
@@ -136,14 +140,18 @@ def _cuda_f32(t: torch.Tensor, what: str) -> torch.Tensor:
 class NativeMesh:
     """Device-resident static geometry (``pbr_mesh_t``)."""
 
-    def __init__(self, pos, nrm, idx, device: torch.device, two_sided: bool = False) -> None:
+    def __init__(self, pos, nrm, idx, device: torch.device, two_sided: bool = False, uv=None) -> None:
         import numpy as np
         pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        uv = None if uv is None else np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+        if uv is not None and uv.shape[0] != pos.shape[0]:
+            raise NativeError("uv must have one row per vertex")
         nrm = np.ascontiguousarray(nrm, dtype=np.float32).reshape(-1, 3)
         idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 3)
         dev_index = device.index if device.index is not None else torch.cuda.current_device()
         handle = ctypes.c_void_p()
-        rc = load().pbr_mesh_create(pos.ctypes.data, nrm.ctypes.data, None, pos.shape[0], idx.ctypes.data,
+        rc = load().pbr_mesh_create(pos.ctypes.data, nrm.ctypes.data, None if uv is None else uv.ctypes.data,
+                                    pos.shape[0], idx.ctypes.data,
                                     idx.shape[0], dev_index, PBR_MESH_TWO_SIDED if two_sided else 0,
                                     ctypes.byref(handle))
         _check(rc, "pbr_mesh_create")
@@ -154,6 +162,32 @@ class NativeMesh:
     def close(self) -> None:
         if getattr(self, "handle", None):
             load().pbr_mesh_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NativeTexture:
+    """Device-resident RGBA8 image (``pbr_texture_t``); ``rgba``: [h, w, 4] uint8, row 0 = v 0."""
+
+    def __init__(self, rgba, device: torch.device) -> None:
+        import numpy as np
+        img = np.ascontiguousarray(rgba, dtype=np.uint8)
+        if img.ndim != 3 or img.shape[2] != 4:
+            raise NativeError("texture must be [h, w, 4] uint8")
+        dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        handle = ctypes.c_void_p()
+        _check(load().pbr_texture_create(img.ctypes.data, img.shape[1], img.shape[0], dev_index, ctypes.byref(handle)),
+               "pbr_texture_create")
+        self.handle = handle
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            load().pbr_texture_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -237,7 +271,8 @@ class Native:
 
     def _frame(self, *, num_scenes, tile_w, tile_h, channels, vp, nodes, out, bg, ambient, dir_dir, dir_col,
                strength, scene_begin=0, scene_count=None, flags=0, base=None):
-        """nodes: list of (NativeMesh, matbuf, colbuf, instances_per_scene, shared[, in_base])."""
+        """nodes: list of (NativeMesh, matbuf, colbuf, instances_per_scene, shared[, in_base[, use_texture,
+        NativeTexture | None]])."""
         _cuda_f32(vp, "viewbuf")
         nd = (_NodeDesc * max(1, len(nodes)))()
         for i, item in enumerate(nodes):
@@ -249,7 +284,8 @@ class Native:
             nd[i].cols = cols.data_ptr()
             nd[i].instances_per_scene = int(inst)
             nd[i].shared = 1 if shared else 0
-            nd[i].use_texture = 0.0
+            nd[i].use_texture = float(item[6]) if len(item) > 6 else 0.0
+            nd[i].texture = item[7].handle if len(item) > 7 and item[7] is not None else None
             nd[i].flags = PBR_NODE_IN_BASE if (len(item) > 5 and item[5]) else 0
         f = _FrameDesc()
         f.num_scenes = int(num_scenes)

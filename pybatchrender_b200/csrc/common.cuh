@@ -19,6 +19,10 @@ struct NodeDev {
     const float4 *tn;     // [T*3] xyz = corner normal
     const float4 *vpos;   // [V]   unique positions (de-duplicated)
     const uint4 *tidx;    // [T]   (i0, i1, i2, flat) into vpos
+    const float2 *tuv;    // [T*3] texture coordinates of the triangle corners, or NULL
+    const uchar4 *tex;    // [th, tw] RGBA8 texels, row 0 = v 0 (bottom), or NULL = untextured
+    int tw, th;
+    float use_tex;        // clamp(useTexture): mix(1, texel, use_tex)
     const float *mats;    // [B,16] column packed
     const float *cols;    // [B,4]
     int n_tris;
@@ -85,13 +89,27 @@ struct __align__(16) SRec {
     float n[3][3];   // world-space unit normals of the three vertices (after a two-sided swap)
     float rw[3];     // 1 / w_clip of the three vertices (perspective-correct weights)
     float col[4];    // instance RGBA
+    float uv[3][2];  // texture coordinates of the three vertices
+    const uchar4 *tex;   // NULL = untextured
+    int tw, th;
+    float use_tex;
+    float pad[5];
 };
-static_assert(sizeof(SRec) == 64, "SRec must be 64 bytes");
+static_assert(sizeof(SRec) == 128, "SRec must be 128 bytes");
 
 struct CV {
     float c[4];      // clip-space position
     float n[3];      // world-space unit normal
 };
+// vertex of the kernels that can texture: CV + texture coordinates
+struct CVT : CV {
+    float uv[2];
+};
+__device__ __forceinline__ void lerp_extra(CV &, const CV &, const CV &, float) {}
+__device__ __forceinline__ void lerp_extra(CVT &w, const CVT &vi, const CVT &vo, float t) {
+    w.uv[0] = fmaf(t, vo.uv[0] - vi.uv[0], vi.uv[0]);
+    w.uv[1] = fmaf(t, vo.uv[1] - vi.uv[1], vi.uv[1]);
+}
 
 struct BBox {
     int bx0, by0, bx1, by1;   // 8x8-pixel blocks, inclusive
@@ -174,8 +192,9 @@ __device__ __forceinline__ bool needs_clip(const float *c) {
 }
 
 // Sutherland-Hodgman against near + guard band; returns vertex count (0 = nothing left).
-__device__ __noinline__ int clip_poly(const CV *in3, CV *a) {
-    CV b[MAX_POLY];
+template <class V>
+__device__ __noinline__ int clip_poly(const V *in3, V *a) {
+    V b[MAX_POLY];
     int n = 3;
     for (int i = 0; i < 3; ++i) a[i] = in3[i];
     for (int p = 0; p < 5 && n >= 3; ++p) {
@@ -184,19 +203,20 @@ __device__ __noinline__ int clip_poly(const CV *in3, CV *a) {
         if (!any_out) continue;
         int m = 0;
         for (int i = 0; i < n; ++i) {
-            const CV &u = a[i];
-            const CV &v = a[(i + 1) % n];
+            const V &u = a[i];
+            const V &v = a[(i + 1) % n];
             float du = plane_dist(u, p), dv = plane_dist(v, p);
             bool iu = !(du < 0.0f), iv = !(dv < 0.0f);
             if (iu) b[m++] = u;
             if (iu != iv) {
-                const CV &vi = iu ? u : v;
-                const CV &vo = iu ? v : u;
+                const V &vi = iu ? u : v;
+                const V &vo = iu ? v : u;
                 float di = iu ? du : dv, dout = iu ? dv : du;
                 float t = di / (di - dout);
-                CV w;
+                V w;
                 for (int k = 0; k < 4; ++k) w.c[k] = fmaf(t, vo.c[k] - vi.c[k], vi.c[k]);
                 for (int k = 0; k < 3; ++k) w.n[k] = fmaf(t, vo.n[k] - vi.n[k], vi.n[k]);
+                lerp_extra(w, vi, vo, t);
                 b[m++] = w;
             }
         }
@@ -419,6 +439,30 @@ __device__ __forceinline__ void depth_update(PixelState &ps, float f1a, float f2
     ps.k1 = w1 ? kc : ps.k1; ps.c1 = w1 ? col : ps.c1; ps.ch1 |= w1;
 }
 
+// GL_REPEAT + GL_LINEAR lookup of an RGBA8 texture, fp32, texel centres at (i + 0.5) / size
+__device__ __forceinline__ void sample_bilinear(const uchar4 *tex, int tw, int th, float u, float v, float *rgb) {
+    u -= floorf(u);
+    v -= floorf(v);
+    const float x = fmaf(u, (float)tw, -0.5f), y = fmaf(v, (float)th, -0.5f);
+    const float xf = floorf(x), yf = floorf(y);
+    const float fx = x - xf, fy = y - yf;
+    int x0 = (int)xf, y0 = (int)yf;
+    x0 = x0 < 0 ? x0 + tw : (x0 >= tw ? x0 - tw : x0);
+    y0 = y0 < 0 ? y0 + th : (y0 >= th ? y0 - th : y0);
+    const int x1 = x0 + 1 >= tw ? 0 : x0 + 1, y1 = y0 + 1 >= th ? 0 : y0 + 1;
+    const uchar4 c00 = __ldg(tex + (size_t)y0 * tw + x0), c10 = __ldg(tex + (size_t)y0 * tw + x1);
+    const uchar4 c01 = __ldg(tex + (size_t)y1 * tw + x0), c11 = __ldg(tex + (size_t)y1 * tw + x1);
+    const float k = 255.0f;
+    const float a00[3] = {c00.x / k, c00.y / k, c00.z / k}, a10[3] = {c10.x / k, c10.y / k, c10.z / k};
+    const float a01[3] = {c01.x / k, c01.y / k, c01.z / k}, a11[3] = {c11.x / k, c11.y / k, c11.z / k};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float lo = fmaf(fx, a10[c] - a00[c], a00[c]);
+        const float hi = fmaf(fx, a11[c] - a01[c], a01[c]);
+        rgb[c] = fmaf(fy, hi - lo, lo);
+    }
+}
+
 // fragment shader for a smooth triangle at one pixel: perspective-correct normal (weights b_i / w_i;
 // their normalisation is dropped because the normal is re-normalised), ambient + Lambert
 __device__ __forceinline__ unsigned shade_pixel(const FrameDev &f, const SRec &sr, float f0, float f1, float f2,
@@ -430,7 +474,20 @@ __device__ __forceinline__ unsigned shade_pixel(const FrameDev &f, const SRec &s
     const float l2 = fmaf(n[2], n[2], fmaf(n[1], n[1], n[0] * n[0]));
     const float inv = 1.0f / sqrtf(l2);
     n[0] *= inv; n[1] *= inv; n[2] *= inv;
-    return shade(f, n, make_float4(sr.col[0], sr.col[1], sr.col[2], sr.col[3]));
+    float4 col = make_float4(sr.col[0], sr.col[1], sr.col[2], sr.col[3]);
+    if (sr.tex != nullptr) {
+        // basic.frag:31-32: base = mix(1, texture(uv).rgb, useTexture); colour = base * v_color
+        const float sum = (p0 + p1) + p2;
+        const float u = fmaf(p2, sr.uv[2][0], fmaf(p1, sr.uv[1][0], p0 * sr.uv[0][0])) / sum;
+        const float v = fmaf(p2, sr.uv[2][1], fmaf(p1, sr.uv[1][1], p0 * sr.uv[0][1])) / sum;
+        float t[3];
+        sample_bilinear(sr.tex, sr.tw, sr.th, u, v, t);
+        const float a = sr.use_tex, oma = 1.0f - sr.use_tex;
+        col.x *= fmaf(t[0], a, oma);
+        col.y *= fmaf(t[1], a, oma);
+        col.z *= fmaf(t[2], a, oma);
+    }
+    return shade(f, n, col);
 }
 
 // one record, any path.  SMOOTH: records flagged M_SMOOTH shade the pixels they win per pixel.

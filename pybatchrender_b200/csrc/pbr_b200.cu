@@ -117,6 +117,13 @@ struct pbr_mesh_s {
     float4 *tn;         // [T*3]
     float4 *vpos;       // [V]
     uint4 *tidx;        // [T]
+    float2 *tuv;        // [T*3] or NULL
+};
+
+struct pbr_texture_s {
+    int device;
+    int w, h;
+    uchar4 *texels;     // [h, w], row 0 = v 0
 };
 
 extern "C" {
@@ -127,13 +134,13 @@ const char *pbr_last_error(void) { return g_err; }
 
 int pbr_mesh_create(const float *pos, const float *nrm, const float *uv, int32_t n_verts, const uint32_t *idx,
                     int32_t n_tris, int32_t device, uint32_t flags, pbr_mesh_t *out) {
-    (void)uv;
     if (!out) return fail(PBR_EINVAL, "pbr_mesh_create: out is NULL");
     *out = nullptr;
     if (!pos || !nrm || !idx || n_verts <= 0 || n_tris <= 0)
         return fail(PBR_EINVAL, "pbr_mesh_create: empty or NULL geometry (n_verts=%d n_tris=%d)", n_verts, n_tris);
     std::vector<float4> tp((size_t)n_tris * 3), tn((size_t)n_tris * 3), vpos;
     std::vector<uint4> tidx((size_t)n_tris);
+    std::vector<float2> tuv(uv ? (size_t)n_tris * 3 : 0);
     struct Key {
         uint32_t a, b, c;
         bool operator<(const Key &o) const { return a != o.a ? a < o.a : (b != o.b ? b < o.b : c < o.c); }
@@ -148,6 +155,7 @@ int pbr_mesh_create(const float *pos, const float *nrm, const float *uv, int32_t
             if (v >= (uint32_t)n_verts) return fail(PBR_EINVAL, "pbr_mesh_create: index %u out of range", v);
             tp[3 * t + k] = make_float4(pos[3 * v], pos[3 * v + 1], pos[3 * v + 2], 0.0f);
             tn[3 * t + k] = make_float4(nrm[3 * v], nrm[3 * v + 1], nrm[3 * v + 2], 0.0f);
+            if (uv) tuv[3 * t + k] = make_float2(uv[2 * (size_t)v], uv[2 * (size_t)v + 1]);
             if (memcmp(nrm + 3 * (size_t)v, nrm + 3 * (size_t)idx[3 * t], 12) != 0) flat = false;
             Key key;
             memcpy(&key, pos + 3 * (size_t)v, 12);
@@ -179,9 +187,11 @@ int pbr_mesh_create(const float *pos, const float *nrm, const float *uv, int32_t
     if (e == cudaSuccess) e = cudaMemcpy(m->tn, tn.data(), tb, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(m->vpos, vpos.data(), vb, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(m->tidx, tidx.data(), ib, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && uv) e = cudaMalloc(&m->tuv, tuv.size() * sizeof(float2));
+    if (e == cudaSuccess && uv) e = cudaMemcpy(m->tuv, tuv.data(), tuv.size() * sizeof(float2), cudaMemcpyHostToDevice);
     cudaSetDevice(prev);
     if (e != cudaSuccess) {
-        cudaFree(m->tp); cudaFree(m->tn); cudaFree(m->vpos); cudaFree(m->tidx);
+        cudaFree(m->tp); cudaFree(m->tn); cudaFree(m->vpos); cudaFree(m->tidx); cudaFree(m->tuv);
         delete m;
         return fail(e == cudaErrorMemoryAllocation ? PBR_ENOMEM : PBR_ECUDA, "pbr_mesh_create: %s", cudaGetErrorString(e));
     }
@@ -191,8 +201,39 @@ int pbr_mesh_create(const float *pos, const float *nrm, const float *uv, int32_t
 
 int pbr_mesh_destroy(pbr_mesh_t m) {
     if (!m) return PBR_OK;
-    cudaFree(m->tp); cudaFree(m->tn); cudaFree(m->vpos); cudaFree(m->tidx);
+    cudaFree(m->tp); cudaFree(m->tn); cudaFree(m->vpos); cudaFree(m->tidx); cudaFree(m->tuv);
     delete m;
+    return PBR_OK;
+}
+
+int pbr_texture_create(const uint8_t *rgba, int32_t width, int32_t height, int32_t device, pbr_texture_t *out) {
+    if (!out) return fail(PBR_EINVAL, "pbr_texture_create: out is NULL");
+    *out = nullptr;
+    if (!rgba || width < 1 || height < 1 || width > 16384 || height > 16384)
+        return fail(PBR_EINVAL, "pbr_texture_create: bad image (%p, %dx%d)", (const void *)rgba, width, height);
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    CUDA_TRY(cudaSetDevice(device));
+    pbr_texture_s *t = new (std::nothrow) pbr_texture_s();
+    if (!t) { cudaSetDevice(prev); return fail(PBR_ENOMEM, "pbr_texture_create: host allocation failed"); }
+    t->device = device; t->w = width; t->h = height; t->texels = nullptr;
+    const size_t bytes = (size_t)width * height * 4;
+    cudaError_t e = cudaMalloc(&t->texels, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(t->texels, rgba, bytes, cudaMemcpyHostToDevice);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) {
+        cudaFree(t->texels);
+        delete t;
+        return fail(e == cudaErrorMemoryAllocation ? PBR_ENOMEM : PBR_ECUDA, "pbr_texture_create: %s", cudaGetErrorString(e));
+    }
+    *out = t;
+    return PBR_OK;
+}
+
+int pbr_texture_destroy(pbr_texture_t t) {
+    if (!t) return PBR_OK;
+    cudaFree(t->texels);
+    delete t;
     return PBR_OK;
 }
 
@@ -226,7 +267,7 @@ static int fill_nodes(const pbr_frame_desc *d, int device, NodeMode mode, FrameD
         if ((reinterpret_cast<size_t>(n.mats) & 15) || (reinterpret_cast<size_t>(n.cols) & 15))
             return fail(PBR_EINVAL, "pbr_render: node %d mats / cols must be 16-byte aligned", i);
         if (n.instances_per_scene < 0) return fail(PBR_EINVAL, "pbr_render: node %d instances_per_scene < 0", i);
-        if (n.use_texture != 0.0f) return fail(PBR_EUNSUPPORTED, "pbr_render: node %d: textures are not implemented", i);
+        if (n.texture && n.texture->device != device) return fail(PBR_EINVAL, "pbr_render: node %d texture lives on device %d, current device is %d", i, n.texture->device, device);
         const long long ntri = (long long)n.instances_per_scene * n.mesh->n_tris;
         const long long id_begin = ids;
         ids += ntri;
@@ -239,6 +280,15 @@ static int fill_nodes(const pbr_frame_desc *d, int device, NodeMode mode, FrameD
         }
         NodeDev &nd = f.nodes[f.n_nodes++];
         nd.tp = n.mesh->tp; nd.tn = n.mesh->tn; nd.vpos = n.mesh->vpos; nd.tidx = n.mesh->tidx;
+        // basic.frag:31-32: base = mix(1, texel, clamp(useTexture)); without a bound image the node is untextured
+        float ut = n.use_texture;
+        ut = !(ut == ut) || ut < 0.0f ? 0.0f : (ut > 1.0f ? 1.0f : ut);
+        const bool textured = n.texture != nullptr && ut > 0.0f;
+        nd.tuv = textured ? n.mesh->tuv : nullptr;
+        nd.tex = textured ? n.texture->texels : nullptr;
+        nd.tw = textured ? n.texture->w : 0; nd.th = textured ? n.texture->h : 0;
+        nd.use_tex = textured ? ut : 0.0f;
+        if (textured) st.any_smooth = true;               // per-pixel shading path
         nd.mats = n.mats; nd.cols = n.cols;
         nd.n_tris = n.mesh->n_tris; nd.n_verts = n.mesh->n_verts;
         nd.inst = n.instances_per_scene; nd.shared = n.shared ? 1 : 0;

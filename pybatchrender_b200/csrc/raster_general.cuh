@@ -23,8 +23,9 @@ constexpr int MW = CH / 32;          // mask words per 8x8 block
 enum { SLOT_SKIP = 0, SLOT_OK = 1, SLOT_CLIP = 2 };
 
 struct SlotGeom {
-    CV v[3];
+    CVT v[3];
     float4 col;
+    const NodeDev *node;  // texture source (node->tex may be NULL)
     bool flat;
     bool two_sided;
     unsigned id;          // 1 + draw index
@@ -53,6 +54,8 @@ __device__ __forceinline__ int load_slot(const FrameDev &f, int scene, int slot,
     }
     g.col = __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4));
     g.two_sided = (nd.flags & PBR_MESH_TWO_SIDED) != 0;
+    g.node = &nd;
+    const bool textured = nd.tex != nullptr;
     g.id = (unsigned)(nd.id_begin + local) + 1u;
 
     const float4 p0 = __ldg(nd.tp + 3 * tri);
@@ -66,6 +69,9 @@ __device__ __forceinline__ int load_slot(const FrameDev &f, int scene, int slot,
         mat_vec4(VP, world[0], world[1], world[2], world[3], g.v[k].c);
         float4 n = (k == 0 || g.flat) ? n0 : __ldg(nd.tn + 3 * tri + k);
         xform_normal(M, n.x, n.y, n.z, g.v[k].n);
+        float2 uv = make_float2(0.0f, 0.0f);
+        if (textured && nd.tuv != nullptr) uv = __ldg(nd.tuv + 3 * tri + k);
+        g.v[k].uv[0] = uv.x; g.v[k].uv[1] = uv.y;
     }
     if (trivially_outside(g.v[0].c, g.v[1].c, g.v[2].c)) return SLOT_SKIP;
     const bool clip = needs_clip(g.v[0].c) || needs_clip(g.v[1].c) || needs_clip(g.v[2].c);
@@ -74,9 +80,13 @@ __device__ __forceinline__ int load_slot(const FrameDev &f, int scene, int slot,
 
 // sr: where the smooth-shading companion of the record goes (may be shared or global memory);
 // only written for non-flat triangles
-__device__ __forceinline__ bool setup_tri(const FrameDev &f, const CV *vin, const float4 col, bool flat,
-                                          bool two_sided, unsigned id, int band_y0, int band_h, Rec &r,
-                                          BBox &bb, SRec *sr = nullptr) {
+__device__ __forceinline__ bool setup_tri(const FrameDev &f, const CVT *vin, const SlotGeom &g, int band_y0,
+                                          int band_h, Rec &r, BBox &bb, SRec *sr = nullptr) {
+    const float4 col = g.col;
+    const bool two_sided = g.two_sided;
+    const unsigned id = g.id;
+    const NodeDev &nd = *g.node;
+    const bool flat = g.flat && nd.tex == nullptr;        // textured triangles shade per pixel
     int X[3], Y[3];
     float z[3], rw[3];
 #pragma unroll
@@ -98,6 +108,10 @@ __device__ __forceinline__ bool setup_tri(const FrameDev &f, const CV *vin, cons
         }
         sr->rw[0] = rw[0]; sr->rw[1] = rw[i1]; sr->rw[2] = rw[i2];
         sr->col[0] = col.x; sr->col[1] = col.y; sr->col[2] = col.z; sr->col[3] = col.w;
+        sr->uv[0][0] = vin[0].uv[0]; sr->uv[0][1] = vin[0].uv[1];
+        sr->uv[1][0] = vin[i1].uv[0]; sr->uv[1][1] = vin[i1].uv[1];
+        sr->uv[2][0] = vin[i2].uv[0]; sr->uv[2][1] = vin[i2].uv[1];
+        sr->tex = nd.tex; sr->tw = nd.tw; sr->th = nd.th; sr->use_tex = nd.use_tex;
     }
     return true;
 }
@@ -262,7 +276,7 @@ __global__ void __launch_bounds__(THREADS) raster_general_kernel(const __grid_co
                 const int st = load_slot(f, scene, slot, g);
                 if (st == SLOT_OK) {
                     BBox bb;
-                    if (setup_tri(f, g.v, g.col, g.flat, g.two_sided, g.id, band_y0, band_h, r, bb, s.srecs + tid))
+                    if (setup_tri(f, g.v, g, band_y0, band_h, r, bb, s.srecs + tid))
                         bin_record<MW>(r, bb, tid, f.nbx, s.masks);
                     else
                         r.meta = 0;
@@ -288,12 +302,12 @@ __global__ void __launch_bounds__(THREADS) raster_general_kernel(const __grid_co
                 const int slot = chunk + s.cliplist[q];
                 SlotGeom g;
                 load_slot(f, scene, slot, g);
-                CV poly[MAX_POLY];
+                CVT poly[MAX_POLY];
                 const int n = clip_poly(g.v, poly);
                 if (k + 2 < n) {
-                    CV tri[3] = {poly[0], poly[k + 1], poly[k + 2]};
+                    CVT tri[3] = {poly[0], poly[k + 1], poly[k + 2]};
                     BBox bb;
-                    if (setup_tri(f, tri, g.col, g.flat, g.two_sided, g.id, band_y0, band_h, r, bb, s.srecs + tid))
+                    if (setup_tri(f, tri, g, band_y0, band_h, r, bb, s.srecs + tid))
                         bin_record<MW>(r, bb, tid, f.nbx, s.masks);
                     else
                         r.meta = 0;

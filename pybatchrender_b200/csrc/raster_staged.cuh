@@ -52,7 +52,8 @@ __device__ __forceinline__ void append_record(const StagedDev &g, const FrameDev
     if (g.srecs != nullptr && (r.meta & M_SMOOTH)) {
         uint4 *sd = reinterpret_cast<uint4 *>(g.srecs + o);
         const uint4 *ss = reinterpret_cast<const uint4 *>(&sr);
-        sd[0] = ss[0]; sd[1] = ss[1]; sd[2] = ss[2]; sd[3] = ss[3];
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(SRec) / 16); ++i) sd[i] = ss[i];
     }
 }
 
@@ -69,14 +70,14 @@ __global__ void __launch_bounds__(G_THREADS) geom_kernel(const __grid_constant__
     SRec sr;
     BBox bb;
     if (st == SLOT_OK) {
-        if (setup_tri(f, sg.v, sg.col, sg.flat, sg.two_sided, sg.id, 0, f.H, r, bb, &sr)) append_record(g, f, local_scene, r, bb, sr);
+        if (setup_tri(f, sg.v, sg, 0, f.H, r, bb, &sr)) append_record(g, f, local_scene, r, bb, sr);
         return;
     }
-    CV poly[MAX_POLY];
+    CVT poly[MAX_POLY];
     const int n = clip_poly(sg.v, poly);
     for (int k = 0; k + 2 < n; ++k) {
-        CV tri[3] = {poly[0], poly[k + 1], poly[k + 2]};
-        if (setup_tri(f, tri, sg.col, sg.flat, sg.two_sided, sg.id, 0, f.H, r, bb, &sr)) append_record(g, f, local_scene, r, bb, sr);
+        CVT tri[3] = {poly[0], poly[k + 1], poly[k + 2]};
+        if (setup_tri(f, tri, sg, 0, f.H, r, bb, &sr)) append_record(g, f, local_scene, r, bb, sr);
     }
 }
 
@@ -179,9 +180,10 @@ __global__ void __launch_bounds__(THREADS) raster_staged_kernel(const __grid_con
     auto issue = [&](int c) {       // thread 0: stage chunk c into buffer c & 1
         const int cnt = min(CH, total - c * CH);
         const unsigned rb = (unsigned)cnt * (unsigned)sizeof(Rec), bb = (unsigned)align16((size_t)cnt * 4);
-        mbar_expect_tx(&s.bar[c & 1], (SMOOTH ? 2 * rb : rb) + bb);
+        const unsigned sb = SMOOTH ? (unsigned)cnt * (unsigned)sizeof(SRec) : 0u;
+        mbar_expect_tx(&s.bar[c & 1], rb + sb + bb);
         tma_load(s.recs[c & 1], grecs + (size_t)c * CH, rb, &s.bar[c & 1]);
-        if (SMOOTH) tma_load(s.srecs[c & 1], g.srecs + (size_t)local_scene * g.cap + (size_t)c * CH, rb, &s.bar[c & 1]);
+        if (SMOOTH) tma_load(s.srecs[c & 1], g.srecs + (size_t)local_scene * g.cap + (size_t)c * CH, sb, &s.bar[c & 1]);
         tma_load(s.bbox[c & 1], gbbox + (size_t)c * CH, bb, &s.bar[c & 1]);
     };
     if (tid == 0 && nchunks > 0) issue(0);

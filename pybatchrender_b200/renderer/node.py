@@ -188,11 +188,32 @@ class PBRNode(PBRShaderContext):
 
     # ------------------------------------------------------------------ misc API
     def set_texture(self, texture=None) -> None:
-        if texture is not None:
-            raise NotImplementedError(
-                "textured nodes are not supported by the B200 rasteriser yet (SURVEY.md 8f-4); "
-                "pass texture=None")
-        self._set_shader_input("useTexture", 0.0)
+        """``None`` / ``False``: untextured.  A file name, ``[h, w, 3|4]`` uint8 array / tensor (row 0
+        = top of the picture) or PIL image: sampled with the mesh's UVs (GL_REPEAT, GL_LINEAR) and
+        multiplied into the instance colour (reference node.py:277-287, basic.frag:31-37).  ``True``
+        without an image keeps the node white, like Panda3D's default texture."""
+        self.texture_image = None            # numpy [h, w, 4] uint8, row 0 = v 0 (bottom row)
+        self._native_texture = None
+        if texture is None or texture is False:
+            self._set_shader_input("useTexture", 0.0)
+        else:
+            if texture is not True:
+                import numpy as np
+                if isinstance(texture, (str, bytes)) or hasattr(texture, "__fspath__"):
+                    from PIL import Image
+                    texture = Image.open(texture)
+                if hasattr(texture, "convert"):                      # PIL image
+                    texture = np.asarray(texture.convert("RGBA"))
+                if isinstance(texture, torch.Tensor):
+                    texture = texture.detach().cpu().numpy()
+                img = np.asarray(texture)
+                if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] not in (3, 4):
+                    raise ValueError("texture must be a file, a PIL image or a [h, w, 3|4] uint8 array")
+                if img.shape[2] == 3:
+                    img = np.concatenate([img, np.full(img.shape[:2] + (1,), 255, np.uint8)], axis=2)
+                self.texture_image = np.ascontiguousarray(img[::-1])
+            self._set_shader_input("useTexture", 1.0)
+        self._touch()
 
     def reparent_to(self, parent) -> None:
         raise NotImplementedError("PBRNode.reparent_to is not implemented yet")

@@ -177,7 +177,10 @@ class PBRRenderer:
                               mats=n.matbuf.detach().cpu().numpy().copy(),
                               cols=n.colbuf.detach().cpu().numpy().copy(),
                               instances_per_scene=n.instances_per_scene, shared=n.shared_across,
-                              flags=1 if n.mesh.two_sided else 0))
+                              flags=1 if n.mesh.two_sided else 0,
+                              uv=None if n.mesh.uv is None else n.mesh.uv.copy(),
+                              texture=None if n.texture_image is None else n.texture_image.copy(),
+                              use_texture=float(n.shader_inputs.get("useTexture", 0.0))))
         return dict(num_scenes=self.num_scenes,
                     tile_w=int(self.cfg.tile_resolution[0]), tile_h=int(self.cfg.tile_resolution[1]),
                     channels=int(self.cfg.num_channels),
@@ -192,9 +195,13 @@ class PBRRenderer:
             if n._native_mesh is None:
                 from .. import _native
                 n._native_mesh = _native.NativeMesh(n.mesh.pos, n.mesh.nrm, n.mesh.idx, self.device,
-                                                    two_sided=n.mesh.two_sided)
+                                                    two_sided=n.mesh.two_sided, uv=n.mesh.uv)
+            if n.texture_image is not None and n._native_texture is None:
+                from .. import _native
+                n._native_texture = _native.NativeTexture(n.texture_image, self.device)
         return [(n._native_mesh, n.matbuf, n.colbuf, n.instances_per_scene, n.shared_across,
-                 in_base and n.shared_across) for n in self._node_cache]
+                 in_base and n.shared_across, float(n.shader_inputs.get("useTexture", 0.0)), n._native_texture)
+                for n in self._node_cache]
 
     def invalidate_static(self) -> None:
         """Force the static layer to be re-rendered (needed only if matbuf / colbuf / viewbuf of a
