@@ -23,6 +23,8 @@ struct NodeDev {
     const uchar4 *tex;    // [th, tw] RGBA8 texels, row 0 = v 0 (bottom), or NULL = untextured
     int tw, th;
     float use_tex;        // clamp(useTexture): mix(1, texel, use_tex)
+    float4 bsphere;       // object-space bounding sphere of the mesh (centre xyz, radius w)
+    int inst_begin;       // index of this node's first instance among the scene's instances
     const float *mats;    // [B,16] column packed
     const float *cols;    // [B,4]
     int n_tris;
@@ -52,13 +54,14 @@ struct FrameDev {
     int vp_scene_override;  // >= 0: use this row of vp for every scene (base pass)
     int scene_begin, scene_count;
     int W, H, C;
-    int n_nodes, total_slots, total_verts;
+    int n_nodes, total_slots, total_verts, total_inst;
     int BH, nbands;         // band height (multiple of 8) and bands per tile
     int nbx, nby;           // 8x8 blocks per band
     unsigned nbx_magic;     // floor(2^32 / nbx) + 1
     int plane_stride;       // bytes between colour planes in shared memory (multiple of 16)
     int linear;             // 1: the shared colour tile is a byte image of out[scene]
-    int smooth;             // 1: some mesh has per-vertex normals (SMOOTH kernel instantiations)
+    int smooth;             // 1: some triangles are shaded per pixel (SMOOTH kernel instantiations)
+    int srec_stride;        // bytes per SRec: SREC_PLAIN, or SREC_TEXTURED when a node is textured
     int debug;              // profiling aid: 1 = stop after the background, 2 = stop after setup
     float hw, hh;
     unsigned bg;            // packed RGBA8 clear colour
@@ -73,6 +76,7 @@ constexpr int DEVSTAT_STAGED_OVERFLOW = 2; // geometry pre-pass ran out of per-s
 // record meta bits
 constexpr unsigned M_VALID = 1u << 16, M_SLOW = 1u << 17, M_SMOOTH = 1u << 18;
 constexpr unsigned M_NB0 = 1u << 19, M_NB1 = 1u << 20, M_NB2 = 1u << 21;
+constexpr unsigned M_TEX = 1u << 22;        // the record's SRec carries a texture part
 
 struct __align__(16) Rec {
     int e[9];        // fast: Eo[3], A[3], B[3]        slow: X0,Y0,X1,Y1,X2,Y2,-,-,-
@@ -85,17 +89,21 @@ static_assert(sizeof(Rec) == 64, "Rec must be 64 bytes");
 
 // companion of a Rec for triangles with per-vertex normals (smooth shading): what the fragment
 // shader interpolates (reference basic.vert:53-54 -> basic.frag:33-38)
+// Stored with a per-frame stride: 64 bytes (first four fields) when no node is textured, 128 bytes
+// otherwise; the texture part is only read for records flagged M_TEX.
 struct __align__(16) SRec {
     float n[3][3];   // world-space unit normals of the three vertices (after a two-sided swap)
     float rw[3];     // 1 / w_clip of the three vertices (perspective-correct weights)
     float col[4];    // instance RGBA
+    // ---- texture part
     float uv[3][2];  // texture coordinates of the three vertices
-    const uchar4 *tex;   // NULL = untextured
+    const uchar4 *tex;
     int tw, th;
     float use_tex;
     float pad[5];
 };
-static_assert(sizeof(SRec) == 128, "SRec must be 128 bytes");
+static_assert(sizeof(SRec) == 128 && offsetof(SRec, uv) == 64, "SRec layout");
+constexpr int SREC_PLAIN = 64, SREC_TEXTURED = 128;
 
 struct CV {
     float c[4];      // clip-space position
@@ -465,8 +473,8 @@ __device__ __forceinline__ void sample_bilinear(const uchar4 *tex, int tw, int t
 
 // fragment shader for a smooth triangle at one pixel: perspective-correct normal (weights b_i / w_i;
 // their normalisation is dropped because the normal is re-normalised), ambient + Lambert
-__device__ __forceinline__ unsigned shade_pixel(const FrameDev &f, const SRec &sr, float f0, float f1, float f2,
-                                                float invA) {
+__device__ __forceinline__ unsigned shade_pixel(const FrameDev &f, const SRec &sr, bool textured, float f0, float f1,
+                                                float f2, float invA) {
     const float p0 = (f0 * invA) * sr.rw[0], p1 = (f1 * invA) * sr.rw[1], p2 = (f2 * invA) * sr.rw[2];
     float n[3];
 #pragma unroll
@@ -475,7 +483,7 @@ __device__ __forceinline__ unsigned shade_pixel(const FrameDev &f, const SRec &s
     const float inv = 1.0f / sqrtf(l2);
     n[0] *= inv; n[1] *= inv; n[2] *= inv;
     float4 col = make_float4(sr.col[0], sr.col[1], sr.col[2], sr.col[3]);
-    if (sr.tex != nullptr) {
+    if (textured) {
         // basic.frag:31-32: base = mix(1, texture(uv).rgb, useTexture); colour = base * v_color
         const float sum = (p0 + p1) + p2;
         const float u = fmaf(p2, sr.uv[2][0], fmaf(p1, sr.uv[1][0], p0 * sr.uv[0][0])) / sum;
@@ -511,8 +519,9 @@ __device__ __forceinline__ void raster_one(const FrameDev &f, const Rec &r, cons
     }
     if (SMOOTH) {
         if (((unsigned)ec.w & M_SMOOTH) && __any_sync(0xffffffffu, w0 || w1)) {
-            const unsigned ca = shade_pixel(f, *sr, f0a, f1a, f2a, zq.w);
-            const unsigned cb = shade_pixel(f, *sr, f0b, f1b, f2b, zq.w);
+            const bool tex = ((unsigned)ec.w & M_TEX) != 0;
+            const unsigned ca = shade_pixel(f, *sr, tex, f0a, f1a, f2a, zq.w);
+            const unsigned cb = shade_pixel(f, *sr, tex, f0b, f1b, f2b, zq.w);
             ps.c0 = w0 ? ca : ps.c0;
             ps.c1 = w1 ? cb : ps.c1;
         }
@@ -524,7 +533,7 @@ __device__ __forceinline__ void raster_one(const FrameDev &f, const Rec &r, cons
 template <int MWORDS, bool SMOOTH = false>
 __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bmask, int px, int py0, bool ok0,
                                              bool ok1, PixelState &ps, const FrameDev *f = nullptr,
-                                             const SRec *srecs = nullptr) {
+                                             const unsigned char *srecs = nullptr) {
 #pragma unroll 1
     for (int w = 0; w < MWORDS; ++w) {
         unsigned m = bmask[w];
@@ -538,7 +547,8 @@ __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bm
             const int4 eb = *reinterpret_cast<const int4 *>(&r.e[4]);         // A1 A2 B0 B1
             const int4 ec = *reinterpret_cast<const int4 *>(&r.e[8]);         // B2 col id meta
             const float4 zq = *reinterpret_cast<const float4 *>(&r.z0);       // z0 dz1 dz2 invA
-            raster_one<SMOOTH>(*f, r, SMOOTH ? srecs + t : nullptr, ea, eb, ec, zq, px, py0, ok0, ok1, ps);
+            raster_one<SMOOTH>(*f, r, SMOOTH ? reinterpret_cast<const SRec *>(srecs + (size_t)t * f->srec_stride) : nullptr,
+                               ea, eb, ec, zq, px, py0, ok0, ok1, ps);
         }
     }
 }

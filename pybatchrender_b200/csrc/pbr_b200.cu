@@ -70,8 +70,10 @@ struct DeviceState {
     bool attr_general = false, attr_warp = false, attr_staged = false;
     // scratch of the geometry pre-pass: per-scene record lists (grown on demand, reused per launch)
     Rec *g_recs = nullptr;
-    SRec *g_srecs = nullptr;
+    unsigned char *g_srecs = nullptr;
     size_t g_srec_cap = 0;
+    unsigned char *g_vis = nullptr;
+    size_t g_vis_cap = 0;
     unsigned *g_bbox = nullptr;
     int *g_count = nullptr;
     size_t g_rec_cap = 0;            // records allocated (all scenes of one launch)
@@ -118,6 +120,7 @@ struct pbr_mesh_s {
     float4 *vpos;       // [V]
     uint4 *tidx;        // [T]
     float2 *tuv;        // [T*3] or NULL
+    float bsphere[4];   // bounding sphere (centre, radius) of the positions
 };
 
 struct pbr_texture_s {
@@ -177,6 +180,24 @@ int pbr_mesh_create(const float *pos, const float *nrm, const float *uv, int32_t
     pbr_mesh_s *m = new (std::nothrow) pbr_mesh_s();
     if (!m) { cudaSetDevice(prev); return fail(PBR_ENOMEM, "pbr_mesh_create: host allocation failed"); }
     memset(m, 0, sizeof(*m));
+    {   // bounding sphere: centre of the bounding box, radius to the farthest vertex (rounded up)
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int v = 0; v < n_verts; ++v)
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = pos[3 * v + a] < lo[a] ? pos[3 * v + a] : lo[a];
+                hi[a] = pos[3 * v + a] > hi[a] ? pos[3 * v + a] : hi[a];
+            }
+        float c[3];
+        for (int a = 0; a < 3; ++a) c[a] = (float)(0.5 * (lo[a] + hi[a]));
+        double r2 = 0.0;
+        for (int v = 0; v < n_verts; ++v) {
+            double d2 = 0.0;
+            for (int a = 0; a < 3; ++a) d2 += ((double)pos[3 * v + a] - c[a]) * ((double)pos[3 * v + a] - c[a]);
+            r2 = d2 > r2 ? d2 : r2;
+        }
+        m->bsphere[0] = c[0]; m->bsphere[1] = c[1]; m->bsphere[2] = c[2];
+        m->bsphere[3] = (float)(sqrt(r2) * 1.00001) + 1e-30f;
+    }
     m->device = device; m->n_tris = n_tris; m->n_verts = (int)vpos.size(); m->all_flat = all_flat; m->flags = flags;
     const size_t tb = (size_t)n_tris * 3 * sizeof(float4), vb = vpos.size() * sizeof(float4), ib = (size_t)n_tris * sizeof(uint4);
     cudaError_t e = cudaMalloc(&m->tp, tb);
@@ -248,8 +269,8 @@ int pbr_mesh_info(pbr_mesh_t m, int32_t *n_tris, int32_t *all_flat, int32_t *dev
 enum NodeMode { NODES_ALL = 0, NODES_SKIP_BASE = 1, NODES_SHARED_ONLY = 2 };
 
 struct NodeStats {
-    long long slots = 0, verts = 0;
-    bool any_smooth = false, warp_ok = true;
+    long long slots = 0, verts = 0, insts = 0;
+    bool any_smooth = false, any_textured = false, warp_ok = true;
     int skipped = 0;
 };
 
@@ -288,12 +309,15 @@ static int fill_nodes(const pbr_frame_desc *d, int device, NodeMode mode, FrameD
         nd.tex = textured ? n.texture->texels : nullptr;
         nd.tw = textured ? n.texture->w : 0; nd.th = textured ? n.texture->h : 0;
         nd.use_tex = textured ? ut : 0.0f;
-        if (textured) st.any_smooth = true;               // per-pixel shading path
+        if (textured) { st.any_smooth = true; st.any_textured = true; }      // per-pixel shading path
         nd.mats = n.mats; nd.cols = n.cols;
         nd.n_tris = n.mesh->n_tris; nd.n_verts = n.mesh->n_verts;
         nd.inst = n.instances_per_scene; nd.shared = n.shared ? 1 : 0;
         nd.slot_begin = (int)st.slots; nd.vert_begin = (int)st.verts; nd.flags = n.mesh->flags;
         nd.id_begin = (int)id_begin;
+        nd.bsphere = make_float4(n.mesh->bsphere[0], n.mesh->bsphere[1], n.mesh->bsphere[2], n.mesh->bsphere[3]);
+        nd.inst_begin = (int)st.insts;
+        st.insts += n.instances_per_scene;
         nd.tri_magic = div_magic((unsigned)n.mesh->n_tris);
         nd.vert_magic = div_magic((unsigned)n.mesh->n_verts);
         st.slots += ntri;
@@ -302,6 +326,9 @@ static int fill_nodes(const pbr_frame_desc *d, int device, NodeMode mode, FrameD
         if (n.instances_per_scene >= 8192 || n.mesh->n_tris >= 8192) st.warp_ok = false;
     }
     f.smooth = st.any_smooth ? 1 : 0;
+    f.srec_stride = st.any_textured ? SREC_TEXTURED : SREC_PLAIN;
+    if (st.insts > 0x7fffffffll) return fail(PBR_EUNSUPPORTED, "pbr_render: more than 2^31 instances per scene");
+    f.total_inst = (int)st.insts;
     f.total_slots = (int)st.slots;
     f.total_verts = (int)(st.verts > 0x7fffffff ? 0x7fffffff : st.verts);
     return PBR_OK;
@@ -360,7 +387,7 @@ static int plan_general(FrameDev &f, DeviceState *st, size_t *smem_out) {
     auto bytes_for = [&](int BH) {
         const int nby = (BH + 7) / 8;
         const int ps = (int)align16((size_t)BH * W);
-        return general_smem_bytes(f.C, ps, nbx * nby, f.smooth != 0);
+        return general_smem_bytes(f.C, ps, nbx * nby, f.smooth ? f.srec_stride : 0);
     };
     const size_t budget = 56 * 1024;
     int BH = H8;
@@ -382,7 +409,7 @@ static int launch_general(FrameDev &f, DeviceState *st, void *stream) {
     size_t smem = 0;
     if (f.BH == 0)
         if (int rc = plan_general(f, st, &smem)) return rc;
-    smem = general_smem_bytes(f.C, f.plane_stride, f.nbx * f.nby, f.smooth != 0);
+    smem = general_smem_bytes(f.C, f.plane_stride, f.nbx * f.nby, f.smooth ? f.srec_stride : 0);
     if (!st->attr_general) {
         CUDA_TRY(cudaFuncSetAttribute(raster_general_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem_optin));
         CUDA_TRY(cudaFuncSetAttribute(raster_general_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem_optin));
@@ -401,14 +428,14 @@ static int launch_general(FrameDev &f, DeviceState *st, void *stream) {
 // geometry pre-pass + TMA-staged raster, in launches of as many scenes as the scratch budget holds
 static int launch_staged(FrameDev &f, DeviceState *st, void *stream) {
     const size_t cap = ((size_t)f.total_slots + (size_t)f.total_slots / 2 + 64 + 3) & ~(size_t)3;
-    static const size_t budget_mb = getenv("PBR_B200_SCRATCH_MB") ? (size_t)atoll(getenv("PBR_B200_SCRATCH_MB")) : 1024;
+    static const size_t budget_mb = getenv("PBR_B200_SCRATCH_MB") ? (size_t)atoll(getenv("PBR_B200_SCRATCH_MB")) : 4096;
     const bool smooth = f.smooth != 0;
-    const size_t per_scene = cap * (sizeof(Rec) + 4 + (smooth ? sizeof(SRec) : 0));
+    const size_t per_scene = cap * (sizeof(Rec) + 4 + (smooth ? (size_t)f.srec_stride : 0));
     size_t per_launch = (budget_mb << 20) / per_scene;
     if (per_launch < 1) per_launch = 1;
     if (per_launch > (size_t)f.scene_count) per_launch = (size_t)f.scene_count;
     if (per_launch > 65535) per_launch = 65535;                     // gridDim.y of the geometry kernel
-    if (per_launch * cap > st->g_rec_cap || per_launch > st->g_scene_cap || (smooth && per_launch * cap > st->g_srec_cap)) {
+    if (per_launch * cap > st->g_rec_cap || per_launch > st->g_scene_cap || (smooth && per_launch * cap * (size_t)f.srec_stride > st->g_srec_cap)) {
         CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
         cudaFree(st->g_recs); cudaFree(st->g_bbox); cudaFree(st->g_count); cudaFree(st->g_srecs);
         st->g_recs = nullptr; st->g_bbox = nullptr; st->g_count = nullptr; st->g_srecs = nullptr;
@@ -418,11 +445,18 @@ static int launch_staged(FrameDev &f, DeviceState *st, void *stream) {
         CUDA_TRY(cudaMalloc(&st->g_count, per_launch * sizeof(int)));
         st->g_rec_cap = per_launch * cap; st->g_scene_cap = per_launch;
         if (smooth) {
-            CUDA_TRY(cudaMalloc(&st->g_srecs, per_launch * cap * sizeof(SRec)));
-            st->g_srec_cap = per_launch * cap;
+            CUDA_TRY(cudaMalloc(&st->g_srecs, per_launch * cap * (size_t)f.srec_stride));
+            st->g_srec_cap = per_launch * cap * (size_t)f.srec_stride;
         }
     }
-    const size_t smem = staged_smem_bytes(f.C, f.plane_stride, f.nbx * f.nby, smooth);
+    if (per_launch * (size_t)f.total_inst > st->g_vis_cap) {
+        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+        cudaFree(st->g_vis);
+        st->g_vis = nullptr; st->g_vis_cap = 0;
+        CUDA_TRY(cudaMalloc(&st->g_vis, per_launch * (size_t)f.total_inst));
+        st->g_vis_cap = per_launch * (size_t)f.total_inst;
+    }
+    const size_t smem = staged_smem_bytes(f.C, f.plane_stride, f.nbx * f.nby, smooth ? f.srec_stride : 0);
     if (smem > (size_t)st->max_smem_optin) return launch_general(f, st, stream);
     if (!st->attr_staged) {
         CUDA_TRY(cudaFuncSetAttribute(raster_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem_optin));
@@ -430,12 +464,21 @@ static int launch_staged(FrameDev &f, DeviceState *st, void *stream) {
         st->attr_staged = true;
     }
     StagedDev g;
+    g.vis = st->g_vis;
     g.recs = st->g_recs; g.srecs = smooth ? st->g_srecs : nullptr; g.bbox = st->g_bbox; g.count = st->g_count; g.cap = (int)cap;
     const int first = f.scene_begin, last = f.scene_begin + f.scene_count;
     for (int s0 = first; s0 < last; s0 += (int)per_launch) {
         const int n = (int)((size_t)(last - s0) < per_launch ? (size_t)(last - s0) : per_launch);
         g.scene0 = s0;
         CUDA_TRY(cudaMemsetAsync(st->g_count, 0, (size_t)n * sizeof(int), (cudaStream_t)stream));
+        dim3 cgrid((unsigned)((f.total_inst + 255) / 256), (unsigned)n);
+        static const bool no_cull = getenv("PBR_B200_NO_CULL") != nullptr;          // A/B timing aid
+        if (no_cull) {
+            CUDA_TRY(cudaMemsetAsync(st->g_vis, 1, (size_t)n * f.total_inst, (cudaStream_t)stream));
+        } else {
+            cull_kernel<<<cgrid, 256, 0, (cudaStream_t)stream>>>(f, g);
+            CUDA_TRY(cudaGetLastError());
+        }
         dim3 ggrid((unsigned)((f.total_slots + G_THREADS - 1) / G_THREADS), (unsigned)n);
         geom_kernel<<<ggrid, G_THREADS, 0, (cudaStream_t)stream>>>(f, g);
         CUDA_TRY(cudaGetLastError());

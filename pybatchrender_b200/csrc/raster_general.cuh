@@ -31,15 +31,20 @@ struct SlotGeom {
     unsigned id;          // 1 + draw index
 };
 
-__device__ __forceinline__ int load_slot(const FrameDev &f, int scene, int slot, SlotGeom &g) {
-    int ni = 0;
+// triangle slot -> (node, instance of the node, triangle of the mesh)
+__device__ __forceinline__ void locate_slot(const FrameDev &f, int slot, int &ni, int &inst, int &tri) {
+    ni = 0;
 #pragma unroll 1
     for (int i = 1; i < f.n_nodes; ++i)
         if (slot >= f.nodes[i].slot_begin) ni = i;
+    const int local = slot - f.nodes[ni].slot_begin;
+    inst = local / f.nodes[ni].n_tris;
+    tri = local - inst * f.nodes[ni].n_tris;
+}
+
+__device__ __forceinline__ int load_slot(const FrameDev &f, int scene, int slot, int ni, int inst, int tri, SlotGeom &g) {
     const NodeDev &nd = f.nodes[ni];
     const int local = slot - nd.slot_begin;
-    const int inst = local / nd.n_tris;
-    const int tri = local - inst * nd.n_tris;
     const size_t b = nd.shared ? (size_t)inst : (size_t)scene * nd.inst + inst;
 
     float M[16], VP[16];
@@ -78,42 +83,72 @@ __device__ __forceinline__ int load_slot(const FrameDev &f, int scene, int slot,
     return clip ? SLOT_CLIP : SLOT_OK;
 }
 
-// sr: where the smooth-shading companion of the record goes (may be shared or global memory);
-// only written for non-flat triangles
+__device__ __forceinline__ int load_slot(const FrameDev &f, int scene, int slot, SlotGeom &g) {
+    int ni, inst, tri;
+    locate_slot(f, slot, ni, inst, tri);
+    return load_slot(f, scene, slot, ni, inst, tri, g);
+}
+
+// what setup_tri hands to write_srec
+struct TriVary {
+    float rw[3];
+    bool swapped;    // vertices 1 and 2 were exchanged (two-sided back face)
+};
+
+// flat triangles are shaded here; the others get M_SMOOTH (| M_TEX) and need write_srec afterwards
 __device__ __forceinline__ bool setup_tri(const FrameDev &f, const CVT *vin, const SlotGeom &g, int band_y0,
-                                          int band_h, Rec &r, BBox &bb, SRec *sr = nullptr) {
+                                          int band_h, Rec &r, BBox &bb, TriVary &tv) {
     const float4 col = g.col;
     const bool two_sided = g.two_sided;
     const unsigned id = g.id;
     const NodeDev &nd = *g.node;
     const bool flat = g.flat && nd.tex == nullptr;        // textured triangles shade per pixel
     int X[3], Y[3];
-    float z[3], rw[3];
+    float z[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
-        if (!project_vertex(f, vin[i].c, X[i], Y[i], z[i], rw[i])) return false;
-    bool swapped;
-    if (!setup_snapped(f, X, Y, z, two_sided, id, band_y0, band_h, r, bb, &swapped)) return false;
+        if (!project_vertex(f, vin[i].c, X[i], Y[i], z[i], tv.rw[i])) return false;
+    if (!setup_snapped(f, X, Y, z, two_sided, id, band_y0, band_h, r, bb, &tv.swapped)) return false;
     if (flat) {
         r.col = shade(f, vin[0].n, col);
     } else {
         r.col = 0;
-        r.meta |= M_SMOOTH;
-        const int i1 = swapped ? 2 : 1, i2 = swapped ? 1 : 2;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            sr->n[0][k] = vin[0].n[k];
-            sr->n[1][k] = vin[i1].n[k];
-            sr->n[2][k] = vin[i2].n[k];
-        }
-        sr->rw[0] = rw[0]; sr->rw[1] = rw[i1]; sr->rw[2] = rw[i2];
-        sr->col[0] = col.x; sr->col[1] = col.y; sr->col[2] = col.z; sr->col[3] = col.w;
-        sr->uv[0][0] = vin[0].uv[0]; sr->uv[0][1] = vin[0].uv[1];
-        sr->uv[1][0] = vin[i1].uv[0]; sr->uv[1][1] = vin[i1].uv[1];
-        sr->uv[2][0] = vin[i2].uv[0]; sr->uv[2][1] = vin[i2].uv[1];
-        sr->tex = nd.tex; sr->tw = nd.tw; sr->th = nd.th; sr->use_tex = nd.use_tex;
+        r.meta |= M_SMOOTH | (nd.tex != nullptr ? M_TEX : 0u);
     }
     return true;
+}
+
+// The per-pixel shading inputs of a M_SMOOTH record, written as 16-byte stores to shared or global
+// memory (dst is 16-byte aligned, f.srec_stride bytes long).  Static indexing only: vin stays in
+// registers.
+__device__ __forceinline__ void write_srec(const FrameDev &f, void *dst, const CVT *vin, const SlotGeom &g,
+                                           const TriVary &tv) {
+    const bool s = tv.swapped;
+    const CVT &a = vin[0];
+    float n1[3], n2[3], uv1[2], uv2[2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        n1[k] = s ? vin[2].n[k] : vin[1].n[k];
+        n2[k] = s ? vin[1].n[k] : vin[2].n[k];
+    }
+    const float rw1 = s ? tv.rw[2] : tv.rw[1], rw2 = s ? tv.rw[1] : tv.rw[2];
+    float4 *q = reinterpret_cast<float4 *>(dst);
+    q[0] = make_float4(a.n[0], a.n[1], a.n[2], n1[0]);
+    q[1] = make_float4(n1[1], n1[2], n2[0], n2[1]);
+    q[2] = make_float4(n2[2], tv.rw[0], rw1, rw2);
+    q[3] = g.col;
+    if (f.srec_stride == SREC_TEXTURED) {
+        const NodeDev &nd = *g.node;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            uv1[k] = s ? vin[2].uv[k] : vin[1].uv[k];
+            uv2[k] = s ? vin[1].uv[k] : vin[2].uv[k];
+        }
+        q[4] = make_float4(a.uv[0], a.uv[1], uv1[0], uv1[1]);
+        const unsigned long long tp = reinterpret_cast<unsigned long long>(nd.tex);
+        q[5] = make_float4(uv2[0], uv2[1], __uint_as_float((unsigned)tp), __uint_as_float((unsigned)(tp >> 32)));
+        q[6] = make_float4(__int_as_float(nd.tw), __int_as_float(nd.th), nd.use_tex, 0.0f);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -123,15 +158,15 @@ struct Smem {
     unsigned char *color;      // [C][plane_stride]
     unsigned long long *ktile; // [nblk*64] block-major (depth bits << 32) | id
     Rec *recs;                 // [CH]
-    SRec *srecs;               // [CH] when the frame has smooth meshes, else unused
+    unsigned char *srecs;      // [CH] x srec_stride bytes when the frame shades per pixel, else unused
     unsigned *masks;           // [nblk*MW]
     unsigned short *blist;     // [nblk]
     unsigned short *cliplist;  // [CH]
     int *ctr;                  // nlist, next, nclip
 };
 
-__host__ __device__ inline size_t general_smem_bytes(int C, int plane_stride, int nblk, bool smooth) {
-    size_t n = smooth ? (size_t)CH * sizeof(SRec) : 0;
+__host__ __device__ inline size_t general_smem_bytes(int C, int plane_stride, int nblk, int srec_bytes) {
+    size_t n = (size_t)CH * srec_bytes;
     n += align16((size_t)C * plane_stride);
     n += 2 * (size_t)nblk * 64 * 4;
     n += (size_t)CH * sizeof(Rec);
@@ -142,12 +177,12 @@ __host__ __device__ inline size_t general_smem_bytes(int C, int plane_stride, in
     return n;
 }
 
-__device__ __forceinline__ Smem carve(unsigned char *base, int C, int plane_stride, int nblk, bool smooth) {
+__device__ __forceinline__ Smem carve(unsigned char *base, int C, int plane_stride, int nblk, int srec_bytes) {
     Smem s;
     s.color = base; base += align16((size_t)C * plane_stride);
     s.ktile = reinterpret_cast<unsigned long long *>(base); base += (size_t)nblk * 64 * 8;
     s.recs = reinterpret_cast<Rec *>(base); base += (size_t)CH * sizeof(Rec);
-    s.srecs = reinterpret_cast<SRec *>(base); base += smooth ? (size_t)CH * sizeof(SRec) : 0;
+    s.srecs = base; base += (size_t)CH * srec_bytes;
     s.masks = reinterpret_cast<unsigned *>(base); base += align16((size_t)nblk * MW * 4);
     s.blist = reinterpret_cast<unsigned short *>(base); base += align16((size_t)nblk * 2);
     s.cliplist = reinterpret_cast<unsigned short *>(base); base += align16((size_t)CH * 2);
@@ -252,7 +287,7 @@ __global__ void __launch_bounds__(THREADS) raster_general_kernel(const __grid_co
     const int band_y0 = band * f.BH;
     const int band_h = min(f.BH, f.H - band_y0);
     const int nblk = f.nbx * f.nby;
-    const Smem s = carve(smem_raw, f.C, f.plane_stride, nblk, SMOOTH);
+    const Smem s = carve(smem_raw, f.C, f.plane_stride, nblk, SMOOTH ? f.srec_stride : 0);
 
     clear_color(f, s.color, tid, THREADS);
     {
@@ -276,10 +311,13 @@ __global__ void __launch_bounds__(THREADS) raster_general_kernel(const __grid_co
                 const int st = load_slot(f, scene, slot, g);
                 if (st == SLOT_OK) {
                     BBox bb;
-                    if (setup_tri(f, g.v, g, band_y0, band_h, r, bb, s.srecs + tid))
+                    TriVary tv;
+                    if (setup_tri(f, g.v, g, band_y0, band_h, r, bb, tv)) {
                         bin_record<MW>(r, bb, tid, f.nbx, s.masks);
-                    else
+                        if (SMOOTH && (r.meta & M_SMOOTH)) write_srec(f, s.srecs + (size_t)tid * f.srec_stride, g.v, g, tv);
+                    } else {
                         r.meta = 0;
+                    }
                 } else if (st == SLOT_CLIP) {
                     s.cliplist[atomicAdd(&s.ctr[2], 1)] = (unsigned short)tid;
                 }
@@ -307,10 +345,13 @@ __global__ void __launch_bounds__(THREADS) raster_general_kernel(const __grid_co
                 if (k + 2 < n) {
                     CVT tri[3] = {poly[0], poly[k + 1], poly[k + 2]};
                     BBox bb;
-                    if (setup_tri(f, tri, g, band_y0, band_h, r, bb, s.srecs + tid))
+                    TriVary tv;
+                    if (setup_tri(f, tri, g, band_y0, band_h, r, bb, tv)) {
                         bin_record<MW>(r, bb, tid, f.nbx, s.masks);
-                    else
+                        if (SMOOTH && (r.meta & M_SMOOTH)) write_srec(f, s.srecs + (size_t)tid * f.srec_stride, tri, g, tv);
+                    } else {
                         r.meta = 0;
+                    }
                 }
             }
             s.recs[tid] = r;

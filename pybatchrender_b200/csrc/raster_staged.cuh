@@ -27,9 +27,10 @@ constexpr int G_THREADS = 256;
 
 struct StagedDev {
     Rec *recs;               // [scenes_in_launch][cap]
-    SRec *srecs;             // [scenes_in_launch][cap] smooth-shading companions, or NULL (all meshes flat)
+    unsigned char *srecs;    // [scenes_in_launch][cap] x srec_stride bytes, or NULL (all triangles flat)
     unsigned *bbox;          // [scenes_in_launch][cap]  bx0 | by0 << 8 | bx1 << 16 | by1 << 24 (tile blocks)
     int *count;              // [scenes_in_launch]
+    unsigned char *vis;      // [scenes_in_launch][total_inst] 1 = instance may touch a pixel (cull_kernel)
     int cap;                 // records per scene (multiple of 4)
     int scene0;              // first scene of this launch (index into vp / out / per-scene rows)
 };
@@ -38,7 +39,7 @@ struct StagedDev {
 // geometry
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void append_record(const StagedDev &g, const FrameDev &f, int local_scene, const Rec &r,
-                                              const BBox &bb, const SRec &sr) {
+                                              const BBox &bb, const CVT *vin, const SlotGeom &sg, const TriVary &tv) {
     const int idx = atomicAdd(&g.count[local_scene], 1);
     if (idx >= g.cap) {
         atomicOr(f.status, DEVSTAT_STAGED_OVERFLOW);
@@ -49,11 +50,101 @@ __device__ __forceinline__ void append_record(const StagedDev &g, const FrameDev
     const uint4 *src = reinterpret_cast<const uint4 *>(&r);
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
     g.bbox[o] = (unsigned)bb.bx0 | ((unsigned)bb.by0 << 8) | ((unsigned)bb.bx1 << 16) | ((unsigned)bb.by1 << 24);
-    if (g.srecs != nullptr && (r.meta & M_SMOOTH)) {
-        uint4 *sd = reinterpret_cast<uint4 *>(g.srecs + o);
-        const uint4 *ss = reinterpret_cast<const uint4 *>(&sr);
+    if (g.srecs != nullptr && (r.meta & M_SMOOTH)) write_srec(f, g.srecs + o * (size_t)f.srec_stride, vin, sg, tv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// instance culling: one thread per (scene, instance).  The mesh's bounding sphere is pushed through
+// M and VP with interval arithmetic; an instance is dropped when every point of the sphere is outside
+// one clip plane (all its triangles would be rejected by trivially_outside) or when the pixel
+// rectangle that bounds its projection contains no pixel centre (no triangle inside it can cover a
+// sample).  Both tests are conservative (margins far above fp32 rounding and the 1/256 px snap), so
+// the image is unchanged; what is saved is the per-triangle transform / setup of instances that
+// are off screen or smaller than the pixel grid (distant obstacles of Steering-v0).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cull_kernel(const __grid_constant__ FrameDev f,
+                                                   const __grid_constant__ StagedDev g) {
+    const int local_scene = blockIdx.y;
+    const int scene = g.scene0 + local_scene;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= f.total_inst) return;
+    int ni = 0;
+#pragma unroll 1
+    for (int i = 1; i < f.n_nodes; ++i)
+        if (k >= f.nodes[i].inst_begin) ni = i;
+    const NodeDev &nd = f.nodes[ni];
+    const int inst = k - nd.inst_begin;
+    const size_t b = nd.shared ? (size_t)inst : (size_t)scene * nd.inst + inst;
+    float M[16], VP[16];
+    const float4 *m4 = reinterpret_cast<const float4 *>(nd.mats + b * 16);
+    const int vp_row = f.vp_scene_override >= 0 ? f.vp_scene_override : scene;
+    const float4 *v4 = reinterpret_cast<const float4 *>(f.vp + (size_t)vp_row * 16);
 #pragma unroll
-        for (int i = 0; i < (int)(sizeof(SRec) / 16); ++i) sd[i] = ss[i];
+    for (int j = 0; j < 4; ++j) {
+        const float4 a = __ldg(m4 + j), c = __ldg(v4 + j);
+        M[4 * j] = a.x; M[4 * j + 1] = a.y; M[4 * j + 2] = a.z; M[4 * j + 3] = a.w;
+        VP[4 * j] = c.x; VP[4 * j + 1] = c.y; VP[4 * j + 2] = c.z; VP[4 * j + 3] = c.w;
+    }
+    float world[4], cc[4];
+    mat_vec4(M, nd.bsphere.x, nd.bsphere.y, nd.bsphere.z, 1.0f, world);
+    mat_vec4(VP, world[0], world[1], world[2], world[3], cc);
+    // radius in world space: largest stretch of A = mat3(M) is sqrt(lambda_max(A^T A)), bounded by
+    // the largest absolute row sum of A^T A (exact for rotation * uniform scale)
+    float gmax = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float rowsum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            rowsum += fabsf(fmaf(M[4 * i], M[4 * j], fmaf(M[4 * i + 1], M[4 * j + 1], M[4 * i + 2] * M[4 * j + 2])));
+        gmax = fmaxf(gmax, rowsum);
+    }
+    const float rw = nd.bsphere.w * sqrtf(gmax) * 1.0001f;
+    float e[4];                        // how far each clip coordinate can move inside the sphere
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float row = sqrtf(fmaf(VP[i], VP[i], fmaf(VP[4 + i], VP[4 + i], VP[8 + i] * VP[8 + i])));
+        e[i] = fmaf(rw, row, 1e-4f * (fabsf(cc[i]) + rw * row)) + 1e-30f;
+        finite &= (fabsf(cc[i]) < 1e30f) && (e[i] < 1e30f);
+    }
+    bool visible = true;
+    if (finite && world[3] == 1.0f) {
+        // clip planes: a >= -w and a <= w for x, y, z
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if ((cc[3] + cc[a]) + (e[3] + e[a]) < 0.0f) visible = false;
+            if ((cc[3] - cc[a]) + (e[3] + e[a]) < 0.0f) visible = false;
+        }
+        const float wl = cc[3] - e[3], wh = cc[3] + e[3];
+        if (visible && wl > 1e-20f) {
+            const float xl = cc[0] - e[0], xh = cc[0] + e[0], yl = cc[1] - e[1], yh = cc[1] + e[1];
+            const float nxl = xl / (xl >= 0.0f ? wh : wl), nxh = xh / (xh >= 0.0f ? wl : wh);
+            const float nyl = yl / (yl >= 0.0f ? wh : wl), nyh = yh / (yh >= 0.0f ? wl : wh);
+            const float mx = 0.0625f + 1e-4f * (float)f.W, my = 0.0625f + 1e-4f * (float)f.H;
+            const float pxl = fmaf(nxl, f.hw, f.hw) - mx, pxh = fmaf(nxh, f.hw, f.hw) + mx;
+            const float pyl = fmaf(-nyh, f.hh, f.hh) - my, pyh = fmaf(-nyl, f.hh, f.hh) + my;
+            // pixel i is sampled at i + 0.5
+            const float ilo = fmaxf(ceilf(pxl - 0.5f), 0.0f), ihi = fminf(floorf(pxh - 0.5f), (float)(f.W - 1));
+            const float jlo = fmaxf(ceilf(pyl - 0.5f), 0.0f), jhi = fminf(floorf(pyh - 0.5f), (float)(f.H - 1));
+            if (ilo > ihi || jlo > jhi) visible = false;
+        }
+    }
+    g.vis[(size_t)local_scene * f.total_inst + k] = visible ? 1 : 0;
+}
+
+// The rare path (triangle crosses the near plane or the guard band), out of line and with the slot
+// passed by value: its arrays live in local memory, and keeping them out of geom_kernel's body keeps
+// the common path's vertices in registers.
+__device__ __noinline__ void geom_clipped(const FrameDev &f, const StagedDev &g, int local_scene, SlotGeom sg) {
+    CVT poly[MAX_POLY];
+    const int n = clip_poly(sg.v, poly);
+    for (int k = 0; k + 2 < n; ++k) {
+        CVT tri[3] = {poly[0], poly[k + 1], poly[k + 2]};
+        Rec r;
+        TriVary tv;
+        BBox bb;
+        if (setup_tri(f, tri, sg, 0, f.H, r, bb, tv)) append_record(g, f, local_scene, r, bb, tri, sg, tv);
     }
 }
 
@@ -63,22 +154,20 @@ __global__ void __launch_bounds__(G_THREADS) geom_kernel(const __grid_constant__
     const int scene = g.scene0 + local_scene;
     const int slot = blockIdx.x * G_THREADS + threadIdx.x;
     if (slot >= f.total_slots) return;
+    int ni, inst, tri;
+    locate_slot(f, slot, ni, inst, tri);
+    if (!g.vis[(size_t)local_scene * f.total_inst + f.nodes[ni].inst_begin + inst]) return;
     SlotGeom sg;
-    const int st = load_slot(f, scene, slot, sg);
+    const int st = load_slot(f, scene, slot, ni, inst, tri, sg);
     if (st == SLOT_SKIP) return;
     Rec r;
-    SRec sr;
+    TriVary tv;
     BBox bb;
     if (st == SLOT_OK) {
-        if (setup_tri(f, sg.v, sg, 0, f.H, r, bb, &sr)) append_record(g, f, local_scene, r, bb, sr);
+        if (setup_tri(f, sg.v, sg, 0, f.H, r, bb, tv)) append_record(g, f, local_scene, r, bb, sg.v, sg, tv);
         return;
     }
-    CVT poly[MAX_POLY];
-    const int n = clip_poly(sg.v, poly);
-    for (int k = 0; k + 2 < n; ++k) {
-        CVT tri[3] = {poly[0], poly[k + 1], poly[k + 2]};
-        if (setup_tri(f, tri, sg, 0, f.H, r, bb, &sr)) append_record(g, f, local_scene, r, bb, sr);
-    }
+    geom_clipped(f, g, local_scene, sg);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -122,7 +211,7 @@ struct StagedSmem {
     unsigned char *color;          // [C][plane_stride]
     unsigned long long *ktile;     // [nblk*64]
     Rec *recs[2];                  // 2 x [CH]
-    SRec *srecs[2];                // 2 x [CH] (smooth frames only)
+    unsigned char *srecs[2];       // 2 x [CH] x srec_stride bytes (per-pixel shading frames only)
     unsigned *bbox[2];             // 2 x [CH]
     unsigned *masks;               // [nblk*MW]
     unsigned short *blist;         // [nblk]
@@ -130,19 +219,19 @@ struct StagedSmem {
     unsigned long long *bar;       // 2 mbarriers
 };
 
-__host__ __device__ inline size_t staged_smem_bytes(int C, int plane_stride, int nblk, bool smooth) {
-    return (smooth ? 2 * (size_t)CH * sizeof(SRec) : 0) + align16((size_t)C * plane_stride) + (size_t)nblk * 64 * 8 + 2 * (size_t)CH * sizeof(Rec) + 2 * (size_t)CH * 4 +
+__host__ __device__ inline size_t staged_smem_bytes(int C, int plane_stride, int nblk, int srec_bytes) {
+    return 2 * (size_t)CH * srec_bytes + align16((size_t)C * plane_stride) + (size_t)nblk * 64 * 8 + 2 * (size_t)CH * sizeof(Rec) + 2 * (size_t)CH * 4 +
            align16((size_t)nblk * MW * 4) + align16((size_t)nblk * 2) + 16 + 16;
 }
 
-__device__ __forceinline__ StagedSmem staged_carve(unsigned char *base, int C, int plane_stride, int nblk, bool smooth) {
+__device__ __forceinline__ StagedSmem staged_carve(unsigned char *base, int C, int plane_stride, int nblk, int srec_bytes) {
     StagedSmem s;
     s.color = base; base += align16((size_t)C * plane_stride);
     s.ktile = reinterpret_cast<unsigned long long *>(base); base += (size_t)nblk * 64 * 8;
     s.recs[0] = reinterpret_cast<Rec *>(base); base += (size_t)CH * sizeof(Rec);
     s.recs[1] = reinterpret_cast<Rec *>(base); base += (size_t)CH * sizeof(Rec);
-    s.srecs[0] = reinterpret_cast<SRec *>(base); base += smooth ? (size_t)CH * sizeof(SRec) : 0;
-    s.srecs[1] = reinterpret_cast<SRec *>(base); base += smooth ? (size_t)CH * sizeof(SRec) : 0;
+    s.srecs[0] = base; base += (size_t)CH * srec_bytes;
+    s.srecs[1] = base; base += (size_t)CH * srec_bytes;
     s.bbox[0] = reinterpret_cast<unsigned *>(base); base += (size_t)CH * 4;
     s.bbox[1] = reinterpret_cast<unsigned *>(base); base += (size_t)CH * 4;
     s.masks = reinterpret_cast<unsigned *>(base); base += align16((size_t)nblk * MW * 4);
@@ -164,7 +253,7 @@ __global__ void __launch_bounds__(THREADS) raster_staged_kernel(const __grid_con
     const int band_h = min(f.BH, f.H - band_y0);
     const int band_by0 = band_y0 / 8;
     const int nblk = f.nbx * f.nby;
-    const StagedSmem s = staged_carve(smem_raw, f.C, f.plane_stride, nblk, SMOOTH);
+    const StagedSmem s = staged_carve(smem_raw, f.C, f.plane_stride, nblk, SMOOTH ? f.srec_stride : 0);
 
     const int total = min(g.count[local_scene], g.cap);
     const Rec *grecs = g.recs + (size_t)local_scene * g.cap;
@@ -180,10 +269,10 @@ __global__ void __launch_bounds__(THREADS) raster_staged_kernel(const __grid_con
     auto issue = [&](int c) {       // thread 0: stage chunk c into buffer c & 1
         const int cnt = min(CH, total - c * CH);
         const unsigned rb = (unsigned)cnt * (unsigned)sizeof(Rec), bb = (unsigned)align16((size_t)cnt * 4);
-        const unsigned sb = SMOOTH ? (unsigned)cnt * (unsigned)sizeof(SRec) : 0u;
+        const unsigned sb = SMOOTH ? (unsigned)cnt * (unsigned)f.srec_stride : 0u;
         mbar_expect_tx(&s.bar[c & 1], rb + sb + bb);
         tma_load(s.recs[c & 1], grecs + (size_t)c * CH, rb, &s.bar[c & 1]);
-        if (SMOOTH) tma_load(s.srecs[c & 1], g.srecs + (size_t)local_scene * g.cap + (size_t)c * CH, sb, &s.bar[c & 1]);
+        if (SMOOTH) tma_load(s.srecs[c & 1], g.srecs + ((size_t)local_scene * g.cap + (size_t)c * CH) * f.srec_stride, sb, &s.bar[c & 1]);
         tma_load(s.bbox[c & 1], gbbox + (size_t)c * CH, bb, &s.bar[c & 1]);
     };
     if (tid == 0 && nchunks > 0) issue(0);

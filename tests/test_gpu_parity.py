@@ -400,3 +400,26 @@ def test_config5_full_size_16384_scenes_256x256():
     assert r._native.device_status(torch.cuda.current_device()) == 0
     again = r.render()
     assert torch.equal(px, again)
+
+
+@pytest.mark.parametrize("seed,scale", [(0, 0.02), (1, 0.05), (2, 0.15)])
+def test_instance_culling_keeps_every_pixel(seed, scale):
+    """Staged path with its instance cull (bounding sphere vs clip planes and vs the pixel grid):
+    hundreds of spheres around one pixel in size, scattered inside and outside the view, must give
+    exactly the oracle's frame (the oracle culls nothing)."""
+    from pybatchrender_b200 import PBRRenderer
+    r = PBRRenderer(dict(num_scenes=6, tile_resolution=(64, 48), device="cuda"))
+    rng = np.random.default_rng(seed)
+    node = r.add_node("models/smiley", instances_per_scene=150)
+    B = node.buf_instances
+    node.set_positions(torch.tensor(rng.uniform(-9, 9, (B, 3)), dtype=torch.float32), lazy=True)
+    node.set_hprs(torch.tensor(rng.uniform(-np.pi, np.pi, (B, 3)), dtype=torch.float32), lazy=True)
+    node.set_scales(torch.tensor(rng.uniform(0.3, 2.0, (B, 1)) * scale, dtype=torch.float32))
+    node.set_colors(torch.tensor(np.concatenate([rng.uniform(0.2, 1, (B, 3)), np.ones((B, 1))], 1), dtype=torch.float32))
+    cam = r.add_camera()
+    cam.set_positions(torch.tensor([0.0, -12.0, 0.0]))
+    r.add_light()
+    r.setup_environment()
+    got = r.render()
+    _assert_same(got, oracle_render(r), f"cull seed={seed} scale={scale}")
+    assert int((got != 0).any(1).sum()) > 5
