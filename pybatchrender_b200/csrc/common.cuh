@@ -39,6 +39,8 @@ struct NodeDev {
     unsigned vert_magic;  // floor(2^32 / n_verts) + 1
 };
 
+struct Rec;
+
 struct FrameDev {
     const float *vp;
     unsigned char *out;
@@ -51,6 +53,10 @@ struct FrameDev {
     // ... and outputs of the pass that renders it (general kernel, one scene)
     unsigned long long *base_keys_out;
     unsigned char *base_flags_out;
+    // small-scene kernel: where records beyond its shared-memory slots go (see raster_warp.cuh)
+    Rec *ovf_recs;               // [n_sm * 32][W_OVF_MAXREC]
+    unsigned *ovf_masks;         // [n_sm * 32][nblk * W_OVF_MW]
+    unsigned *ovf_busy;          // [n_sm] one bit per pool entry of that SM
     int vp_scene_override;  // >= 0: use this row of vp for every scene (base pass)
     int scene_begin, scene_count;
     int W, H, C;

@@ -86,6 +86,11 @@ struct DeviceState {
     unsigned char *bgtile = nullptr;
     size_t bgtile_bytes = 0;
     unsigned bg_sig[4] = {0, 0, 0, 0};   // W, H, C, packed colour of the current contents
+    // small-scene kernel's record overflow pool: sm_count * W_POOL_PER_SM entries
+    Rec *ovf_recs = nullptr;
+    unsigned *ovf_masks = nullptr;
+    unsigned *ovf_busy = nullptr;
+    size_t ovf_mask_words = 0;           // mask words per entry currently allocated
 };
 std::mutex g_mu;
 DeviceState g_dev[64];
@@ -96,6 +101,12 @@ int device_state(int device, DeviceState **out) {
         CUDA_TRY(cudaDeviceGetAttribute(&st.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         CUDA_TRY(cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, device));
         CUDA_TRY(cudaMalloc(&st.status, sizeof(int)));
+        {   // %smid ranges over [0, %nsmid), which may exceed the SM count: size per-SM tables by it
+            nsmid_kernel<<<1, 1>>>(st.status);
+            int nsmid = 0;
+            CUDA_TRY(cudaMemcpy(&nsmid, st.status, sizeof(int), cudaMemcpyDeviceToHost));
+            if (nsmid > st.sm_count) st.sm_count = nsmid;
+        }
         CUDA_TRY(cudaMemset(st.status, 0, sizeof(int)));
         int *hp = nullptr;
         CUDA_TRY(cudaHostAlloc(&hp, sizeof(int), cudaHostAllocMapped));
@@ -389,7 +400,8 @@ static int plan_general(FrameDev &f, DeviceState *st, size_t *smem_out) {
         const int ps = (int)align16((size_t)BH * W);
         return general_smem_bytes(f.C, ps, nbx * nby, f.smooth ? f.srec_stride : 0);
     };
-    const size_t budget = 56 * 1024;
+    static const size_t budget_kb = getenv("PBR_B200_BAND_KB") ? (size_t)atoi(getenv("PBR_B200_BAND_KB")) : 56;   // band-height experiments
+    const size_t budget = budget_kb * 1024;
     int BH = H8;
     while (BH > 8 && bytes_for(BH) > budget) BH -= 8;
     if (bytes_for(BH) > (size_t)st->max_smem_optin)
@@ -555,6 +567,23 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
                 st->bg_sig[0] = (unsigned)W; st->bg_sig[1] = (unsigned)H; st->bg_sig[2] = (unsigned)f.C; st->bg_sig[3] = f.bg;
             }
             f.base_color = st->bgtile;
+        }
+        {   // record overflow pool (claimed per SM inside the kernel, see raster_warp.cuh)
+            const size_t entries = (size_t)st->sm_count * W_POOL_PER_SM;
+            if (!st->ovf_recs) {
+                CUDA_TRY(cudaMalloc(&st->ovf_recs, entries * W_OVF_MAXREC * sizeof(Rec)));
+                CUDA_TRY(cudaMalloc(&st->ovf_busy, (size_t)st->sm_count * sizeof(unsigned)));
+                CUDA_TRY(cudaMemset(st->ovf_busy, 0, (size_t)st->sm_count * sizeof(unsigned)));
+            }
+            const size_t words = (size_t)f.nbx * f.nby * W_OVF_MW;
+            if (words > st->ovf_mask_words) {
+                CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+                cudaFree(st->ovf_masks);
+                st->ovf_masks = nullptr; st->ovf_mask_words = 0;
+                CUDA_TRY(cudaMalloc(&st->ovf_masks, entries * words * sizeof(unsigned)));
+                st->ovf_mask_words = words;
+            }
+            f.ovf_recs = st->ovf_recs; f.ovf_masks = st->ovf_masks; f.ovf_busy = st->ovf_busy;
         }
         if (!st->attr_warp) {
             CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));

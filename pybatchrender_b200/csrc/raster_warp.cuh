@@ -38,10 +38,20 @@ constexpr int W_MW = 2;          // mask words per block (64 record bits)
 #define W_WARPS 4                // scenes (= warps) per CTA
 #endif
 
+// Record overflow.  A triangle clipped against the near plane and the guard band becomes a fan of up
+// to 6 triangles, so a scene of S <= W_MAXSLOT slots can need up to 6 S records; shared memory holds
+// W_MAXREC.  The rest goes to a pool entry in global memory (records + per-block masks) that the warp
+// claims on its SM for the rest of the kernel: at most 32 warps of this kernel are resident per SM
+// (64 registers x 1024 threads), so 32 entries per SM always suffice and the frame stays exact.
+constexpr int W_OVF_MW = 6;                       // mask words per block for pool records
+constexpr int W_OVF_MAXREC = 32 * W_OVF_MW;       // 192 >= 6 * W_MAXSLOT - W_MAXREC
+constexpr int W_POOL_PER_SM = 32;
+static_assert(6 * W_MAXSLOT - W_MAXREC <= W_OVF_MAXREC, "overflow pool too small for the worst case");
+
 // shared memory of one scene
 __host__ __device__ inline size_t warp_scene_bytes(int nblk) {
     return (size_t)W_MAXVERT * 32 + (size_t)W_MAXREC * sizeof(Rec) + align16((size_t)nblk * W_MW * 4) +
-           align16((size_t)nblk * 2) + 2 * W_MAXREC * 4;
+           align16((size_t)nblk * 2) + 2 * W_MAXREC * 4 + 16;
 }
 // shared memory of a CTA of `warps` scenes: scene regions + block queue + counters
 __host__ __device__ inline size_t warp_smem_bytes(int nblk, int warps) {
@@ -138,6 +148,72 @@ __device__ __forceinline__ void write_background_part(const FrameDev &f, unsigne
     for (; i < v1; i += 32) dst[i] = __ldg(src + i);
 }
 
+// One block of a scene that has records in the overflow pool: shared-memory records, then pool
+// records, then the pixel patch.  Out of line and only run by the scene's own warp, so the main
+// sweep loop carries no trace of the overflow machinery.
+__device__ __noinline__ void overflow_block(const FrameDev &f, const Rec *srecs, const unsigned *smasks, int entry,
+                                            int nblk, int packed, unsigned char *out_scene, int lane) {
+    const int bx = packed & 255, by = (packed >> 8) & 255;
+    const int HW = f.H * f.W;
+    const int px = bx * 8 + (lane & 7), py0 = by * 8 + (lane >> 3);
+    const bool ok0 = px < f.W && py0 < f.H, ok1 = px < f.W && py0 + 4 < f.H;
+    const int b = by * f.nbx + bx;
+    PixelState ps;
+    ps.k0 = ps.k1 = KEY_CLEAR;
+    if (f.base_flags != nullptr && __ldg(f.base_flags + b) != 0) {
+        ps.k0 = __ldg(f.base_keys + (size_t)b * 64 + lane);
+        ps.k1 = __ldg(f.base_keys + (size_t)b * 64 + 32 + lane);
+    }
+    ps.c0 = ps.c1 = 0u;
+    ps.ch0 = ps.ch1 = false;
+    raster_block<W_MW, false>(srecs, smasks + b * W_MW, px, py0, ok0, ok1, ps, &f);
+    raster_block<W_OVF_MW, false>(f.ovf_recs + (size_t)entry * W_OVF_MAXREC,
+                                  f.ovf_masks + ((size_t)entry * nblk + b) * W_OVF_MW, px, py0, ok0, ok1, ps, &f);
+    unsigned char *p = out_scene + py0 * f.W + px;
+    if (ps.ch0) {
+        p[0] = (unsigned char)(ps.c0 & 255u);
+        p[HW] = (unsigned char)((ps.c0 >> 8) & 255u);
+        p[2 * HW] = (unsigned char)((ps.c0 >> 16) & 255u);
+        if (f.C == 4) p[3 * HW] = (unsigned char)(ps.c0 >> 24);
+    }
+    if (ps.ch1) {
+        p += 4 * f.W;
+        p[0] = (unsigned char)(ps.c1 & 255u);
+        p[HW] = (unsigned char)((ps.c1 >> 8) & 255u);
+        p[2 * HW] = (unsigned char)((ps.c1 >> 16) & 255u);
+        if (f.C == 4) p[3 * HW] = (unsigned char)(ps.c1 >> 24);
+    }
+}
+
+// Block lists of a scene with an overflow pool entry: blocks with pool records go to the back of
+// blist (for overflow_block), the others with any record to the front (shared sweep).  A block is in
+// at most one list, so the two cannot meet.  Returns front count | back count << 16.
+__device__ __noinline__ int overflow_lists(const FrameDev &f, const unsigned *masks, unsigned short *blist, int entry,
+                                           int nblk, int lane) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int nlist = 0, novf = 0;
+#pragma unroll 1
+    for (int b0 = 0; b0 < nblk; b0 += 32) {
+        const int b = b0 + lane;
+        bool nz = false, ov = false;
+        int packed = 0;
+        if (b < nblk) {
+            const unsigned *om = f.ovf_masks + ((size_t)entry * nblk + b) * W_OVF_MW;
+#pragma unroll
+            for (int k = 0; k < W_OVF_MW; ++k) ov |= om[k] != 0u;
+            nz = !ov && (masks[b * W_MW] | masks[b * W_MW + 1]) != 0u;
+            const int by = fast_div(b, f.nbx_magic);
+            packed = (by << 8) | (b - by * f.nbx);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, nz), obal = __ballot_sync(0xffffffffu, ov);
+        if (nz) blist[nlist + __popc(bal & lt_mask)] = (unsigned short)packed;
+        if (ov) blist[nblk - 1 - novf - __popc(obal & lt_mask)] = (unsigned short)packed;
+        nlist += __popc(bal);
+        novf += __popc(obal);
+    }
+    return nlist | (novf << 16);
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(const __grid_constant__ FrameDev f) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -160,11 +236,14 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
     unsigned short *blist = reinterpret_cast<unsigned short *>(masks + align16((size_t)nblk * W_MW * 4) / 4);
     unsigned *live = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(blist) + align16((size_t)nblk * 2));
     unsigned *clipl = live + W_MAXREC;
+    int *ovf_entry = reinterpret_cast<int *>(clipl + W_MAXREC);          // pool entry of this scene once claimed
     unsigned *queue = reinterpret_cast<unsigned *>(smem_raw + (size_t)WARPS * region);   // [WARPS * nblk]
     int *qctr = reinterpret_cast<int *>(smem_raw + (size_t)WARPS * region + align16((size_t)WARPS * nblk * 4));
     if (WARPS > 1 && threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; }
 
-    int nlist = 0;
+    // blocks for the shared sweep; novf: 0 = no overflow pool entry claimed, else 1 + number of blocks
+    // that have records in the pool (swept by overflow_block after the shared sweep)
+    int nlist = 0, novf = 0;
     if (active) {
         unsigned char *out_scene = f.out + (size_t)scene * scene_bytes_out;
 
@@ -307,7 +386,9 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
 
             // ---- B3: clipped triangles -> fan triangles in the spare record slots
             if (nclip > 0) {
-                bool overflow = false;
+                int entry = -1;                          // warp-uniform
+                Rec *orecs = nullptr;
+                unsigned *omasks = nullptr;
 #pragma unroll 1
                 for (int base = 0; base < nclip; base += 32) {
                     const int j = base + lane;
@@ -348,10 +429,32 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
                     }
                     const int total = __shfl_sync(0xffffffffu, incl, 31);
                     const int start = nrec + incl - cnt;
+                    if (entry < 0 && nrec + total > W_MAXREC) {
+                        // claim a pool entry of this SM (lane 0), then clear its masks (all lanes)
+                        unsigned smid;
+                        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                        if (lane == 0) {
+                            unsigned *busy = f.ovf_busy + smid;
+                            while (entry < 0) {
+                                const unsigned free_bits = ~atomicOr(busy, 0u);
+                                if (free_bits == 0u) continue;
+                                const int bit = __ffs(free_bits) - 1;
+                                if (!(atomicOr(busy, 1u << bit) & (1u << bit))) entry = (int)smid * W_POOL_PER_SM + bit;
+                            }
+                            *ovf_entry = entry;
+                            atomicOr(f.status, DEVSTAT_WARP_OVERFLOW);
+                            *f.status_host = DEVSTAT_WARP_OVERFLOW;      // host prefers the general kernel from now on
+                        }
+                        entry = __shfl_sync(0xffffffffu, entry, 0);
+                        novf = 1;
+                        orecs = f.ovf_recs + (size_t)entry * W_OVF_MAXREC;
+                        omasks = f.ovf_masks + (size_t)entry * nblk * W_OVF_MW;
+                        for (int i = lane; i < nblk * W_OVF_MW; i += 32) omasks[i] = 0u;
+                        __syncwarp();
+                    }
 #pragma unroll 1
                     for (int k = 0; k < cnt; ++k) {
                         const int idx = start + k;
-                        if (idx >= W_MAXREC) { overflow = true; break; }
                         int X[3], Y[3];
                         float z[3];
                         const bool ok = project_vertex(f, poly[0].c, X[0], Y[0], z[0]) &&
@@ -361,34 +464,41 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
                         BBox bb;
                         if (ok && setup_snapped(f, X, Y, z, two_sided, id, 0, f.H, r, bb)) {
                             r.col = shade(f, poly[0].n, col);
-                            recs[idx] = r;
-                            bin_record<W_MW>(r, bb, idx, f.nbx, masks);
+                            if (idx < W_MAXREC) {
+                                recs[idx] = r;
+                                bin_record<W_MW>(r, bb, idx, f.nbx, masks);
+                            } else {
+                                orecs[idx - W_MAXREC] = r;
+                                bin_record<W_OVF_MW>(r, bb, idx - W_MAXREC, f.nbx, omasks);
+                            }
                         }
                     }
-                    nrec = min(nrec + total, W_MAXREC);
-                }
-                if (__any_sync(0xffffffffu, overflow) && lane == 0) {
-                    atomicOr(f.status, DEVSTAT_WARP_OVERFLOW);
-                    *f.status_host = DEVSTAT_WARP_OVERFLOW;      // host stops choosing this kernel
+                    nrec += total;
                 }
             }
             __syncwarp();     // records + masks complete; background stores ordered before patches
 
             // ---- list of this scene's non-empty blocks
             if (f.debug != 2) {
+                if (novf == 0) {
 #pragma unroll 1
-                for (int b0 = 0; b0 < nblk; b0 += 32) {
-                    const int b = b0 + lane;
-                    bool nz = false;
-                    int packed = 0;
-                    if (b < nblk) {
-                        nz = (masks[b * W_MW] | masks[b * W_MW + 1]) != 0u;
-                        const int by = fast_div(b, f.nbx_magic);
-                        packed = (by << 8) | (b - by * f.nbx);
+                    for (int b0 = 0; b0 < nblk; b0 += 32) {
+                        const int b = b0 + lane;
+                        bool nz = false;
+                        int packed = 0;
+                        if (b < nblk) {
+                            nz = (masks[b * W_MW] | masks[b * W_MW + 1]) != 0u;
+                            const int by = fast_div(b, f.nbx_magic);
+                            packed = (by << 8) | (b - by * f.nbx);
+                        }
+                        const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                        if (nz) blist[nlist + __popc(bal & lt_mask)] = (unsigned short)packed;
+                        nlist += __popc(bal);
                     }
-                    const unsigned bal = __ballot_sync(0xffffffffu, nz);
-                    if (nz) blist[nlist + __popc(bal & lt_mask)] = (unsigned short)packed;
-                    nlist += __popc(bal);
+                } else {
+                    const int both = overflow_lists(f, masks, blist, *ovf_entry, nblk, lane);
+                    nlist = both & 0xffff;
+                    novf = 1 + (both >> 16);
                 }
                 __syncwarp();
             }
@@ -457,6 +567,15 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
             p[2 * HW] = (unsigned char)((ps.c1 >> 16) & 255u);
             if (f.C == 4) p[3 * HW] = (unsigned char)(ps.c1 >> 24);
         }
+    }
+    // blocks with records in the overflow pool: swept by the scene's own warp, then the entry is released
+    if (novf > 0) {
+        const int e = *ovf_entry;
+#pragma unroll 1
+        for (int i = 0; i + 1 < novf; ++i)
+            overflow_block(f, recs, masks, e, nblk, blist[nblk - 1 - i], f.out + (size_t)scene * scene_bytes_out, lane);
+        __syncwarp();
+        if (lane == 0) atomicAnd(f.ovf_busy + e / W_POOL_PER_SM, ~(1u << (e % W_POOL_PER_SM)));
     }
 }
 

@@ -8,6 +8,12 @@ namespace pbr {
 // instance-transform kernels
 // ------------------------------------------------------------------------------------------------
 // plane c of a [C, hw] byte image = byte c of the packed colour
+__global__ void nsmid_kernel(int *out) {
+    unsigned n;
+    asm volatile("mov.u32 %0, %%nsmid;" : "=r"(n));
+    *out = (int)n;
+}
+
 __global__ void fill_planes_kernel(unsigned char *dst, int hw, int C, unsigned rgba) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < hw * C) dst[i] = (unsigned char)((rgba >> (8 * (i / hw))) & 255u);

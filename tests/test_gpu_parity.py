@@ -281,27 +281,27 @@ def test_static_layer_non_square_tiles_and_rgba():
         _assert_same(px, oracle_render(r), f"static layer {tile} C={ch}")
 
 
-def test_record_overflow_falls_back_to_the_general_kernel():
+def test_record_overflow_is_exact_and_sticky():
     """Camera inside the geometry: so many triangles are clipped into fans that the small-scene
-    kernel can run out of record slots.  It then raises the sticky status bit (also in host-mapped
-    memory) and every later frame on this device takes the general kernel, which is exact."""
+    kernel runs out of shared-memory record slots.  The surplus goes to its global overflow pool, so
+    the frame in flight is still exact; the sticky status bit (also in host-mapped memory) then
+    steers later frames on this device to the general kernel, which is exact as well."""
     dev = torch.cuda.current_device()
-    found = False
+    overflowed = 0
     for seed in range(40, 60):
-        r = many_cubes_renderer(num_scenes=16, instances=4, tile=(64, 64), device="cuda", seed=seed, spread=0.3,
+        inst = 3 if seed % 2 else 4          # 36 slots (the kernel's maximum) and 48 -> general kernel
+        r = many_cubes_renderer(num_scenes=16, instances=inst, tile=(64, 64), device="cuda", seed=seed, spread=0.3,
                                 eye=(0.0, 0.0, 0.0), two_sided=True)
         r._native.device_status(dev, clear=True)
         first = r.step()
         status = r._native.device_status(dev, clear=False)
         second = r.step()                      # general kernel if the flag was raised
         ref = oracle_render(r)
-        _assert_same(second, ref, f"after overflow check, seed {seed}")
-        if status & 1:
-            found = True
-            break
-        _assert_same(first, ref, f"no overflow, seed {seed}")
+        _assert_same(first, ref, f"frame in flight, seed {seed}, status {status}")
+        _assert_same(second, ref, f"frame after the overflow check, seed {seed}")
+        overflowed += status & 1
     r._native.device_status(dev, clear=True)   # do not leave the device in general-only mode
-    assert found, "no seed produced a record overflow (test scene needs adjusting)"
+    assert overflowed >= 3, "too few seeds produced a record overflow (test scene needs adjusting)"
 
 
 # ------------------------------------------------------------------ BASELINE configs at full size
