@@ -386,9 +386,14 @@ __device__ __forceinline__ void bin_record(const Rec &r, const BBox &bb, int t, 
 // ------------------------------------------------------------------------------------------------
 struct PixelState {
     unsigned long long k0, k1;   // (depth bits << 32) | id   -- smaller wins (LESS, ties to the earlier draw)
-    unsigned c0, c1;             // packed RGBA8 of the current winner
-    bool ch0, ch1;
+    unsigned c0, c1;             // packed RGBA8 of the current winner (valid once the key's id changed)
 };
+
+// Did a record of this sweep win the pixel?  Every triangle slot has its own id and the fan
+// triangles of one slot never cover the same sample, so "the winner changed" == "the id changed".
+__device__ __forceinline__ bool key_changed(unsigned long long key, unsigned id_before) {
+    return (unsigned)key != id_before;
+}
 
 constexpr unsigned long long KEY_CLEAR = 0x3F80000000000000ull;   // depth 1.0, id 0
 
@@ -449,8 +454,8 @@ __device__ __forceinline__ void depth_update(PixelState &ps, float f1a, float f2
     const unsigned long long ka = make_key(za, id), kc = make_key(zc, id);
     w0 = cov0 & (ka < ps.k0);
     w1 = cov1 & (kc < ps.k1);
-    ps.k0 = w0 ? ka : ps.k0; ps.c0 = w0 ? col : ps.c0; ps.ch0 |= w0;
-    ps.k1 = w1 ? kc : ps.k1; ps.c1 = w1 ? col : ps.c1; ps.ch1 |= w1;
+    ps.k0 = w0 ? ka : ps.k0; ps.c0 = w0 ? col : ps.c0;
+    ps.k1 = w1 ? kc : ps.k1; ps.c1 = w1 ? col : ps.c1;
 }
 
 // GL_REPEAT + GL_LINEAR lookup of an RGBA8 texture, fp32, texel centres at (i + 0.5) / size

@@ -200,13 +200,13 @@ __device__ __forceinline__ void general_block(const FrameDev &f, const Smem &s, 
     ps.k0 = s.ktile[b * 64 + lane];
     ps.k1 = s.ktile[b * 64 + 32 + lane];
     ps.c0 = ps.c1 = 0;
-    ps.ch0 = ps.ch1 = false;
+    const unsigned id0 = (unsigned)ps.k0, id1 = (unsigned)ps.k1;
     raster_block<MW, SMOOTH>(s.recs, s.masks + b * MW, px, py0, ok0, ok1, ps, &f, s.srecs);
-    if (ps.ch0) {
+    if (key_changed(ps.k0, id0)) {
         s.ktile[b * 64 + lane] = ps.k0;
         put_pixel(s.color, f.plane_stride, f.C, f.W, px, py0, ps.c0);
     }
-    if (ps.ch1) {
+    if (key_changed(ps.k1, id1)) {
         s.ktile[b * 64 + 32 + lane] = ps.k1;
         put_pixel(s.color, f.plane_stride, f.C, f.W, px, py1, ps.c1);
     }

@@ -342,13 +342,13 @@ __global__ void __launch_bounds__(THREADS) raster_staged_kernel(const __grid_con
             ps.k0 = s.ktile[b * 64 + lane];
             ps.k1 = s.ktile[b * 64 + 32 + lane];
             ps.c0 = ps.c1 = 0;
-            ps.ch0 = ps.ch1 = false;
+            const unsigned id0 = (unsigned)ps.k0, id1 = (unsigned)ps.k1;
             raster_block<MW, SMOOTH>(recs, s.masks + b * MW, px, py0, ok0, ok1, ps, &f, s.srecs[buf]);
-            if (ps.ch0) {
+            if (key_changed(ps.k0, id0)) {
                 s.ktile[b * 64 + lane] = ps.k0;
                 put_pixel(s.color, f.plane_stride, f.C, f.W, px, py0 - band_y0, ps.c0);
             }
-            if (ps.ch1) {
+            if (key_changed(ps.k1, id1)) {
                 s.ktile[b * 64 + 32 + lane] = ps.k1;
                 put_pixel(s.color, f.plane_stride, f.C, f.W, px, py1 - band_y0, ps.c1);
             }

@@ -165,18 +165,18 @@ __device__ __noinline__ void overflow_block(const FrameDev &f, const Rec *srecs,
         ps.k1 = __ldg(f.base_keys + (size_t)b * 64 + 32 + lane);
     }
     ps.c0 = ps.c1 = 0u;
-    ps.ch0 = ps.ch1 = false;
+    const unsigned id0 = (unsigned)ps.k0, id1 = (unsigned)ps.k1;
     raster_block<W_MW, false>(srecs, smasks + b * W_MW, px, py0, ok0, ok1, ps, &f);
     raster_block<W_OVF_MW, false>(f.ovf_recs + (size_t)entry * W_OVF_MAXREC,
                                   f.ovf_masks + ((size_t)entry * nblk + b) * W_OVF_MW, px, py0, ok0, ok1, ps, &f);
     unsigned char *p = out_scene + py0 * f.W + px;
-    if (ps.ch0) {
+    if (key_changed(ps.k0, id0)) {
         p[0] = (unsigned char)(ps.c0 & 255u);
         p[HW] = (unsigned char)((ps.c0 >> 8) & 255u);
         p[2 * HW] = (unsigned char)((ps.c0 >> 16) & 255u);
         if (f.C == 4) p[3 * HW] = (unsigned char)(ps.c0 >> 24);
     }
-    if (ps.ch1) {
+    if (key_changed(ps.k1, id1)) {
         p += 4 * f.W;
         p[0] = (unsigned char)(ps.c1 & 255u);
         p[HW] = (unsigned char)((ps.c1 >> 8) & 255u);
@@ -512,7 +512,16 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
         int qbase = 0;
         if (lane == 0 && nlist > 0) qbase = atomicAdd(&qctr[0], nlist);
         qbase = __shfl_sync(0xffffffffu, qbase, 0);
-        for (int i = lane; i < nlist; i += 32) queue[qbase + i] = ((unsigned)warp << 16) | blist[i];
+        // bit 31: the static layer covers part of the block (looked up here, one lane per item, so
+        // that the sweep does not start every item with a dependent global load)
+        for (int i = lane; i < nlist; i += 32) {
+            unsigned it = ((unsigned)warp << 16) | blist[i];
+            if (f.base_flags != nullptr) {
+                const int bb = (int)((it >> 8) & 255u) * f.nbx + (int)(it & 255u);
+                if (__ldg(f.base_flags + bb) != 0) it |= 0x80000000u;
+            }
+            queue[qbase + i] = it;
+        }
         __syncthreads();                                  // every scene of the CTA is set up and queued
     }
     const int nitems = WARPS > 1 ? qctr[0] : nlist;
@@ -532,8 +541,10 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
             i = next++;
             if (i >= nitems) break;
             item = blist[i];
+            if (f.base_flags != nullptr && __ldg(f.base_flags + (int)((item >> 8) & 255u) * f.nbx + (int)(item & 255u)) != 0)
+                item |= 0x80000000u;
         }
-        const int w = (int)(item >> 16);
+        const int w = (int)((item >> 16) & 0x7fffu);
         const int bx = (int)(item & 255u), by = (int)((item >> 8) & 255u);
         const unsigned char *sreg = smem_raw + (size_t)w * region;
         const Rec *srecs = reinterpret_cast<const Rec *>(sreg + (size_t)W_MAXVERT * 32);
@@ -545,22 +556,22 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
         const int b = by * f.nbx + bx;
         PixelState ps;
         ps.k0 = ps.k1 = KEY_CLEAR;
-        if (f.base_flags != nullptr && __ldg(f.base_flags + b) != 0) {   // static layer covers part of this block
+        if (item & 0x80000000u) {                         // static layer covers part of this block
             ps.k0 = __ldg(f.base_keys + (size_t)b * 64 + lane);
             ps.k1 = __ldg(f.base_keys + (size_t)b * 64 + 32 + lane);
         }
         ps.c0 = ps.c1 = 0u;
-        ps.ch0 = ps.ch1 = false;
+        const unsigned id0 = (unsigned)ps.k0, id1 = (unsigned)ps.k1;
         raster_block<W_MW, false>(srecs, smasks + b * W_MW, px, py0, ok0, ok1, ps, &f);
         if (f.debug == 3) continue;
         unsigned char *p = out_scene + py0 * f.W + px;
-        if (ps.ch0) {
+        if (key_changed(ps.k0, id0)) {
             p[0] = (unsigned char)(ps.c0 & 255u);
             p[HW] = (unsigned char)((ps.c0 >> 8) & 255u);
             p[2 * HW] = (unsigned char)((ps.c0 >> 16) & 255u);
             if (f.C == 4) p[3 * HW] = (unsigned char)(ps.c0 >> 24);
         }
-        if (ps.ch1) {
+        if (key_changed(ps.k1, id1)) {
             p += 4 * f.W;
             p[0] = (unsigned char)(ps.c1 & 255u);
             p[HW] = (unsigned char)((ps.c1 >> 8) & 255u);
