@@ -64,6 +64,7 @@ struct FrameDev {
     int BH, nbands;         // band height (multiple of 8) and bands per tile
     int nbx, nby;           // 8x8 blocks per band
     unsigned nbx_magic;     // floor(2^32 / nbx) + 1
+    int w_region;           // small-scene kernel: bytes of one scene's shared-memory region
     int plane_stride;       // bytes between colour planes in shared memory (multiple of 16)
     int linear;             // 1: the shared colour tile is a byte image of out[scene]
     int smooth;             // 1: some triangles are shaded per pixel (SMOOTH kernel instantiations)
@@ -134,6 +135,52 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t
 // exact x / d for x * d < 2^32 (d >= 2), via a precomputed magic = floor(2^32 / d) + 1; d == 1 -> magic 0
 __host__ inline unsigned div_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)(0x100000000ull / d) + 1u; }
 __device__ __forceinline__ int fast_div(int x, unsigned magic) { return magic ? (int)__umulhi((unsigned)x, magic) : x; }
+
+// ------------------------------------------------------------------------------------------------
+// TMA bulk copy + mbarrier (sm_90+ PTX)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy (bytes: multiple of 16, both addresses 16-byte aligned); completion is
+// signalled on the mbarrier as transaction bytes
+__device__ __forceinline__ void tma_load(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void tma_store(void *dst_gmem, const void *src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread complete: their global writes are performed
+__device__ __forceinline__ void tma_wait_all() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
 
 // ------------------------------------------------------------------------------------------------
 // math shared with the oracle (same operation order)

@@ -547,6 +547,7 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
     if (warp_eligible(ns)) {
         f.BH = H8; f.nbands = 1; f.nbx = nbx; f.nby = H8 / 8;
         f.nbx_magic = div_magic((unsigned)nbx);
+        f.w_region = (int)warp_scene_bytes(nbx * (H8 / 8));
         f.plane_stride = H * W;
         f.linear = 1;
         f.debug = (int)((d->flags >> 8) & 3u);
@@ -586,13 +587,26 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
             f.ovf_recs = st->ovf_recs; f.ovf_masks = st->ovf_masks; f.ovf_busy = st->ovf_busy;
         }
         if (!st->attr_warp) {
-            CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS_TMA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS_TMA, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             st->attr_warp = true;
         }
-        static const size_t smem_pad = getenv("PBR_B200_WARP_SMEM_PAD") ? (size_t)atoi(getenv("PBR_B200_WARP_SMEM_PAD")) : 0;   // occupancy experiments
-        const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS - 1) / W_WARPS);
-        raster_warp_kernel<W_WARPS><<<wgrid, 32 * W_WARPS, warp_smem + smem_pad, (cudaStream_t)stream>>>(f);
+        // background by TMA (7 scenes per CTA + the image in shared memory) when 4 such CTAs fit an SM
+        static const int tma_mode = getenv("PBR_B200_WARP_TMA") ? atoi(getenv("PBR_B200_WARP_TMA")) : -1;   // 0 / 1 force, else auto
+        const size_t tile_bytes = (size_t)f.C * H * W;
+        const size_t tma_smem = warp_smem_bytes(nbx * (H8 / 8), W_WARPS_TMA, tile_bytes);
+        const bool tma_ok = f.base_color != nullptr && (tile_bytes & 15) == 0 && tma_smem <= 100 * 1024;
+        const bool use_tma = tma_ok && (tma_mode == 1 || (tma_mode != 0 && tma_smem <= 56000));
+        if (use_tma) {
+            const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS_TMA - 1) / W_WARPS_TMA);
+            raster_warp_kernel<W_WARPS_TMA, true><<<wgrid, 32 * W_WARPS_TMA, tma_smem, (cudaStream_t)stream>>>(f);
+        } else {
+            static const size_t smem_pad = getenv("PBR_B200_WARP_SMEM_PAD") ? (size_t)atoi(getenv("PBR_B200_WARP_SMEM_PAD")) : 0;   // occupancy experiments
+            const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS - 1) / W_WARPS);
+            raster_warp_kernel<W_WARPS, false><<<wgrid, 32 * W_WARPS, warp_smem + smem_pad, (cudaStream_t)stream>>>(f);
+        }
         CUDA_TRY(cudaGetLastError());
         return PBR_OK;
     }

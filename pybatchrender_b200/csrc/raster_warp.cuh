@@ -53,10 +53,13 @@ __host__ __device__ inline size_t warp_scene_bytes(int nblk) {
     return (size_t)W_MAXVERT * 32 + (size_t)W_MAXREC * sizeof(Rec) + align16((size_t)nblk * W_MW * 4) +
            align16((size_t)nblk * 2) + 2 * W_MAXREC * 4 + 16;
 }
-// shared memory of a CTA of `warps` scenes: scene regions + block queue + counters
-__host__ __device__ inline size_t warp_smem_bytes(int nblk, int warps) {
-    return (size_t)warps * warp_scene_bytes(nblk) + align16((size_t)warps * nblk * 4) + 16;
+// shared memory of a CTA of `warps` scenes: scene regions + block queue + counters (+ mbarrier and the
+// background image when the background is written by TMA)
+__host__ __device__ inline size_t warp_smem_bytes(int nblk, int warps, size_t tma_tile_bytes = 0) {
+    return (size_t)warps * warp_scene_bytes(nblk) + align16((size_t)warps * nblk * 4) + 16 +
+           (tma_tile_bytes ? 16 + align16(tma_tile_bytes) : 0);
 }
+constexpr int W_WARPS_TMA = 7;      // scenes per CTA when the background goes through TMA (see kernel comment)
 
 struct WSlot {
     int ni, inst, tri;
@@ -214,7 +217,26 @@ __device__ __noinline__ int overflow_lists(const FrameDev &f, const unsigned *ma
     return nlist | (novf << 16);
 }
 
-template <int WARPS>
+// thread 0 of a TMA_BG CTA, once the image has landed in shared memory (mbarrier at qctr + 4 ints, image
+// at qctr + 8 ints): one bulk store per scene of the CTA, committed as one bulk group
+__device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int warps) {
+    mbar_wait(reinterpret_cast<unsigned long long *>(qctr + 4), 0);
+    const size_t bytes = (size_t)f.C * f.H * f.W;
+    const int first = f.scene_begin + (int)blockIdx.x * warps;
+    const int n = min(warps, f.scene_begin + f.scene_count - first);
+    for (int w = 0; w < n; ++w) tma_store(f.out + (size_t)(first + w) * bytes, qctr + 8, (unsigned)bytes);
+    tma_commit();
+}
+
+// TMA_BG: the background / static-layer image of every scene of the CTA is written by the TMA engine
+// instead of by the warps: one bulk load brings the C*H*W image (L2 resident, shared by all scenes)
+// into shared memory once per CTA, then one bulk store per scene sends it to out[scene]; thread 0
+// waits for the stores just before the CTA barrier that precedes the pixel patches.  The warps issue
+// no background instruction at all (the copy was ~9 % of their instructions and the source of the
+// lg_throttle stalls).  The image costs C*H*W bytes of shared memory per CTA, which is why this
+// variant packs 7 scenes per CTA: 4 CTAs of 7 warps keep 28 scenes per SM resident, enough for the
+// 4096-scene batch to stay one wave on 148 SMs.
+template <int WARPS, bool TMA_BG>
 __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(const __grid_constant__ FrameDev f) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -227,8 +249,8 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
     const size_t scene_bytes_out = (size_t)f.C * HW;
 
     // ---- carve shared memory: one region per scene, then the CTA's block queue
-    const size_t region = warp_scene_bytes(nblk);
-    unsigned char *my = smem_raw + (size_t)warp * region;
+    const unsigned region = (unsigned)f.w_region;       // == warp_scene_bytes(nblk), precomputed by the host
+    unsigned char *my = smem_raw + warp * region;
     float4 *clipc = reinterpret_cast<float4 *>(my);                      // [W_MAXVERT]
     int4 *proj = reinterpret_cast<int4 *>(my + (size_t)W_MAXVERT * 16);  // [W_MAXVERT]
     Rec *recs = reinterpret_cast<Rec *>(my + (size_t)W_MAXVERT * 32);
@@ -237,20 +259,30 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
     unsigned *live = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(blist) + align16((size_t)nblk * 2));
     unsigned *clipl = live + W_MAXREC;
     int *ovf_entry = reinterpret_cast<int *>(clipl + W_MAXREC);          // pool entry of this scene once claimed
-    unsigned *queue = reinterpret_cast<unsigned *>(smem_raw + (size_t)WARPS * region);   // [WARPS * nblk]
-    int *qctr = reinterpret_cast<int *>(smem_raw + (size_t)WARPS * region + align16((size_t)WARPS * nblk * 4));
+    unsigned *queue = reinterpret_cast<unsigned *>(smem_raw + WARPS * region);   // [WARPS * nblk]
+    int *qctr = reinterpret_cast<int *>(smem_raw + WARPS * region + align16((size_t)WARPS * nblk * 4));
     if (WARPS > 1 && threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; }
+    if (TMA_BG && threadIdx.x == 0) {
+        unsigned long long *bg_bar = reinterpret_cast<unsigned long long *>(qctr + 4);
+        mbar_init(bg_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bg_bar, (unsigned)scene_bytes_out);
+        tma_load(qctr + 8, f.base_color, (unsigned)scene_bytes_out, bg_bar);
+    }
 
     // blocks for the shared sweep; novf: 0 = no overflow pool entry claimed, else 1 + number of blocks
     // that have records in the pool (swept by overflow_block after the shared sweep)
     int nlist = 0, novf = 0;
+    if (TMA_BG && f.debug == 1 && threadIdx.x == 0) issue_bg_stores(f, qctr, WARPS);
     if (active) {
         unsigned char *out_scene = f.out + (size_t)scene * scene_bytes_out;
 
         // ---- 0: background
-        const bool split_bg = f.base_color != nullptr && ((f.C * HW) & 15) == 0 && f.debug != 1;
-        if (split_bg) write_background_part(f, out_scene, HW, lane, 0);
-        else write_background(f, out_scene, HW, lane);
+        const bool split_bg = !TMA_BG && f.base_color != nullptr && ((f.C * HW) & 15) == 0 && f.debug != 1;
+        if (!TMA_BG) {
+            if (split_bg) write_background_part(f, out_scene, HW, lane, 0);
+            else write_background(f, out_scene, HW, lane);
+        }
 
         if (f.debug != 1) {
             {   // masks are 8 bytes per block, region padded to 16 bytes: clear with 128-bit stores
@@ -295,6 +327,7 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
                     proj[v] = make_int4(X, Y, __float_as_int(z), flags);
                 }
             }
+            if (TMA_BG && threadIdx.x == 0) issue_bg_stores(f, qctr, WARPS);      // the load has had phase A to arrive
             __syncwarp();
 
             // setup + shade + bin one surviving triangle into record j
@@ -507,6 +540,7 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
 
     // ---- D: raster.  One (scene, block) item at a time; with several warps per CTA the items of
     // all its scenes sit in one queue so that light scenes help heavy ones.
+    if (TMA_BG && threadIdx.x == 0) tma_wait_all();      // background written before any pixel patch
     if (WARPS > 1) {
         __syncthreads();                                  // queue counters initialised
         int qbase = 0;
@@ -533,7 +567,8 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
         unsigned item;
         if (WARPS > 1) {
             i = 0;
-            if (lane == 0) i = atomicAdd(&qctr[1], 1);
+            if (lane == 0)      // plain PTX: keeps the compiler from wrapping it in warp-aggregation code
+                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(i) : "r"(smem_u32(&qctr[1])) : "memory");
             i = __shfl_sync(0xffffffffu, i, 0);
             if (i >= nitems) break;
             item = queue[i];
@@ -546,7 +581,7 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
         }
         const int w = (int)((item >> 16) & 0x7fffu);
         const int bx = (int)(item & 255u), by = (int)((item >> 8) & 255u);
-        const unsigned char *sreg = smem_raw + (size_t)w * region;
+        const unsigned char *sreg = smem_raw + w * region;
         const Rec *srecs = reinterpret_cast<const Rec *>(sreg + (size_t)W_MAXVERT * 32);
         const unsigned *smasks = reinterpret_cast<const unsigned *>(srecs + W_MAXREC);
         unsigned char *out_scene = f.out + (size_t)(f.scene_begin + (int)blockIdx.x * WARPS + w) * scene_bytes_out;
