@@ -65,6 +65,7 @@ struct FrameDev {
     int nbx, nby;           // 8x8 blocks per band
     unsigned nbx_magic;     // floor(2^32 / nbx) + 1
     int w_region;           // small-scene kernel: bytes of one scene's shared-memory region
+    int w_qctr_off;         // ... and offset of the CTA's queue counters (after the regions and the queue)
     int plane_stride;       // bytes between colour planes in shared memory (multiple of 16)
     int linear;             // 1: the shared colour tile is a byte image of out[scene]
     int smooth;             // 1: some triangles are shaded per pixel (SMOOTH kernel instantiations)

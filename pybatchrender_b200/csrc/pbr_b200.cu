@@ -548,6 +548,7 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         f.BH = H8; f.nbands = 1; f.nbx = nbx; f.nby = H8 / 8;
         f.nbx_magic = div_magic((unsigned)nbx);
         f.w_region = (int)warp_scene_bytes(nbx * (H8 / 8));
+        // w_qctr_off is set where the kernel variant (scenes per CTA) is chosen
         f.plane_stride = H * W;
         f.linear = 1;
         f.debug = (int)((d->flags >> 8) & 3u);
@@ -601,10 +602,12 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         const bool use_tma = tma_ok && (tma_mode == 1 || (tma_mode != 0 && tma_smem <= 56000));
         if (use_tma) {
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS_TMA - 1) / W_WARPS_TMA);
+            f.w_qctr_off = (int)(W_WARPS_TMA * (size_t)f.w_region + align16((size_t)W_WARPS_TMA * nbx * (H8 / 8) * 4));
             raster_warp_kernel<W_WARPS_TMA, true><<<wgrid, 32 * W_WARPS_TMA, tma_smem, (cudaStream_t)stream>>>(f);
         } else {
             static const size_t smem_pad = getenv("PBR_B200_WARP_SMEM_PAD") ? (size_t)atoi(getenv("PBR_B200_WARP_SMEM_PAD")) : 0;   // occupancy experiments
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS - 1) / W_WARPS);
+            f.w_qctr_off = (int)(W_WARPS * (size_t)f.w_region + align16((size_t)W_WARPS * nbx * (H8 / 8) * 4));
             raster_warp_kernel<W_WARPS, false><<<wgrid, 32 * W_WARPS, warp_smem + smem_pad, (cudaStream_t)stream>>>(f);
         }
         CUDA_TRY(cudaGetLastError());

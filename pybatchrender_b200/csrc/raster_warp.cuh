@@ -259,8 +259,10 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
     unsigned *live = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(blist) + align16((size_t)nblk * 2));
     unsigned *clipl = live + W_MAXREC;
     int *ovf_entry = reinterpret_cast<int *>(clipl + W_MAXREC);          // pool entry of this scene once claimed
+    unsigned char **out_slot = reinterpret_cast<unsigned char **>(ovf_entry + 2);   // out[scene], for the sweep
+    if (lane == 0) *out_slot = f.out + (size_t)scene * scene_bytes_out;
     unsigned *queue = reinterpret_cast<unsigned *>(smem_raw + WARPS * region);   // [WARPS * nblk]
-    int *qctr = reinterpret_cast<int *>(smem_raw + WARPS * region + align16((size_t)WARPS * nblk * 4));
+    int *qctr = reinterpret_cast<int *>(smem_raw + f.w_qctr_off);
     if (WARPS > 1 && threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; }
     if (TMA_BG && threadIdx.x == 0) {
         unsigned long long *bg_bar = reinterpret_cast<unsigned long long *>(qctr + 4);
@@ -586,7 +588,7 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
         const unsigned char *sreg = smem_raw + w * region;
         const Rec *srecs = reinterpret_cast<const Rec *>(sreg + (size_t)W_MAXVERT * 32);
         const unsigned *smasks = reinterpret_cast<const unsigned *>(srecs + W_MAXREC);
-        unsigned char *out_scene = f.out + (size_t)(f.scene_begin + (int)blockIdx.x * WARPS + w) * scene_bytes_out;
+        unsigned char *out_scene = *reinterpret_cast<unsigned char *const *>(sreg + region - 8);
 
         const int px = bx * 8 + lx, py0 = by * 8 + ly;
         const bool ok0 = px < f.W && py0 < f.H, ok1 = px < f.W && py0 + 4 < f.H;
