@@ -571,8 +571,10 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
             i = 0;
             // (measured on one box: popping two items per atomic 27.1 us, static round robin without any
             // atomic 27.2 us, this single pop 25.3 us -- the dynamic balance is worth its ~30 instructions)
+            // atom.inc with a bound below 2^32 - 1 stays one ATOMS.INC; ptxas rewrites a single-lane
+            // atom.add (and inc with bound 0xffffffff) into leader election + popc + ATOMS.ADD (~20 instr)
             if (lane == 0)
-                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(i) : "r"(smem_u32(&qctr[1])) : "memory");
+                asm volatile("atom.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(i) : "r"(smem_u32(&qctr[1])) : "memory");
             i = __shfl_sync(0xffffffffu, i, 0);
             if (i >= nitems) break;
             item = queue[i];
