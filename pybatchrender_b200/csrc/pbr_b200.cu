@@ -277,6 +277,25 @@ int pbr_mesh_info(pbr_mesh_t m, int32_t *n_tris, int32_t *all_flat, int32_t *dev
     return PBR_OK;
 }
 
+// Launch with programmatic stream serialisation: the kernel may begin once the preceding kernel in
+// the stream has triggered launch_dependents (only compose_kernel does; after any other kernel this
+// is an ordinary launch) and orders itself with griddepcontrol.wait.
+static cudaError_t launch_dependent(void (*kernel)(FrameDev), unsigned grid, unsigned block, size_t smem, void *stream,
+                                    const FrameDev &f) {
+    static const bool off = getenv("PBR_B200_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, f);
+}
+
 enum NodeMode { NODES_ALL = 0, NODES_SKIP_BASE = 1, NODES_SHARED_ONLY = 2 };
 
 struct NodeStats {
@@ -605,12 +624,12 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         if (use_tma) {
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS_TMA - 1) / W_WARPS_TMA);
             f.w_qctr_off = (int)(W_WARPS_TMA * (size_t)f.w_region + align16((size_t)W_WARPS_TMA * nbx * (H8 / 8) * 4));
-            raster_warp_kernel<W_WARPS_TMA, true><<<wgrid, 32 * W_WARPS_TMA, tma_smem, (cudaStream_t)stream>>>(f);
+            CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS_TMA, true>, wgrid, 32 * W_WARPS_TMA, tma_smem, stream, f));
         } else {
             static const size_t smem_pad = getenv("PBR_B200_WARP_SMEM_PAD") ? (size_t)atoi(getenv("PBR_B200_WARP_SMEM_PAD")) : 0;   // occupancy experiments
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS - 1) / W_WARPS);
             f.w_qctr_off = (int)(W_WARPS * (size_t)f.w_region + align16((size_t)W_WARPS * nbx * (H8 / 8) * 4));
-            raster_warp_kernel<W_WARPS, false><<<wgrid, 32 * W_WARPS, warp_smem + smem_pad, (cudaStream_t)stream>>>(f);
+            CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS, false>, wgrid, 32 * W_WARPS, warp_smem + smem_pad, stream, f));
         }
         CUDA_TRY(cudaGetLastError());
         return PBR_OK;

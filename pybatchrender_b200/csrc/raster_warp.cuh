@@ -294,6 +294,9 @@ __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(con
             }
 
             // ---- A: vertices
+            // (launched as a programmatic dependent: everything above overlaps the tail of the pose
+            // kernel; its matrices are read from here on.  A no-op after any other predecessor.)
+            asm volatile("griddepcontrol.wait;" ::: "memory");
             {
                 float VP[16];
                 load_mat(f.vp + (size_t)scene * 16, VP);

@@ -54,6 +54,9 @@ __device__ __forceinline__ float chan(const pbr_channel &c, int b) {
 }
 
 __global__ void compose_kernel(const __grid_constant__ PoseBatch pb) {
+    // programmatic dependent launch: the raster kernel that follows may start its prologue (background
+    // copy, mask clearing) now; it executes griddepcontrol.wait before it reads the matrices written here
+    asm volatile("griddepcontrol.launch_dependents;");
     const pbr_pose_desc &d = pb.p[blockIdx.y];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= d.n_instances) return;
