@@ -423,3 +423,29 @@ def test_instance_culling_keeps_every_pixel(seed, scale):
     got = r.render()
     _assert_same(got, oracle_render(r), f"cull seed={seed} scale={scale}")
     assert int((got != 0).any(1).sum()) > 5
+
+
+def test_small_scene_kernel_variants_agree_with_the_oracle():
+    """The small-scene kernel has two builds -- background written by the warps (<4, false>) or by TMA with
+    7 scenes per CTA (<7, true>) -- that the host picks by tile size.  Force each on tile sizes on both
+    sides of the automatic choice (the switch is read once per process, hence the subprocesses)."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    script = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {os.path.dirname(here)!r}); sys.path.insert(0, {here!r})\n"
+        "from util import cartpole_states, oracle_render\n"
+        "from pybatchrender_b200.envs.cartpole import CartPoleRenderer\n"
+        "for n, tile in ((37, (64, 64)), (19, (48, 40)), (9, (96, 72))):\n"
+        "    r = CartPoleRenderer(dict(num_scenes=n, tile_resolution=tile, device='cuda'))\n"
+        "    got = r.step(cartpole_states(n, seed=n).cuda()).cpu().numpy()\n"
+        "    assert np.array_equal(got, oracle_render(r)), (n, tile)\n"
+        "    r.static_layer = False\n"
+        "    assert np.array_equal(r.render().cpu().numpy(), oracle_render(r)), ('no static layer', n, tile)\n"
+        "print('ok')\n")
+    for mode in ("0", "1"):
+        env = dict(os.environ, PBR_B200_WARP_TMA=mode)
+        out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and out.stdout.strip().endswith("ok"), f"PBR_B200_WARP_TMA={mode}: {out.stderr[-2000:]}"
