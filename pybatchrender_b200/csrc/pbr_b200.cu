@@ -74,6 +74,9 @@ struct DeviceState {
     size_t g_srec_cap = 0;
     unsigned char *g_vis = nullptr;
     size_t g_vis_cap = 0;
+    int *g_bcount = nullptr;
+    unsigned *g_bidx = nullptr;
+    size_t g_bcount_cap = 0, g_bidx_cap = 0;
     unsigned *g_bbox = nullptr;
     int *g_count = nullptr;
     size_t g_rec_cap = 0;            // records allocated (all scenes of one launch)
@@ -461,7 +464,11 @@ static int launch_staged(FrameDev &f, DeviceState *st, void *stream) {
     const size_t cap = ((size_t)f.total_slots + (size_t)f.total_slots / 2 + 64 + 3) & ~(size_t)3;
     static const size_t budget_mb = getenv("PBR_B200_SCRATCH_MB") ? (size_t)atoll(getenv("PBR_B200_SCRATCH_MB")) : 4096;
     const bool smooth = f.smooth != 0;
-    const size_t per_scene = cap * (sizeof(Rec) + 4 + (smooth ? (size_t)f.srec_stride : 0));
+    // per-band index lists pay when a tile has several bands (each band CTA would otherwise scan
+    // all of the scene's records)
+    static const int band_lists_min = getenv("PBR_B200_BAND_LISTS_MIN") ? atoi(getenv("PBR_B200_BAND_LISTS_MIN")) : 2;
+    const bool band_lists = f.nbands >= band_lists_min;
+    const size_t per_scene = cap * (sizeof(Rec) + 4 + (smooth ? (size_t)f.srec_stride : 0) + (band_lists ? (size_t)f.nbands * 4 : 0));
     size_t per_launch = (budget_mb << 20) / per_scene;
     if (per_launch < 1) per_launch = 1;
     if (per_launch > (size_t)f.scene_count) per_launch = (size_t)f.scene_count;
@@ -487,6 +494,14 @@ static int launch_staged(FrameDev &f, DeviceState *st, void *stream) {
         CUDA_TRY(cudaMalloc(&st->g_vis, per_launch * (size_t)f.total_inst));
         st->g_vis_cap = per_launch * (size_t)f.total_inst;
     }
+    if (band_lists && (per_launch * (size_t)f.nbands > st->g_bcount_cap || per_launch * (size_t)f.nbands * cap > st->g_bidx_cap)) {
+        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+        cudaFree(st->g_bcount); cudaFree(st->g_bidx);
+        st->g_bcount = nullptr; st->g_bidx = nullptr; st->g_bcount_cap = st->g_bidx_cap = 0;
+        CUDA_TRY(cudaMalloc(&st->g_bcount, per_launch * (size_t)f.nbands * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&st->g_bidx, per_launch * (size_t)f.nbands * cap * sizeof(unsigned)));
+        st->g_bcount_cap = per_launch * (size_t)f.nbands; st->g_bidx_cap = per_launch * (size_t)f.nbands * cap;
+    }
     const size_t smem = staged_smem_bytes(f.C, f.plane_stride, f.nbx * f.nby, smooth ? f.srec_stride : 0);
     if (smem > (size_t)st->max_smem_optin) return launch_general(f, st, stream);
     if (!st->attr_staged) {
@@ -496,12 +511,15 @@ static int launch_staged(FrameDev &f, DeviceState *st, void *stream) {
     }
     StagedDev g;
     g.vis = st->g_vis;
+    g.bcount = band_lists ? st->g_bcount : nullptr;
+    g.bidx = band_lists ? st->g_bidx : nullptr;
     g.recs = st->g_recs; g.srecs = smooth ? st->g_srecs : nullptr; g.bbox = st->g_bbox; g.count = st->g_count; g.cap = (int)cap;
     const int first = f.scene_begin, last = f.scene_begin + f.scene_count;
     for (int s0 = first; s0 < last; s0 += (int)per_launch) {
         const int n = (int)((size_t)(last - s0) < per_launch ? (size_t)(last - s0) : per_launch);
         g.scene0 = s0;
         CUDA_TRY(cudaMemsetAsync(st->g_count, 0, (size_t)n * sizeof(int), (cudaStream_t)stream));
+        if (band_lists) CUDA_TRY(cudaMemsetAsync(st->g_bcount, 0, (size_t)n * f.nbands * sizeof(int), (cudaStream_t)stream));
         dim3 cgrid((unsigned)((f.total_inst + 255) / 256), (unsigned)n);
         static const bool no_cull = getenv("PBR_B200_NO_CULL") != nullptr;          // A/B timing aid
         if (no_cull) {

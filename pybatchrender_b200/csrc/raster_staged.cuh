@@ -31,6 +31,10 @@ struct StagedDev {
     unsigned *bbox;          // [scenes_in_launch][cap]  bx0 | by0 << 8 | bx1 << 16 | by1 << 24 (tile blocks)
     int *count;              // [scenes_in_launch]
     unsigned char *vis;      // [scenes_in_launch][total_inst] 1 = instance may touch a pixel (cull_kernel)
+    // per-band index lists (tiles with several bands): which records touch the band, so that a band's
+    // CTA stages only those instead of scanning the whole scene.  NULL = one list per scene.
+    int *bcount;             // [scenes_in_launch][nbands]
+    unsigned *bidx;          // [scenes_in_launch][nbands][cap] indices into the scene's records
     int cap;                 // records per scene (multiple of 4)
     int scene0;              // first scene of this launch (index into vp / out / per-scene rows)
 };
@@ -51,6 +55,14 @@ __device__ __forceinline__ void append_record(const StagedDev &g, const FrameDev
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
     g.bbox[o] = (unsigned)bb.bx0 | ((unsigned)bb.by0 << 8) | ((unsigned)bb.bx1 << 16) | ((unsigned)bb.by1 << 24);
     if (g.srecs != nullptr && (r.meta & M_SMOOTH)) write_srec(f, g.srecs + o * (size_t)f.srec_stride, vin, sg, tv);
+    if (g.bidx != nullptr) {
+        const int b0 = bb.by0 / f.nby, b1 = bb.by1 / f.nby;             // bands are f.nby block rows high
+        for (int band = b0; band <= b1; ++band) {
+            const size_t l = (size_t)local_scene * f.nbands + band;
+            const int pos = atomicAdd(&g.bcount[l], 1);                 // < cap: a record enters a band's list once
+            g.bidx[l * g.cap + pos] = (unsigned)idx;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -221,9 +233,12 @@ __global__ void __launch_bounds__(THREADS) raster_staged_kernel(const __grid_con
     const int nblk = f.nbx * f.nby;
     const StagedSmem s = staged_carve(smem_raw, f.C, f.plane_stride, nblk, SMOOTH ? f.srec_stride : 0);
 
-    const int total = min(g.count[local_scene], g.cap);
+    const bool gather = g.bidx != nullptr;
+    const size_t blist_row = (size_t)local_scene * f.nbands + band;
+    const int total = gather ? min(g.bcount[blist_row], g.cap) : min(g.count[local_scene], g.cap);
     const Rec *grecs = g.recs + (size_t)local_scene * g.cap;
     const unsigned *gbbox = g.bbox + (size_t)local_scene * g.cap;
+    const unsigned *glist = gather ? g.bidx + blist_row * g.cap : nullptr;
     const int nchunks = (total + CH - 1) / CH;
 
     if (tid == 0) {
@@ -232,16 +247,34 @@ __global__ void __launch_bounds__(THREADS) raster_staged_kernel(const __grid_con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int c) {       // thread 0: stage chunk c into buffer c & 1
+    // stage chunk c into buffer c & 1.  One list per scene: thread 0 issues three bulk copies of contiguous
+    // ranges.  Per-band lists: thread i gathers record list[c * CH + i] with its own 64-byte bulk copy
+    // (thread 0 arms the mbarrier with the total; completions that overtake it only drive the pending
+    // byte count negative for a moment, the phase cannot complete before its arrival).
+    auto issue = [&](int c) {
         const int cnt = min(CH, total - c * CH);
-        const unsigned rb = (unsigned)cnt * (unsigned)sizeof(Rec), bb = (unsigned)align16((size_t)cnt * 4);
+        const unsigned rb = (unsigned)cnt * (unsigned)sizeof(Rec);
         const unsigned sb = SMOOTH ? (unsigned)cnt * (unsigned)f.srec_stride : 0u;
-        mbar_expect_tx(&s.bar[c & 1], rb + sb + bb);
-        tma_load(s.recs[c & 1], grecs + (size_t)c * CH, rb, &s.bar[c & 1]);
-        if (SMOOTH) tma_load(s.srecs[c & 1], g.srecs + ((size_t)local_scene * g.cap + (size_t)c * CH) * f.srec_stride, sb, &s.bar[c & 1]);
-        tma_load(s.bbox[c & 1], gbbox + (size_t)c * CH, bb, &s.bar[c & 1]);
+        unsigned long long *bar = &s.bar[c & 1];
+        if (gather) {
+            if (tid == 0) mbar_expect_tx(bar, rb + sb);
+            if (tid < cnt) {
+                const unsigned ridx = glist[(size_t)c * CH + tid];
+                tma_load(&s.recs[c & 1][tid], grecs + ridx, (unsigned)sizeof(Rec), bar);
+                if (SMOOTH)
+                    tma_load(s.srecs[c & 1] + (size_t)tid * f.srec_stride,
+                             g.srecs + ((size_t)local_scene * g.cap + ridx) * f.srec_stride, (unsigned)f.srec_stride, bar);
+                s.bbox[c & 1][tid] = __ldg(gbbox + ridx);       // read back by this thread only
+            }
+        } else if (tid == 0) {
+            const unsigned bb = (unsigned)align16((size_t)cnt * 4);
+            mbar_expect_tx(bar, rb + sb + bb);
+            tma_load(s.recs[c & 1], grecs + (size_t)c * CH, rb, bar);
+            if (SMOOTH) tma_load(s.srecs[c & 1], g.srecs + ((size_t)local_scene * g.cap + (size_t)c * CH) * f.srec_stride, sb, bar);
+            tma_load(s.bbox[c & 1], gbbox + (size_t)c * CH, bb, bar);
+        }
     };
-    if (tid == 0 && nchunks > 0) issue(0);
+    if (nchunks > 0) issue(0);
 
     clear_color(f, s.color, tid, THREADS);
     {
@@ -258,7 +291,7 @@ __global__ void __launch_bounds__(THREADS) raster_staged_kernel(const __grid_con
         if (tid == 0) { s.ctr[0] = 0; s.ctr[1] = 0; }
         __syncthreads();                         // masks cleared; buffer buf^1 no longer read by anyone
         const int cnt = min(CH, total - c * CH);
-        if (tid == 0 && c + 1 < nchunks) issue(c + 1);
+        if (c + 1 < nchunks) issue(c + 1);
         // one lane per warp polls the mbarrier, then the warp reconverges: lanes leaving a spin loop
         // at different times would reach the aligned __syncthreads below diverged
         if (lane == 0) mbar_wait(&s.bar[buf], (unsigned)((c >> 1) & 1));
