@@ -26,7 +26,8 @@ def main():
             continue
         if r[0] != "":
             d = dict(zip(hdr, r))
-            lines.append((int(r[0]), r[1], int(d["Instructions Executed"] or 0), int(d["# Samples"] or 0), d))
+            num = lambda v: int(v) if v and v.lstrip("-").isdigit() else 0
+            lines.append((int(r[0]), r[1], num(d["Instructions Executed"]), num(d["# Samples"]), d))
     tot_i = sum(l[2] for l in lines) or 1
     tot_s = sum(l[3] for l in lines) or 1
     print(f"total warp instructions {tot_i}, samples {tot_s}")
@@ -36,7 +37,7 @@ def main():
     print("-- by stall samples")
     keys = [k for k in hdr if k.startswith("stall_") and "Not Issued" not in k]
     for ln, src, n, s, d in sorted(lines, key=lambda l: -l[3])[:top]:
-        st = sorted(((int(d[k] or 0), k[6:]) for k in keys), reverse=True)[:3]
+        st = sorted(((int(d[k]) if d[k] and d[k].isdigit() else 0, k[6:]) for k in keys), reverse=True)[:3]
         print(f"{ln:5d} {100.0 * s / tot_s:5.1f}% smp {100.0 * n / tot_i:5.1f}% inst  "
               f"{' '.join(f'{k}:{v}' for v, k in st if v)}  | {src.strip()[:80]}")
 
