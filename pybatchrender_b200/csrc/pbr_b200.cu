@@ -64,10 +64,10 @@ unsigned host_unorm8(float c) {
     return (unsigned)(int)w;
 }
 
-struct DeviceState {
-    int max_smem_optin = 0;
-    int sm_count = 0;
-    bool attr_general = false, attr_warp = false, attr_staged = false;
+// Buffers that a frame in flight owns until its kernels have run: one set per (device, stream), so
+// that frames issued on different streams do not share them.  (A CUDA graph that captured a frame keeps
+// using the set of its capture stream; a later, larger frame on that stream re-allocates it.)
+struct StreamScratch {
     // scratch of the geometry pre-pass: per-scene record lists (grown on demand, reused per launch)
     Rec *g_recs = nullptr;
     unsigned char *g_srecs = nullptr;
@@ -81,14 +81,21 @@ struct DeviceState {
     int *g_count = nullptr;
     size_t g_rec_cap = 0;            // records allocated (all scenes of one launch)
     size_t g_scene_cap = 0;          // scenes allocated in g_count
-    int *status = nullptr;           // device word with sticky DEVSTAT_* bits
-    volatile int *status_host = nullptr;   // host-mapped copy (pinned, zero-copy): polled without a sync
-    int *status_host_dev = nullptr;        // device alias of status_host
     // clear-colour image [C,H,W]: copy source of the small-scene kernel's background when there is
     // no static layer (one code path for both; the 12 KB tile stays in L1/L2)
     unsigned char *bgtile = nullptr;
     size_t bgtile_bytes = 0;
     unsigned bg_sig[4] = {0, 0, 0, 0};   // W, H, C, packed colour of the current contents
+};
+
+struct DeviceState {
+    int max_smem_optin = 0;
+    int sm_count = 0;
+    bool attr_general = false, attr_warp = false, attr_staged = false;
+    int *status = nullptr;           // device word with sticky DEVSTAT_* bits
+    volatile int *status_host = nullptr;   // host-mapped copy (pinned, zero-copy): polled without a sync
+    int *status_host_dev = nullptr;        // device alias of status_host
+    std::map<void *, StreamScratch> per_stream;
     // small-scene kernel's record overflow pool: sm_count * W_POOL_PER_SM entries
     Rec *ovf_recs = nullptr;
     unsigned *ovf_masks = nullptr;
@@ -461,6 +468,7 @@ static int launch_general(FrameDev &f, DeviceState *st, void *stream) {
 
 // geometry pre-pass + TMA-staged raster, in launches of as many scenes as the scratch budget holds
 static int launch_staged(FrameDev &f, DeviceState *st, void *stream) {
+    StreamScratch *ss = &st->per_stream[stream];
     const size_t cap = ((size_t)f.total_slots + (size_t)f.total_slots / 2 + 64 + 3) & ~(size_t)3;
     static const size_t budget_mb = getenv("PBR_B200_SCRATCH_MB") ? (size_t)atoll(getenv("PBR_B200_SCRATCH_MB")) : 4096;
     const bool smooth = f.smooth != 0;
@@ -473,34 +481,34 @@ static int launch_staged(FrameDev &f, DeviceState *st, void *stream) {
     if (per_launch < 1) per_launch = 1;
     if (per_launch > (size_t)f.scene_count) per_launch = (size_t)f.scene_count;
     if (per_launch > 65535) per_launch = 65535;                     // gridDim.y of the geometry kernel
-    if (per_launch * cap > st->g_rec_cap || per_launch > st->g_scene_cap || (smooth && per_launch * cap * (size_t)f.srec_stride > st->g_srec_cap)) {
+    if (per_launch * cap > ss->g_rec_cap || per_launch > ss->g_scene_cap || (smooth && per_launch * cap * (size_t)f.srec_stride > ss->g_srec_cap)) {
         CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-        cudaFree(st->g_recs); cudaFree(st->g_bbox); cudaFree(st->g_count); cudaFree(st->g_srecs);
-        st->g_recs = nullptr; st->g_bbox = nullptr; st->g_count = nullptr; st->g_srecs = nullptr;
-        st->g_rec_cap = 0; st->g_scene_cap = 0; st->g_srec_cap = 0;
-        CUDA_TRY(cudaMalloc(&st->g_recs, per_launch * cap * sizeof(Rec)));
-        CUDA_TRY(cudaMalloc(&st->g_bbox, per_launch * cap * 4 + 64));
-        CUDA_TRY(cudaMalloc(&st->g_count, per_launch * sizeof(int)));
-        st->g_rec_cap = per_launch * cap; st->g_scene_cap = per_launch;
+        cudaFree(ss->g_recs); cudaFree(ss->g_bbox); cudaFree(ss->g_count); cudaFree(ss->g_srecs);
+        ss->g_recs = nullptr; ss->g_bbox = nullptr; ss->g_count = nullptr; ss->g_srecs = nullptr;
+        ss->g_rec_cap = 0; ss->g_scene_cap = 0; ss->g_srec_cap = 0;
+        CUDA_TRY(cudaMalloc(&ss->g_recs, per_launch * cap * sizeof(Rec)));
+        CUDA_TRY(cudaMalloc(&ss->g_bbox, per_launch * cap * 4 + 64));
+        CUDA_TRY(cudaMalloc(&ss->g_count, per_launch * sizeof(int)));
+        ss->g_rec_cap = per_launch * cap; ss->g_scene_cap = per_launch;
         if (smooth) {
-            CUDA_TRY(cudaMalloc(&st->g_srecs, per_launch * cap * (size_t)f.srec_stride));
-            st->g_srec_cap = per_launch * cap * (size_t)f.srec_stride;
+            CUDA_TRY(cudaMalloc(&ss->g_srecs, per_launch * cap * (size_t)f.srec_stride));
+            ss->g_srec_cap = per_launch * cap * (size_t)f.srec_stride;
         }
     }
-    if (per_launch * (size_t)f.total_inst > st->g_vis_cap) {
+    if (per_launch * (size_t)f.total_inst > ss->g_vis_cap) {
         CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-        cudaFree(st->g_vis);
-        st->g_vis = nullptr; st->g_vis_cap = 0;
-        CUDA_TRY(cudaMalloc(&st->g_vis, per_launch * (size_t)f.total_inst));
-        st->g_vis_cap = per_launch * (size_t)f.total_inst;
+        cudaFree(ss->g_vis);
+        ss->g_vis = nullptr; ss->g_vis_cap = 0;
+        CUDA_TRY(cudaMalloc(&ss->g_vis, per_launch * (size_t)f.total_inst));
+        ss->g_vis_cap = per_launch * (size_t)f.total_inst;
     }
-    if (band_lists && (per_launch * (size_t)f.nbands > st->g_bcount_cap || per_launch * (size_t)f.nbands * cap > st->g_bidx_cap)) {
+    if (band_lists && (per_launch * (size_t)f.nbands > ss->g_bcount_cap || per_launch * (size_t)f.nbands * cap > ss->g_bidx_cap)) {
         CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-        cudaFree(st->g_bcount); cudaFree(st->g_bidx);
-        st->g_bcount = nullptr; st->g_bidx = nullptr; st->g_bcount_cap = st->g_bidx_cap = 0;
-        CUDA_TRY(cudaMalloc(&st->g_bcount, per_launch * (size_t)f.nbands * sizeof(int)));
-        CUDA_TRY(cudaMalloc(&st->g_bidx, per_launch * (size_t)f.nbands * cap * sizeof(unsigned)));
-        st->g_bcount_cap = per_launch * (size_t)f.nbands; st->g_bidx_cap = per_launch * (size_t)f.nbands * cap;
+        cudaFree(ss->g_bcount); cudaFree(ss->g_bidx);
+        ss->g_bcount = nullptr; ss->g_bidx = nullptr; ss->g_bcount_cap = ss->g_bidx_cap = 0;
+        CUDA_TRY(cudaMalloc(&ss->g_bcount, per_launch * (size_t)f.nbands * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&ss->g_bidx, per_launch * (size_t)f.nbands * cap * sizeof(unsigned)));
+        ss->g_bcount_cap = per_launch * (size_t)f.nbands; ss->g_bidx_cap = per_launch * (size_t)f.nbands * cap;
     }
     const size_t smem = staged_smem_bytes(f.C, f.plane_stride, f.nbx * f.nby, smooth ? f.srec_stride : 0);
     if (smem > (size_t)st->max_smem_optin) return launch_general(f, st, stream);
@@ -510,20 +518,20 @@ static int launch_staged(FrameDev &f, DeviceState *st, void *stream) {
         st->attr_staged = true;
     }
     StagedDev g;
-    g.vis = st->g_vis;
-    g.bcount = band_lists ? st->g_bcount : nullptr;
-    g.bidx = band_lists ? st->g_bidx : nullptr;
-    g.recs = st->g_recs; g.srecs = smooth ? st->g_srecs : nullptr; g.bbox = st->g_bbox; g.count = st->g_count; g.cap = (int)cap;
+    g.vis = ss->g_vis;
+    g.bcount = band_lists ? ss->g_bcount : nullptr;
+    g.bidx = band_lists ? ss->g_bidx : nullptr;
+    g.recs = ss->g_recs; g.srecs = smooth ? ss->g_srecs : nullptr; g.bbox = ss->g_bbox; g.count = ss->g_count; g.cap = (int)cap;
     const int first = f.scene_begin, last = f.scene_begin + f.scene_count;
     for (int s0 = first; s0 < last; s0 += (int)per_launch) {
         const int n = (int)((size_t)(last - s0) < per_launch ? (size_t)(last - s0) : per_launch);
         g.scene0 = s0;
-        CUDA_TRY(cudaMemsetAsync(st->g_count, 0, (size_t)n * sizeof(int), (cudaStream_t)stream));
-        if (band_lists) CUDA_TRY(cudaMemsetAsync(st->g_bcount, 0, (size_t)n * f.nbands * sizeof(int), (cudaStream_t)stream));
+        CUDA_TRY(cudaMemsetAsync(ss->g_count, 0, (size_t)n * sizeof(int), (cudaStream_t)stream));
+        if (band_lists) CUDA_TRY(cudaMemsetAsync(ss->g_bcount, 0, (size_t)n * f.nbands * sizeof(int), (cudaStream_t)stream));
         dim3 cgrid((unsigned)((f.total_inst + 255) / 256), (unsigned)n);
         static const bool no_cull = getenv("PBR_B200_NO_CULL") != nullptr;          // A/B timing aid
         if (no_cull) {
-            CUDA_TRY(cudaMemsetAsync(st->g_vis, 1, (size_t)n * f.total_inst, (cudaStream_t)stream));
+            CUDA_TRY(cudaMemsetAsync(ss->g_vis, 1, (size_t)n * f.total_inst, (cudaStream_t)stream));
         } else {
             cull_kernel<<<cgrid, 256, 0, (cudaStream_t)stream>>>(f, g);
             CUDA_TRY(cudaGetLastError());
@@ -555,6 +563,7 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
     if (int rc = device_state(device, &st)) return rc;
     f.status = st->status;
     f.status_host = st->status_host_dev;
+    StreamScratch *ss = &st->per_stream[stream];
 
     const int W = f.W, H = f.H;
     const int nbx = (W + 7) / 8;
@@ -593,19 +602,19 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
             f.base_color = base->color; f.base_keys = base->keys; f.base_flags = base->flags;
         } else if ((((size_t)f.C * H * W) & 15) == 0) {
             const size_t need = (size_t)f.C * H * W;
-            if (need > st->bgtile_bytes) {
+            if (need > ss->bgtile_bytes) {
                 CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-                cudaFree(st->bgtile);
-                st->bgtile = nullptr; st->bgtile_bytes = 0; st->bg_sig[0] = 0;
-                CUDA_TRY(cudaMalloc(&st->bgtile, need));
-                st->bgtile_bytes = need;
+                cudaFree(ss->bgtile);
+                ss->bgtile = nullptr; ss->bgtile_bytes = 0; ss->bg_sig[0] = 0;
+                CUDA_TRY(cudaMalloc(&ss->bgtile, need));
+                ss->bgtile_bytes = need;
             }
-            if (st->bg_sig[0] != (unsigned)W || st->bg_sig[1] != (unsigned)H || st->bg_sig[2] != (unsigned)f.C || st->bg_sig[3] != f.bg) {
-                fill_planes_kernel<<<(unsigned)((need + 255) / 256), 256, 0, (cudaStream_t)stream>>>(st->bgtile, H * W, f.C, f.bg);
+            if (ss->bg_sig[0] != (unsigned)W || ss->bg_sig[1] != (unsigned)H || ss->bg_sig[2] != (unsigned)f.C || ss->bg_sig[3] != f.bg) {
+                fill_planes_kernel<<<(unsigned)((need + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ss->bgtile, H * W, f.C, f.bg);
                 CUDA_TRY(cudaGetLastError());
-                st->bg_sig[0] = (unsigned)W; st->bg_sig[1] = (unsigned)H; st->bg_sig[2] = (unsigned)f.C; st->bg_sig[3] = f.bg;
+                ss->bg_sig[0] = (unsigned)W; ss->bg_sig[1] = (unsigned)H; ss->bg_sig[2] = (unsigned)f.C; ss->bg_sig[3] = f.bg;
             }
-            f.base_color = st->bgtile;
+            f.base_color = ss->bgtile;
         }
         {   // record overflow pool (claimed per SM inside the kernel, see raster_warp.cuh)
             const size_t entries = (size_t)st->sm_count * W_POOL_PER_SM;
@@ -616,7 +625,7 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
             }
             const size_t words = (size_t)f.nbx * f.nby * W_OVF_MW;
             if (words > st->ovf_mask_words) {
-                CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+                CUDA_TRY(cudaDeviceSynchronize());             // shared by every stream of the device
                 cudaFree(st->ovf_masks);
                 st->ovf_masks = nullptr; st->ovf_mask_words = 0;
                 CUDA_TRY(cudaMalloc(&st->ovf_masks, entries * words * sizeof(unsigned)));

@@ -449,3 +449,25 @@ def test_small_scene_kernel_variants_agree_with_the_oracle():
         env = dict(os.environ, PBR_B200_WARP_TMA=mode)
         out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=300)
         assert out.returncode == 0 and out.stdout.strip().endswith("ok"), f"PBR_B200_WARP_TMA={mode}: {out.stderr[-2000:]}"
+
+
+def test_frames_on_two_streams_do_not_share_scratch():
+    """Two large-scene frames (geometry pre-pass + staged raster, scratch record lists) enqueued back to
+    back on different CUDA streams: each stream has its own scratch, both frames equal the oracle."""
+    a = many_cubes_renderer(num_scenes=8, instances=40, tile=(96, 96), device="cuda", seed=5)
+    b = many_cubes_renderer(num_scenes=8, instances=40, tile=(96, 96), device="cuda", seed=6)
+    a.render(); b.render()                       # allocations, static data
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            pa = a.render()
+        with torch.cuda.stream(s2):
+            pb = b.render()
+        outs.append((pa, pb))
+    torch.cuda.synchronize()
+    ra, rb = oracle_render(a), oracle_render(b)
+    for pa, pb in outs:
+        _assert_same(pa, ra, "stream 1")
+        _assert_same(pb, rb, "stream 2")
