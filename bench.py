@@ -367,7 +367,7 @@ def run_ours(args):
                          "traffic_note": "dram__bytes_read+write of one isolated launch under ncu (profiles/r01k_*): "
                                          "the 50 MB of pixel writes are still dirty in the 126 MB L2 when the kernel "
                                          "ends, so DRAM sees them later; no re-reads",
-                         "kernel": "raster_warp_kernel<7, true>",
+                         "kernel": "raster_warp_kernel<14, true>",
                          "kernel_ms": raster_ms_max, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SCENE * N,
                          "peak_source": peak_src},
             "e2e": {"value": total_scenes * e2e_steps / (e2e_ms_max * 1e-3), "unit": "scene-frames/s",

@@ -636,7 +636,7 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         if (!st->attr_warp) {
             CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS_TMA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS_TMA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem_optin));
             CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS_TMA, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             st->attr_warp = true;
         }
@@ -644,10 +644,10 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         static const int tma_mode = getenv("PBR_B200_WARP_TMA") ? atoi(getenv("PBR_B200_WARP_TMA")) : -1;   // 0 / 1 force, else auto
         const size_t tile_bytes = (size_t)f.C * H * W;
         const size_t tma_smem = warp_smem_bytes(nbx * (H8 / 8), W_WARPS_TMA, tile_bytes);
-        const bool tma_ok = f.base_color != nullptr && (tile_bytes & 15) == 0 && tma_smem <= 100 * 1024;
-        // measured (profiles/README.md): a gain for 64x64 tiles (12 KB image, 4 CTAs per SM), a small loss
-        // for 84x84 (3 CTAs per SM) and for 32x32 (the copy is cheap, the 7-warp barrier is not)
-        const bool use_tma = tma_ok && (tma_mode == 1 || (tma_mode != 0 && tma_smem <= 56000 && tile_bytes >= 8192));
+        const bool tma_ok = f.base_color != nullptr && (tile_bytes & 15) == 0 && tma_smem <= (size_t)st->max_smem_optin;
+        // measured: faster for 64x64 (0.348 vs 0.302 of the roofline) and 84x84 (0.55 vs 0.52), slower for
+        // 32x32 (the copy is cheap, the wide barrier is not) and 128x128 (the image crowds out the scenes)
+        const bool use_tma = tma_ok && (tma_mode == 1 || (tma_mode != 0 && tma_smem <= 120 * 1024 && tile_bytes >= 8192));
         if (use_tma) {
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS_TMA - 1) / W_WARPS_TMA);
             f.w_qctr_off = (int)(W_WARPS_TMA * (size_t)f.w_region + align16((size_t)W_WARPS_TMA * nbx * (H8 / 8) * 4));

@@ -59,7 +59,10 @@ __host__ __device__ inline size_t warp_smem_bytes(int nblk, int warps, size_t tm
     return (size_t)warps * warp_scene_bytes(nblk) + align16((size_t)warps * nblk * 4) + 16 +
            (tma_tile_bytes ? 16 + align16(tma_tile_bytes) : 0);
 }
-constexpr int W_WARPS_TMA = 7;      // scenes per CTA when the background goes through TMA (see kernel comment)
+#ifndef PBR_W_WARPS_TMA
+#define PBR_W_WARPS_TMA 14
+#endif
+constexpr int W_WARPS_TMA = PBR_W_WARPS_TMA;      // scenes per CTA when the background goes through TMA (see kernel comment)
 
 struct WSlot {
     int ni, inst, tri;
@@ -234,8 +237,10 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 // waits for the stores just before the CTA barrier that precedes the pixel patches.  The warps issue
 // no background instruction at all (the copy was ~9 % of their instructions and the source of the
 // lg_throttle stalls).  The image costs C*H*W bytes of shared memory per CTA, which is why this
-// variant packs 7 scenes per CTA: 4 CTAs of 7 warps keep 28 scenes per SM resident, enough for the
-// 4096-scene batch to stay one wave on 148 SMs.
+// variant packs 14 scenes per CTA: 2 CTAs of 14 warps keep 28 scenes per SM resident, enough for the
+// 4096-scene batch to stay one wave on 148 SMs (measured on one box: 7 scenes x 4 CTAs 23.6 us,
+// 10 x 3 24.2, 14 x 2 22.8, 28 x 1 23.7 -- larger CTAs balance the shared sweep better and hold fewer
+// copies of the image, until the barrier spans too many warps).
 template <int WARPS, bool TMA_BG>
 __global__ void __launch_bounds__(32 * WARPS, 32 / WARPS) raster_warp_kernel(const __grid_constant__ FrameDev f) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
