@@ -6,13 +6,14 @@
 // design goals are (a) as many resident warps per SM as possible -- the per-scene shared-memory
 // footprint is ~6 KB (records, masks, parked vertices), so 28-32 scenes share an SM and the whole
 // 4096-scene batch is a single wave; (b) no wasted memory traffic: the background (or the
-// pre-rendered static layer) goes straight to out[scene] as 128-bit stores and only covered pixels
-// are patched afterwards (the lines are still dirty in L2, DRAM sees each byte once); (c) balance:
+// pre-rendered static layer) goes straight to out[scene] -- by TMA bulk stores from one shared-memory
+// copy per CTA, or as 128-bit stores by the warps -- and only covered pixels are patched afterwards
+// (the lines are still dirty in L2, DRAM sees each byte once); (c) balance:
 // scenes differ a lot in raster work, so the non-empty 8x8 blocks of the CTA's scenes go into one
 // queue that all warps of the CTA drain.
 //
 // Per warp / scene:
-//   0  background 128-bit stores of the clear colour / static layer over out[scene]
+//   0  background the clear colour / static layer image over out[scene] (TMA, or 128-bit stores)
 //   A  vertices   lanes = (instance, unique vertex): clip = VP*(M*v), outcodes, project + snap,
 //                 parked in shared memory                                        (basic.vert:24-43)
 //   B  setup      lanes = triangle slots: trivial reject / needs-clip / back-face cull from the
@@ -20,7 +21,7 @@
 //                 (basic.frag:31-38) -> 64-byte record, binned into per-8x8-block 64-bit masks
 //                 (with > 32 slots survivors are first compacted with ballots)
 //   B3 clip       lanes = triangles crossing the near plane / guard band: Sutherland-Hodgman, fan
-//                 triangles appended to the spare record slots
+//                 triangles appended to the spare record slots, then to the per-SM overflow pool
 // Per CTA:
 //   D  raster     warps pull (scene, block) items from the shared queue; every lane owns 2 pixels
 //                 of the block and keeps their (depth|id) key and colour in registers across the
