@@ -651,7 +651,7 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         if (use_tma) {
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS_TMA - 1) / W_WARPS_TMA);
             f.w_qctr_off = (int)(W_WARPS_TMA * (size_t)f.w_region + align16((size_t)W_WARPS_TMA * nbx * (H8 / 8) * 4));
-            CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS_TMA, true>, wgrid, 32 * W_WARPS_TMA, tma_smem, stream, f));
+            CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS_TMA, true>, wgrid, 32 * (W_WARPS_TMA + PBR_W_HELPERS), tma_smem, stream, f));
         } else {
             static const size_t smem_pad = getenv("PBR_B200_WARP_SMEM_PAD") ? (size_t)atoi(getenv("PBR_B200_WARP_SMEM_PAD")) : 0;   // occupancy experiments
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS - 1) / W_WARPS);
