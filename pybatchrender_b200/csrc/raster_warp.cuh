@@ -278,6 +278,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     unsigned *queue = reinterpret_cast<unsigned *>(smem_raw + WARPS * region);   // [WARPS * nblk]
     int *qctr = reinterpret_cast<int *>(smem_raw + f.w_qctr_off);
     if (WARPS > 1 && threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; }
+    if (WARPS > 1) __syncthreads();          // queue counters initialised (all warps arrive together: cheap)
     if (TMA_BG && threadIdx.x == 0) {
         unsigned long long *bg_bar = reinterpret_cast<unsigned long long *>(qctr + 4);
         mbar_init(bg_bar, 1);
@@ -561,7 +562,6 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     // all its scenes sit in one queue so that light scenes help heavy ones.
     if (TMA_BG && threadIdx.x == 0) tma_wait_all();      // background written before any pixel patch
     if (WARPS > 1) {
-        __syncthreads();                                  // queue counters initialised
         int qbase = 0;
         if (lane == 0 && nlist > 0) qbase = atomicAdd(&qctr[0], nlist);
         qbase = __shfl_sync(0xffffffffu, qbase, 0);
