@@ -366,7 +366,10 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                     xform_normal(M, n0.x, n0.y, n0.z, n);
                     r.col = shade(f, n, __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4)));
                     recs[j] = r;
-                    bin_record<W_MW>(r, bb, j, f.nbx, masks);
+                    // block box of the record, binned below with one lane per (record, block) pair
+                    live[j] = (unsigned)bb.bx0 | ((unsigned)bb.by0 << 8) | ((unsigned)bb.bx1 << 16) | ((unsigned)bb.by1 << 24);
+                } else {
+                    live[j] = 0xffffffffu;
                 }
             };
 
@@ -378,6 +381,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             int nlive = 0, nclip = 0;
             const int S = f.total_slots;
             const bool direct = S <= 32;
+            if (direct) live[lane] = 0xffffffffu;        // record index = slot: dead slots have no box
 #pragma unroll 1
             for (int base = 0; base < S; base += 32) {
                 const int s = base + lane;
@@ -436,6 +440,51 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             }
             int nrec = nlive;
             if (split_bg) write_background_part(f, out_scene, HW, lane, 2);
+
+            // ---- B2: bin.  One lane per (record, block of its box) pair instead of one lane per record
+            // looping over its box: the boxes are small and uneven (1-8 blocks), a per-record loop runs as
+            // long as the largest box while most lanes idle.
+            __syncwarp();
+#pragma unroll 1
+            for (int base = 0; base < nlive; base += 32) {
+                const int j = base + lane;
+                const unsigned pk = j < nlive ? live[j] : 0xffffffffu;
+                const int cnt = pk == 0xffffffffu ? 0
+                                                  : ((int)((pk >> 16) & 255u) - (int)(pk & 255u) + 1) *
+                                                        ((int)(pk >> 24) - (int)((pk >> 8) & 255u) + 1);
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += o;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                const int start = incl - cnt;
+#pragma unroll 1
+                for (int pb = 0; pb < total; pb += 32) {
+                    const int p = pb + lane;
+                    int lo = 0;                       // last record whose first pair index is <= p
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const int sv = __shfl_sync(0xffffffffu, start, lo + step);
+                        if (sv <= p) lo += step;
+                    }
+                    const unsigned rpk = __shfl_sync(0xffffffffu, pk, lo);
+                    const int rst = __shfl_sync(0xffffffffu, start, lo);
+                    if (p < total) {
+                        BBox bb;
+                        bb.bx0 = (int)(rpk & 255u); bb.by0 = (int)((rpk >> 8) & 255u);
+                        bb.bx1 = (int)((rpk >> 16) & 255u); bb.by1 = (int)(rpk >> 24);
+                        const int bw = bb.bx1 - bb.bx0 + 1, k = p - rst;
+                        const int yy = (int)__fdividef((float)k + 0.5f, (float)bw);     // exact: never within 1/512 of an integer
+                        const int bx = bb.bx0 + k - yy * bw, by = bb.by0 + yy;
+                        const int t = base + lo;
+                        const bool small = (bb.bx1 - bb.bx0) + (bb.by1 - bb.by0) <= 1;
+                        if (small || block_hit(recs[t], bb, bx, by))
+                            atomicOr(&masks[(by * f.nbx + bx) * W_MW + (t >> 5)], 1u << (t & 31));
+                    }
+                }
+            }
 
             // ---- B3: clipped triangles -> fan triangles in the spare record slots
             if (nclip > 0) {
