@@ -12,7 +12,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpbr_b200.so")
+# PBR_B200_LIB: another build of the same library (A/B measurements of kernel variants on one box)
+LIB_PATH = os.environ.get("PBR_B200_LIB") or os.path.join(_HERE, "csrc", "libpbr_b200.so")
 
 PBR_MAX_NODES = 24
 PBR_MESH_TWO_SIDED = 1

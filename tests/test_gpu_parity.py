@@ -438,7 +438,7 @@ def test_small_scene_kernel_variants_agree_with_the_oracle():
         f"sys.path.insert(0, {os.path.dirname(here)!r}); sys.path.insert(0, {here!r})\n"
         "from util import cartpole_states, oracle_render\n"
         "from pybatchrender_b200.envs.cartpole import CartPoleRenderer\n"
-        "for n, tile, ch in ((37, (64, 64), 3), (19, (48, 40), 3), (9, (96, 72), 3), (15, (64, 64), 4), (30, (84, 84), 3)):\n"
+        "for n, tile, ch in ((37, (64, 64), 3), (19, (48, 40), 3), (9, (96, 72), 3), (15, (64, 64), 4), (30, (84, 84), 3), (21, (128, 128), 3)):\n"
         "    r = CartPoleRenderer(dict(num_scenes=n, tile_resolution=tile, device='cuda', num_channels=ch))\n"
         "    got = r.step(cartpole_states(n, seed=n).cuda()).cpu().numpy()\n"
         "    assert np.array_equal(got, oracle_render(r)), (n, tile)\n"
