@@ -366,11 +366,13 @@ __device__ __forceinline__ bool setup_snapped(const FrameDev &f, int *X, int *Y,
     const long long spany = max((long long)ymax, ry1) - min((long long)ymin, ry0);
     const bool fast = spanx < (1ll << 30) && spany < (1ll << 30) && spanx * spany < (1ll << 29);
     if (fast) {
-        const int pax = bb.bx0 * 2048 + 128, pay = bb.by0 * 2048 + 128;
+        // biased edge value at the centre of pixel (0, 0), modulo 2^32: the raster loop adds A*px + B*py in
+        // unsigned arithmetic, and the true value at every sample it visits fits an int (|F| < 2^30 over
+        // the hull), so intermediate wrap-around is harmless and no per-record origin has to be unpacked
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const int a = (i + 1) % 3;
-            r.e[i] = dy[i] * (pax - X[a]) - dx[i] * (pay - Y[a]) + bias[i];
+            r.e[i] = (int)((unsigned)dy[i] * (unsigned)(128 - X[a]) - (unsigned)dx[i] * (unsigned)(128 - Y[a]) + (unsigned)bias[i]);
             r.e[3 + i] = dy[i] * 256;
             r.e[6 + i] = -dx[i] * 256;
         }
@@ -397,7 +399,7 @@ __device__ __forceinline__ long long slow_edge(const Rec &r, int i, int px, int 
 __device__ __forceinline__ bool block_hit(const Rec &r, const BBox &bb, int bx, int by) {
     bool hit = true;
     if (!(r.meta & M_SLOW)) {
-        const int ox = (bx - bb.bx0) * 8, oy = (by - bb.by0) * 8;
+        const int ox = bx * 8, oy = by * 8;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const int A = r.e[3 + i], B = r.e[6 + i];
@@ -475,8 +477,7 @@ struct FastCov {
 __device__ __forceinline__ FastCov fast_cover(const int4 &ea, const int4 &eb, const int4 &ec, int px, int py0,
                                               bool ok0, bool ok1) {
     const unsigned meta = (unsigned)ec.w;
-    const unsigned rx = (unsigned)px - (meta & 255u) * 8u;
-    const unsigned ry = (unsigned)py0 - ((meta >> 8) & 255u) * 8u;
+    const unsigned rx = (unsigned)px, ry = (unsigned)py0;       // record edge values are relative to pixel (0, 0)
     const int B2 = ec.x;
     const int F0 = (int)((unsigned)ea.x + (unsigned)ea.w * rx + (unsigned)eb.z * ry);
     const int F1 = (int)((unsigned)ea.y + (unsigned)eb.x * rx + (unsigned)eb.w * ry);

@@ -180,6 +180,48 @@ def test_deterministic_and_stream_ordered():
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("tile", [(64, 64), (32, 32)], ids=["tma", "warp-copy"])
+def test_back_to_back_steps_into_one_buffer_stay_ordered(tile):
+    """The pose kernel and the small-scene raster kernel are launched as programmatic dependents of
+    each other (raster(n) -> pose(n+1) -> raster(n+1): the next kernel's CTAs are scheduled while the
+    previous one drains).  Frames written back to back into ONE output buffer must not leak into each
+    other: after a burst of steps with different states -- eager and replayed from a CUDA graph -- the
+    buffer holds exactly the last state's frame."""
+    n = 4096
+    r = _cartpole(n, tile=tile)
+    states = [cartpole_states(n, seed=40 + i).cuda() for i in range(6)]
+    out = torch.empty((n, 3, tile[1], tile[0]), dtype=torch.uint8, device="cuda")
+    want = [r.step(s).clone() for s in states]
+    torch.cuda.synchronize()
+    for rounds in range(3):
+        for i, s in enumerate(states):
+            r.step(s, out=out)
+        assert torch.equal(out, want[-1]), f"eager burst {rounds}"
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        r.step(states[0], out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i, s in enumerate(states):
+            r.step(s, out=out)
+        for i in (3, 1, 4):
+            r.step(states[i], out=out)
+    for rounds in range(5):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want[4]), "graph replay"
+    # and each frame of a burst, read back by a copy enqueued right behind it
+    snaps = []
+    for i, s in enumerate(states):
+        snaps.append(r.step(s, out=out).clone())
+    torch.cuda.synchronize()
+    for i in range(len(states)):
+        assert torch.equal(snaps[i], want[i]), f"frame {i} of a burst"
+
+
 def test_full_size_properties_4096():
     """BASELINE config 2 size: size-independent properties instead of the (slow) full oracle pass --
     scene i of the big batch equals the same state rendered in a small batch at the same aspect,
