@@ -669,6 +669,20 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
     return launch_general(f, st, stream);
 }
 
+#ifdef PBR_W_TIMING
+// timing build only: copy the head of the overflow pool (where the kernel dumps its time stamps) to the host
+int pbr_debug_pool(void *dst, size_t bytes) {
+    int device = 0;
+    cudaGetDevice(&device);
+    std::lock_guard<std::mutex> lock(g_mu);
+    DeviceState *st = nullptr;
+    if (int rc = device_state(device, &st)) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(dst, st->ovf_recs, bytes, cudaMemcpyDeviceToHost));
+    return PBR_OK;
+}
+#endif
+
 int pbr_base_create(int32_t device, pbr_base_t *out) {
     if (!out) return fail(PBR_EINVAL, "pbr_base_create: out is NULL");
     pbr_base_s *b = new (std::nothrow) pbr_base_s();

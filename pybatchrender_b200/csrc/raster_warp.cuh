@@ -248,12 +248,23 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 #ifndef PBR_W_HELPERS
 #define PBR_W_HELPERS 2
 #endif
+#ifndef PBR_W_BG_HELPER
+#define PBR_W_BG_HELPER 1
+#endif
 template <int WARPS, bool TMA_BG>
 __global__ void __launch_bounds__(32 * (WARPS + (TMA_BG ? PBR_W_HELPERS : 0)), 32 / (WARPS + (TMA_BG ? PBR_W_HELPERS : 0)))
 raster_warp_kernel(const __grid_constant__ FrameDev f) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+#ifdef PBR_W_TIMING
+    unsigned long long *tdump = reinterpret_cast<unsigned long long *>(f.ovf_recs) + ((size_t)blockIdx.x * 16 + warp) * 8;
+#define W_STAMP(k) do { if (lane == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tdump[k] = t_; } } while (0)
+    W_STAMP(0);
+    if (lane == 0) { unsigned smid_; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_)); tdump[7] = smid_; }
+#else
+#define W_STAMP(k) do { } while (0)
+#endif
     const unsigned lt_mask = (1u << lane) - 1u;
     const int scene = f.scene_begin + (int)blockIdx.x * WARPS + warp;
     const bool helper = warp >= WARPS;                    // extra warps without a scene: they only sweep
@@ -279,18 +290,27 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     int *qctr = reinterpret_cast<int *>(smem_raw + f.w_qctr_off);
     if (WARPS > 1 && threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; }
     if (WARPS > 1) __syncthreads();          // queue counters initialised (all warps arrive together: cheap)
-    if (TMA_BG && threadIdx.x == 0) {
+    // The thread that drives the TMA engine: lane 0 of the first helper warp when there is one.  Issuing the
+    // CTA's bulk stores blocks the issuing thread for microseconds (time stamps: a scene warp that did it
+    // reached the sweep 3.5 us after its 13 neighbours, and the whole CTA waited for it at the barrier), so
+    // it must not be a warp that has a scene to set up.  The helper loads the image, waits for it, issues the
+    // stores and waits for them while the scene warps do geometry.  (The stores precede the
+    // programmatic-dependency wait: the pose kernel ahead of us does not touch `out`, and everything ahead
+    // of the pose kernel has completed before the pose kernel started.)
+    constexpr int BG_T = (TMA_BG && PBR_W_HELPERS > 0 && PBR_W_BG_HELPER != 0) ? WARPS * 32 : 0;
+    if (TMA_BG && threadIdx.x == BG_T) {
         unsigned long long *bg_bar = reinterpret_cast<unsigned long long *>(qctr + 4);
         mbar_init(bg_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(bg_bar, (unsigned)scene_bytes_out);
         tma_load(qctr + 8, f.base_color, (unsigned)scene_bytes_out, bg_bar);
+        if (BG_T != 0) issue_bg_stores(f, qctr, WARPS);
     }
 
     // blocks for the shared sweep; novf: 0 = no overflow pool entry claimed, else 1 + number of blocks
     // that have records in the pool (swept by overflow_block after the shared sweep)
     int nlist = 0, novf = 0;
-    if (TMA_BG && f.debug == 1 && threadIdx.x == 0) issue_bg_stores(f, qctr, WARPS);
+    if (TMA_BG && BG_T == 0 && f.debug == 1 && threadIdx.x == 0) issue_bg_stores(f, qctr, WARPS);
     if (active) {
         unsigned char *out_scene = f.out + (size_t)scene * scene_bytes_out;
 
@@ -347,7 +367,8 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                     proj[v] = make_int4(X, Y, __float_as_int(z), flags);
                 }
             }
-            if (TMA_BG && threadIdx.x == 0) issue_bg_stores(f, qctr, WARPS);      // the load has had phase A to arrive
+            W_STAMP(1);
+            if (TMA_BG && BG_T == 0 && threadIdx.x == 0) issue_bg_stores(f, qctr, WARPS);      // the load has had phase A to arrive
             __syncwarp();
 
             // setup + shade + bin one surviving triangle into record j
@@ -439,6 +460,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 nlive = S;
             }
             int nrec = nlive;
+            W_STAMP(2);
             if (split_bg) write_background_part(f, out_scene, HW, lane, 2);
 
             // ---- B2: bin.  One lane per (record, block of its box) pair instead of one lane per record
@@ -609,7 +631,10 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
 
     // ---- D: raster.  One (scene, block) item at a time; with several warps per CTA the items of
     // all its scenes sit in one queue so that light scenes help heavy ones.
-    if (TMA_BG && threadIdx.x == 0) tma_wait_all();      // background written before any pixel patch
+    W_STAMP(3);
+    if (TMA_BG && threadIdx.x == BG_T) tma_wait_all();   // background written before any pixel patch
+    if (TMA_BG && warp == BG_T / 32) __syncwarp();       // lane 0 spun on the mbarrier / the bulk group: reconverge
+    W_STAMP(4);
     if (WARPS > 1) {
         int qbase = 0;
         if (lane == 0 && nlist > 0) qbase = atomicAdd(&qctr[0], nlist);
@@ -626,6 +651,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         }
         __syncthreads();                                  // every scene of the CTA is set up and queued
     }
+    W_STAMP(5);
     const int nitems = WARPS > 1 ? qctr[0] : nlist;
     const int lx = lane & 7, ly = lane >> 3;
     int next = 0;
@@ -686,6 +712,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             if (f.C == 4) p[3 * HW] = (unsigned char)(ps.c1 >> 24);
         }
     }
+    W_STAMP(6);
     // blocks with records in the overflow pool: swept by the scene's own warp, then the entry is released
     if (novf > 0) {
         const int e = *ovf_entry;
