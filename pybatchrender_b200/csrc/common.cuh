@@ -559,13 +559,14 @@ __device__ __forceinline__ unsigned shade_pixel(const FrameDev &f, const SRec &s
 }
 
 // one record, any path.  SMOOTH: records flagged M_SMOOTH shade the pixels they win per pixel.
-template <bool SMOOTH>
+// CHECK_SLOW = false: the caller knows that none of the records is a slow-path (int64) record
+template <bool SMOOTH, bool CHECK_SLOW = true>
 __device__ __forceinline__ void raster_one(const FrameDev &f, const Rec &r, const SRec *sr, const int4 &ea,
                                            const int4 &eb, const int4 &ec, const float4 &zq, int px, int py0,
                                            bool ok0, bool ok1, PixelState &ps) {
     bool w0, w1;
     float f0a = 0.f, f1a, f2a, f0b = 0.f, f1b, f2b;
-    if (!((unsigned)ec.w & M_SLOW)) {
+    if (!CHECK_SLOW || !((unsigned)ec.w & M_SLOW)) {
         const FastCov c = fast_cover(ea, eb, ec, px, py0, ok0, ok1);
         if (!__any_sync(0xffffffffu, c.cov0 || c.cov1)) return;
         f1a = (float)c.F1; f2a = (float)c.F2; f1b = (float)c.G1; f2b = (float)c.G2;
@@ -590,7 +591,7 @@ __device__ __forceinline__ void raster_one(const FrameDev &f, const Rec &r, cons
 
 // All records of one block, in draw order.  (A two-records-per-iteration variant was measured:
 // slower -- register pressure and the wasted second evaluation on odd counts outweigh the ILP.)
-template <int MWORDS, bool SMOOTH = false>
+template <int MWORDS, bool SMOOTH = false, bool CHECK_SLOW = true>
 __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bmask, int px, int py0, bool ok0,
                                              bool ok1, PixelState &ps, const FrameDev *f = nullptr,
                                              const unsigned char *srecs = nullptr) {
@@ -607,7 +608,7 @@ __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bm
             const int4 eb = *reinterpret_cast<const int4 *>(&r.e[4]);         // A1 A2 B0 B1
             const int4 ec = *reinterpret_cast<const int4 *>(&r.e[8]);         // B2 col id meta
             const float4 zq = *reinterpret_cast<const float4 *>(&r.z0);       // z0 dz1 dz2 invA
-            raster_one<SMOOTH>(*f, r, SMOOTH ? reinterpret_cast<const SRec *>(srecs + (size_t)t * f->srec_stride) : nullptr,
+            raster_one<SMOOTH, CHECK_SLOW>(*f, r, SMOOTH ? reinterpret_cast<const SRec *>(srecs + (size_t)t * f->srec_stride) : nullptr,
                                ea, eb, ec, zq, px, py0, ok0, ok1, ps);
         }
     }

@@ -310,6 +310,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     // blocks for the shared sweep; novf: 0 = no overflow pool entry claimed, else 1 + number of blocks
     // that have records in the pool (swept by overflow_block after the shared sweep)
     int nlist = 0, novf = 0;
+    bool scene_slow = false;                 // the scene has int64 (slow-path) records: its items say so (bit 30)
     if (TMA_BG && BG_T == 0 && f.debug == 1 && threadIdx.x == 0) issue_bg_stores(f, qctr, WARPS);
     if (active) {
         unsigned char *out_scene = f.out + (size_t)scene * scene_bytes_out;
@@ -371,6 +372,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             if (TMA_BG && BG_T == 0 && threadIdx.x == 0) issue_bg_stores(f, qctr, WARPS);      // the load has had phase A to arrive
             __syncwarp();
 
+            bool my_slow = false;
             // setup + shade + bin one surviving triangle into record j
             auto setup_live = [&](const NodeDev &nd, int inst, int tri, const int4 &q0, const int4 &q1,
                                   const int4 &q2, int j) {
@@ -386,6 +388,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                     const float4 n0 = __ldg(nd.tn + 3 * tri);
                     xform_normal(M, n0.x, n0.y, n0.z, n);
                     r.col = shade(f, n, __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4)));
+                    my_slow |= (r.meta & M_SLOW) != 0u;
                     recs[j] = r;
                     // block box of the record, binned below with one lane per (record, block) pair
                     live[j] = (unsigned)bb.bx0 | ((unsigned)bb.by0 << 8) | ((unsigned)bb.bx1 << 16) | ((unsigned)bb.by1 << 24);
@@ -460,6 +463,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 nlive = S;
             }
             int nrec = nlive;
+            scene_slow = nclip > 0 || __any_sync(0xffffffffu, my_slow);     // (clipped fans: not tracked, assume so)
             W_STAMP(2);
             if (split_bg) write_background_part(f, out_scene, HW, lane, 2);
 
@@ -642,7 +646,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         // bit 31: the static layer covers part of the block (looked up here, one lane per item, so
         // that the sweep does not start every item with a dependent global load)
         for (int i = lane; i < nlist; i += 32) {
-            unsigned it = ((unsigned)warp << 16) | blist[i];
+            unsigned it = ((unsigned)warp << 16) | blist[i] | (scene_slow ? 0x40000000u : 0u);
             if (f.base_flags != nullptr) {
                 const int bb = (int)((it >> 8) & 255u) * f.nbx + (int)(it & 255u);
                 if (__ldg(f.base_flags + bb) != 0) it |= 0x80000000u;
@@ -677,7 +681,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             if (f.base_flags != nullptr && __ldg(f.base_flags + (int)((item >> 8) & 255u) * f.nbx + (int)(item & 255u)) != 0)
                 item |= 0x80000000u;
         }
-        const int w = (int)((item >> 16) & 0x7fffu);
+        const int w = (int)((item >> 16) & 0x3fffu);
         const int bx = (int)(item & 255u), by = (int)((item >> 8) & 255u);
         const unsigned char *sreg = smem_raw + w * region;
         const Rec *srecs = reinterpret_cast<const Rec *>(sreg + (size_t)W_MAXVERT * 32);
@@ -695,7 +699,10 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         }
         ps.c0 = ps.c1 = 0u;
         const unsigned id0 = (unsigned)ps.k0, id1 = (unsigned)ps.k1;
-        raster_block<W_MW, false>(srecs, smasks + b * W_MW, px, py0, ok0, ok1, ps, &f);
+        if (WARPS > 1 && !(item & 0x40000000u))
+            raster_block<W_MW, false, false>(srecs, smasks + b * W_MW, px, py0, ok0, ok1, ps, &f);
+        else
+            raster_block<W_MW, false, true>(srecs, smasks + b * W_MW, px, py0, ok0, ok1, ps, &f);
         if (f.debug == 3) continue;
         unsigned char *p = out_scene + py0 * f.W + px;
         if (key_changed(ps.k0, id0)) {
