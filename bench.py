@@ -37,7 +37,7 @@ TILE = (64, 64)
 ALGO_BYTES_PER_SCENE = 3 * 64 * 64 + 64 + 2 * (64 + 16)      # 12,512 B
 STATE_RING = 16
 OUT_RING = 4            # 4 x 50.3 MB of output > 126 MB L2, so pixel writes cannot stay cached
-NCU_DRAM_BYTES_PER_LAUNCH = 999936 + 1042688       # ncu --set full, profiles/r01n_raster_warp_ncu.txt
+NCU_DRAM_BYTES_PER_LAUNCH = 1001472 + 1627648      # ncu --set full, profiles/r01n_raster_warp_ncu.txt
 
 
 def parse():
