@@ -640,7 +640,7 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
             CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS_TMA, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             st->attr_warp = true;
         }
-        // background by TMA (7 scenes per CTA + the image in shared memory) when 4 such CTAs fit an SM
+        // background by TMA (14 scenes + 2 helper warps per CTA + the image in shared memory) when 2 such CTAs fit an SM
         static const int tma_mode = getenv("PBR_B200_WARP_TMA") ? atoi(getenv("PBR_B200_WARP_TMA")) : -1;   // 0 / 1 force, else auto
         const size_t tile_bytes = (size_t)f.C * H * W;
         const size_t tma_smem = warp_smem_bytes(nbx * (H8 / 8), W_WARPS_TMA, tile_bytes);

@@ -221,7 +221,7 @@ __device__ __noinline__ int overflow_lists(const FrameDev &f, const unsigned *ma
     return nlist | (novf << 16);
 }
 
-// thread 0 of a TMA_BG CTA, once the image has landed in shared memory (mbarrier at qctr + 4 ints, image
+// the TMA thread of a TMA_BG CTA (lane 0 of its first helper warp), once the image has landed in shared memory (mbarrier at qctr + 4 ints, image
 // at qctr + 8 ints): one bulk store per scene of the CTA, committed as one bulk group
 __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int warps) {
     mbar_wait(reinterpret_cast<unsigned long long *>(qctr + 4), 0);
@@ -234,8 +234,9 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 
 // TMA_BG: the background / static-layer image of every scene of the CTA is written by the TMA engine
 // instead of by the warps: one bulk load brings the C*H*W image (L2 resident, shared by all scenes)
-// into shared memory once per CTA, then one bulk store per scene sends it to out[scene]; thread 0
-// waits for the stores just before the CTA barrier that precedes the pixel patches.  The warps issue
+// into shared memory once per CTA, then one bulk store per scene sends it to out[scene]; the TMA
+// thread (lane 0 of the first helper warp) waits for the stores just before the CTA barrier that
+// precedes the pixel patches.  The warps issue
 // no background instruction at all (the copy was ~9 % of their instructions and the source of the
 // lg_throttle stalls).  The image costs C*H*W bytes of shared memory per CTA, which is why this
 // variant packs 14 scenes per CTA: 2 CTAs of 14 warps keep 28 scenes per SM resident, enough for the
@@ -244,7 +245,8 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 // copies of the image, until the barrier spans too many warps).
 // Helper warps: the TMA build adds two warps per CTA that own no scene and only join the shared sweep
 // (16 warps x 2 CTAs fill the SM's 1024 threads at 64 registers).  Measured on one box: 22.8 us
-// without, 22.7 with one, 22.4 with two.
+// without, 22.7 with one, 22.4 with two.  The first of them also drives the TMA engine (PBR_W_BG_HELPER;
+// with the engine driven by a scene warp: 21.5 us against 20.5).
 #ifndef PBR_W_HELPERS
 #define PBR_W_HELPERS 2
 #endif

@@ -469,7 +469,7 @@ def test_instance_culling_keeps_every_pixel(seed, scale):
 
 def test_small_scene_kernel_variants_agree_with_the_oracle():
     """The small-scene kernel has two builds -- background written by the warps (<4, false>) or by TMA with
-    7 scenes per CTA (<7, true>) -- that the host picks by tile size.  Force each on tile sizes on both
+    14 scenes per CTA (<14, true>) -- that the host picks by tile size.  Force each on tile sizes on both
     sides of the automatic choice (the switch is read once per process, hence the subprocesses)."""
     import os
     import subprocess
