@@ -140,6 +140,28 @@ def test_small_scene_with_clipping(general, seed, eye, spread):
     assert r._native.device_status(torch.cuda.current_device()) == 0
 
 
+@pytest.mark.parametrize("tile", [(80, 80), (200, 200)], ids=["tma", "warp-copy"])
+def test_small_scene_with_huge_triangles_int64_records(tile):
+    """Boxes larger than the tile (not clipped: inside the guard band, in front of the near plane) give
+    records whose edge functions do not fit an int over their hull: the int64 path.  The small-scene
+    kernel keeps that path out of its pair loop with a per-scene flag in the queue items, so scenes
+    with and without such records are mixed inside every CTA here."""
+    n = 96
+    r = many_cubes_renderer(num_scenes=n, instances=2, tile=tile, device="cuda", seed=31, spread=2.0,
+                            eye=(0.0, -14.0, 0.0))
+    node = r._pbr_nodes[0]
+    rng = np.random.default_rng(77)
+    big = rng.random(n) < 0.5
+    sc = np.where(np.repeat(big, 2), rng.uniform(5.0, 9.0, 2 * n), rng.uniform(0.4, 1.5, 2 * n))
+    node.set_scales(torch.tensor(sc.reshape(-1, 1), dtype=torch.float32))
+    px = r.step()
+    ref = oracle_render(r)
+    covered = (ref != 0).any(1).reshape(n, -1).mean(1)
+    assert covered.max() > 0.6 and covered.min() < 0.2          # some scenes filled, some nearly empty
+    _assert_same(px, ref, "huge triangles")
+    assert r._native.device_status(torch.cuda.current_device()) == 0
+
+
 def test_shared_node_many_instances():
     r = many_cubes_renderer(num_scenes=10, instances=9, tile=(64, 64), device="cuda", seed=5, shared=True)
     px = r.step()
