@@ -1,0 +1,47 @@
+"""One build of libpbr_b200.so (PBR_B200_LIB): raster kernel time on config 2 and a slice of config 4,
+checksum of the frames, parity of a prefix against the oracle."""
+import os, sys, hashlib
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import numpy as np, torch
+from pybatchrender_b200.envs.cartpole import CartPoleRenderer
+import bench
+from util import oracle_render, cartpole_states
+
+def timeit(N, tile, reps=40):
+    r = CartPoleRenderer(dict(num_scenes=N, tile_resolution=tile, device='cuda'))
+    st = [bench.cartpole_state(N, i, torch).cuda() for i in range(4)]
+    nout = max(2, int(2.5e8 // (N * 3 * tile[0] * tile[1])) + 1)
+    outs = [torch.empty((N, 3, tile[1], tile[0]), dtype=torch.uint8, device='cuda') for _ in range(nout)]
+    for i in range(5): r.step(st[i % 4], out=outs[i % nout])
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(16): r.render(out=outs[i % nout])
+    gs = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gs):
+        for i in range(16): r.step(st[i % 4], out=outs[i % nout])
+    res = []
+    for gg in (g, gs):
+        for _ in range(3): gg.replay()
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps): gg.replay()
+            e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / (reps * 16) * 1000)
+        res.append(best)
+    r.step(st[0], out=outs[0]); torch.cuda.synchronize()
+    h = hashlib.sha1(outs[0].cpu().numpy().tobytes()).hexdigest()[:12]
+    return res, h
+
+name = sys.argv[1]
+(k2, s2), h2 = timeit(4096, (64, 64))
+(k4, s4), h4 = timeit(16384, (84, 84), reps=10)
+# parity prefix
+n = 300
+r = CartPoleRenderer(dict(num_scenes=n, tile_resolution=(64, 64), device='cuda'))
+got = r.step(cartpole_states(n, seed=3).cuda()).cpu().numpy()
+ok = bool(np.array_equal(got, oracle_render(r)))
+print(f"AB {name}: cfg2 raster {k2:.2f} us step {s2:.2f} us | 84x84x16384 raster {k4:.1f} us step {s4:.1f} | sha {h2} {h4} | parity300 {ok}", flush=True)

@@ -1,0 +1,71 @@
+"""Time stamps inside raster_warp_kernel (%globaltimer per warp at phase boundaries).
+
+Build a timing library first (it dumps the stamps into the head of the overflow pool and exports pbr_debug_pool):
+    cd pybatchrender_b200/csrc && nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -fmad=false -Xcompiler -fPIC \
+        -DPBR_W_TIMING -shared -o /tmp/timing.so pbr_b200.cu -lcudart
+    python profiles/kernel_timestamps.py /tmp/timing.so
+"""
+import os, sys, ctypes
+os.environ['PBR_B200_LIB'] = os.path.abspath(sys.argv[1])      # a build with -DPBR_W_TIMING
+sys.path.insert(0, '/root/repo')
+import numpy as np, torch
+from pybatchrender_b200.envs.cartpole import CartPoleRenderer
+from pybatchrender_b200 import _native
+import bench
+N = 4096
+r = CartPoleRenderer(dict(num_scenes=N, tile_resolution=(64, 64), device='cuda'))
+st = [bench.cartpole_state(N, i, torch).cuda() for i in range(4)]
+outs = [torch.empty((N, 3, 64, 64), dtype=torch.uint8, device='cuda') for _ in range(5)]
+for i in range(20): r.step(st[i % 4], out=outs[i % 5])
+torch.cuda.synchronize()
+lib = ctypes.CDLL(os.environ['PBR_B200_LIB'])
+nc = (N + 13) // 14
+buf = np.zeros((nc, 16, 8), dtype=np.uint64)
+rc = lib.pbr_debug_pool(buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(buf.nbytes))
+assert rc == 0
+t = buf[:, :, :7].astype(np.int64)
+t0 = t[:, :, 0].min()
+rel = (t - t0) / 1000.0
+names = ['entry', 'after A (vertices)', 'after setup', 'before tma wait/queue', 'after tma wait', 'after barrier', 'sweep done']
+scene_w = slice(0, 14)
+for k, nm in enumerate(names):
+    w = scene_w if k in (1, 2) else slice(0, 16)
+    v = rel[:, w, k]
+    print(f"{nm:26s} mean {v.mean():6.2f}  p10 {np.percentile(v,10):6.2f}  p50 {np.percentile(v,50):6.2f}  p90 {np.percentile(v,90):6.2f}  max {v.max():6.2f} us")
+# per-SM end time
+sm = buf[:, 0, 7].astype(int)
+end = rel[:, :, 6].max(1)
+per_sm = {}
+for s_, e in zip(sm, end): per_sm[s_] = max(per_sm.get(s_, 0), e)
+e = np.array(list(per_sm.values()))
+print('per-SM end: mean %.2f min %.2f max %.2f' % (e.mean(), e.min(), e.max()), 'SMs', len(e))
+# barrier skew within CTA: after barrier - own arrival
+skew = rel[:, :14, 5] - rel[:, :14, 3]
+print('barrier wait per scene warp: mean %.2f p90 %.2f max %.2f' % (skew.mean(), np.percentile(skew, 90), skew.max()))
+sw = rel[:, :, 6] - rel[:, :, 5]
+print('sweep duration per warp: mean %.2f p10 %.2f p90 %.2f' % (sw.mean(), np.percentile(sw, 10), np.percentile(sw, 90)))
+cta_end = rel[:, :, 6].max(1); cta_first = rel[:, :, 6].min(1)
+print('sweep end skew within CTA: mean %.2f' % (cta_end - cta_first).mean())
+bar = rel[:, :, 5].max(1)
+order = np.argsort(-bar)
+print('CTAs with barrier release > 8 us:', int((bar > 8).sum()), 'of', nc, '; > 7 us:', int((bar > 7).sum()))
+for c in order[:8]:
+    a = rel[c, :14, 1]; s2 = rel[c, :14, 2]; q = rel[c, :14, 3]
+    print(f" cta {c} sm {sm[c]} barrier {bar[c]:.2f} end {cta_end[c]:.2f}  slowest warp: afterA {a.max():.2f} setup {s2.max():.2f} queue {q.max():.2f} (median queue {np.median(q):.2f})")
+late = np.argsort(-cta_end)[:8]
+for c in late:
+    print(f" late cta {c} sm {sm[c]} barrier {bar[c]:.2f} end {cta_end[c]:.2f}")
+print('corr(barrier, end) = %.2f' % np.corrcoef(bar, cta_end)[0, 1])
+# how long after the barrier does the CTA run
+print('sweep span per CTA (end - barrier): mean %.2f p10 %.2f p90 %.2f max %.2f' % ((cta_end - bar).mean(), np.percentile(cta_end - bar, 10), np.percentile(cta_end - bar, 90), (cta_end - bar).max()))
+print('per warp index (mean over CTAs): afterA, setup, queue, sweepdone')
+for w in range(16):
+    v = rel[:-1, w, :]
+    print(f"  warp {w:2d}: A {v[:,1].mean():6.2f} setup {v[:,2].mean():6.2f} queue {v[:,3].mean():6.2f} barrier {v[:,5].mean():6.2f} done {v[:,6].mean():6.2f}")
+d = (rel[:-1, :14, 2] - rel[:-1, :14, 1]).ravel()
+print('setup - afterA histogram (us):', np.histogram(d, bins=[0,1,2,3,4,5,6,7,8,12])[0].tolist())
+d = (rel[:-1, :14, 3] - rel[:-1, :14, 2]).ravel()
+print('queue - setup histogram (us):', np.histogram(d, bins=[0,0.5,1,1.5,2,3,4,5,8])[0].tolist())
+c = 100
+print('cta 100 per warp setup-A:', np.round(rel[c, :14, 2] - rel[c, :14, 1], 2).tolist())
+print('cta 100 per warp queue-setup:', np.round(rel[c, :14, 3] - rel[c, :14, 2], 2).tolist())
