@@ -57,6 +57,7 @@ struct FrameDev {
     Rec *ovf_recs;               // [n_sm * 32][W_OVF_MAXREC]
     unsigned *ovf_masks;         // [n_sm * 32][nblk * W_OVF_MW]
     unsigned *ovf_busy;          // [n_sm] one bit per pool entry of that SM
+    unsigned *bg_ticket, *bg_done;   // [n_sm] each: order of the CTAs' bulk-store phases on an SM (PBR_W_BG_SERIAL)
     int vp_scene_override;  // >= 0: use this row of vp for every scene (base pass)
     int scene_begin, scene_count;
     int W, H, C;

@@ -620,8 +620,8 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
             const size_t entries = (size_t)st->sm_count * W_POOL_PER_SM;
             if (!st->ovf_recs) {
                 CUDA_TRY(cudaMalloc(&st->ovf_recs, entries * W_OVF_MAXREC * sizeof(Rec)));
-                CUDA_TRY(cudaMalloc(&st->ovf_busy, (size_t)st->sm_count * sizeof(unsigned)));
-                CUDA_TRY(cudaMemset(st->ovf_busy, 0, (size_t)st->sm_count * sizeof(unsigned)));
+                CUDA_TRY(cudaMalloc(&st->ovf_busy, 3 * (size_t)st->sm_count * sizeof(unsigned)));     // busy bits, tickets, done counts
+                CUDA_TRY(cudaMemset(st->ovf_busy, 0, 3 * (size_t)st->sm_count * sizeof(unsigned)));
             }
             const size_t words = (size_t)f.nbx * f.nby * W_OVF_MW;
             if (words > st->ovf_mask_words) {
@@ -632,6 +632,7 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
                 st->ovf_mask_words = words;
             }
             f.ovf_recs = st->ovf_recs; f.ovf_masks = st->ovf_masks; f.ovf_busy = st->ovf_busy;
+            f.bg_ticket = st->ovf_busy + st->sm_count; f.bg_done = st->ovf_busy + 2 * st->sm_count;
         }
         if (!st->attr_warp) {
             CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
