@@ -265,6 +265,13 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 #ifndef PBR_W_BG_SERIAL
 #define PBR_W_BG_SERIAL 2
 #endif
+// The barrier before the sweep only waits for the geometry of the CTA's scenes; the CTA's bulk stores are
+// waited for by the TMA thread *after* it, which then raises a flag (qctr[3]).  A sweeping warp evaluates
+// its first item and looks at the flag just before its first pixel patch: the CTA whose turn at the write
+// path comes second does one item per warp of useful work while its stores drain.
+#ifndef PBR_W_LATE_WAIT
+#define PBR_W_LATE_WAIT 1
+#endif
 template <int WARPS, bool TMA_BG>
 __global__ void __launch_bounds__(32 * (WARPS + (TMA_BG ? PBR_W_HELPERS : 0)), 32 / (WARPS + (TMA_BG ? PBR_W_HELPERS : 0)))
 raster_warp_kernel(const __grid_constant__ FrameDev f) {
@@ -302,7 +309,8 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     if (lane == 0 && !helper) *out_slot = f.out + (size_t)scene * scene_bytes_out;
     unsigned *queue = reinterpret_cast<unsigned *>(smem_raw + WARPS * region);   // [WARPS * nblk]
     int *qctr = reinterpret_cast<int *>(smem_raw + f.w_qctr_off);
-    if (WARPS > 1 && threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; }
+    constexpr bool LATE_WAIT = TMA_BG && PBR_W_LATE_WAIT != 0;
+    if (WARPS > 1 && threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; qctr[3] = 0; }
     if (WARPS > 1) __syncthreads();          // queue counters initialised (all warps arrive together: cheap)
     // The thread that drives the TMA engine: lane 0 of the first helper warp when there is one.  Issuing the
     // CTA's bulk stores blocks the issuing thread for microseconds (time stamps: a scene warp that did it
@@ -661,7 +669,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     // ---- D: raster.  One (scene, block) item at a time; with several warps per CTA the items of
     // all its scenes sit in one queue so that light scenes help heavy ones.
     W_STAMP(3);
-    if (TMA_BG && threadIdx.x == BG_T) {
+    if (TMA_BG && !LATE_WAIT && threadIdx.x == BG_T) {
         tma_wait_all();                                  // background written before any pixel patch
         if (PBR_W_BG_SERIAL == 1 && BG_T != 0) atomicAdd(f.bg_done + bg_sm, 1u);      // next CTA of this SM: your turn
     }
@@ -684,6 +692,16 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         __syncthreads();                                  // every scene of the CTA is set up and queued
     }
     W_STAMP(5);
+    bool stores_done = !LATE_WAIT;                        // this warp has seen the CTA's bulk stores complete
+    if (LATE_WAIT) {
+        if (threadIdx.x == BG_T) {
+            tma_wait_all();
+            if (PBR_W_BG_SERIAL == 1 && BG_T != 0) atomicAdd(f.bg_done + bg_sm, 1u);
+            __threadfence_block();
+            *reinterpret_cast<volatile int *>(&qctr[3]) = 1;
+        }
+        if (warp == BG_T / 32) { __syncwarp(); stores_done = true; }
+    }
     const int nitems = WARPS > 1 ? qctr[0] : nlist;
     const int lx = lane & 7, ly = lane >> 3;
     int next = 0;
@@ -732,6 +750,13 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         else
             raster_block<W_MW, false, true>(srecs, smasks + b * W_MW, px, py0, ok0, ok1, ps, &f);
         if (f.debug == 3) continue;
+        if (LATE_WAIT && !stores_done) {                  // first patch of this warp: the background has to be there
+            if (lane == 0)
+                while (*reinterpret_cast<volatile int *>(&qctr[3]) == 0) __nanosleep(40);
+            __syncwarp();
+            __threadfence_block();
+            stores_done = true;
+        }
         unsigned char *p = out_scene + py0 * f.W + px;
         if (key_changed(ps.k0, id0)) {
             p[0] = (unsigned char)(ps.c0 & 255u);
@@ -750,6 +775,12 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     W_STAMP(6);
     // blocks with records in the overflow pool: swept by the scene's own warp, then the entry is released
     if (novf > 0) {
+        if (LATE_WAIT && !stores_done) {
+            if (lane == 0)
+                while (*reinterpret_cast<volatile int *>(&qctr[3]) == 0) __nanosleep(40);
+            __syncwarp();
+            __threadfence_block();
+        }
         const int e = *ovf_entry;
 #pragma unroll 1
         for (int i = 0; i + 1 < novf; ++i)
