@@ -37,9 +37,9 @@ if ROOT not in sys.path:
 SCENES_PER_GPU = 4096
 TILE = (64, 64)
 ALGO_BYTES_PER_SCENE = 3 * 64 * 64 + 64 + 2 * (64 + 16)      # 12,512 B
-NCU_DRAM_BYTES_PER_LAUNCH = 1003520 + 1705472      # ncu --set full, profiles/r01p_raster_warp_ncu.txt
+STATE_RING = 16
 OUT_RING = 4            # 4 x 50.3 MB of output > 126 MB L2, so pixel writes cannot stay cached
-NCU_DRAM_BYTES_PER_LAUNCH = 1001472 + 1627648      # ncu --set full, profiles/r01n_raster_warp_ncu.txt
+NCU_DRAM_BYTES_PER_LAUNCH = 1003520 + 1705472      # ncu --set full, profiles/r01p_raster_warp_ncu.txt
 
 
 def parse():

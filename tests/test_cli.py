@@ -31,3 +31,24 @@ def test_render_run_and_gif(tmp_path):
     assert out["scenes"] == 64 and any(f.endswith(".png") for f in os.listdir(tmp_path))
     g = cli.run(cli.parse_args(["--num-scenes", "16", "--gif", "--gif-steps", "6", "--save-dir", str(tmp_path)]))
     assert os.path.getsize(g["gif"]) > 1000
+
+
+def test_bench_module_constants_exist():
+    """bench.py's GPU arm cannot run here; at least every module-level constant its functions read must
+    be defined (a constant once disappeared in an edit and only the GPU box noticed)."""
+    import ast
+    import builtins
+    import importlib
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    bench = importlib.import_module("bench")
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+    local = {"K", "W", "N"}                      # locals of run_ours
+    missing = {n.id for n in ast.walk(tree)
+               if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load) and n.id.isupper() and len(n.id) > 1
+               and not hasattr(bench, n.id) and not hasattr(builtins, n.id) and n.id not in local}
+    assert not missing, missing
+    assert bench.STATE_RING >= 1 and bench.OUT_RING * bench.SCENES_PER_GPU * 3 * 64 * 64 > 126e6
