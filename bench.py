@@ -39,7 +39,7 @@ TILE = (64, 64)
 ALGO_BYTES_PER_SCENE = 3 * 64 * 64 + 64 + 2 * (64 + 16)      # 12,512 B
 STATE_RING = 16
 OUT_RING = 4            # 4 x 50.3 MB of output > 126 MB L2, so pixel writes cannot stay cached
-NCU_DRAM_BYTES_PER_LAUNCH = 1003520 + 1705472      # ncu --set full, profiles/r01p_raster_warp_ncu.txt
+NCU_DRAM_BYTES_PER_LAUNCH = 1003008 + 1779712      # ncu --set full, profiles/r01q_raster_warp_ncu.txt
 
 
 def parse():
@@ -404,7 +404,7 @@ def run_ours(args):
                        "launch": f"CUDA graphs of {STATE_RING} steps; raster kernel as a programmatic dependent of the pose kernel"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_note": "dram__bytes_read+write of one isolated launch under ncu (profiles/r01p_*): "
+                         "traffic_note": "dram__bytes_read+write of one isolated launch under ncu (profiles/r01q_*): "
                                          "the 50 MB of pixel writes are still dirty in the 126 MB L2 when the kernel "
                                          "ends, so DRAM sees them later; no re-reads",
                          "kernel": "raster_warp_kernel<14, true>",
