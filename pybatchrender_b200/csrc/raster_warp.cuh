@@ -12,8 +12,11 @@
 // scenes differ a lot in raster work, so the non-empty 8x8 blocks of the CTA's scenes go into one
 // queue that all warps of the CTA drain.
 //
+// Per CTA (TMA build): lane 0 of the first helper warp loads the background image into shared memory and,
+// when its CTA's turn on this SM has come, issues one bulk store per scene; it waits for them behind the
+// pre-sweep barrier.
 // Per warp / scene:
-//   0  background the clear colour / static layer image over out[scene] (TMA, or 128-bit stores)
+//   0  background the clear colour / static layer image over out[scene] (128-bit stores; TMA build: none)
 //   A  vertices   lanes = (instance, unique vertex): clip = VP*(M*v), outcodes, project + snap,
 //                 parked in shared memory                                        (basic.vert:24-43)
 //   B  setup      lanes = triangle slots: trivial reject / needs-clip / back-face cull from the
@@ -236,8 +239,9 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 // TMA_BG: the background / static-layer image of every scene of the CTA is written by the TMA engine
 // instead of by the warps: one bulk load brings the C*H*W image (L2 resident, shared by all scenes)
 // into shared memory once per CTA, then one bulk store per scene sends it to out[scene]; the TMA
-// thread (lane 0 of the first helper warp) waits for the stores just before the CTA barrier that
-// precedes the pixel patches.  The warps issue
+// thread (lane 0 of the first helper warp) waits for the stores behind the CTA barrier that precedes
+// the sweep and raises a flag that every warp checks before its first pixel patch (PBR_W_LATE_WAIT);
+// the CTAs of an SM take turns at issuing their stores (PBR_W_BG_SERIAL).  The warps issue
 // no background instruction at all (the copy was ~9 % of their instructions and the source of the
 // lg_throttle stalls).  The image costs C*H*W bytes of shared memory per CTA, which is why this
 // variant packs 14 scenes per CTA: 2 CTAs of 14 warps keep 28 scenes per SM resident, enough for the
