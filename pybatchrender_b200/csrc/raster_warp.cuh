@@ -702,7 +702,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             tma_wait_all();
             if (PBR_W_BG_SERIAL == 1 && BG_T != 0) atomicAdd(f.bg_done + bg_sm, 1u);
             __threadfence_block();
-            *reinterpret_cast<volatile int *>(&qctr[3]) = 1;
+            atomicExch(&qctr[3], 1);                      // (atomics on both sides: a flag, not a data race)
         }
         if (warp == BG_T / 32) { __syncwarp(); stores_done = true; }
     }
@@ -756,7 +756,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         if (f.debug == 3) continue;
         if (LATE_WAIT && !stores_done) {                  // first patch of this warp: the background has to be there
             if (lane == 0)
-                while (*reinterpret_cast<volatile int *>(&qctr[3]) == 0) __nanosleep(40);
+                while (atomicAdd(&qctr[3], 0) == 0) __nanosleep(40);
             __syncwarp();
             __threadfence_block();
             stores_done = true;
@@ -781,7 +781,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     if (novf > 0) {
         if (LATE_WAIT && !stores_done) {
             if (lane == 0)
-                while (*reinterpret_cast<volatile int *>(&qctr[3]) == 0) __nanosleep(40);
+                while (atomicAdd(&qctr[3], 0) == 0) __nanosleep(40);
             __syncwarp();
             __threadfence_block();
         }
