@@ -21,13 +21,14 @@
 #ifndef PBR_B200_H
 #define PBR_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define PBR_B200_VERSION 100            /* major*10000 + minor*100 + patch */
+#define PBR_B200_VERSION 101            /* major*10000 + minor*100 + patch */
 #define PBR_MAX_NODES 24                /* nodes per frame (kernel parameter space) */
 #define PBR_MAX_TILE 2048               /* max tile width / height in pixels */
 
@@ -36,13 +37,36 @@ typedef enum {
     PBR_EINVAL = -1,        /* bad argument (null pointer, misaligned buffer, bad size) */
     PBR_ECUDA = -2,         /* a CUDA runtime call failed; see pbr_last_error() */
     PBR_ENOMEM = -3,
-    PBR_EUNSUPPORTED = -4   /* valid request outside what this build implements */
+    PBR_EUNSUPPORTED = -4,  /* valid request outside what this build implements */
+    PBR_EOVERFLOW = -5      /* an EARLIER frame dropped triangles (record lists too small); nothing was launched by
+                               this call, capacity has been raised, call again */
 } pbr_status;
 
 #define PBR_MESH_TWO_SIDED 1u           /* do not cull back faces of this mesh */
 
 typedef struct pbr_mesh_s *pbr_mesh_t;  /* device-resident static geometry */
 typedef struct pbr_texture_s *pbr_texture_t;   /* device-resident RGBA8 image (p3d_Texture0) */
+
+/* Pose channels: value of instance b = ptr ? ptr[b*stride] : constant (device pointer, stride in floats). */
+typedef struct {
+    const float *ptr;           /* device pointer or NULL */
+    int32_t stride;             /* in floats */
+    float constant;
+} pbr_channel;
+
+/* One node's pose: position xyz, Euler H/P/R in radians (R = Rz(H) Ry(P) Rx(R), reference
+ * shader_context.py:47-84) and uniform scale -> column-packed matrices.  Fuses what the reference
+ * does in set_positions + set_hprs + set_scales + upload (node.py:128-154) into one pass.  Used two
+ * ways: pbr_compose_transforms writes the matrices of several nodes in one launch; a pose attached
+ * to a pbr_node_desc makes pbr_render compute them inside the raster kernel (no matrix buffer is
+ * read or written on the small-scene path). */
+typedef struct {
+    pbr_channel pos[3];
+    pbr_channel hpr[3];
+    pbr_channel scale;
+    float *out_mats;            /* device [n_instances,16] */
+    int32_t n_instances;
+} pbr_pose_desc;
 
 /* One PBRNode: replaces the `matbuf` / `colbuf` / `instancesPerScene` / `shareAcrossScenes`
  * shader inputs of reference node.py:85-91 and the instanced draw of node.py:68. */
@@ -57,6 +81,13 @@ typedef struct {
                                    base = mix(1, texture(uv).rgb, clamp(use_texture, 0, 1)) */
     uint32_t flags;             /* PBR_NODE_* */
     pbr_texture_t texture;      /* image sampled when use_texture > 0; NULL = white (node stays untextured) */
+    const pbr_pose_desc *pose;  /* optional (host pointer, copied during the call).  When set, the node's model
+                                   matrices are DEFINED by these channels at the time the frame executes -- the
+                                   reference's per-step set_positions / set_hprs (envs/cartpole/renderer.py:125-138)
+                                   folded into the frame.  `mats` is then ignored; pose->out_mats (required,
+                                   [B,16]) receives the matrices whenever the library has to materialise them
+                                   (large-scene paths, static layer, PBR_FRAME_WRITE_MATS) and is left untouched
+                                   by the small-scene kernel otherwise; pose->n_instances must equal B. */
 } pbr_node_desc;
 
 #define PBR_NODE_IN_BASE 1u             /* already rendered into frame->base: skipped by pbr_render,
@@ -92,6 +123,8 @@ typedef struct {
 } pbr_frame_desc;
 
 #define PBR_FRAME_FORCE_GENERAL 1u      /* skip the small-scene fast kernel (testing / debugging) */
+#define PBR_FRAME_WRITE_MATS 4u          /* posed nodes: also write their matrices to pose->out_mats on the
+                                           small-scene path (tests; costs the overlap between frames) */
 #define PBR_FRAME_FORCE_FUSED 2u        /* general path: keep geometry fused into the raster kernel
                                            instead of the geometry pre-pass + TMA-staged raster */
 
@@ -131,30 +164,26 @@ int pbr_base_render(pbr_base_t base, const pbr_frame_desc *frame, void *stream);
 int pbr_pack_transforms(float *transforms_b44, const float *rot_b33, const float *scale_b,
                         float *out_mats, int32_t n_instances, void *stream);
 
-/* Pose channels for pbr_compose_transforms: value = ptr ? ptr[b*stride] : constant. */
-typedef struct {
-    const float *ptr;           /* device pointer or NULL */
-    int32_t stride;             /* in floats */
-    float constant;
-} pbr_channel;
-
-/* One node's pose: position xyz, Euler H/P/R in radians (R = Rz(H) Ry(P) Rx(R), reference
- * shader_context.py:47-84) and uniform scale -> column-packed matrices.  Fuses what the reference
- * does in set_positions + set_hprs + set_scales + upload (node.py:128-154) into one pass; several
- * nodes are batched into one launch. */
-typedef struct {
-    pbr_channel pos[3];
-    pbr_channel hpr[3];
-    pbr_channel scale;
-    float *out_mats;            /* device [n_instances,16] */
-    int32_t n_instances;
-} pbr_pose_desc;
-
+/* Pose kernel: out_mats of every pose <- matrices of its channels (one launch per 8 poses).  Same
+ * arithmetic, bit for bit, as a pose attached to a node of pbr_render. */
 int pbr_compose_transforms(const pbr_pose_desc *poses, int32_t n_poses, void *stream);
 
 /* Sticky per-device status bits written by the kernels (diagnostics; synchronises the device).
- * bit 0: the small-scene kernel ran out of record slots for clipped triangles in some scene. */
+ * bit 0: the small-scene kernel ran out of shared-memory record slots for clipped triangles in some
+ *        scene (the frame is still exact: the surplus went to the overflow pool; later frames on this
+ *        device take the general kernel until the bit is cleared);
+ * bit 1: the geometry pre-pass of a large scene ran out of per-scene record capacity and DROPPED
+ *        triangles -- the frame is wrong; the Python wrapper raises when it sees this bit. */
 int pbr_device_status(int32_t device, int32_t *status_bits, int32_t clear);
+
+/* The same bits without a device synchronisation: read from host-mapped memory the kernels also write
+ * (may lag behind frames still in flight). */
+int pbr_device_status_nosync(int32_t device, int32_t *status_bits);
+
+#ifdef PBR_W_TIMING
+/* timing builds only (profiles/kernel_timestamps.py): copies the time stamps the small-scene kernel dumped */
+int pbr_debug_pool(void *dst, size_t bytes);
+#endif
 
 #ifdef __cplusplus
 }

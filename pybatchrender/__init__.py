@@ -10,12 +10,12 @@ import sys
 
 import pybatchrender_b200 as _impl
 from pybatchrender_b200 import *  # noqa: F401,F403
-from pybatchrender_b200 import (PBRCam, PBRConfig, PBREnv, PBRLight, PBRNode, PBRRenderer, PBRShaderContext,
-                                __version__, envs)
+from pybatchrender_b200 import (CPUFrameGrabber, FrameGrabber, GPUFrameGrabber, PBRCam, PBRConfig, PBREnv, PBRLight,
+                                PBRNode, PBRRenderer, PBRShaderContext, __version__, envs)
 
 for _name in ("config", "env", "envs", "envs.cartpole", "envs.cartpole.config", "envs.cartpole.env",
               "envs.cartpole.renderer", "renderer", "renderer.renderer", "renderer.node", "renderer.camera",
-              "renderer.light", "renderer.shader_context", "meshes", "dist"):
+              "renderer.light", "renderer.shader_context", "renderer.frame_grabber", "meshes", "dist"):
     try:
         sys.modules[f"{__name__}.{_name}"] = importlib.import_module(f"pybatchrender_b200.{_name}")
     except Exception:  # pragma: no cover - optional pieces

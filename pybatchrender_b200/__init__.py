@@ -15,6 +15,7 @@ from .renderer.node import PBRNode
 from .renderer.camera import PBRCam
 from .renderer.light import PBRLight
 from .renderer.renderer import PBRRenderer
+from .renderer.frame_grabber import CPUFrameGrabber, GPUFrameGrabber
 from . import dist
 
 
@@ -27,6 +28,7 @@ def native_available() -> bool:
 
 
 GPU_AVAILABLE = None  # resolved lazily by native_available(); kept for reference API parity
+FrameGrabber = GPUFrameGrabber   # reference __init__.py:43-50: "prefer GPU if available"; rendering here is GPU-only
 
 try:  # env layer is optional (mirrors the guarded imports of the reference package)
     from .env import PBREnv
@@ -36,4 +38,4 @@ except Exception:  # pragma: no cover
     envs = None
 
 __all__ = ["PBRConfig", "PBRShaderContext", "PBRNode", "PBRCam", "PBRLight", "PBRRenderer", "PBREnv",
-           "envs", "dist", "native_available", "__version__"]
+           "envs", "dist", "native_available", "GPUFrameGrabber", "CPUFrameGrabber", "FrameGrabber", "__version__"]

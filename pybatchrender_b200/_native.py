@@ -18,11 +18,28 @@ LIB_PATH = os.environ.get("PBR_B200_LIB") or os.path.join(_HERE, "csrc", "libpbr
 PBR_MAX_NODES = 24
 PBR_MESH_TWO_SIDED = 1
 PBR_FRAME_FORCE_GENERAL = 1
+PBR_FRAME_FORCE_FUSED = 2
+PBR_FRAME_WRITE_MATS = 4
+PBR_EOVERFLOW = -5
 PBR_NODE_IN_BASE = 1
 
 
 class NativeError(RuntimeError):
     pass
+
+
+class _Channel(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_void_p), ("stride", ctypes.c_int32), ("constant", ctypes.c_float)]
+
+
+class _PoseDesc(ctypes.Structure):
+    _fields_ = [
+        ("pos", _Channel * 3),
+        ("hpr", _Channel * 3),
+        ("scale", _Channel),
+        ("out_mats", ctypes.c_void_p),
+        ("n_instances", ctypes.c_int32),
+    ]
 
 
 class _NodeDesc(ctypes.Structure):
@@ -35,6 +52,7 @@ class _NodeDesc(ctypes.Structure):
         ("use_texture", ctypes.c_float),
         ("flags", ctypes.c_uint32),
         ("texture", ctypes.c_void_p),
+        ("pose", ctypes.POINTER(_PoseDesc)),
     ]
 
 
@@ -60,20 +78,6 @@ class _FrameDesc(ctypes.Structure):
     ]
 
 
-class _Channel(ctypes.Structure):
-    _fields_ = [("ptr", ctypes.c_void_p), ("stride", ctypes.c_int32), ("constant", ctypes.c_float)]
-
-
-class _PoseDesc(ctypes.Structure):
-    _fields_ = [
-        ("pos", _Channel * 3),
-        ("hpr", _Channel * 3),
-        ("scale", _Channel),
-        ("out_mats", ctypes.c_void_p),
-        ("n_instances", ctypes.c_int32),
-    ]
-
-
 _EXPORTS = {
     "pbr_version": (ctypes.c_int, []),
     "pbr_last_error": (ctypes.c_char_p, []),
@@ -94,6 +98,7 @@ _EXPORTS = {
     "pbr_pack_transforms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_int32, ctypes.c_void_p]),
     "pbr_compose_transforms": (ctypes.c_int, [ctypes.POINTER(_PoseDesc), ctypes.c_int32, ctypes.c_void_p]),
+    "pbr_device_status_nosync": (ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
 }
 
 _lib = None
@@ -228,6 +233,12 @@ class Native:
     def version(self) -> int:
         return int(self.lib.pbr_version())
 
+    def device_status_nosync(self, device_index: int) -> int:
+        """The same bits from host-mapped memory, without synchronising (may lag behind frames in flight)."""
+        v = ctypes.c_int32(0)
+        _check(self.lib.pbr_device_status_nosync(int(device_index), ctypes.byref(v)), "pbr_device_status_nosync")
+        return int(v.value)
+
     def device_status(self, device_index: int, clear: bool = True) -> int:
         """Sticky diagnostic bits written by the kernels (synchronises the device)."""
         v = ctypes.c_int32(0)
@@ -239,33 +250,42 @@ class Native:
         for t, w in ((transforms_b44, "transforms_b44"), (rot_b33, "rot3_b33"), (scale_b11, "scale_b11"),
                      (matbuf, "matbuf")):
             _cuda_f32(t, w)
+            if t.shape[0] != n:
+                raise NativeError(f"{w} has {t.shape[0]} rows, matbuf has {n}")
         with torch.cuda.device(matbuf.device):
             rc = self.lib.pbr_pack_transforms(transforms_b44.data_ptr(), rot_b33.data_ptr(), scale_b11.data_ptr(),
                                               matbuf.data_ptr(), n, _stream_ptr(matbuf.device))
         _check(rc, "pbr_pack_transforms")
 
-    def compose(self, poses: list[dict], device: torch.device) -> None:
-        """poses: [{pos: (c,c,c), hpr: (c,c,c), scale: c, out: tensor[B,16]}], c = float | (tensor1d_view)."""
-        arr = (_PoseDesc * len(poses))()
-        keep = []
+    @staticmethod
+    def fill_pose(dst: "_PoseDesc", p: dict) -> None:
+        """p: {pos: (c,c,c), hpr: (c,c,c), scale: c, out: tensor[B,16]}, c = float | 1-D float32 CUDA view with one
+        element per instance (the caller keeps the tensors alive)."""
+        out = _cuda_f32(p["out"], "pose out")
+        n = int(out.shape[0])
 
-        def chan(dst, v):
+        def chan(d, v):
             if isinstance(v, torch.Tensor):
                 if not v.is_cuda or v.dtype != torch.float32 or v.dim() != 1:
                     raise NativeError("pose channel tensors must be 1-D float32 CUDA views")
-                dst.ptr, dst.stride, dst.constant = v.data_ptr(), int(v.stride(0)), 0.0
-                keep.append(v)
+                if v.shape[0] != n:
+                    raise NativeError(f"pose channel has {v.shape[0]} elements, node has {n} instances")
+                d.ptr, d.stride, d.constant = v.data_ptr(), int(v.stride(0)), 0.0
             else:
-                dst.ptr, dst.stride, dst.constant = None, 0, float(v)
+                d.ptr, d.stride, d.constant = None, 0, float(v)
 
+        for k in range(3):
+            chan(dst.pos[k], p["pos"][k])
+            chan(dst.hpr[k], p["hpr"][k])
+        chan(dst.scale, p.get("scale", 1.0))
+        dst.out_mats = out.data_ptr()
+        dst.n_instances = n
+
+    def compose(self, poses: list[dict], device: torch.device) -> None:
+        """Write the matrices of several poses (see ``fill_pose``) in one launch."""
+        arr = (_PoseDesc * len(poses))()
         for i, p in enumerate(poses):
-            for k in range(3):
-                chan(arr[i].pos[k], p["pos"][k])
-                chan(arr[i].hpr[k], p["hpr"][k])
-            chan(arr[i].scale, p.get("scale", 1.0))
-            out = _cuda_f32(p["out"], "pose out")
-            arr[i].out_mats = out.data_ptr()
-            arr[i].n_instances = int(out.shape[0])
+            self.fill_pose(arr[i], p)
         with torch.cuda.device(device):
             rc = self.lib.pbr_compose_transforms(arr, len(poses), _stream_ptr(device))
         _check(rc, "pbr_compose_transforms")
@@ -273,9 +293,12 @@ class Native:
     def _frame(self, *, num_scenes, tile_w, tile_h, channels, vp, nodes, out, bg, ambient, dir_dir, dir_col,
                strength, scene_begin=0, scene_count=None, flags=0, base=None):
         """nodes: list of (NativeMesh, matbuf, colbuf, instances_per_scene, shared[, in_base[, use_texture,
-        NativeTexture | None]])."""
+        NativeTexture | None[, pose dict | None]]])."""
         _cuda_f32(vp, "viewbuf")
         nd = (_NodeDesc * max(1, len(nodes)))()
+        n_posed = sum(1 for item in nodes if len(item) > 8 and item[8] is not None)
+        poses = (_PoseDesc * max(1, n_posed))()
+        k_pose = 0
         for i, item in enumerate(nodes):
             mesh, mats, cols, inst, shared = item[:5]
             _cuda_f32(mats, "matbuf")
@@ -288,6 +311,10 @@ class Native:
             nd[i].use_texture = float(item[6]) if len(item) > 6 else 0.0
             nd[i].texture = item[7].handle if len(item) > 7 and item[7] is not None else None
             nd[i].flags = PBR_NODE_IN_BASE if (len(item) > 5 and item[5]) else 0
+            if len(item) > 8 and item[8] is not None:
+                self.fill_pose(poses[k_pose], item[8])
+                nd[i].pose = ctypes.pointer(poses[k_pose])
+                k_pose += 1
         f = _FrameDesc()
         f.num_scenes = int(num_scenes)
         f.scene_begin = int(scene_begin)
@@ -304,7 +331,7 @@ class Native:
         f.out = out.data_ptr() if out is not None else None
         f.flags = int(flags)
         f.base = base.handle if base is not None else None
-        return f, nd
+        return f, (nd, poses)
 
     def render(self, *, out, **kw) -> None:
         if not out.is_cuda or out.dtype != torch.uint8 or not out.is_contiguous():

@@ -14,6 +14,13 @@ constexpr int FAN = 8;               // max fan triangles of a clipped polygon
 // ------------------------------------------------------------------------------------------------
 // device-side frame description (kernel parameter, < 4 KB)
 // ------------------------------------------------------------------------------------------------
+// pose channels of a node whose matrices are computed in the kernel (pbr_node_desc.pose)
+struct PoseDev {
+    pbr_channel pos[3], hpr[3], scale;
+    float *out_mats;      // [B,16]: written only when the frame asks for it (PBR_FRAME_WRITE_MATS)
+};
+constexpr int MAX_FRAME_POSES = 4;   // posed nodes per frame handled in-kernel; more are materialised by compose_kernel
+
 struct NodeDev {
     const float4 *tp;     // [T*3] triangle soup: xyz = position, w of corner 0 = flat flag (int bits)
     const float4 *tn;     // [T*3] xyz = corner normal
@@ -37,6 +44,7 @@ struct NodeDev {
     int id_begin;         // draw index of this node's first triangle in the full frame (skipped nodes count)
     unsigned tri_magic;   // floor(2^32 / n_tris) + 1   (x / n_tris == __umulhi(x, magic) for x * n_tris < 2^32)
     unsigned vert_magic;  // floor(2^32 / n_verts) + 1
+    int pose_idx;         // >= 0: matrices come from FrameDev::poses[pose_idx] instead of mats
 };
 
 struct Rec;
@@ -76,8 +84,41 @@ struct FrameDev {
     unsigned bg;            // packed RGBA8 clear colour
     float amb[3], dcol[3], ldir[3];
     float s, oms;           // clamp(strength), 1 - clamp(strength)
+    int write_mats;         // small-scene kernel: posed nodes also write their matrices to out_mats
+    int sync_early;         // small-scene kernel: wait for the previous grid before the first write to `out`
+                            // (the previous launch on this stream may still be writing the same buffer)
+    PoseDev poses[MAX_FRAME_POSES];
     NodeDev nodes[PBR_MAX_NODES];
 };
+static_assert(sizeof(FrameDev) <= 8192, "FrameDev is a kernel parameter");
+
+// ------------------------------------------------------------------------------------------------
+// pose -> column-packed model matrix (reference shader_context.py:47-84: R = Rz(h) Ry(p) Rx(r);
+// node.py:116-126: M = [R*s | t]).  One function for compose_kernel and for the small-scene raster
+// kernel, so that a pose folded into the frame gives the same bits as the materialised matrices.
+// An angle channel that is the constant 0 skips sincosf (sin = 0, cos = 1 exactly, as sincosf returns).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pose_chan(const pbr_channel &c, size_t b) {
+    return c.ptr ? __ldg(c.ptr + b * (size_t)c.stride) : c.constant;
+}
+__device__ __forceinline__ void pose_angle(const pbr_channel &c, size_t b, float &sn, float &cs) {
+    sn = 0.0f; cs = 1.0f;
+    if (c.ptr != nullptr || c.constant != 0.0f) sincosf(pose_chan(c, b), &sn, &cs);
+}
+__device__ __forceinline__ void pose_matrix(const PoseDev &d, size_t b, float *M) {
+    float sh, ch, sp, cp, sr, cr;
+    pose_angle(d.hpr[0], b, sh, ch);
+    pose_angle(d.hpr[1], b, sp, cp);
+    pose_angle(d.hpr[2], b, sr, cr);
+    const float s = pose_chan(d.scale, b);
+    const float r00 = ch * cp, r01 = ch * sp * sr - sh * cr, r02 = ch * sp * cr + sh * sr;
+    const float r10 = sh * cp, r11 = sh * sp * sr + ch * cr, r12 = sh * sp * cr - ch * sr;
+    const float r20 = -sp, r21 = cp * sr, r22 = cp * cr;
+    M[0] = r00 * s; M[1] = r10 * s; M[2] = r20 * s; M[3] = 0.0f;
+    M[4] = r01 * s; M[5] = r11 * s; M[6] = r21 * s; M[7] = 0.0f;
+    M[8] = r02 * s; M[9] = r12 * s; M[10] = r22 * s; M[11] = 0.0f;
+    M[12] = pose_chan(d.pos[0], b); M[13] = pose_chan(d.pos[1], b); M[14] = pose_chan(d.pos[2], b); M[15] = 1.0f;
+}
 
 constexpr int DEVSTAT_WARP_OVERFLOW = 1;   // small-scene kernel ran out of record slots
 constexpr int DEVSTAT_STAGED_OVERFLOW = 2; // geometry pre-pass ran out of per-scene record capacity

@@ -86,6 +86,10 @@ struct StreamScratch {
     unsigned char *bgtile = nullptr;
     size_t bgtile_bytes = 0;
     unsigned bg_sig[4] = {0, 0, 0, 0};   // W, H, C, packed colour of the current contents
+    // output range of the last small-scene launch on this stream, if nothing else of ours followed it: the
+    // next small-scene launch may start while that one drains, and must order itself behind it when the two
+    // write overlapping memory (see raster_warp.cuh, "programmatic launch chain")
+    const unsigned char *last_out_lo[2] = {nullptr, nullptr}, *last_out_hi[2] = {nullptr, nullptr};
 };
 
 struct DeviceState {
@@ -101,6 +105,7 @@ struct DeviceState {
     unsigned *ovf_masks = nullptr;
     unsigned *ovf_busy = nullptr;
     size_t ovf_mask_words = 0;           // mask words per entry currently allocated
+    bool cap_worst_case = false;         // staged path: a frame overflowed its record lists -> size them for 6 per slot
 };
 std::mutex g_mu;
 DeviceState g_dev[64];
@@ -119,8 +124,8 @@ int device_state(int device, DeviceState **out) {
         }
         CUDA_TRY(cudaMemset(st.status, 0, sizeof(int)));
         int *hp = nullptr;
-        CUDA_TRY(cudaHostAlloc(&hp, sizeof(int), cudaHostAllocMapped));
-        *hp = 0;
+        CUDA_TRY(cudaHostAlloc(&hp, 2 * sizeof(int), cudaHostAllocMapped));     // [0] small-scene overflow, [1] staged overflow
+        hp[0] = hp[1] = 0;
         CUDA_TRY(cudaHostGetDevicePointer(&st.status_host_dev, hp, 0));
         st.status_host = hp;
     }
@@ -306,13 +311,53 @@ static cudaError_t launch_dependent(void (*kernel)(FrameDev), unsigned grid, uns
     return cudaLaunchKernelEx(&cfg, kernel, f);
 }
 
+static void pose_to_dev(const pbr_pose_desc &p, PoseDev &o) {
+    for (int k = 0; k < 3; ++k) { o.pos[k] = p.pos[k]; o.hpr[k] = p.hpr[k]; }
+    o.scale = p.scale;
+    o.out_mats = p.out_mats;
+}
+
+static int launch_compose(const pbr_pose_desc *const *poses, int n_poses, void *stream) {
+    for (int base = 0; base < n_poses; base += MAX_POSES) {
+        PoseBatch pb;
+        pb.n = n_poses - base < MAX_POSES ? n_poses - base : MAX_POSES;
+        int max_n = 0;
+        for (int i = 0; i < pb.n; ++i) {
+            const pbr_pose_desc &p = *poses[base + i];
+            if (!p.out_mats || (reinterpret_cast<size_t>(p.out_mats) & 15))
+                return fail(PBR_EINVAL, "pbr_compose_transforms: pose %d out_mats NULL or not 16-byte aligned", base + i);
+            if (p.n_instances < 0) return fail(PBR_EINVAL, "pbr_compose_transforms: pose %d n_instances < 0", base + i);
+            pose_to_dev(p, pb.p[i]);
+            pb.n_inst[i] = p.n_instances;
+            if (p.n_instances > max_n) max_n = p.n_instances;
+        }
+        if (max_n == 0) continue;
+        dim3 grid((max_n + 127) / 128, pb.n);
+        compose_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(pb);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return PBR_OK;
+}
+
+// write the matrices of every posed node of the frame to its pose->out_mats (paths that read matrix buffers)
+static int materialise_poses(const pbr_frame_desc *d, void *stream) {
+    std::vector<const pbr_pose_desc *> ptrs;
+    for (int i = 0; i < d->n_nodes; ++i)
+        if (d->nodes[i].pose && d->nodes[i].instances_per_scene > 0) ptrs.push_back(d->nodes[i].pose);
+    return ptrs.empty() ? PBR_OK : launch_compose(ptrs.data(), (int)ptrs.size(), stream);
+}
+
 enum NodeMode { NODES_ALL = 0, NODES_SKIP_BASE = 1, NODES_SHARED_ONLY = 2 };
 
 struct NodeStats {
     long long slots = 0, verts = 0, insts = 0;
     bool any_smooth = false, any_textured = false, warp_ok = true;
     int skipped = 0;
+    int n_poses = 0;          // posed nodes among the active ones (all of them in f.poses when <= MAX_FRAME_POSES)
+    bool poses_in_frame = false;
 };
+
+
 
 // Fill f.nodes from the host descriptors.  Draw indices (id_begin) always count every node so
 // that a frame split into static layer + per-scene part numbers its triangles like the full frame.
@@ -324,9 +369,15 @@ static int fill_nodes(const pbr_frame_desc *d, int device, NodeMode mode, FrameD
         const pbr_node_desc &n = d->nodes[i];
         if (!n.mesh) return fail(PBR_EINVAL, "pbr_render: node %d has no mesh", i);
         if (n.mesh->device != device) return fail(PBR_EINVAL, "pbr_render: node %d mesh lives on device %d, current device is %d", i, n.mesh->device, device);
-        if (!n.mats || !n.cols) return fail(PBR_EINVAL, "pbr_render: node %d mats / cols is NULL", i);
-        if ((reinterpret_cast<size_t>(n.mats) & 15) || (reinterpret_cast<size_t>(n.cols) & 15))
+        const float *mats = n.pose ? n.pose->out_mats : n.mats;
+        if (!mats || !n.cols) return fail(PBR_EINVAL, "pbr_render: node %d mats%s / cols is NULL", i, n.pose ? " (pose->out_mats)" : "");
+        if ((reinterpret_cast<size_t>(mats) & 15) || (reinterpret_cast<size_t>(n.cols) & 15))
             return fail(PBR_EINVAL, "pbr_render: node %d mats / cols must be 16-byte aligned", i);
+        if (n.pose) {
+            const long long B = n.shared ? (long long)n.instances_per_scene : (long long)d->num_scenes * n.instances_per_scene;
+            if (n.pose->n_instances != B)
+                return fail(PBR_EINVAL, "pbr_render: node %d pose has %d instances, node has %lld", i, n.pose->n_instances, B);
+        }
         if (n.instances_per_scene < 0) return fail(PBR_EINVAL, "pbr_render: node %d instances_per_scene < 0", i);
         if (n.texture && n.texture->device != device) return fail(PBR_EINVAL, "pbr_render: node %d texture lives on device %d, current device is %d", i, n.texture->device, device);
         const long long ntri = (long long)n.instances_per_scene * n.mesh->n_tris;
@@ -350,7 +401,15 @@ static int fill_nodes(const pbr_frame_desc *d, int device, NodeMode mode, FrameD
         nd.tw = textured ? n.texture->w : 0; nd.th = textured ? n.texture->h : 0;
         nd.use_tex = textured ? ut : 0.0f;
         if (textured) { st.any_smooth = true; st.any_textured = true; }      // per-pixel shading path
-        nd.mats = n.mats; nd.cols = n.cols;
+        nd.mats = mats; nd.cols = n.cols;
+        nd.pose_idx = -1;
+        if (n.pose) {
+            if (st.n_poses < MAX_FRAME_POSES) {
+                nd.pose_idx = st.n_poses;
+                pose_to_dev(*n.pose, f.poses[st.n_poses]);
+            }
+            st.n_poses++;
+        }
         nd.n_tris = n.mesh->n_tris; nd.n_verts = n.mesh->n_verts;
         nd.inst = n.instances_per_scene; nd.shared = n.shared ? 1 : 0;
         nd.slot_begin = (int)st.slots; nd.vert_begin = (int)st.verts; nd.flags = n.mesh->flags;
@@ -365,6 +424,9 @@ static int fill_nodes(const pbr_frame_desc *d, int device, NodeMode mode, FrameD
         if (!n.mesh->all_flat) st.any_smooth = true;
         if (n.instances_per_scene >= 8192 || n.mesh->n_tris >= 8192) st.warp_ok = false;
     }
+    st.poses_in_frame = st.n_poses > 0 && st.n_poses <= MAX_FRAME_POSES;
+    if (!st.poses_in_frame)
+        for (int i = 0; i < f.n_nodes; ++i) f.nodes[i].pose_idx = -1;
     f.smooth = st.any_smooth ? 1 : 0;
     f.srec_stride = st.any_textured ? SREC_TEXTURED : SREC_PLAIN;
     if (st.insts > 0x7fffffffll) return fail(PBR_EUNSUPPORTED, "pbr_render: more than 2^31 instances per scene");
@@ -469,7 +531,17 @@ static int launch_general(FrameDev &f, DeviceState *st, void *stream) {
 // geometry pre-pass + TMA-staged raster, in launches of as many scenes as the scratch budget holds
 static int launch_staged(FrameDev &f, DeviceState *st, void *stream) {
     StreamScratch *ss = &st->per_stream[stream];
-    const size_t cap = ((size_t)f.total_slots + (size_t)f.total_slots / 2 + 64 + 3) & ~(size_t)3;
+    // A scene's record list holds 1.5 records per triangle slot (+ 64): only clipped triangles need more than
+    // one, up to 6.  If an earlier frame ran out (geom_kernel raised the flag in host-mapped memory and dropped
+    // records) that frame is wrong: say so once, and size the lists for the worst case from now on.
+    if (st->status_host[1] != 0) {
+        st->status_host[1] = 0;
+        st->cap_worst_case = true;
+        return fail(PBR_EOVERFLOW, "pbr_render: an earlier large-scene frame on this device dropped triangles (more than 1.5 "
+                                   "records per triangle slot after clipping); record capacity is now sized for the worst case -- render again");
+    }
+    const size_t cap = st->cap_worst_case ? (((size_t)f.total_slots * 6 + 64 + 3) & ~(size_t)3)
+                                          : (((size_t)f.total_slots + (size_t)f.total_slots / 2 + 64 + 3) & ~(size_t)3);
     static const size_t budget_mb = getenv("PBR_B200_SCRATCH_MB") ? (size_t)atoll(getenv("PBR_B200_SCRATCH_MB")) : 4096;
     const bool smooth = f.smooth != 0;
     // per-band index lists pay when a tile has several bands (each band CTA would otherwise scan
@@ -572,7 +644,7 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
     auto warp_eligible = [&](const NodeStats &ns) {
         // once a scene overflowed the small-scene kernel's record slots (too many clipped fan
         // triangles; sticky flag in host-mapped memory) this device keeps to the general kernel
-        return ns.warp_ok && !ns.any_smooth && *st->status_host == 0 && !(d->flags & PBR_FRAME_FORCE_GENERAL) && ns.slots <= W_MAXSLOT && ns.verts <= W_MAXVERT &&
+        return ns.warp_ok && !ns.any_smooth && st->status_host[0] == 0 && !(d->flags & PBR_FRAME_FORCE_GENERAL) && ns.slots <= W_MAXSLOT && ns.verts <= W_MAXVERT && ns.insts <= W_MAXINST &&
                nbx <= 256 && H8 / 8 <= 256 && warp_smem <= 100 * 1024 && warp_smem <= (size_t)st->max_smem_optin;
     };
 
@@ -598,6 +670,21 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         f.plane_stride = H * W;
         f.linear = 1;
         f.debug = (int)((d->flags >> 8) & 3u);
+        // posed nodes: computed in the kernel when they fit f.poses, else materialised first
+        if (ns.n_poses > 0 && !ns.poses_in_frame)
+            if (int rc = materialise_poses(d, stream)) return rc;
+        f.write_mats = (ns.poses_in_frame && (d->flags & PBR_FRAME_WRITE_MATS)) ? 1 : 0;
+        {   // programmatic launch chain: this launch may start while the previous small-scene launches on the
+            // stream drain; it orders itself behind them when it writes memory they write (see raster_warp.cuh)
+            const unsigned char *lo = f.out + (size_t)f.scene_begin * f.C * H * W;
+            const unsigned char *hi = lo + (size_t)f.scene_count * f.C * H * W;
+            bool overlap = false;
+            for (int k = 0; k < 2; ++k)
+                overlap |= ss->last_out_lo[k] != nullptr && lo < ss->last_out_hi[k] && ss->last_out_lo[k] < hi;
+            f.sync_early = (overlap || f.write_mats) ? 1 : 0;
+            ss->last_out_lo[1] = ss->last_out_lo[0]; ss->last_out_hi[1] = ss->last_out_hi[0];
+            ss->last_out_lo[0] = lo; ss->last_out_hi[0] = hi;
+        }
         if (use_base) {
             f.base_color = base->color; f.base_keys = base->keys; f.base_flags = base->flags;
         } else if ((((size_t)f.C * H * W) & 15) == 0) {
@@ -663,6 +750,10 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         return PBR_OK;
     }
     // large scenes: geometry once per frame into per-scene record lists, then TMA-staged raster
+    // (ordinary launches: they start after everything before them on the stream has completed)
+    ss->last_out_lo[0] = ss->last_out_lo[1] = nullptr;
+    if (ns.n_poses > 0)
+        if (int rc = materialise_poses(d, stream)) return rc;
     size_t smem_fused = 0;
     if (int rc = plan_general(f, st, &smem_fused)) return rc;
     if (!(d->flags & PBR_FRAME_FORCE_FUSED) && (ns.slots > CH || f.nbands > 1))
@@ -718,6 +809,12 @@ int pbr_base_render(pbr_base_t b, const pbr_frame_desc *d, void *stream) {
     f.status_host = st->status_host_dev;
     NodeStats ns;
     if (int rc = fill_nodes(d, device, NODES_SHARED_ONLY, f, ns)) return rc;
+    {
+        StreamScratch *ss = &st->per_stream[stream];
+        ss->last_out_lo[0] = ss->last_out_lo[1] = nullptr;
+    }
+    if (ns.n_poses > 0)
+        if (int rc = materialise_poses(d, stream)) return rc;
 
     // (re)allocate the layer: colour image + keys for every 8x8 block of every band
     size_t smem_unused = 0;
@@ -755,7 +852,7 @@ int pbr_device_status(int32_t device, int32_t *status_bits, int32_t clear) {
     if (rc == PBR_OK) {
         int v = 0;
         cudaError_t e = cudaMemcpy(&v, st->status, sizeof(int), cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess && clear) { e = cudaMemset(st->status, 0, sizeof(int)); *st->status_host = 0; }
+        if (e == cudaSuccess && clear) { e = cudaMemset(st->status, 0, sizeof(int)); st->status_host[0] = 0; st->status_host[1] = 0; }
         if (e != cudaSuccess) rc = fail(PBR_ECUDA, "pbr_device_status: %s", cudaGetErrorString(e));
         *status_bits = v;
     }
@@ -776,22 +873,17 @@ int pbr_pack_transforms(float *transforms_b44, const float *rot_b33, const float
 
 int pbr_compose_transforms(const pbr_pose_desc *poses, int32_t n_poses, void *stream) {
     if (n_poses < 0 || (n_poses > 0 && !poses)) return fail(PBR_EINVAL, "pbr_compose_transforms: bad arguments");
-    for (int base = 0; base < n_poses; base += MAX_POSES) {
-        PoseBatch pb;
-        pb.n = n_poses - base < MAX_POSES ? n_poses - base : MAX_POSES;
-        int max_n = 0;
-        for (int i = 0; i < pb.n; ++i) {
-            pb.p[i] = poses[base + i];
-            if (!pb.p[i].out_mats || (reinterpret_cast<size_t>(pb.p[i].out_mats) & 15))
-                return fail(PBR_EINVAL, "pbr_compose_transforms: pose %d out_mats NULL or not 16-byte aligned", base + i);
-            if (pb.p[i].n_instances < 0) return fail(PBR_EINVAL, "pbr_compose_transforms: pose %d n_instances < 0", base + i);
-            if (pb.p[i].n_instances > max_n) max_n = pb.p[i].n_instances;
-        }
-        if (max_n == 0) continue;
-        dim3 grid((max_n + 127) / 128, pb.n);
-        compose_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(pb);
-        CUDA_TRY(cudaGetLastError());
-    }
+    std::vector<const pbr_pose_desc *> ptrs((size_t)n_poses);
+    for (int i = 0; i < n_poses; ++i) ptrs[i] = poses + i;
+    return launch_compose(ptrs.data(), n_poses, stream);
+}
+
+int pbr_device_status_nosync(int32_t device, int32_t *status_bits) {
+    if (!status_bits) return fail(PBR_EINVAL, "pbr_device_status_nosync: NULL output");
+    if (device < 0 || device >= 64) return fail(PBR_EINVAL, "pbr_device_status_nosync: bad device %d", device);
+    std::lock_guard<std::mutex> lock(g_mu);
+    const DeviceState &st = g_dev[device];
+    *status_bits = st.status_host ? ((st.status_host[0] ? DEVSTAT_WARP_OVERFLOW : 0) | (st.status_host[1] ? DEVSTAT_STAGED_OVERFLOW : 0)) : 0;
     return PBR_OK;
 }
 

@@ -47,6 +47,7 @@ __device__ __forceinline__ void append_record(const StagedDev &g, const FrameDev
     const int idx = atomicAdd(&g.count[local_scene], 1);
     if (idx >= g.cap) {
         atomicOr(f.status, DEVSTAT_STAGED_OVERFLOW);
+        f.status_host[1] = 1;            // host-mapped: the next large-scene call reports it and grows the lists
         return;
     }
     const size_t o = (size_t)local_scene * g.cap + idx;

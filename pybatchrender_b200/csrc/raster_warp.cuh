@@ -37,6 +37,8 @@ namespace pbr {
 constexpr int W_MAXREC = 48;     // records per scene (triangle slots that survive + clipped fans); < 64 (mask bits)
 constexpr int W_MAXSLOT = 36;    // eligibility: leaves >= 12 spare records for clipped fans
 constexpr int W_MAXVERT = 48;    // (instance, vertex) pairs per scene
+constexpr int W_MAXINST = 16;    // instances per scene (their 3x3 model matrices are parked in shared memory)
+constexpr int W_GEOM_BYTES = W_MAXVERT * 32 + W_MAXINST * 48;    // parked vertices (clip + projected) and matrices
 constexpr int W_MW = 2;          // mask words per block (64 record bits)
 #ifndef W_WARPS
 #define W_WARPS 4                // scenes (= warps) per CTA
@@ -54,7 +56,7 @@ static_assert(6 * W_MAXSLOT - W_MAXREC <= W_OVF_MAXREC, "overflow pool too small
 
 // shared memory of one scene
 __host__ __device__ inline size_t warp_scene_bytes(int nblk) {
-    return (size_t)W_MAXVERT * 32 + (size_t)W_MAXREC * sizeof(Rec) + align16((size_t)nblk * W_MW * 4) +
+    return (size_t)W_GEOM_BYTES + (size_t)W_MAXREC * sizeof(Rec) + align16((size_t)nblk * W_MW * 4) +
            align16((size_t)nblk * 2) + 2 * W_MAXREC * 4 + 16;
 }
 // shared memory of a CTA of `warps` scenes: scene regions + block queue + counters (+ mbarrier and the
@@ -88,6 +90,13 @@ __device__ __forceinline__ void load_mat(const float *m, float *M) {
         const float4 a = __ldg(m4 + j);
         M[4 * j] = a.x; M[4 * j + 1] = a.y; M[4 * j + 2] = a.z; M[4 * j + 3] = a.w;
     }
+}
+
+// xform_normal with the matrix given as its first three columns (parked in shared memory by phase A)
+__device__ __forceinline__ void xform_normal_cols(const float4 *c, float nx, float ny, float nz, float *r) {
+    const float4 c0 = c[0], c1 = c[1], c2 = c[2];
+    const float m[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+    xform_normal(m, nx, ny, nz, r);
 }
 
 // vertex flags
@@ -276,6 +285,23 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 #ifndef PBR_W_LATE_WAIT
 #define PBR_W_LATE_WAIT 1
 #endif
+// Programmatic launch chain.  The kernel is launched with programmatic stream serialisation and triggers its
+// dependents (PBR_W_TRIGGER: 1 = at entry, 2 = behind the pre-sweep barrier, 3 = at the end of the sweep, 0 = never):
+// when the next launch on the stream is another frame of this kernel -- the loop `renderer.step(state)` produces
+// exactly that now that the pose is computed in phase A -- its CTAs are scheduled on each SM as soon as this
+// frame's CTAs leave it, instead of after the slowest SM of this frame has finished and the launch latency has
+// passed.  Nothing a frame reads is written by the frame before it (state, matrices, colours, the static layer are
+// produced by ordinary launches, which complete before this kernel starts and never trigger early), so the only
+// hazards are the writes: two frames in flight into overlapping `out` memory, or into the same out_mats.  The
+// host knows the output ranges of the last two small-scene launches on the stream and sets f.sync_early when the
+// new frame overlaps one of them (or writes matrices): every warp then executes griddepcontrol.wait before its
+// first global write.  Two ranges suffice: frame n+2 cannot start before every CTA of frame n+1 is resident,
+// i.e. before frame n has all but drained, and no CTA of frame n exits before frame n-1 has completed, because
+// every thread ends with griddepcontrol.wait -- which also makes "this grid has completed" imply "every earlier
+// frame has completed" for whatever follows on the stream (copies, torch kernels: ordinary, fully ordered launches).
+#ifndef PBR_W_TRIGGER
+#define PBR_W_TRIGGER 1
+#endif
 template <int WARPS, bool TMA_BG>
 __global__ void __launch_bounds__(32 * (WARPS + (TMA_BG ? PBR_W_HELPERS : 0)), 32 / (WARPS + (TMA_BG ? PBR_W_HELPERS : 0)))
 raster_warp_kernel(const __grid_constant__ FrameDev f) {
@@ -290,6 +316,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
 #else
 #define W_STAMP(k) do { } while (0)
 #endif
+    if (PBR_W_TRIGGER == 1) asm volatile("griddepcontrol.launch_dependents;");
     const unsigned lt_mask = (1u << lane) - 1u;
     const int scene = f.scene_begin + (int)blockIdx.x * WARPS + warp;
     const bool helper = warp >= WARPS;                    // extra warps without a scene: they only sweep
@@ -303,7 +330,8 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     unsigned char *my = smem_raw + warp * region;
     float4 *clipc = reinterpret_cast<float4 *>(my);                      // [W_MAXVERT]
     int4 *proj = reinterpret_cast<int4 *>(my + (size_t)W_MAXVERT * 16);  // [W_MAXVERT]
-    Rec *recs = reinterpret_cast<Rec *>(my + (size_t)W_MAXVERT * 32);
+    float4 *minst = reinterpret_cast<float4 *>(my + (size_t)W_MAXVERT * 32);   // [W_MAXINST][3] columns 0..2 of M
+    Rec *recs = reinterpret_cast<Rec *>(my + (size_t)W_GEOM_BYTES);
     unsigned *masks = reinterpret_cast<unsigned *>(recs + W_MAXREC);
     unsigned short *blist = reinterpret_cast<unsigned short *>(masks + align16((size_t)nblk * W_MW * 4) / 4);
     unsigned *live = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(blist) + align16((size_t)nblk * 2));
@@ -320,9 +348,8 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     // CTA's bulk stores blocks the issuing thread for microseconds (time stamps: a scene warp that did it
     // reached the sweep 3.5 us after its 13 neighbours, and the whole CTA waited for it at the barrier), so
     // it must not be a warp that has a scene to set up.  The helper loads the image, waits for it, issues the
-    // stores and waits for them while the scene warps do geometry.  (The stores precede the
-    // programmatic-dependency wait: the pose kernel ahead of us does not touch `out`, and everything ahead
-    // of the pose kernel has completed before the pose kernel started.)
+    // stores and waits for them while the scene warps do geometry.  (When the frame before this one may still
+    // be writing the same memory -- f.sync_early -- it first waits for that grid to complete.)
     constexpr int BG_T = (TMA_BG && PBR_W_HELPERS > 0 && PBR_W_BG_HELPER != 0) ? WARPS * 32 : 0;
     unsigned bg_turn = 0, bg_sm = 0;
     if (TMA_BG && threadIdx.x == BG_T) {
@@ -331,6 +358,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(bg_bar, (unsigned)scene_bytes_out);
         tma_load(qctr + 8, f.base_color, (unsigned)scene_bytes_out, bg_bar);
+        if (f.sync_early) asm volatile("griddepcontrol.wait;" ::: "memory");
         if (BG_T != 0) {
             if (PBR_W_BG_SERIAL) {
                 unsigned smid;
@@ -351,6 +379,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     if (TMA_BG && BG_T == 0 && f.debug == 1 && threadIdx.x == 0) issue_bg_stores(f, qctr, WARPS);
     if (active) {
         unsigned char *out_scene = f.out + (size_t)scene * scene_bytes_out;
+        if (f.sync_early) asm volatile("griddepcontrol.wait;" ::: "memory");
 
         // ---- 0: background
         const bool split_bg = !TMA_BG && f.base_color != nullptr && ((f.C * HW) & 15) == 0 && f.debug != 1;
@@ -366,10 +395,10 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 for (int i = lane; i < n16; i += 32) m4[i] = make_uint4(0u, 0u, 0u, 0u);
             }
 
-            // ---- A: vertices
-            // (launched as a programmatic dependent: everything above overlaps the tail of the pose
-            // kernel; its matrices are read from here on.  A no-op after any other predecessor.)
-            asm volatile("griddepcontrol.wait;" ::: "memory");
+            // ---- A: vertices.  A posed node's model matrix is computed here from its pose channels (the state
+            // tensor of the caller: reference envs/cartpole/renderer.py:125-138 + shader_context.py:47-84),
+            // other nodes' matrices are read from their matrix buffer; lane "vertex 0" of an instance parks
+            // the 3x3 part in shared memory for the normals of phase B.
             {
                 float VP[16];
                 load_mat(f.vp + (size_t)scene * 16, VP);
@@ -385,7 +414,18 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                     const int vert = local - inst * nd.n_verts;
                     const size_t b = nd.shared ? (size_t)inst : (size_t)scene * nd.inst + inst;
                     float M[16];
-                    load_mat(nd.mats + b * 16, M);
+                    if (nd.pose_idx >= 0) pose_matrix(f.poses[nd.pose_idx], b, M);
+                    else load_mat(nd.mats + b * 16, M);
+                    if (vert == 0) {
+                        float4 *mi = minst + (nd.inst_begin + inst) * 3;
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) mi[j] = make_float4(M[4 * j], M[4 * j + 1], M[4 * j + 2], M[4 * j + 3]);
+                        if (f.write_mats && nd.pose_idx >= 0) {
+                            float4 *o = reinterpret_cast<float4 *>(f.poses[nd.pose_idx].out_mats + b * 16);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) o[j] = make_float4(M[4 * j], M[4 * j + 1], M[4 * j + 2], M[4 * j + 3]);
+                        }
+                    }
                     const float4 p = __ldg(nd.vpos + vert);
                     float world[4], c[4];
                     mat_vec4(M, p.x, p.y, p.z, 1.0f, world);
@@ -420,10 +460,9 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 BBox bb;
                 if (setup_snapped(f, X, Y, z, (nd.flags & PBR_MESH_TWO_SIDED) != 0, id, 0, f.H, r, bb)) {
                     const size_t b = nd.shared ? (size_t)inst : (size_t)scene * nd.inst + inst;
-                    float M[16], n[3];
-                    load_mat(nd.mats + b * 16, M);
+                    float n[3];
                     const float4 n0 = __ldg(nd.tn + 3 * tri);
-                    xform_normal(M, n0.x, n0.y, n0.z, n);
+                    xform_normal_cols(minst + (nd.inst_begin + inst) * 3, n0.x, n0.y, n0.z, n);
                     r.col = shade(f, n, __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4)));
                     my_slow |= (r.meta & M_SLOW) != 0u;
                     recs[j] = r;
@@ -568,10 +607,9 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                         const uint4 ti = __ldg(nd.tidx + ws.tri);
                         const int vb = nd.vert_begin + ws.inst * nd.n_verts;
                         const size_t b = nd.shared ? (size_t)ws.inst : (size_t)scene * nd.inst + ws.inst;
-                        float M[16], n[3];
-                        load_mat(nd.mats + b * 16, M);
+                        float n[3];
                         const float4 n0 = __ldg(nd.tn + 3 * ws.tri);
-                        xform_normal(M, n0.x, n0.y, n0.z, n);
+                        xform_normal_cols(minst + (nd.inst_begin + ws.inst) * 3, n0.x, n0.y, n0.z, n);
                         col = __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4));
                         id = (unsigned)(nd.id_begin + ws.inst * nd.n_tris + ws.tri) + 1u;
                         two_sided = (nd.flags & PBR_MESH_TWO_SIDED) != 0;
@@ -695,6 +733,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         }
         __syncthreads();                                  // every scene of the CTA is set up and queued
     }
+    if (PBR_W_TRIGGER == 2) asm volatile("griddepcontrol.launch_dependents;");
     W_STAMP(5);
     bool stores_done = !LATE_WAIT;                        // this warp has seen the CTA's bulk stores complete
     if (LATE_WAIT) {
@@ -734,7 +773,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         const int w = (int)((item >> 16) & 0x3fffu);
         const int bx = (int)(item & 255u), by = (int)((item >> 8) & 255u);
         const unsigned char *sreg = smem_raw + w * region;
-        const Rec *srecs = reinterpret_cast<const Rec *>(sreg + (size_t)W_MAXVERT * 32);
+        const Rec *srecs = reinterpret_cast<const Rec *>(sreg + (size_t)W_GEOM_BYTES);
         const unsigned *smasks = reinterpret_cast<const unsigned *>(srecs + W_MAXREC);
         unsigned char *out_scene = *reinterpret_cast<unsigned char *const *>(sreg + region - 8);
 
@@ -777,6 +816,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         }
     }
     W_STAMP(6);
+    if (PBR_W_TRIGGER == 3) asm volatile("griddepcontrol.launch_dependents;");
     // blocks with records in the overflow pool: swept by the scene's own warp, then the entry is released
     if (novf > 0) {
         if (LATE_WAIT && !stores_done) {
@@ -792,6 +832,8 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         __syncwarp();
         if (lane == 0) atomicAnd(f.ovf_busy + e / W_POOL_PER_SM, ~(1u << (e % W_POOL_PER_SM)));
     }
+    // no CTA leaves before the frame ahead of this one has completed (see "programmatic launch chain")
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 }  // namespace pbr

@@ -9,9 +9,10 @@ to the pole's P angle (a rotation about +Y in the reference's own HPR convention
 ``shader_context.py:47-84``).
 
 What differs from the reference: the state is consumed where it lives.  The reference moves it to
-the CPU and re-uploads three whole buffers per step (``renderer.py:112,130-138``); here one fused
-pose kernel (``pbr_compose_transforms``) reads ``state[:, 0]`` / ``state[:, 2]`` through strided
-views and writes both nodes' matrix buffers.  Without a GPU (``cfg.device == 'cpu'``) the generic
+the CPU and re-uploads three whole buffers per step (``renderer.py:112,130-138``); here the two
+nodes are *bound* to ``state[:, 0]`` / ``state[:, 2]`` (``PBRNode.set_pose``, strided views) and the
+raster kernel computes their model matrices itself while it transforms the vertices: a step is one
+kernel launch.  Without a GPU (``cfg.device == 'cpu'``) the generic
 torch setters run instead so that the host logic stays testable -- rendering itself needs CUDA.
 """
 from __future__ import annotations
@@ -100,12 +101,10 @@ class CartPoleRenderer(PBRRenderer):
         x, theta = state[:, 0], state[:, 2]
 
         if self._native is not None:
-            # cart = T(x, 0, 0); pole = T(x, pole_y, 0) . Ry(theta) -- one launch for both nodes
-            self._native.compose([
-                dict(out=self.cart.matbuf, pos=(x, 0.0, 0.0), hpr=(0.0, 0.0, 0.0), scale=1.0),
-                dict(out=self.pole.matbuf, pos=(x, self.pole_y, 0.0), hpr=(0.0, theta, 0.0), scale=1.0),
-            ], self.device)
-            self._last_state = state       # keeps the strided views alive until the launch is enqueued
+            # cart = T(x, 0, 0); pole = T(x, pole_y, 0) . Ry(theta): bound to the state columns, evaluated by
+            # the raster kernel itself -- no launch, no matrix buffer written or read
+            self.cart.set_pose(pos=(x, 0.0, 0.0))
+            self.pole.set_pose(pos=(x, self.pole_y, 0.0), hpr=(0.0, theta, 0.0))
             return
 
         # generic path (CPU): same sequence of setter calls as the reference

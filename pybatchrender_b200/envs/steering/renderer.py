@@ -136,12 +136,9 @@ class SteeringRenderer(PBRRenderer):
         self._left_border_pos[:, 0, 1] = y
         self._right_border_pos[:, 0, 1] = y
         if self._native is not None:
-            self._native.compose([
-                dict(out=self.player_node.matbuf, pos=(x, y, 0.0), hpr=(0.0, 0.0, 0.0), scale=1.0),
-                dict(out=self.left_border.matbuf, pos=(self._rail_x[0], y, self._rail_z), hpr=(0.0, 0.0, 0.0), scale=1.0),
-                dict(out=self.right_border.matbuf, pos=(self._rail_x[1], y, self._rail_z), hpr=(0.0, 0.0, 0.0), scale=1.0),
-            ], self.device)
-            self._last_state = state
+            self.player_node.set_pose(pos=(x, y, 0.0))
+            self.left_border.set_pose(pos=(self._rail_x[0], y, self._rail_z))
+            self.right_border.set_pose(pos=(self._rail_x[1], y, self._rail_z))
         else:
             self.player_node.set_positions(self._player_pos)
             self.left_border.set_positions(self._left_border_pos)

@@ -67,14 +67,13 @@ class PBRCam(PBRShaderContext):
         self._proj_cache = None
         self.P_k44 = self._get_projection()
 
+        # True while every scene provably has the same view (every input that feeds V -- given or reused from
+        # an earlier call -- was a broadcast (3,) vector): lets the renderer pre-render shared nodes once
+        self._uni = {"eye": True, "fwd": True, "up": True}
         self._update_view(eye_k3=torch.tensor([0.0, -12.0, 0.0]),
                           forward_k3=torch.tensor([0.0, 1.0, 0.0]),
                           up_k3=torch.tensor([0.0, 0.0, 1.0]))
         self._update_vp()
-
-        # True while every scene provably has the same view (all inputs so far were broadcast (3,)
-        # vectors): lets the renderer pre-render shared nodes once (static layer)
-        self._uni = {"eye": True, "fwd": True, "up": True}
         self.sync_from_base_cam = False
         if getattr(self.base, "_pbr_nodes", None):
             self.attach_all()
@@ -169,8 +168,19 @@ class PBRCam(PBRShaderContext):
     def _normalize(v: torch.Tensor) -> torch.Tensor:
         return v / torch.linalg.norm(v, dim=-1, keepdim=True).clamp_min(1e-8)
 
-    def _update_view(self, eye_k3=None, forward_k3=None, up_k3=None) -> None:
+    def _update_view(self, eye_k3=None, forward_k3=None, up_k3=None, fwd_uniform=None, up_uniform=None) -> None:
+        """``fwd_uniform`` / ``up_uniform``: whether the given forward / up input is the same for every
+        scene.  An omitted input reuses the current rows of V (reference camera.py:221), which may be
+        per-scene from an earlier call, so the uniformity of the *result* is tracked here: the basis
+        (rows s, u) is uniform only when both of its inputs -- given or reused -- are."""
         basis_changed = forward_k3 is not None or up_k3 is not None
+        if basis_changed:
+            f_uni = self._uni["fwd"] if forward_k3 is None else bool(self._bcast(forward_k3) if fwd_uniform is None else fwd_uniform)
+            u_uni = self._uni["up"] if up_k3 is None else bool(self._bcast(up_k3) if up_uniform is None else up_uniform)
+            self._uni["fwd"] = f_uni
+            self._uni["up"] = f_uni and u_uni
+        if eye_k3 is not None:
+            self._uni["eye"] = self._bcast(eye_k3)
         eye_changed = eye_k3 is not None
         if not basis_changed and not eye_changed:
             return
@@ -225,8 +235,8 @@ class PBRCam(PBRShaderContext):
 
     # ------------------------------------------------------------------ public API
     def look_at(self, target_k3, lazy: bool = False) -> None:
-        self._uni["fwd"] = self._uni["eye"] and self._bcast(target_k3)
-        self._update_view(forward_k3=self._fwd_from_lookat(target_k3))
+        self._update_view(forward_k3=self._fwd_from_lookat(target_k3),
+                          fwd_uniform=self._uni["eye"] and self._bcast(target_k3))
         if not lazy:
             self._update_vp()
 
@@ -237,11 +247,11 @@ class PBRCam(PBRShaderContext):
         self.set_eye(eye_k3, lazy=lazy)
 
     def set_positions_and_lookat(self, eye_k3, target_k3, lazy: bool = False) -> None:
-        self._uni["eye"] = self._bcast(eye_k3)
-        self._uni["fwd"] = self._uni["eye"] and self._bcast(target_k3)
+        uni = self._bcast(eye_k3) and self._bcast(target_k3)
         eye = self._ensure_kx3(eye_k3, "eye_k3")
         target = self._ensure_kx3(target_k3, "target_k3")
-        self._update_view(eye_k3=eye, forward_k3=self._fwd_from_lookat(target, eye))
+        self._update_view(eye_k3=eye, forward_k3=self._fwd_from_lookat(target, eye), fwd_uniform=uni)
+        self._uni["eye"] = self._bcast(eye_k3)
         if not lazy:
             self._update_vp()
 
@@ -250,35 +260,32 @@ class PBRCam(PBRShaderContext):
         return self._ensure_kx3(target_k3, "target_k3") - eye
 
     def set_hprs(self, hpr_k3, lazy: bool = False) -> None:
-        self._uni["fwd"] = self._uni["up"] = self._bcast(hpr_k3)
+        uni = self._bcast(hpr_k3)
         fwd, up = self._fwd_up_from_hpr(self._ensure_kx3(hpr_k3, "hpr_k3"))
-        self._update_view(forward_k3=fwd, up_k3=up)
+        self._update_view(forward_k3=fwd, up_k3=up, fwd_uniform=uni, up_uniform=uni)
         if not lazy:
             self._update_vp()
 
     def set_eye(self, eye_k3, lazy: bool = False) -> None:
-        self._uni["eye"] = self._bcast(eye_k3)
         self._update_view(eye_k3=eye_k3)
         if not lazy:
             self._update_vp()
 
     def set_forward(self, forward_k3, lazy: bool = False) -> None:
-        self._uni["fwd"] = self._bcast(forward_k3)
         self._update_view(forward_k3=forward_k3)
         if not lazy:
             self._update_vp()
 
     def set_up(self, up_k3, lazy: bool = False) -> None:
-        self._uni["up"] = self._bcast(up_k3)
         self._update_view(up_k3=up_k3)
         if not lazy:
             self._update_vp()
 
     def set_right(self, right_k3, lazy: bool = False) -> None:
-        self._uni["up"] = self._uni["fwd"] and self._bcast(right_k3)
         right = self._normalize(self._ensure_kx3(right_k3, "right_k3"))
         f = -self.V_k44[:, 2, 0:3]
-        self._update_view(forward_k3=f, up_k3=torch.cross(right, f, dim=-1))
+        self._update_view(forward_k3=f, up_k3=torch.cross(right, f, dim=-1), fwd_uniform=self._uni["fwd"],
+                          up_uniform=self._uni["fwd"] and self._bcast(right_k3))
         if not lazy:
             self._update_vp()
 

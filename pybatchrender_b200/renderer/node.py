@@ -16,6 +16,14 @@ What changed: ``matbuf`` / ``colbuf`` are float32 tensors on the renderer's devi
 the exact byte layout of the reference's RGBA32F buffer textures) that the CUDA rasteriser reads in
 place; nothing is serialised or re-uploaded per step.  On CUDA the upload is one fused kernel
 (``pbr_pack_transforms``) instead of a chain of torch ops.
+
+``set_pose`` (new) binds the node's matrices to *pose channels* -- position / HPR / scale given as
+constants or as 1-D views of a device tensor (typically columns of the simulation state).  The
+raster kernel then computes ``M = [Rz(h) Ry(p) Rx(r) * s | t]`` per instance itself when the frame
+runs: the reference's per-step ``set_positions`` + ``set_hprs`` + upload (node.py:128-143) cost no
+launch and no matrix traffic.  ``matbuf`` and the host mirrors are refreshed from the channels on
+demand (reading them materialises the matrices with ``pbr_compose_transforms``, the same device
+function the raster kernel uses); any generic setter ends the binding.
 """
 from __future__ import annotations
 
@@ -106,14 +114,110 @@ class PBRNode(PBRShaderContext):
 
         if self.has_geometry:
             dev, B = self.device, self.buf_instances
-            self.matbuf = torch.zeros((B, 16), dtype=torch.float32, device=dev)
+            self._matbuf = torch.zeros((B, 16), dtype=torch.float32, device=dev)
+            self._pose = None              # dict(pos, hpr, scale) while the matrices are bound to pose channels
+            self._mirror_stale = False
             self.colbuf = torch.ones((B, 4), dtype=torch.float32, device=dev)
             self._set_shader_input("instancesPerScene", self.instances_per_scene)
             self._set_shader_input("shareAcrossScenes", 1 if self.shared_across else 0)
-            self.transforms_b44 = torch.eye(4, dtype=torch.float32, device=dev).repeat(B, 1, 1)
-            self.rot3_b33 = torch.eye(3, dtype=torch.float32, device=dev).repeat(B, 1, 1)
-            self.scale_b11 = torch.ones((B, 1, 1), dtype=torch.float32, device=dev)
+            self._transforms_b44 = torch.eye(4, dtype=torch.float32, device=dev).repeat(B, 1, 1)
+            self._rot3_b33 = torch.eye(3, dtype=torch.float32, device=dev).repeat(B, 1, 1)
+            self._scale_b11 = torch.ones((B, 1, 1), dtype=torch.float32, device=dev)
             self._upload_current_transforms()
+
+    # ------------------------------------------------------------------ pose binding + lazy mirrors
+    def set_pose(self, pos=(0.0, 0.0, 0.0), hpr=(0.0, 0.0, 0.0), scale=1.0) -> None:
+        """Bind the matrices to pose channels: each of ``pos[0..2]``, ``hpr[0..2]`` (radians, the
+        reference's own convention R = Rz(H) Ry(P) Rx(R), shader_context.py:47-84) and ``scale`` is a
+        float or a 1-D float32 view with one element per instance (any stride) on the node's device.
+        The channels are read when a frame executes, so the tensors must hold the wanted state then
+        (they are kept alive here).  Equivalent to ``set_positions`` + ``set_hprs`` + ``set_scales``."""
+        if not self.has_geometry:
+            return
+        pos, hpr = tuple(pos), tuple(hpr)
+        if len(pos) != 3 or len(hpr) != 3:
+            raise ValueError("set_pose: pos and hpr take three channels each")
+        native = getattr(self.base, "_native", None)
+        if native is None or not self._matbuf.is_cuda:
+            # no GPU: the generic torch path (host logic stays testable; rendering needs CUDA anyway)
+            B = self.buf_instances
+
+            def col(c):
+                if isinstance(c, torch.Tensor):
+                    return c.reshape(-1).to(device=self.device, dtype=torch.float32)
+                return torch.full((B,), float(c), dtype=torch.float32, device=self.device)
+            self.set_positions(torch.stack([col(c) for c in pos], 1), lazy=True)
+            self.set_hprs(torch.stack([col(c) for c in hpr], 1), lazy=True)
+            self.set_scales(col(scale).reshape(-1, 1))
+            return
+        for c in pos + hpr + (scale,):
+            if isinstance(c, torch.Tensor) and (c.dim() != 1 or c.shape[0] != self.buf_instances or not c.is_cuda
+                                                or c.dtype != torch.float32):
+                raise ValueError(f"set_pose: channel tensors must be 1-D float32 CUDA views of {self.buf_instances} elements")
+        self._pose = dict(pos=pos, hpr=hpr, scale=scale)
+        self._mirror_stale = True
+        self._touch()
+
+    def _pose_desc(self):
+        """What the native layer needs to evaluate the pose (None: matrices come from matbuf)."""
+        return None if self._pose is None else dict(out=self._matbuf, **self._pose)
+
+    def _materialise_pose(self) -> None:
+        if self._pose is not None:
+            self.base._native.compose([self._pose_desc()], self.device)
+
+    def _sync_mirrors(self) -> None:
+        """Refresh transforms_b44 / rot3_b33 / scale_b11 from the bound pose (reference keeps them current on
+        every setter, node.py:116-134; here they are derived when somebody looks)."""
+        if not self._mirror_stale:
+            return
+        self._mirror_stale = False
+        self._materialise_pose()
+        B = self.buf_instances
+        T = self._matbuf.view(B, 4, 4).transpose(1, 2).contiguous()
+        sc = self._pose["scale"]
+        sc = sc.reshape(B, 1, 1).clone() if isinstance(sc, torch.Tensor) else torch.full(
+            (B, 1, 1), float(sc), dtype=torch.float32, device=self.device)
+        self._transforms_b44, self._scale_b11 = T, sc
+        self._rot3_b33 = T[:, 0:3, 0:3] / sc
+
+    def _end_pose(self) -> None:
+        """A generic setter takes over: bring the mirrors up to date, then drop the binding."""
+        if self.has_geometry and self._pose is not None:
+            self._sync_mirrors()
+            self._pose = None
+
+    @property
+    def matbuf(self) -> torch.Tensor:
+        self._materialise_pose()
+        return self._matbuf
+
+    @property
+    def transforms_b44(self) -> torch.Tensor:
+        self._sync_mirrors()
+        return self._transforms_b44
+
+    @transforms_b44.setter
+    def transforms_b44(self, v: torch.Tensor) -> None:
+        self._transforms_b44 = v
+
+    @property
+    def rot3_b33(self) -> torch.Tensor:
+        self._sync_mirrors()
+        return self._rot3_b33
+
+    @rot3_b33.setter
+    def rot3_b33(self, v: torch.Tensor) -> None:
+        self._rot3_b33 = v
+
+    @property
+    def scale_b11(self) -> torch.Tensor:
+        self._sync_mirrors()
+        return self._scale_b11
+
+    @scale_b11.setter
+    def scale_b11(self, v: torch.Tensor) -> None:
+        self._scale_b11 = v
 
     # ------------------------------------------------------------------ uploads
     def _as_rows(self, value, width: int) -> torch.Tensor:
@@ -125,18 +229,29 @@ class PBRNode(PBRShaderContext):
     def _upload_mat(self, mats: torch.Tensor) -> None:
         if not self.has_geometry:
             return
-        self.matbuf.view(-1, 4, 4).copy_(mats.transpose(1, 2))
+        self._end_pose()
+        self._matbuf.view(-1, 4, 4).copy_(mats.transpose(1, 2))
         self._touch()
 
     def _upload_current_transforms(self) -> None:
         if not self.has_geometry:
             return
+        self._end_pose()
+        B = self._matbuf.shape[0]
+        if self.scale_b11.shape[0] != B:
+            # the reference broadcasts a short scale tensor (rot3_b33 * scale_b11, node.py:119)
+            if self.scale_b11.shape[0] != 1:
+                raise ValueError(f"scale has {self.scale_b11.shape[0]} rows, node has {B} instances")
+            self.scale_b11 = self.scale_b11.expand(B, 1, 1).contiguous()
+        if self.transforms_b44.shape[0] != B or self.rot3_b33.shape[0] != B:
+            raise ValueError(f"transforms / rotations have {self.transforms_b44.shape[0]} / {self.rot3_b33.shape[0]} "
+                             f"rows, node has {B} instances")
         native = getattr(self.base, "_native", None)
-        if native is not None and self.matbuf.is_cuda:
-            native.pack_transforms(self.transforms_b44, self.rot3_b33, self.scale_b11, self.matbuf)
+        if native is not None and self._matbuf.is_cuda:
+            native.pack_transforms(self.transforms_b44, self.rot3_b33, self.scale_b11, self._matbuf)
         else:
             self.transforms_b44[:, 0:3, 0:3] = self.rot3_b33 * self.scale_b11
-            self.matbuf.view(-1, 4, 4).copy_(self.transforms_b44.transpose(1, 2))
+            self._matbuf.view(-1, 4, 4).copy_(self.transforms_b44.transpose(1, 2))
         self._touch()
 
     def _touch(self) -> None:
@@ -146,6 +261,7 @@ class PBRNode(PBRShaderContext):
     def set_positions(self, pos_si3, lazy: bool = False) -> None:
         if not self.has_geometry:
             return
+        self._end_pose()
         self.transforms_b44[:, 0:3, 3] = self._as_rows(pos_si3, 3)
         if not lazy:
             self._upload_current_transforms()
@@ -153,6 +269,7 @@ class PBRNode(PBRShaderContext):
     def set_hprs(self, hpr_si3, lazy: bool = False) -> None:
         if not self.has_geometry:
             return
+        self._end_pose()
         self.rot3_b33[:, :, :] = type(self)._rotation_mats_from_hpr(self._as_rows(hpr_si3, 3))
         if not lazy:
             self._upload_current_transforms()
@@ -160,6 +277,7 @@ class PBRNode(PBRShaderContext):
     def set_scales(self, scale_si1, lazy: bool = False) -> None:
         if not self.has_geometry:
             return
+        self._end_pose()
         if isinstance(scale_si1, (float, int)):
             self.scale_b11 = torch.full((self.buf_instances, 1, 1), float(scale_si1),
                                         dtype=torch.float32, device=self.device)
@@ -178,7 +296,10 @@ class PBRNode(PBRShaderContext):
         """Full per-instance matrices; split into rotation and mean-column-norm scale (node.py:163-178)."""
         if not self.has_geometry:
             return
+        self._end_pose()
         m = torch.as_tensor(mats_b44, dtype=torch.float32).to(self.device).reshape(-1, 4, 4)
+        if m.shape[0] != self.buf_instances:
+            raise ValueError(f"set_transforms: got {m.shape[0]} matrices for {self.buf_instances} instances")
         self.transforms_b44 = m.clone()
         r = self.transforms_b44[:, 0:3, 0:3].clone()
         s = torch.linalg.norm(r, dim=2).mean(dim=1).clamp_min(1e-8)

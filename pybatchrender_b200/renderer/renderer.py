@@ -199,8 +199,9 @@ class PBRRenderer:
             if n.texture_image is not None and n._native_texture is None:
                 from .. import _native
                 n._native_texture = _native.NativeTexture(n.texture_image, self.device)
-        return [(n._native_mesh, n.matbuf, n.colbuf, n.instances_per_scene, n.shared_across,
-                 in_base and n.shared_across, float(n.shader_inputs.get("useTexture", 0.0)), n._native_texture)
+        return [(n._native_mesh, n._matbuf, n.colbuf, n.instances_per_scene, n.shared_across,
+                 in_base and n.shared_across, float(n.shader_inputs.get("useTexture", 0.0)), n._native_texture,
+                 n._pose_desc())
                 for n in self._node_cache]
 
     def invalidate_static(self) -> None:

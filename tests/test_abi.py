@@ -14,6 +14,7 @@ HEADER = os.path.join(ROOT, "include", "pbr_b200.h")
 def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"#ifdef PBR_W_TIMING.*?#endif", "", src, flags=re.S)      # timing builds only (profiles/)
     return sorted(set(re.findall(r"\b(pbr_[a-z_0-9]+)\s*\(", src)))
 
 

@@ -19,6 +19,32 @@ def oracle_render(renderer, n_threads: int = 8, **kw) -> np.ndarray:
     return oracle.render(oracle_frame(renderer), n_threads=n_threads, **kw)
 
 
+def oracle_subset(renderer, scenes, n_threads: int = 8) -> np.ndarray:
+    """Oracle frames of the listed scenes only, as a compact [len(scenes), C, H, W] array: the per-scene rows
+    (VP, instance matrices and colours) of those scenes are gathered into a small frame, so sampling a huge
+    batch costs neither a full-size output nor one oracle call per scene."""
+    fa = renderer.frame_arrays()
+    scenes = np.asarray(list(scenes), dtype=np.int64)
+    nodes = []
+    for n in fa["nodes"]:
+        n = dict(n)
+        if not n["shared"]:
+            I = n["instances_per_scene"]
+            rows = (scenes[:, None] * I + np.arange(I)[None, :]).reshape(-1)
+            n["mats"], n["cols"] = n["mats"][rows], n["cols"][rows]
+        nodes.append(oracle.OracleNode(**n))
+    fr = oracle.OracleFrame(
+        num_scenes=len(scenes), tile_w=fa["tile_w"], tile_h=fa["tile_h"], channels=fa["channels"],
+        vp=fa["vp"][scenes], bg=fa["bg"], ambient=fa["ambient"], dir_dir=fa["dir_dir"], dir_col=fa["dir_col"],
+        strength=fa["strength"], nodes=nodes)
+    return oracle.render(fr, n_threads=n_threads)
+
+
+def host_threads() -> int:
+    import os
+    return max(1, min(64, os.cpu_count() or 1))
+
+
 def cartpole_states(n: int, seed: int = 0, device="cpu") -> torch.Tensor:
     """x ~ U(-2,2), theta ~ U(-30deg,30deg) (reference envs/cartpole/config.py:57-62)."""
     g = torch.Generator().manual_seed(seed)
