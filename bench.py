@@ -1,30 +1,39 @@
 #!/usr/bin/env python
-"""bench.py -- scene-frames/s of the CartPole 4096 x 64^2 render-to-tensor hot path.
+"""bench.py -- scene-frames/s of the render-to-tensor hot path on the BASELINE configurations.
 
 Contract (see DESIGN.md section "Measurement"):
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config {2,3,4,5}]
 
-* a *step* = ``renderer.step(state)``: pose kernel + raster kernel for one batch of 4096 CartPole
-  scenes (BASELINE.json configs[1]); per-GPU work is fixed, scenes are sharded with no collective
-  (``scaling: weak``); under torchrun every rank renders its own 4096 scenes.
-* ``value``: whole-job scene-frames/s with the state ring already resident in HBM, K steps replayed
-  from CUDA graphs, timed with CUDA events on the launching stream, max over ranks.
-* ``e2e``: same metric through the public API with HOST buffers: pinned state -> H2D -> step ->
-  D2H of the uint8 frames into pinned memory, every step, copies inside the timed region.  Two pinned
-  frame buffers: the D2H of frame i runs beside the H2D + render of frame i+1 and the host waits for
-  every frame (``value_sync_every_step``: the same loop with a stream synchronize after every frame).
-* ``roofline``: the raster kernel alone (same inputs), algorithmic bytes / average launch time
-  against MEASURED_PEAKS.json's HBM copy bandwidth.
-* ``cpu_baseline``: the CPU oracle (``oracle/``, a port of the reference pipeline) timed on the
-  host cores on a bounded sample of the same workload (rank 0, N=1 only).
-* ``--impl reference``: the reference's own pipeline cannot run (Panda3D/OpenGL absent), so this arm
-  times the oracle port on all host cores, on the same config / metric.
+Headline = ``--config 2`` (default): CartPole 4096 x 64^2 per GPU (BASELINE.json configs[1]); scenes are sharded
+with no collective (``scaling: weak``), under torchrun every rank renders its own 4096 scenes.  The other BASELINE
+configurations -- 3: many-cubes 1024 x 256 boxes at 128^2 (weak), 4: CartPole 65,536 x 84^2 *strong*-sharded over
+the ranks, 5: mixed-mesh 16,384 x 64 instances at 256^2 (strong) -- are measured in the same run with a short
+device-timed loop and reported under ``extra`` (``--no-extras`` skips them; ``--config C`` makes C the headline).
+
+* a *step* = ``renderer.step(state)``: ONE raster kernel for CartPole (the pose of cart and pole is computed in the
+  kernel from the state tensor), geometry pre-pass + staged raster for the large scenes.
+* ``value``: whole-job scene-frames/s with the inputs already resident in HBM, K steps (CartPole: replayed from
+  CUDA graphs that were replayed before the timed region as well), CUDA events on the launching stream, max over ranks.
+  ``value_eager``: the same K steps issued eagerly through ``renderer.step`` (host-side launch cost included).
+* ``verified``: after the timed region every output-ring buffer is compared with the CPU oracle's frame of the state
+  that was rendered into it last (all scenes; config 5: 64 scenes spread over the batch).  A mismatch aborts the line.
+* ``e2e``: same metric through the public API with HOST buffers: pinned inputs -> H2D -> step -> D2H of the uint8
+  frames into pinned memory, every step, copies inside the timed region (two pinned frame buffers; the host waits for
+  every frame).  ``d2h_ceiling_GBps``: a plain pinned D2H copy of one frame on all ranks at once, the bound of e2e.
+* ``roofline``: the dominant raster kernel alone (same inputs), algorithmic bytes / average launch time against
+  MEASURED_PEAKS.json's HBM copy bandwidth; ``traffic`` from the ncu range capture committed under profiles/.
+* ``env_step``: full ``env.step`` of the CartPole environment (physics + render, no per-step sync; 5 warm-up + 100
+  steps: the protocol of the reference's examples/scripts/cartpole_benchmark.py:135-168).
+* ``gather`` (N > 1): NCCL gather of all ranks' frames onto rank 0, timed separately, never part of ``value``.
+* ``cpu_baseline`` / ``--impl reference``: the CPU oracle (``oracle/``, a port of the reference pipeline -- Panda3D +
+  OpenGL cannot run here) on all host cores, persistent thread pool, frame marshalled once, best of 5 (3) blocks of >= 1 s (3 s).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -34,12 +43,32 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-SCENES_PER_GPU = 4096
-TILE = (64, 64)
-ALGO_BYTES_PER_SCENE = 3 * 64 * 64 + 64 + 2 * (64 + 16)      # 12,512 B
 STATE_RING = 16
-OUT_RING = 4            # 4 x 50.3 MB of output > 126 MB L2, so pixel writes cannot stay cached
-NCU_DRAM_BYTES_PER_LAUNCH = 1003008 + 1779712      # ncu --set full, profiles/r01q_raster_warp_ncu.txt
+
+# name, scenes (global for strong scaling, per GPU for weak), tile, algorithmic bytes per scene-frame
+CONFIGS = {
+    2: dict(kind="cartpole", scenes=4096, tile=(64, 64), scaling="weak", algo=3 * 64 * 64 + 64 + 2 * 80,
+            metric="scene-frames/sec to torch tensor (CartPole 4096x64^2)",
+            workload="CartPole-v0 num_scenes=4096 per GPU, tile 64x64 (BASELINE configs[1])"),
+    3: dict(kind="cubes", scenes=1024, tile=(128, 128), scaling="weak", algo=3 * 128 * 128 + 64 + 256 * 80,
+            metric="scene-frames/sec to torch tensor (many-cubes 1024x256 boxes, 128^2)",
+            workload="demo_many_cubes: 1024 scenes x 256 box instances per GPU, tile 128x128 (BASELINE configs[2])"),
+    4: dict(kind="cartpole", scenes=65536, tile=(84, 84), scaling="strong", algo=3 * 84 * 84 + 64 + 2 * 80,
+            metric="scene-frames/sec to torch tensor (CartPole 65536x84^2, scene-sharded)",
+            workload="CartPole-v0 num_scenes=65536 in total, tile 84x84, scene-sharded over the GPUs (BASELINE configs[3])"),
+    5: dict(kind="mixed", scenes=16384, tile=(256, 256), scaling="strong", algo=3 * 256 * 256 + 64 + 64 * 80,
+            metric="scene-frames/sec to torch tensor (mixed-mesh 16384x64 instances, 256^2, scene-sharded)",
+            workload="mixed-mesh: 16384 scenes x 64 instances (box, cone.egg, cylinder glTF, sphere) in total, tile "
+                     "256x256, scene-sharded over the GPUs (BASELINE configs[4])"),
+}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of raster_warp_kernel<14, true> from an ncu range over
+# consecutive launches cycling the 4-buffer output ring (profiles/r02*_traffic_range.txt); None until captured
+NCU_TRAFFIC = {2: None}
+try:
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as _f:
+        NCU_TRAFFIC.update({int(k): v for k, v in json.load(_f).items()})
+except Exception:
+    pass
 
 
 def parse():
@@ -48,10 +77,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer loop (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", action="store_true",
-                    help="N>1: also time the optional NCCL gather of all frames onto rank 0 (reported separately)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs and env_step")
+    ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NCCL gather timing")
+    ap.add_argument("--gather", action="store_true", help="(default at N>1; kept for compatibility)")
+    ap.add_argument("--no-verify", action="store_true", help="profiling runs only: skip the oracle comparison")
     return ap.parse_args()
 
 
@@ -65,7 +97,7 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------------------------
-# clocks sampler (NVML), runs while the timed region executes
+# clocks sampler (NVML), runs while the timed regions execute
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     def __init__(self, index: int):
@@ -119,51 +151,112 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-# workload
+# oracle helpers (the checker of `verified`, and the CPU legs)
 # ------------------------------------------------------------------------------------------------
-def cartpole_state(n, seed, torch):
-    """x ~ U(-2,2), theta ~ U(-30deg,30deg): reference envs/cartpole/config.py:57-62 reset ranges."""
-    g = torch.Generator().manual_seed(seed)
-    s = torch.zeros(n, 4)
-    s[:, 0] = torch.rand(n, generator=g) * 4.0 - 2.0
-    s[:, 1] = torch.rand(n, generator=g) * 2.0 - 1.0
-    s[:, 2] = (torch.rand(n, generator=g) * 60.0 - 30.0) * (3.141592653589793 / 180.0)
-    s[:, 3] = (torch.rand(n, generator=g) * 30.0 - 15.0) * (3.141592653589793 / 180.0)
-    return s
+def oracle_frame_of(renderer, scenes=None):
+    """Renderer state -> oracle frame; ``scenes``: gather only those scenes' rows into a compact frame."""
+    import numpy as np
 
-
-def oracle_frame_of(renderer):
     import oracle
     fa = renderer.frame_arrays()
-    return oracle.OracleFrame(num_scenes=fa["num_scenes"], tile_w=fa["tile_w"], tile_h=fa["tile_h"],
-                              channels=fa["channels"], vp=fa["vp"], bg=fa["bg"], ambient=fa["ambient"],
-                              dir_dir=fa["dir_dir"], dir_col=fa["dir_col"], strength=fa["strength"],
-                              nodes=[oracle.OracleNode(**nd) for nd in fa["nodes"]])
+    nodes = []
+    vp = fa["vp"]
+    K = fa["num_scenes"]
+    if scenes is not None:
+        scenes = np.asarray(list(scenes), dtype=np.int64)
+        vp, K = vp[scenes], len(scenes)
+    for n in fa["nodes"]:
+        n = dict(n)
+        if scenes is not None and not n["shared"]:
+            I = n["instances_per_scene"]
+            rows = (scenes[:, None] * I + np.arange(I)[None, :]).reshape(-1)
+            n["mats"], n["cols"] = n["mats"][rows], n["cols"][rows]
+        nodes.append(oracle.OracleNode(**n))
+    return oracle.OracleFrame(num_scenes=K, tile_w=fa["tile_w"], tile_h=fa["tile_h"], channels=fa["channels"], vp=vp,
+                              bg=fa["bg"], ambient=fa["ambient"], dir_dir=fa["dir_dir"], dir_col=fa["dir_col"],
+                              strength=fa["strength"], nodes=nodes)
 
 
-def time_cpu_oracle(target_s: float, cores: int, seed0: int = 1000):
-    """Times the oracle port: whole CartPole 4096x64^2 steps (host pose update + raster) until about
-    ``target_s`` seconds have elapsed.  Returns (scene_frames_per_s, steps, seconds)."""
-    import numpy as np
-    import torch
+class CpuArm:
+    """The CPU port on the same workload: a renderer on the CPU device (host pose update, the reference's
+    envs/cartpole/renderer.py:98-138 on the host) + the oracle rasteriser, frame marshalled once."""
 
-    import oracle
-    from pybatchrender_b200.envs.cartpole import CartPoleRenderer
-    r = CartPoleRenderer(dict(num_scenes=SCENES_PER_GPU, tile_resolution=TILE, device="cpu"))
-    out = np.zeros((SCENES_PER_GPU, 3, TILE[1], TILE[0]), np.uint8)
-    states = [cartpole_state(SCENES_PER_GPU, seed0 + i, torch) for i in range(4)]
-    r._step(states[0])
-    oracle.render(oracle_frame_of(r), n_threads=cores, out=out)     # warm-up (page faults, lib load)
-    t0 = time.perf_counter()
-    steps = 0
-    while True:
-        r._step(states[steps % 4])
-        oracle.render(oracle_frame_of(r), n_threads=cores, out=out)
-        steps += 1
-        dt = time.perf_counter() - t0
-        if dt >= target_s or steps >= 4096:
-            break
-    return SCENES_PER_GPU * steps / dt, steps, dt
+    def __init__(self, config: int, cores: int, sample_scenes: int | None = None):
+        import numpy as np
+        import torch
+
+        import oracle
+        from pybatchrender_b200 import workloads
+        from pybatchrender_b200.envs.cartpole import CartPoleRenderer
+        c = CONFIGS[config]
+        self.c, self.cores = c, cores
+        W, H = c["tile"]
+        # the host pose update is a few small torch ops; with torch's own thread pool left on, its spinning
+        # OpenMP workers fight the rasteriser's threads for the cores (measured: 20 ms per step instead of 8)
+        torch.set_num_threads(1)
+        if c["kind"] == "cartpole":
+            n = c["scenes"]
+            self.r = CartPoleRenderer(dict(num_scenes=n, tile_resolution=c["tile"], device="cpu"))
+            self.states = [workloads.cartpole_state(n, 1000 + i) for i in range(4)]
+            self.r._step(self.states[0])
+            scenes = None
+        else:
+            build = workloads.many_cubes if c["kind"] == "cubes" else workloads.mixed_meshes
+            self.r = build(device="cpu")
+            self.states = None
+            n = c["scenes"]
+            scenes = None
+        # bounded sample: a contiguous prefix of the scenes (the scenes are i.i.d.)
+        self.n_total = n
+        self.n = n if sample_scenes is None else min(n, sample_scenes)
+        fa_frame = oracle_frame_of(self.r)
+        if self.states is not None:
+            # alias the live CPU matrix buffers so that the per-step host pose update is seen without re-marshalling
+            live = [nd for nd in self.r._drawable_nodes()]
+            for on, nd in zip(fa_frame.nodes, live):
+                on.mats = nd._matbuf.numpy()
+                on.cols = nd.colbuf.numpy()
+        self.out = np.zeros((n, 3, H, W), np.uint8)
+        self.packed = oracle.PackedFrame(fa_frame, self.out, n_threads=cores, scene_begin=0, scene_count=self.n)
+
+    def step(self, i: int) -> None:
+        if self.states is not None:
+            self.r._step(self.states[i % 4])
+        self.packed.render()
+
+    def time_blocks(self, steps_per_block: int, blocks: int = 3, min_block_s: float = 1.0, warmup: int = 3):
+        for i in range(max(1, warmup)):
+            self.step(i)
+        per = None
+        for i in range(3):                       # fastest of three single steps sizes the blocks
+            t0 = time.perf_counter()
+            self.step(i)
+            dt = max(time.perf_counter() - t0, 1e-4)
+            per = dt if per is None or dt < per else per
+        # a block lasts >= min_block_s and at most ~4 s however many steps were asked for
+        target_s = min(max(min_block_s, steps_per_block * per), max(min_block_s, 4.0))
+        n_steps = max(1, int(math.ceil(target_s / per)))
+        best = None
+        self.blocks = blocks
+        done = 0
+        while done < blocks:
+            t0 = time.perf_counter()
+            for i in range(n_steps):
+                self.step(i)
+            dt = time.perf_counter() - t0
+            if dt < 0.8 * min_block_s:
+                # the sizing steps were slower than the steady state: lengthen the block, do not count this one
+                n_steps = int(math.ceil(n_steps * 1.1 * min_block_s / dt))
+                best = None
+                done = 0
+                continue
+            best = dt if best is None or dt < best else best
+            done += 1
+        return self.n * n_steps / best, n_steps, best
+
+    def sample_text(self, n_steps, dt):
+        part = "full frames" if self.n == self.n_total else f"frames of the first {self.n} of {self.n_total} scenes"
+        return f"best of {self.blocks} blocks of {n_steps} {part} ({dt:.2f} s per block), {self.cores} threads, persistent pool"
 
 
 def run_reference(args):
@@ -171,44 +264,381 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    c = CONFIGS[args.config]
     K, W = max(1, args.steps), max(0, args.warmup)
-    # bounded sample: each "step" here is one full 4096-scene frame on the CPU; cap the wall time
-    import numpy as np
-    import torch
-
-    import oracle
-    from pybatchrender_b200.envs.cartpole import CartPoleRenderer
-    r = CartPoleRenderer(dict(num_scenes=SCENES_PER_GPU, tile_resolution=TILE, device="cpu"))
-    out = np.zeros((SCENES_PER_GPU, 3, TILE[1], TILE[0]), np.uint8)
-    states = [cartpole_state(SCENES_PER_GPU, 1000 + i, torch) for i in range(4)]
-    budget_s = 120.0
-    t_w = time.perf_counter()
-    for i in range(min(W, 3)):
-        r._step(states[i % 4])
-        oracle.render(oracle_frame_of(r), n_threads=cores, out=out)
-    per = (time.perf_counter() - t_w) / max(1, min(W, 3)) if W else 0.2
-    k_eff = max(1, min(K, int(budget_s / max(per, 1e-3))))
-    t0 = time.perf_counter()
-    for i in range(k_eff):
-        r._step(states[i % 4])
-        oracle.render(oracle_frame_of(r), n_threads=cores, out=out)
-    dt = time.perf_counter() - t0
-    value = SCENES_PER_GPU * k_eff / dt
+    sample = {2: None, 3: 256, 4: 16384, 5: 64}[args.config]
+    arm = CpuArm(args.config, cores, sample)
+    value, n_steps, dt = arm.time_blocks(K, blocks=5, min_block_s=1.0, warmup=min(W, 50))
     line = {
-        "impl": "reference",
-        "metric": "scene-frames/sec to torch tensor (CartPole 4096x64^2)",
-        "value": value, "unit": "scene-frames/s", "n_gpus": args.gpus, "steps": k_eff, "warmup": min(W, 3),
-        "ms_per_step": 1e3 * dt / k_eff, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32+i64 (u8 out)", "data": "synthetic",
-        "config": {"workload": "CartPole-v0 num_scenes=4096 tile 64x64 (BASELINE configs[1])",
-                   "note": "reference pipeline (Panda3D + OpenGL) cannot run in this image; this arm times "
-                           "the CPU oracle port of it on the host cores"},
+        "impl": "reference", "metric": c["metric"], "value": value, "unit": "scene-frames/s", "n_gpus": args.gpus,
+        "steps": K, "warmup": W, "ms_per_step": 1e3 * dt / n_steps * (arm.n_total / arm.n), "higher_is_better": True,
+        "scaling": c["scaling"], "vs_baseline": None, "dtype": "f32+i64 (u8 out)", "data": "synthetic",
+        "config": {"workload": c["workload"],
+                   "note": "reference pipeline (Panda3D + OpenGL) cannot run in this image; this arm times the CPU "
+                           "oracle port of it on the host cores; ms_per_step is scaled to the full batch"},
         "cpu_baseline": {"value": value, "unit": "scene-frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{k_eff} full frames of 4096 scenes ({dt:.1f} s)"},
+                         "sample": arm.sample_text(n_steps, dt)},
         "e2e": {"value": value, "unit": "scene-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU workloads
+# ------------------------------------------------------------------------------------------------
+class Workload:
+    """One BASELINE configuration on this rank: renderer, input ring, output ring, step functions."""
+
+    def __init__(self, config: int, dev, rank: int, world: int):
+        import torch
+
+        from pybatchrender_b200 import workloads
+        from pybatchrender_b200.dist import shard_config
+        from pybatchrender_b200.envs.cartpole import CartPoleConfig, CartPoleRenderer
+        c = CONFIGS[config]
+        self.c, self.config, self.dev, self.rank, self.world = c, config, dev, rank, world
+        W, H = c["tile"]
+        strong = c["scaling"] == "strong"
+        self.total_scenes = c["scenes"] if strong else c["scenes"] * world
+        if c["kind"] == "cartpole":
+            cfg = CartPoleConfig(num_scenes=c["scenes"], tile_resolution=c["tile"], device="cuda")
+            if strong and world > 1:
+                cfg = shard_config(cfg, rank, world)
+            self.r = CartPoleRenderer(cfg)
+            n = int(cfg.num_scenes)
+            self.states = [workloads.cartpole_state(n, 1000 * rank + i).to(dev) for i in range(STATE_RING)]
+            self.kernel = "raster_warp_kernel<14, true>"
+        else:
+            build = workloads.many_cubes if c["kind"] == "cubes" else workloads.mixed_meshes
+            if strong:
+                self.r = build(device="cuda", rank=rank, world_size=world)
+            else:
+                self.r = build(device="cuda", seed=123 + rank)
+            n = int(self.r.num_scenes)
+            self.states = None
+            self.kernel = "cull_kernel + geom_kernel + raster_staged_kernel<%s> (the whole large-scene pipeline)" % (
+                "true" if c["kind"] == "mixed" else "false")
+        self.n = n
+        self.frame_bytes = n * 3 * H * W
+        # output ring: more than the 126 MB L2 in flight, and >= 3 buffers where it is cheap so that consecutive
+        # frames (which overlap through the programmatic launch chain) never write the same memory
+        self.out_ring = 4 if self.frame_bytes <= (256 << 20) else (3 if self.frame_bytes <= (2 << 30) else 1)
+        self.outs = [torch.empty((n, 3, H, W), dtype=torch.uint8, device=dev) for _ in range(self.out_ring)]
+        self.use_graphs = c["kind"] == "cartpole"
+
+    def step(self, i: int):
+        out = self.outs[i % self.out_ring]
+        if self.states is not None:
+            return self.r.step(self.states[i % STATE_RING], out=out)
+        return self.r.render(out=out)
+
+    def raster_only(self, i: int):
+        return self.r.render(out=self.outs[i % self.out_ring])
+
+    # e2e: host inputs of one step
+    def make_host_inputs(self):
+        import torch
+
+        from pybatchrender_b200 import workloads
+        if self.states is not None:
+            self.h_in = [[workloads.cartpole_state(self.n, 5000 + 1000 * self.rank + i).pin_memory()] for i in range(4)]
+            self.d_in = [torch.empty((self.n, 4), dtype=torch.float32, device=self.dev)]
+        else:
+            nodes = [nd for nd in self.r._drawable_nodes() if not nd.shared_across]
+            self.d_in = [nd._matbuf for nd in nodes]
+            self.h_in = [[t.cpu().pin_memory() for t in self.d_in] for _ in range(2)]
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.d_in)
+
+    def e2e_render(self, i: int):
+        for h, d in zip(self.h_in[i % len(self.h_in)], self.d_in):
+            d.copy_(h, non_blocking=True)
+        out = self.outs[i % self.out_ring]
+        if self.states is not None:
+            return self.r.step(self.d_in[0], out=out)
+        return self.r.render(out=out)
+
+    def verify(self, last_step_of_buffer: dict, cores: int):
+        """Every ring buffer against the oracle's frame of the state rendered into it last."""
+        import numpy as np
+        import torch
+
+        import oracle
+        checked = 0
+        for b, i in sorted(last_step_of_buffer.items()):
+            got = self.outs[b]
+            if self.states is not None:
+                self.r._step(self.states[i % STATE_RING])
+            if self.c["kind"] == "mixed":
+                sample = sorted(set(range(0, self.n, max(1, self.n // 64))) | {self.n - 1})
+                ref = oracle.render(oracle_frame_of(self.r, sample), n_threads=cores)
+                got = got[torch.tensor(sample, device=got.device)]
+            elif self.states is None and checked > 0:
+                ref = None                      # static scene: the other ring buffers must equal the verified one
+                if not torch.equal(got, self.outs[sorted(last_step_of_buffer)[0]]):
+                    return False, f"ring buffer {b} differs from buffer 0"
+            else:
+                ref = oracle.render(oracle_frame_of(self.r), n_threads=cores)
+            if ref is not None:
+                same = np.array_equal(got.cpu().numpy(), ref)
+                if not same:
+                    return False, f"ring buffer {b} (step {i}) differs from the oracle"
+            checked += 1
+        what = "64 sampled scenes" if self.c["kind"] == "mixed" else "all scenes"
+        return True, f"{checked} ring buffer(s), {what} each, bit-exact vs the CPU oracle"
+
+
+def timed_run(wl: Workload, K: int, W: int, barrier, native):
+    """K steps of ``wl.step`` timed with CUDA events (graphs for CartPole); returns (ms, launches, last writer of
+    every ring buffer)."""
+    import torch
+    last = {}
+    if wl.use_graphs:
+        side = torch.cuda.Stream(wl.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(3):
+                wl.step(i)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+
+        def capture(n_steps):
+            g = torch.cuda.CUDAGraph()
+            l0 = native.kernel_launches()
+            with torch.cuda.graph(g):
+                for i in range(n_steps):
+                    wl.step(i)
+            return g, native.kernel_launches() - l0
+
+        g_full, l_full = capture(STATE_RING)
+        tail = K % STATE_RING
+        g_tail, l_tail = capture(tail) if tail else (None, 0)
+
+        def run_steps(k):
+            # exactly k steps: whole graphs, then the tail graph (k % STATE_RING == tail by construction)
+            for _ in range(k // STATE_RING):
+                g_full.replay()
+            if k % STATE_RING:
+                g_tail.replay()
+        # warm-up: >= W steps and, whatever W is, at least two replays of every graph that is timed
+        for _ in range(max(2, (W + STATE_RING - 1) // STATE_RING)):
+            g_full.replay()
+        if g_tail is not None:
+            for _ in range(2):
+                g_tail.replay()
+        launches = (K // STATE_RING) * l_full + (l_tail if tail else 0)
+        # what each ring buffer holds at the end: the full graph ran (in the warm-up at least), then the tail graph
+        for i in list(range(STATE_RING)) + list(range(tail)):
+            last[i % wl.out_ring] = i
+    else:
+        for i in range(max(3, W)):
+            wl.step(i)
+
+        def run_steps(k):
+            for i in range(k):
+                wl.step(i)
+        launches = None
+        for i in range(K):
+            last[i % wl.out_ring] = i
+    barrier()
+    l0 = native.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_steps(K)
+    e1.record()
+    barrier()
+    if launches is None:
+        launches = native.kernel_launches() - l0
+    return e0.elapsed_time(e1), launches, last
+
+
+def roofline_leg(wl: Workload, K: int):
+    """The raster kernel(s) alone on resident inputs: average launch time over the same number of steps."""
+    import torch
+    reps = max(1, K // STATE_RING)
+    if wl.use_graphs:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(STATE_RING):
+                wl.raster_only(i)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(reps):
+            g.replay()
+        r1.record()
+        torch.cuda.synchronize()
+        return r0.elapsed_time(r1) / (reps * STATE_RING)
+    n = max(2, min(K, 20))
+    for i in range(2):
+        wl.raster_only(i)
+    torch.cuda.synchronize()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for i in range(n):
+        wl.raster_only(i)
+    r1.record()
+    torch.cuda.synchronize()
+    return r0.elapsed_time(r1) / n
+
+
+def max_over_ranks(values, dev, distributed):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(values, dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def measure_config(config, K, W, dev, rank, world, distributed, barrier, native, cores, verify=True, full=False,
+                   e2e_steps=0):
+    """Device-timed value + roofline + verification of one configuration; ``full`` adds eager and e2e legs."""
+    import torch
+    wl = Workload(config, dev, rank, world)
+    c = wl.c
+    ms, launches, last = timed_run(wl, K, W, barrier, native)
+    res = {}
+    if verify:
+        ok, how = wl.verify(last, cores)
+        flag = max_over_ranks([0.0 if ok else 1.0], dev, distributed)[0]
+        if flag != 0.0:
+            raise SystemExit(f"bench.py: config {config}: frames differ from the oracle on some rank ({how}); no line printed")
+        res["verified"], res["verified_how"] = True, how
+    else:
+        res["verified"], res["verified_how"] = None, "skipped (--no-verify)"
+    raster_ms = roofline_leg(wl, K)
+    legs = [ms, raster_ms]
+
+    if full:
+        # eager: the same K steps issued one by one through renderer.step (bounded so that it stays short)
+        k_e = min(K, 2000)
+        for i in range(16):
+            wl.step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(k_e):
+            wl.step(i)
+        host_s = time.perf_counter() - t0
+        e1.record()
+        barrier()
+        eager_ms = e0.elapsed_time(e1)
+        legs += [eager_ms / k_e, host_s * 1e3 / k_e]
+
+        # e2e, host buffers: sync after every frame, and pipelined over two pinned frame buffers
+        wl.make_host_inputs()
+        H, Wd = c["tile"][1], c["tile"][0]
+        h_outs = [torch.empty((wl.n, 3, H, Wd), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        n_e2e = e2e_steps or max(8, min(K, 200 if wl.frame_bytes < (256 << 20) else 10))
+
+        def e2e_sync(i):
+            px = wl.e2e_render(i)
+            h_outs[0].copy_(px, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for i in range(3):
+            e2e_sync(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            e2e_sync(i)
+        barrier()
+        e2e_sync_s = time.perf_counter() - t0
+
+        copy_stream = torch.cuda.Stream(dev)
+        landed = [None, None]
+
+        def e2e_pipe(i):
+            px = wl.e2e_render(i)
+            rendered = torch.cuda.Event()
+            rendered.record()
+            if landed[i % 2] is not None:
+                landed[i % 2].synchronize()             # frame i-2 is on the host: its buffer is free again
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(rendered)
+                h_outs[i % 2].copy_(px, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            landed[i % 2] = ev
+
+        def drain():
+            for ev in landed:
+                if ev is not None:
+                    ev.synchronize()
+
+        for i in range(4):
+            e2e_pipe(i)
+        drain()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            e2e_pipe(i)
+        drain()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+
+        # the bound of e2e: plain pinned D2H copies of one frame, all ranks at once
+        for _ in range(2):
+            h_outs[0].copy_(wl.outs[0], non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        n_copy = 10
+        for k in range(n_copy):
+            h_outs[k % 2].copy_(wl.outs[0], non_blocking=True)
+        barrier()
+        d2h_s = (time.perf_counter() - t0) / n_copy
+        legs += [e2e_s * 1e3, e2e_sync_s * 1e3, d2h_s * 1e3]
+
+    legs = max_over_ranks(legs, dev, distributed)
+    ms, raster_ms = legs[0], legs[1]
+    peak, peak_src = measured_peak()
+    per_rank = wl.n
+    value = wl.total_scenes * K / (ms * 1e-3)
+    achieved = c["algo"] * per_rank / (raster_ms * 1e-3) / 1e9
+    traffic = NCU_TRAFFIC.get(config)
+    res.update({
+        "metric": c["metric"], "value": value, "unit": "scene-frames/s", "ms_per_step": ms / K, "steps": K,
+        "scaling": c["scaling"],
+        "config": {"workload": c["workload"], "scenes_per_gpu": per_rank, "scenes_total": wl.total_scenes,
+                   "tile": list(c["tile"]), "channels": 3,
+                   "parallelism": f"scene-sharded x{world}, no collective",
+                   "l2": f"output ring of {wl.out_ring} x {wl.frame_bytes / 1e6:.1f} MB (> 126 MB L2 in flight)"
+                         + (f"; state ring of {STATE_RING}" if wl.states is not None else ""),
+                   "launch": (f"CUDA graphs of {STATE_RING} steps, each replayed before the timed region; one kernel "
+                              "per step, consecutive frames overlap through programmatic dependent launch")
+                   if wl.use_graphs else "eager: instance cull + geometry pre-pass + staged raster per launch chunk"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic,
+                     "traffic_over_algorithmic": None if traffic is None else traffic / (c["algo"] * per_rank),
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu range over consecutive "
+                                     "launches cycling the output ring (profiles/)" if traffic is not None
+                     else "not captured for this configuration",
+                     "kernel": wl.kernel, "kernel_ms": raster_ms,
+                     "algorithmic_bytes_per_launch": c["algo"] * per_rank, "peak_source": peak_src},
+        "gpu_launches": launches,
+    })
+    if full:
+        eager_ms_step, host_ms_step, e2e_ms, e2e_sync_ms, d2h_ms = legs[2:7]
+        res["value_eager"] = {"value": wl.total_scenes / (eager_ms_step * 1e-3), "unit": "scene-frames/s",
+                              "ms_per_step": eager_ms_step, "host_ms_per_step": host_ms_step,
+                              "how": "the same steps issued eagerly through renderer.step (no CUDA graph), CUDA events; "
+                                     "host_ms_per_step = wall time the Python loop spends per call"}
+        ceiling = wl.frame_bytes * world / (d2h_ms * 1e-3) / 1e9
+        e2e_val = wl.total_scenes * n_e2e / (e2e_ms * 1e-3)
+        res["e2e"] = {"value": e2e_val, "unit": "scene-frames/s", "h2d_bytes_per_step": wl.h2d_bytes,
+                      "d2h_bytes_per_step": wl.frame_bytes, "steps": n_e2e,
+                      "how": "pinned host inputs -> H2D -> step -> D2H of the frames every step; two pinned frame buffers, "
+                             "the D2H of frame i overlaps the H2D + render of frame i+1, the host waits for every frame",
+                      "value_sync_every_step": wl.total_scenes * n_e2e / (e2e_sync_ms * 1e-3),
+                      "d2h_ceiling_GBps": ceiling,
+                      "d2h_GBps": e2e_val * 3 * c["tile"][0] * c["tile"][1] / 1e9,
+                      "frac_of_d2h_ceiling": (e2e_val * 3 * c["tile"][0] * c["tile"][1] / 1e9) / ceiling,
+                      "ceiling_note": "plain pinned device->host copies of one frame issued on all ranks at once (aggregate GB/s)"}
+    return res, wl
 
 
 def run_ours(args):
@@ -228,48 +658,10 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from pybatchrender_b200.config import grid_for
-    from pybatchrender_b200.envs.cartpole import CartPoleRenderer
-
+    from pybatchrender_b200 import _native
+    native = _native.Native()
+    cores = os.cpu_count() or 1
     K, W = max(1, args.steps), max(3, args.warmup)
-    N = SCENES_PER_GPU
-    r = CartPoleRenderer(dict(num_scenes=N, tile_resolution=TILE, device="cuda"))
-    states = [cartpole_state(N, 1000 * rank + i, torch).to(dev) for i in range(STATE_RING)]
-    outs = [torch.empty((N, 3, TILE[1], TILE[0]), dtype=torch.uint8, device=dev) for _ in range(OUT_RING)]
-    launches_per_step = 2          # pose kernel + raster kernel
-
-    def step(i):
-        return r.step(states[i % STATE_RING], out=outs[i % OUT_RING])
-
-    # ---- graphs: STATE_RING steps per replay (+ a tail graph so that exactly K steps are timed)
-    side = torch.cuda.Stream(dev)
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for i in range(3):
-            step(i)
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-
-    def capture(n_steps, fn):
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for i in range(n_steps):
-                fn(i)
-        return g
-
-    g_full = capture(STATE_RING, step)
-    tail = K % STATE_RING
-    g_tail = capture(tail, step) if tail else None
-
-    def run_steps(k):
-        for _ in range(k // STATE_RING):
-            g_full.replay()
-        if k % STATE_RING:
-            if k % STATE_RING == tail and g_tail is not None:
-                g_tail.replay()
-            else:
-                for i in range(k % STATE_RING):
-                    step(i)
 
     def barrier():
         if distributed:
@@ -279,155 +671,99 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
 
-    run_steps(W)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run_steps(K)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    head, wl = measure_config(args.config, K, W, dev, rank, world, distributed, barrier, native, cores,
+                              verify=not args.no_verify, full=True, e2e_steps=args.e2e_steps)
 
-    # ---- roofline leg: the raster kernel alone
-    def raster_only(i):
-        r.render(out=outs[i % OUT_RING])
-    g_r = capture(STATE_RING, raster_only)
-    for _ in range(3):
-        g_r.replay()
-    torch.cuda.synchronize()
-    reps = max(1, K // STATE_RING)
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    r0.record()
-    for _ in range(reps):
-        g_r.replay()
-    r1.record()
-    torch.cuda.synchronize()
-    raster_ms = r0.elapsed_time(r1) / (reps * STATE_RING)
-
-    # ---- e2e leg: host buffers, copies inside the timed region, result on the host every step
-    e2e_steps = args.e2e_steps or max(8, min(K, 200))
-    h_states = [cartpole_state(N, 5000 + 1000 * rank + i, torch).pin_memory() for i in range(4)]
-    h_out = torch.empty((N, 3, TILE[1], TILE[0]), dtype=torch.uint8).pin_memory()
-    d_state = torch.empty((N, 4), dtype=torch.float32, device=dev)
-
-    def e2e_step(i):
-        d_state.copy_(h_states[i % 4], non_blocking=True)
-        px = r.step(d_state, out=outs[i % OUT_RING])
-        h_out.copy_(px, non_blocking=True)
-        torch.cuda.current_stream().synchronize()       # the caller owns the frame on the host now
-
-    for i in range(3):
-        e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    barrier()
-    e2e_sync_s = time.perf_counter() - t0
-
-    # the same loop the way a consumer of frames would write it: two pinned host buffers, the D2H copy of
-    # frame i runs on a copy stream beside the H2D + render of frame i+1; the host owns frame i when its
-    # copy event has completed (waited for before that buffer is reused, and for all frames at the end).
-    # Every step still moves its own state in and its own frame out inside the timed region.
-    h_outs = [h_out, torch.empty_like(h_out).pin_memory()]
-    copy_stream = torch.cuda.Stream(dev)
-    landed = [None, None]
-
-    def e2e_step_pipelined(i):
-        d_state.copy_(h_states[i % 4], non_blocking=True)
-        px = r.step(d_state, out=outs[i % OUT_RING])
-        rendered = torch.cuda.Event()
-        rendered.record()
-        if landed[i % 2] is not None:
-            landed[i % 2].synchronize()                 # frame i-2 is on the host: its buffer is free again
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(rendered)
-            h_outs[i % 2].copy_(px, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        landed[i % 2] = ev
-
-    def e2e_drain():
-        for ev in landed:
-            if ev is not None:
-                ev.synchronize()
-
-    for i in range(4):
-        e2e_step_pipelined(i)
-    e2e_drain()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step_pipelined(i)
-    e2e_drain()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-
-    # ---- optional: frames of all ranks onto rank 0 (NCCL gather over NVLink); never part of step()
-    gather_ms = None
-    if distributed and args.gather:
+    # ---- frames of all ranks onto rank 0 (NCCL gather over NVLink); never part of step()
+    gather = None
+    if distributed and not args.no_gather:
         from pybatchrender_b200.dist import gather_frames
         for _ in range(2):
-            gather_frames(outs[0], dst=0)
+            gather_frames(wl.outs[0], dst=0)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for _ in range(10):
-            gather_frames(outs[0], dst=0)
+            gather_frames(wl.outs[0], dst=0)
         g1.record()
         barrier()
-        gather_ms = g0.elapsed_time(g1) / 10
+        g_ms = max_over_ranks([g0.elapsed_time(g1) / 10], dev, distributed)[0]
+        nbytes = (world - 1) * wl.frame_bytes
+        gather = {"ms": g_ms, "bytes_into_rank0": nbytes, "GBps_into_rank0": nbytes / (g_ms * 1e-3) / 1e9,
+                  "note": "optional collective (torch.distributed gather, NCCL), timed separately, not part of value / e2e"}
+
+    # ---- env.step of the CartPole environment (reference examples/scripts/cartpole_benchmark.py:135-168)
+    env_step = None
+    if CONFIGS[args.config]["kind"] == "cartpole" and not args.no_extras:
+        import pybatchrender_b200 as pbr
+        n_env = wl.n
+        env = pbr.envs.make("CartPole-v0", num_scenes=n_env, tile_resolution=CONFIGS[args.config]["tile"], device="cuda")
+        td = env.reset()
+        for _ in range(5):
+            td["action"] = env.action_spec.rand()
+            td = env.step(td)["next"]
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(100):
+            td["action"] = env.action_spec.rand()
+            td = env.step(td)["next"]
+        barrier()
+        env_s = max_over_ranks([time.perf_counter() - t0], dev, distributed)[0]
+        env_step = {"value": n_env * world * 100 / env_s, "unit": "scene-frames/s", "ms_per_step": env_s * 10.0,
+                    "steps": 100, "warmup": 5,
+                    "how": "pbr.envs.make('CartPole-v0').step: physics + render + auto-reset, random actions, no "
+                           "per-step sync, wall clock (reference on an NVIDIA L4: 980,562 scene-frames/s at 4096 "
+                           "scenes, examples/notebooks/cartpole_benchmark.ipynb raw line 886)"}
+        del env, td
+
+    del wl
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configurations, short device-timed loops
+    extra = {}
+    if not args.no_extras:
+        short = {2: (min(K, 200), 16), 3: (min(K, 50), 3), 4: (min(K, 48), 16), 5: (min(K, 3), 1)}
+        for cfg_id in sorted(CONFIGS):
+            if cfg_id == args.config:
+                continue
+            k_c, w_c = short[cfg_id]
+            try:
+                res, w2 = measure_config(cfg_id, k_c, w_c, dev, rank, world, distributed, barrier, native, cores,
+                                         verify=not args.no_verify, full=False)
+                del w2
+                extra[f"config{cfg_id}"] = {k: res[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "scaling",
+                                                                "verified", "verified_how", "gpu_launches")}
+                extra[f"config{cfg_id}"]["workload"] = res["config"]["workload"]
+                extra[f"config{cfg_id}"]["scenes_per_gpu"] = res["config"]["scenes_per_gpu"]
+                extra[f"config{cfg_id}"]["roofline_frac"] = res["roofline"]["frac"]
+                extra[f"config{cfg_id}"]["kernel_ms"] = res["roofline"]["kernel_ms"]
+                extra[f"config{cfg_id}"]["kernel"] = res["roofline"]["kernel"]
+            except SystemExit:
+                raise
+            except Exception as e:      # an extra must not take the headline down; say what happened
+                extra[f"config{cfg_id}"] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
 
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
-    t_ms = torch.tensor([ms, e2e_s * 1e3, raster_ms, e2e_sync_s * 1e3], dtype=torch.float64, device=dev)
-    if distributed:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max, raster_ms_max, e2e_sync_ms_max = (float(x) for x in t_ms.tolist())
-
     if rank == 0:
-        peak, peak_src = measured_peak()
-        total_scenes = N * world
-        value = total_scenes * K / (ms_max * 1e-3)
-        achieved = ALGO_BYTES_PER_SCENE * N / (raster_ms_max * 1e-3) / 1e9
+        c = CONFIGS[args.config]
         line = {
-            "metric": "scene-frames/sec to torch tensor (CartPole 4096x64^2)",
-            "value": value, "unit": "scene-frames/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32+i32 (u8 out)", "data": "synthetic",
-            "config": {"workload": "CartPole-v0 num_scenes=4096 per GPU, tile 64x64 (BASELINE configs[1])",
-                       "scenes_per_gpu": N, "tile": list(TILE), "channels": 3,
-                       "parallelism": f"scene-sharded x{world}, no collective",
-                       "l2": f"output ring of {OUT_RING} x {N * 3 * TILE[0] * TILE[1] / 1e6:.1f} MB (> 126 MB L2); "
-                             f"state ring of {STATE_RING}",
-                       "launch": f"CUDA graphs of {STATE_RING} steps; raster kernel as a programmatic dependent of the pose kernel"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_note": "dram__bytes_read+write of one isolated launch under ncu (profiles/r01q_*): "
-                                         "the 50 MB of pixel writes are still dirty in the 126 MB L2 when the kernel "
-                                         "ends, so DRAM sees them later; no re-reads",
-                         "kernel": "raster_warp_kernel<14, true>",
-                         "kernel_ms": raster_ms_max, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SCENE * N,
-                         "peak_source": peak_src},
-            "e2e": {"value": total_scenes * e2e_steps / (e2e_ms_max * 1e-3), "unit": "scene-frames/s",
-                    "h2d_bytes_per_step": N * 4 * 4, "d2h_bytes_per_step": N * 3 * TILE[0] * TILE[1],
-                    "steps": e2e_steps,
-                    "how": "pinned host state -> H2D -> step -> D2H of the frames every step; two pinned frame buffers, "
-                           "the D2H of frame i overlaps the H2D + render of frame i+1, the host waits for every frame",
-                    "value_sync_every_step": total_scenes * e2e_steps / (e2e_sync_ms_max * 1e-3)},
-            "gpu_launches": launches_per_step * K,
-            "clocks": sampler.summary(),
-            "gather": None if gather_ms is None else {
-                "ms": gather_ms, "bytes_into_rank0": (world - 1) * N * 3 * TILE[0] * TILE[1],
-                "GBps_into_rank0": (world - 1) * N * 3 * TILE[0] * TILE[1] / (gather_ms * 1e-3) / 1e9,
-                "note": "optional collective, timed separately, not part of value / e2e"},
+            "metric": head["metric"], "value": head["value"], "unit": "scene-frames/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": c["scaling"],
+            "vs_baseline": None, "dtype": "f32+i32 (u8 out)", "data": "synthetic", "config": head["config"],
+            "verified": head["verified"], "verified_how": head["verified_how"],
+            "roofline": head["roofline"], "e2e": head["e2e"], "value_eager": head["value_eager"],
+            "gpu_launches": head["gpu_launches"], "clocks": sampler.summary(), "gather": gather,
+            "env_step": env_step, "extra": extra,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            v, steps, dt = time_cpu_oracle(10.0, cores)
+            sample = {2: None, 3: 256, 4: 16384, 5: 64}[args.config]
+            arm = CpuArm(args.config, cores, sample)
+            v, n_steps, dt = arm.time_blocks(8, blocks=3, min_block_s=3.0)
             line["cpu_baseline"] = {"value": v, "unit": "scene-frames/s", "cores": cores, "kind": "port",
-                                    "sample": f"{steps} full frames of 4096 scenes in {dt:.1f} s"}
+                                    "sample": arm.sample_text(n_steps, dt)}
         print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier()

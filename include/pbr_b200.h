@@ -180,6 +180,10 @@ int pbr_device_status(int32_t device, int32_t *status_bits, int32_t clear);
  * (may lag behind frames still in flight). */
 int pbr_device_status_nosync(int32_t device, int32_t *status_bits);
 
+/* Number of kernels this library has enqueued (or captured into a CUDA graph) in this process so far:
+ * lets a benchmark count the launches of its timed region instead of assuming them. */
+unsigned long long pbr_kernel_launches(void);
+
 #ifdef PBR_W_TIMING
 /* timing builds only (profiles/kernel_timestamps.py): copies the time stamps the small-scene kernel dumped */
 int pbr_debug_pool(void *dst, size_t bytes);

@@ -184,6 +184,27 @@ def _pack(frame: OracleFrame, out: np.ndarray, scene_begin: int, scene_count: in
     return f, keep
 
 
+class PackedFrame:
+    """A frame marshalled once and rendered many times (bench.py's CPU legs): the ctypes structures keep
+    pointing at the numpy arrays handed in, so arrays that alias live buffers (e.g. ``tensor.numpy()`` of a
+    renderer's CPU matrix buffers) are re-read on every ``render()`` without any per-frame Python work."""
+
+    def __init__(self, frame: OracleFrame, out: np.ndarray, n_threads: int = 1, scene_begin: int = 0,
+                 scene_count: int | None = None) -> None:
+        K = int(frame.num_scenes)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous
+        self.out = out
+        self._f, self._keep = _pack(frame, out, scene_begin, K - scene_begin if scene_count is None else scene_count,
+                                    n_threads)
+        self._lib = lib()
+
+    def render(self) -> np.ndarray:
+        rc = self._lib.orc_render(ctypes.byref(self._f))
+        if rc != 0:
+            raise ValueError(f"orc_render failed: {rc}")
+        return self.out
+
+
 def render(frame: OracleFrame, n_threads: int = 1, scene_begin: int = 0, scene_count: int | None = None,
            out: np.ndarray | None = None) -> np.ndarray:
     """Render scenes [scene_begin, scene_begin+scene_count) -> uint8 [K,C,H,W] (other rows untouched)."""

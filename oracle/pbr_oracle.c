@@ -2,7 +2,7 @@
  * pbr_oracle.c -- CPU oracle for the PyBatchRender pixel path.  TEST INFRASTRUCTURE ONLY
  * (see pbr_oracle.h for who may load it and for the parity status: PINNED on the notebook goldens).
  *
- * Build: make -C oracle   (gcc -O2 -ffp-contract=off; every fused multiply-add below is an explicit
+ * Build: make -C oracle   (gcc -O3 -ffp-contract=off; every fused multiply-add below is an explicit
  * fmaf(), so the float32 results are reproducible and are what the CUDA path is compared against
  * bit for bit).
  *
@@ -364,14 +364,26 @@ static void make_light(const orc_frame *f, light_t *L) {
     L->s = fminf(fmaxf(f->strength, 0.0f), 1.0f);
 }
 
-typedef struct {
-    const orc_frame *f;
-    int s0, s1;
-} job_t;
+/* ---- scene-parallel driver: a persistent pool of pthreads (created on first use, grown on demand) that pull
+ * chunks of scenes from a shared counter.  Persistent + dynamic so that a timed run (bench.py's CPU baseline)
+ * measures rasterisation, not 32 pthread_create calls per frame or the slowest static slice. */
+#define ORC_CHUNK 16
+#define ORC_MAX_THREADS 256
 
-static void *worker(void *arg) {
-    job_t *j = (job_t *)arg;
-    const orc_frame *f = j->f;
+static struct {
+    pthread_mutex_t mu;
+    pthread_cond_t go, done;
+    pthread_t th[ORC_MAX_THREADS];
+    int n_threads;            /* workers created */
+    int want;                 /* workers taking part in the current frame */
+    unsigned long generation; /* bumped per frame */
+    int running;              /* participants that have not finished the current frame */
+    const orc_frame *f;
+    int next;                 /* next scene to hand out (atomic) */
+    int end;
+} pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, {0}, 0, 0, 0, 0, NULL, 0, 0};
+
+static void render_chunks(const orc_frame *f) {
     light_t L;
     make_light(f, &L);
     target_t T;
@@ -379,35 +391,77 @@ static void *worker(void *arg) {
     size_t npx = (size_t)T.W * T.H;
     T.depth = (float *)malloc(npx * sizeof(float));
     T.prim = (uint32_t *)malloc(npx * sizeof(uint32_t));
-    for (int s = j->s0; s < j->s1; ++s) {
-        T.out = f->out + (size_t)s * T.C * npx;
-        render_scene(f, s, &L, &T);
+    for (;;) {
+        int s0 = __atomic_fetch_add(&pool.next, ORC_CHUNK, __ATOMIC_RELAXED);
+        if (s0 >= pool.end) break;
+        int s1 = s0 + ORC_CHUNK < pool.end ? s0 + ORC_CHUNK : pool.end;
+        for (int s = s0; s < s1; ++s) {
+            T.out = f->out + (size_t)s * T.C * npx;
+            render_scene(f, s, &L, &T);
+        }
     }
     free(T.depth);
     free(T.prim);
+}
+
+static void *pool_worker(void *arg) {
+    const int me = (int)(size_t)arg;
+    unsigned long seen = 0;
+    pthread_mutex_lock(&pool.mu);
+    for (;;) {
+        while (pool.generation == seen || me >= pool.want) {
+            if (pool.generation != seen) seen = pool.generation;     /* a frame this worker sits out */
+            pthread_cond_wait(&pool.go, &pool.mu);
+        }
+        seen = pool.generation;
+        const orc_frame *f = pool.f;
+        pthread_mutex_unlock(&pool.mu);
+        render_chunks(f);
+        pthread_mutex_lock(&pool.mu);
+        if (--pool.running == 0) pthread_cond_signal(&pool.done);
+    }
     return NULL;
+}
+
+static pthread_mutex_t frame_mu = PTHREAD_MUTEX_INITIALIZER;    /* one frame at a time through the pool */
+
+static int render_locked(const orc_frame *f) {
+    int nt = f->n_threads < 1 ? 1 : f->n_threads;
+    if (nt > ORC_MAX_THREADS) nt = ORC_MAX_THREADS;
+    const int chunks = (f->scene_count + ORC_CHUNK - 1) / ORC_CHUNK;
+    if (nt > chunks) nt = chunks > 0 ? chunks : 1;
+    pthread_mutex_lock(&pool.mu);
+    pool.f = f;
+    pool.next = f->scene_begin;
+    pool.end = f->scene_begin + f->scene_count;
+    if (nt == 1) {
+        pthread_mutex_unlock(&pool.mu);
+        render_chunks(f);
+        return 0;
+    }
+    while (pool.n_threads < nt - 1) {             /* the caller is the nt-th participant */
+        if (pthread_create(&pool.th[pool.n_threads], NULL, pool_worker, (void *)(size_t)pool.n_threads) != 0) break;
+        pthread_detach(pool.th[pool.n_threads]);
+        pool.n_threads++;
+    }
+    pool.want = nt - 1 < pool.n_threads ? nt - 1 : pool.n_threads;
+    pool.running = pool.want;
+    pool.generation++;
+    pthread_cond_broadcast(&pool.go);
+    pthread_mutex_unlock(&pool.mu);
+    render_chunks(f);
+    pthread_mutex_lock(&pool.mu);
+    while (pool.running > 0) pthread_cond_wait(&pool.done, &pool.mu);
+    pthread_mutex_unlock(&pool.mu);
+    return 0;
 }
 
 int orc_render(const orc_frame *f) {
     if (check_frame(f)) return -1;
-    int nt = f->n_threads < 1 ? 1 : f->n_threads;
-    if (nt > 256) nt = 256;
-    if (nt > f->scene_count) nt = f->scene_count > 0 ? f->scene_count : 1;
-    pthread_t th[256];
-    job_t jobs[256];
-    int per = (f->scene_count + nt - 1) / nt;
-    for (int i = 0; i < nt; ++i) {
-        jobs[i].f = f;
-        jobs[i].s0 = f->scene_begin + i * per;
-        jobs[i].s1 = jobs[i].s0 + per;
-        int end = f->scene_begin + f->scene_count;
-        if (jobs[i].s0 > end) jobs[i].s0 = end;
-        if (jobs[i].s1 > end) jobs[i].s1 = end;
-    }
-    if (nt == 1) { worker(&jobs[0]); return 0; }
-    for (int i = 0; i < nt; ++i) pthread_create(&th[i], NULL, worker, &jobs[i]);
-    for (int i = 0; i < nt; ++i) pthread_join(th[i], NULL);
-    return 0;
+    pthread_mutex_lock(&frame_mu);
+    const int rc = render_locked(f);
+    pthread_mutex_unlock(&frame_mu);
+    return rc;
 }
 
 int orc_render_scene_debug(const orc_frame *f, int scene, uint8_t *out_chw, float *depth, uint32_t *prim) {

@@ -99,6 +99,7 @@ _EXPORTS = {
                                            ctypes.c_int32, ctypes.c_void_p]),
     "pbr_compose_transforms": (ctypes.c_int, [ctypes.POINTER(_PoseDesc), ctypes.c_int32, ctypes.c_void_p]),
     "pbr_device_status_nosync": (ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
+    "pbr_kernel_launches": (ctypes.c_ulonglong, []),
 }
 
 _lib = None
@@ -232,6 +233,10 @@ class Native:
 
     def version(self) -> int:
         return int(self.lib.pbr_version())
+
+    def kernel_launches(self) -> int:
+        """Kernels enqueued or captured by the library in this process so far."""
+        return int(self.lib.pbr_kernel_launches())
 
     def device_status_nosync(self, device_index: int) -> int:
         """The same bits from host-mapped memory, without synchronising (may lag behind frames in flight)."""

@@ -19,6 +19,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -39,6 +40,8 @@ using namespace pbr;
 namespace {
 
 thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};     // kernels of this library enqueued (or captured) by this process
+#define COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -334,6 +337,7 @@ static int launch_compose(const pbr_pose_desc *const *poses, int n_poses, void *
         if (max_n == 0) continue;
         dim3 grid((max_n + 127) / 128, pb.n);
         compose_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(pb);
+        COUNT_LAUNCH();
         CUDA_TRY(cudaGetLastError());
     }
     return PBR_OK;
@@ -524,6 +528,7 @@ static int launch_general(FrameDev &f, DeviceState *st, void *stream) {
         raster_general_kernel<true><<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(f);
     else
         raster_general_kernel<false><<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(f);
+    COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
     return PBR_OK;
 }
@@ -606,10 +611,12 @@ static int launch_staged(FrameDev &f, DeviceState *st, void *stream) {
             CUDA_TRY(cudaMemsetAsync(ss->g_vis, 1, (size_t)n * f.total_inst, (cudaStream_t)stream));
         } else {
             cull_kernel<<<cgrid, 256, 0, (cudaStream_t)stream>>>(f, g);
+            COUNT_LAUNCH();
             CUDA_TRY(cudaGetLastError());
         }
         dim3 ggrid((unsigned)((f.total_slots + G_THREADS - 1) / G_THREADS), (unsigned)n);
         geom_kernel<<<ggrid, G_THREADS, 0, (cudaStream_t)stream>>>(f, g);
+        COUNT_LAUNCH();
         CUDA_TRY(cudaGetLastError());
         const long long grid = (long long)n * f.nbands;
         if (grid > 0x7fffffffll) return fail(PBR_EUNSUPPORTED, "pbr_render: grid too large");
@@ -617,6 +624,7 @@ static int launch_staged(FrameDev &f, DeviceState *st, void *stream) {
             raster_staged_kernel<true><<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(f, g);
         else
             raster_staged_kernel<false><<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(f, g);
+        COUNT_LAUNCH();
         CUDA_TRY(cudaGetLastError());
     }
     return PBR_OK;
@@ -698,6 +706,7 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
             }
             if (ss->bg_sig[0] != (unsigned)W || ss->bg_sig[1] != (unsigned)H || ss->bg_sig[2] != (unsigned)f.C || ss->bg_sig[3] != f.bg) {
                 fill_planes_kernel<<<(unsigned)((need + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ss->bgtile, H * W, f.C, f.bg);
+                COUNT_LAUNCH();
                 CUDA_TRY(cudaGetLastError());
                 ss->bg_sig[0] = (unsigned)W; ss->bg_sig[1] = (unsigned)H; ss->bg_sig[2] = (unsigned)f.C; ss->bg_sig[3] = f.bg;
             }
@@ -740,11 +749,13 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS_TMA - 1) / W_WARPS_TMA);
             f.w_qctr_off = (int)(W_WARPS_TMA * (size_t)f.w_region + align16((size_t)W_WARPS_TMA * nbx * (H8 / 8) * 4));
             CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS_TMA, true>, wgrid, 32 * (W_WARPS_TMA + PBR_W_HELPERS), tma_smem, stream, f));
+            COUNT_LAUNCH();
         } else {
             static const size_t smem_pad = getenv("PBR_B200_WARP_SMEM_PAD") ? (size_t)atoi(getenv("PBR_B200_WARP_SMEM_PAD")) : 0;   // occupancy experiments
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS - 1) / W_WARPS);
             f.w_qctr_off = (int)(W_WARPS * (size_t)f.w_region + align16((size_t)W_WARPS * nbx * (H8 / 8) * 4));
             CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS, false>, wgrid, 32 * W_WARPS, warp_smem + smem_pad, stream, f));
+            COUNT_LAUNCH();
         }
         CUDA_TRY(cudaGetLastError());
         return PBR_OK;
@@ -867,6 +878,7 @@ int pbr_pack_transforms(float *transforms_b44, const float *rot_b33, const float
     if (!transforms_b44 || !rot_b33 || !scale_b || !out_mats) return fail(PBR_EINVAL, "pbr_pack_transforms: NULL pointer");
     if (reinterpret_cast<size_t>(out_mats) & 15) return fail(PBR_EINVAL, "pbr_pack_transforms: out_mats must be 16-byte aligned");
     pack_transforms_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(transforms_b44, rot_b33, scale_b, out_mats, n);
+    COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
     return PBR_OK;
 }
@@ -877,6 +889,8 @@ int pbr_compose_transforms(const pbr_pose_desc *poses, int32_t n_poses, void *st
     for (int i = 0; i < n_poses; ++i) ptrs[i] = poses + i;
     return launch_compose(ptrs.data(), n_poses, stream);
 }
+
+unsigned long long pbr_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int pbr_device_status_nosync(int32_t device, int32_t *status_bits) {
     if (!status_bits) return fail(PBR_EINVAL, "pbr_device_status_nosync: NULL output");
