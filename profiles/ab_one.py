@@ -4,12 +4,12 @@ import os, sys, hashlib
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import numpy as np, torch
 from pybatchrender_b200.envs.cartpole import CartPoleRenderer
-import bench
+from pybatchrender_b200 import workloads
 from util import oracle_render, cartpole_states
 
 def timeit(N, tile, reps=40):
     r = CartPoleRenderer(dict(num_scenes=N, tile_resolution=tile, device='cuda'))
-    st = [bench.cartpole_state(N, i, torch).cuda() for i in range(4)]
+    st = [workloads.cartpole_state(N, i).cuda() for i in range(4)]
     nout = max(2, int(2.5e8 // (N * 3 * tile[0] * tile[1])) + 1)
     outs = [torch.empty((N, 3, tile[1], tile[0]), dtype=torch.uint8, device='cuda') for _ in range(nout)]
     for i in range(5): r.step(st[i % 4], out=outs[i % nout])

@@ -46,9 +46,11 @@ def test_bench_module_constants_exist():
         sys.path.insert(0, root)
     bench = importlib.import_module("bench")
     tree = ast.parse(open(os.path.join(root, "bench.py")).read())
-    local = {"K", "W", "N"}                      # locals of run_ours
+    local = {"K", "W", "N", "H", "I", "B"}       # one-letter-style locals of bench.py's functions
     missing = {n.id for n in ast.walk(tree)
                if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load) and n.id.isupper() and len(n.id) > 1
                and not hasattr(bench, n.id) and not hasattr(builtins, n.id) and n.id not in local}
     assert not missing, missing
-    assert bench.STATE_RING >= 1 and bench.OUT_RING * bench.SCENES_PER_GPU * 3 * 64 * 64 > 126e6
+    assert bench.STATE_RING >= 1 and sorted(bench.CONFIGS) == [2, 3, 4, 5]
+    assert bench.CONFIGS[2]["algo"] == 12512 and bench.CONFIGS[4]["algo"] == 21392
+    assert bench.CONFIGS[3]["algo"] == 69696 and bench.CONFIGS[5]["algo"] == 201792
