@@ -391,8 +391,11 @@ class Workload:
 def timed_run(wl: Workload, K: int, W: int, barrier, native):
     """K steps of ``wl.step`` timed with CUDA events (graphs for CartPole); returns (ms, launches, last writer of
     every ring buffer)."""
+    import gc
+
     import torch
     last = {}
+    gc.collect()            # renderers of earlier legs are destroyed now, not in the middle of a capture
     if wl.use_graphs:
         side = torch.cuda.Stream(wl.dev)
         side.wait_stream(torch.cuda.current_stream())

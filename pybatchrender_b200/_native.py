@@ -144,6 +144,31 @@ def _cuda_f32(t: torch.Tensor, what: str) -> torch.Tensor:
     return t
 
 
+# Handles whose owner was garbage-collected while a CUDA graph was being captured: destroying them calls
+# cudaFree, which is prohibited during a capture (it invalidates the capture in torch's default "global" error
+# mode) -- and Python may collect an old renderer at any moment.  They are parked here and destroyed by the next
+# create / close that runs outside a capture.
+_deferred_frees: list = []
+
+
+def _capturing() -> bool:
+    try:
+        return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+    except Exception:
+        return False
+
+
+def _destroy(fn_name: str, handle) -> None:
+    if _capturing():
+        _deferred_frees.append((fn_name, handle))
+        return
+    lib = load()
+    while _deferred_frees:
+        name, h = _deferred_frees.pop()
+        getattr(lib, name)(h)
+    getattr(lib, fn_name)(handle)
+
+
 class NativeMesh:
     """Device-resident static geometry (``pbr_mesh_t``)."""
 
@@ -168,7 +193,7 @@ class NativeMesh:
 
     def close(self) -> None:
         if getattr(self, "handle", None):
-            load().pbr_mesh_destroy(self.handle)
+            _destroy("pbr_mesh_destroy", self.handle)
             self.handle = None
 
     def __del__(self):
@@ -194,7 +219,7 @@ class NativeTexture:
 
     def close(self) -> None:
         if getattr(self, "handle", None):
-            load().pbr_texture_destroy(self.handle)
+            _destroy("pbr_texture_destroy", self.handle)
             self.handle = None
 
     def __del__(self):
@@ -215,7 +240,7 @@ class NativeBase:
 
     def close(self) -> None:
         if getattr(self, "handle", None):
-            load().pbr_base_destroy(self.handle)
+            _destroy("pbr_base_destroy", self.handle)
             self.handle = None
 
     def __del__(self):
