@@ -74,7 +74,8 @@ struct FrameDev {
     int nbx, nby;           // 8x8 blocks per band
     unsigned nbx_magic;     // floor(2^32 / nbx) + 1
     int w_region;           // small-scene kernel: bytes of one scene's shared-memory region
-    int w_qctr_off;         // ... and offset of the CTA's queue counters (after the regions and the queue)
+    int w_qctr_off;         // ... and offset of the CTA's queue counters (after the regions, the queue and the live list)
+    unsigned w_inst_magic, w_vert_magic, w_slot_magic;   // div_magic of total_inst / total_verts / total_slots
     int plane_stride;       // bytes between colour planes in shared memory (multiple of 16)
     int linear;             // 1: the shared colour tile is a byte image of out[scene]
     int smooth;             // 1: some triangles are shaded per pixel (SMOOTH kernel instantiations)

@@ -674,6 +674,9 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         f.BH = H8; f.nbands = 1; f.nbx = nbx; f.nby = H8 / 8;
         f.nbx_magic = div_magic((unsigned)nbx);
         f.w_region = (int)warp_scene_bytes(nbx * (H8 / 8));
+        f.w_inst_magic = div_magic((unsigned)f.total_inst);
+        f.w_vert_magic = div_magic((unsigned)f.total_verts);
+        f.w_slot_magic = div_magic((unsigned)f.total_slots);
         // w_qctr_off is set where the kernel variant (scenes per CTA) is chosen
         f.plane_stride = H * W;
         f.linear = 1;
@@ -744,16 +747,16 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         const bool tma_ok = f.base_color != nullptr && (tile_bytes & 15) == 0 && tma_smem <= (size_t)st->max_smem_optin;
         // measured: faster for 64x64 (0.348 vs 0.302 of the roofline) and 84x84 (0.55 vs 0.52), slower for
         // 32x32 (the copy is cheap, the wide barrier is not) and 128x128 (the image crowds out the scenes)
-        const bool use_tma = tma_ok && (tma_mode == 1 || (tma_mode != 0 && tma_smem <= 120 * 1024 && tile_bytes >= 8192));
+        const bool use_tma = tma_ok && (tma_mode == 1 || (tma_mode != 0 && tma_smem <= 136 * 1024 && tile_bytes >= 8192));
         if (use_tma) {
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS_TMA - 1) / W_WARPS_TMA);
-            f.w_qctr_off = (int)(W_WARPS_TMA * (size_t)f.w_region + align16((size_t)W_WARPS_TMA * nbx * (H8 / 8) * 4));
+            f.w_qctr_off = (int)warp_qctr_offset(nbx * (H8 / 8), W_WARPS_TMA);
             CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS_TMA, true>, wgrid, 32 * (W_WARPS_TMA + PBR_W_HELPERS), tma_smem, stream, f));
             COUNT_LAUNCH();
         } else {
             static const size_t smem_pad = getenv("PBR_B200_WARP_SMEM_PAD") ? (size_t)atoi(getenv("PBR_B200_WARP_SMEM_PAD")) : 0;   // occupancy experiments
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS - 1) / W_WARPS);
-            f.w_qctr_off = (int)(W_WARPS * (size_t)f.w_region + align16((size_t)W_WARPS * nbx * (H8 / 8) * 4));
+            f.w_qctr_off = (int)warp_qctr_offset(nbx * (H8 / 8), W_WARPS);
             CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS, false>, wgrid, 32 * W_WARPS, warp_smem + smem_pad, stream, f));
             COUNT_LAUNCH();
         }

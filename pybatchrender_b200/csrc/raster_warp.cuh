@@ -38,7 +38,7 @@ constexpr int W_MAXREC = 48;     // records per scene (triangle slots that survi
 constexpr int W_MAXSLOT = 36;    // eligibility: leaves >= 12 spare records for clipped fans
 constexpr int W_MAXVERT = 48;    // (instance, vertex) pairs per scene
 constexpr int W_MAXINST = 16;    // instances per scene (their 3x3 model matrices are parked in shared memory)
-constexpr int W_GEOM_BYTES = W_MAXVERT * 32 + W_MAXINST * 48;    // parked vertices (clip + projected) and matrices
+constexpr int W_GEOM_BYTES = W_MAXVERT * 32 + W_MAXINST * 64;    // parked vertices (clip + projected) and matrices
 constexpr int W_MW = 2;          // mask words per block (64 record bits)
 #ifndef W_WARPS
 #define W_WARPS 4                // scenes (= warps) per CTA
@@ -57,18 +57,55 @@ static_assert(6 * W_MAXSLOT - W_MAXREC <= W_OVF_MAXREC, "overflow pool too small
 // shared memory of one scene
 __host__ __device__ inline size_t warp_scene_bytes(int nblk) {
     return (size_t)W_GEOM_BYTES + (size_t)W_MAXREC * sizeof(Rec) + align16((size_t)nblk * W_MW * 4) +
-           align16((size_t)nblk * 2) + 2 * W_MAXREC * 4 + 16;
+           align16((size_t)nblk * 2) + 2 * W_MAXREC * 4 + 32;
+}
+// offset of the CTA's counters: behind the scene regions, the block queue and the live list
+__host__ __device__ inline size_t warp_qctr_offset(int nblk, int warps) {
+    return (size_t)warps * warp_scene_bytes(nblk) + align16((size_t)warps * nblk * 4) + align16((size_t)warps * W_MAXSLOT * 4);
 }
 // shared memory of a CTA of `warps` scenes: scene regions + block queue + counters (+ mbarrier and the
 // background image when the background is written by TMA)
 __host__ __device__ inline size_t warp_smem_bytes(int nblk, int warps, size_t tma_tile_bytes = 0) {
-    return (size_t)warps * warp_scene_bytes(nblk) + align16((size_t)warps * nblk * 4) + 16 +
-           (tma_tile_bytes ? 16 + align16(tma_tile_bytes) : 0);
+    return warp_qctr_offset(nblk, warps) + 16 + (tma_tile_bytes ? 16 + align16(tma_tile_bytes) : 0);
 }
 #ifndef PBR_W_WARPS_TMA
 #define PBR_W_WARPS_TMA 14
 #endif
 constexpr int W_WARPS_TMA = PBR_W_WARPS_TMA;      // scenes per CTA when the background goes through TMA (see kernel comment)
+
+// views into one scene's shared-memory region (layout: warp_scene_bytes)
+struct WScene {
+    float4 *clipc;            // [W_MAXVERT] clip-space positions
+    int4 *proj;               // [W_MAXVERT] snapped x, y, depth bits, flags
+    float4 *minst;            // [W_MAXINST][4] columns of the model matrices
+    Rec *recs;                // [W_MAXREC]
+    unsigned *masks;          // [nblk][W_MW]
+    unsigned short *blist;    // [nblk]
+    unsigned *live;           // [W_MAXREC] block box of each record (0xffffffff: none)
+    unsigned *clipl;          // [W_MAXREC] packed slots of the triangles that need clipping
+    int *ctr;                 // [4] overflow pool entry, clipped triangles, records drawn (S > 32), has int64 records
+    unsigned char **out_slot; // out[scene], for the sweep
+};
+__device__ __forceinline__ WScene wscene(unsigned char *base, int nblk) {
+    WScene s;
+    s.clipc = reinterpret_cast<float4 *>(base);
+    s.proj = reinterpret_cast<int4 *>(base + (size_t)W_MAXVERT * 16);
+    s.minst = reinterpret_cast<float4 *>(base + (size_t)W_MAXVERT * 32);
+    s.recs = reinterpret_cast<Rec *>(base + (size_t)W_GEOM_BYTES);
+    s.masks = reinterpret_cast<unsigned *>(s.recs + W_MAXREC);
+    s.blist = reinterpret_cast<unsigned short *>(s.masks + align16((size_t)nblk * W_MW * 4) / 4);
+    s.live = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(s.blist) + align16((size_t)nblk * 2));
+    s.clipl = s.live + W_MAXREC;
+    s.ctr = reinterpret_cast<int *>(s.clipl + W_MAXREC);
+    s.out_slot = reinterpret_cast<unsigned char **>(s.ctr + 6);
+    return s;
+}
+
+// named barrier 1 over the first THREADS threads of the CTA (the warps that share the geometry work)
+template <int THREADS_>
+__device__ __forceinline__ void group_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(THREADS_) : "memory");
+}
 
 struct WSlot {
     int ni, inst, tri;
@@ -92,7 +129,7 @@ __device__ __forceinline__ void load_mat(const float *m, float *M) {
     }
 }
 
-// xform_normal with the matrix given as its first three columns (parked in shared memory by phase A)
+// xform_normal with the matrix given as its columns (parked in shared memory by phase M)
 __device__ __forceinline__ void xform_normal_cols(const float4 *c, float nx, float ny, float nz, float *r) {
     const float4 c0 = c[0], c1 = c[1], c2 = c[2];
     const float m[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
@@ -325,32 +362,28 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     const int HW = f.H * f.W;
     const size_t scene_bytes_out = (size_t)f.C * HW;
 
-    // ---- carve shared memory: one region per scene, then the CTA's block queue
+    // ---- carve shared memory: one region per scene, then the CTA's block queue, live list and counters
     const unsigned region = (unsigned)f.w_region;       // == warp_scene_bytes(nblk), precomputed by the host
-    unsigned char *my = smem_raw + warp * region;
-    float4 *clipc = reinterpret_cast<float4 *>(my);                      // [W_MAXVERT]
-    int4 *proj = reinterpret_cast<int4 *>(my + (size_t)W_MAXVERT * 16);  // [W_MAXVERT]
-    float4 *minst = reinterpret_cast<float4 *>(my + (size_t)W_MAXVERT * 32);   // [W_MAXINST][3] columns 0..2 of M
-    Rec *recs = reinterpret_cast<Rec *>(my + (size_t)W_GEOM_BYTES);
-    unsigned *masks = reinterpret_cast<unsigned *>(recs + W_MAXREC);
-    unsigned short *blist = reinterpret_cast<unsigned short *>(masks + align16((size_t)nblk * W_MW * 4) / 4);
-    unsigned *live = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(blist) + align16((size_t)nblk * 2));
-    unsigned *clipl = live + W_MAXREC;
-    int *ovf_entry = reinterpret_cast<int *>(clipl + W_MAXREC);          // pool entry of this scene once claimed
-    unsigned char **out_slot = reinterpret_cast<unsigned char **>(ovf_entry + 2);   // out[scene], for the sweep
-    if (lane == 0 && !helper) *out_slot = f.out + (size_t)scene * scene_bytes_out;
+    const WScene me = wscene(smem_raw + warp * region, nblk);
+    if (lane == 0 && !helper) *me.out_slot = f.out + (size_t)scene * scene_bytes_out;
     unsigned *queue = reinterpret_cast<unsigned *>(smem_raw + WARPS * region);   // [WARPS * nblk]
     int *qctr = reinterpret_cast<int *>(smem_raw + f.w_qctr_off);
+    unsigned *livelist = reinterpret_cast<unsigned *>(qctr) - WARPS * W_MAXSLOT; // [WARPS * W_MAXSLOT], just below the counters
     constexpr bool LATE_WAIT = TMA_BG && PBR_W_LATE_WAIT != 0;
-    if (WARPS > 1 && threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; qctr[3] = 0; }
-    if (WARPS > 1) __syncthreads();          // queue counters initialised (all warps arrive together: cheap)
-    // The thread that drives the TMA engine: lane 0 of the first helper warp when there is one.  Issuing the
+    if (threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; qctr[2] = 0; qctr[3] = 0; }
+    __syncthreads();          // counters initialised (all warps arrive together: cheap)
+    // The thread that drives the TMA engine: lane 0 of the LAST helper warp when there is one.  Issuing the
     // CTA's bulk stores blocks the issuing thread for microseconds (time stamps: a scene warp that did it
     // reached the sweep 3.5 us after its 13 neighbours, and the whole CTA waited for it at the barrier), so
-    // it must not be a warp that has a scene to set up.  The helper loads the image, waits for it, issues the
-    // stores and waits for them while the scene warps do geometry.  (When the frame before this one may still
+    // it must not be a warp that has geometry to do.  It loads the image, waits for it, issues the
+    // stores and waits for them while the other warps do geometry.  (When the frame before this one may still
     // be writing the same memory -- f.sync_early -- it first waits for that grid to complete.)
-    constexpr int BG_T = (TMA_BG && PBR_W_HELPERS > 0 && PBR_W_BG_HELPER != 0) ? WARPS * 32 : 0;
+    constexpr int HELP = TMA_BG ? PBR_W_HELPERS : 0;
+    constexpr bool BG_HELP = TMA_BG && HELP > 0 && PBR_W_BG_HELPER != 0;
+    constexpr int BG_T = BG_HELP ? (WARPS + HELP - 1) * 32 : 0;
+    // the warps that share the geometry work: the scene warps and the helpers that do not drive the TMA engine
+    constexpr int GW = BG_HELP ? WARPS + HELP - 1 : WARPS + HELP;
+    const bool worker = warp < GW;
     unsigned bg_turn = 0, bg_sm = 0;
     if (TMA_BG && threadIdx.x == BG_T) {
         unsigned long long *bg_bar = reinterpret_cast<unsigned long long *>(qctr + 4);
@@ -377,117 +410,140 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     int nlist = 0, novf = 0;
     bool scene_slow = false;                 // the scene has int64 (slow-path) records: its items say so (bit 30)
     if (TMA_BG && BG_T == 0 && f.debug == 1 && threadIdx.x == 0) issue_bg_stores(f, qctr, WARPS);
-    if (active) {
-        unsigned char *out_scene = f.out + (size_t)scene * scene_bytes_out;
-        if (f.sync_early) asm volatile("griddepcontrol.wait;" ::: "memory");
 
-        // ---- 0: background
-        const bool split_bg = !TMA_BG && f.base_color != nullptr && ((f.C * HW) & 15) == 0 && f.debug != 1;
+    // =====================================================================================================
+    // Geometry, shared by the CTA.  A scene has far fewer vertices / triangles than a warp has lanes
+    // (CartPole: 16 vertices, 24 triangle slots of which ~11 face the camera), so a warp that works on its
+    // own scene alone runs the expensive phases with a third of its lanes.  Instead the worker warps of the
+    // CTA flatten (scene, item) pairs of all its scenes into full warps, phase by phase, with a named
+    // barrier (bar.sync 1, the TMA warp is not part of it) between the phases:
+    //   M  instances  lanes = (scene, instance): model matrix from the pose channels / matrix buffer
+    //   A  vertices   lanes = (scene, instance, unique vertex): clip = VP*(M*v), outcodes, project + snap
+    //   B  classify   lanes = (scene, triangle slot): reject / cull / clip from the parked vertices; survivors
+    //                 go to the CTA's live list
+    //   S  set-up     lanes = live list entries: edge equations, depth plane, flat shade -> record
+    // and each scene's own warp finishes with binning, clipped fans and the block list.
+    // =====================================================================================================
+    const int first_scene = f.scene_begin + (int)blockIdx.x * WARPS;
+    const int n_sc = min(WARPS, f.scene_begin + f.scene_count - first_scene);
+    const bool geom = f.debug != 1;
+    const int S = f.total_slots;
+    const bool direct = S <= 32;             // record index = slot; else survivors draw an index per scene
+    unsigned char *const out_scene = f.out + (size_t)scene * scene_bytes_out;
+    const bool split_bg = !TMA_BG && f.base_color != nullptr && ((f.C * HW) & 15) == 0 && geom;
+    if (active) {
+        if (f.sync_early) asm volatile("griddepcontrol.wait;" ::: "memory");
+        // ---- 0: background (warp-copy build only; three bursts between the phases)
         if (!TMA_BG) {
             if (split_bg) write_background_part(f, out_scene, HW, lane, 0);
             else write_background(f, out_scene, HW, lane);
         }
-
-        if (f.debug != 1) {
+        if (geom) {
             {   // masks are 8 bytes per block, region padded to 16 bytes: clear with 128-bit stores
-                uint4 *m4 = reinterpret_cast<uint4 *>(masks);
+                uint4 *m4 = reinterpret_cast<uint4 *>(me.masks);
                 const int n16 = (int)(align16((size_t)nblk * W_MW * 4) / 16);
                 for (int i = lane; i < n16; i += 32) m4[i] = make_uint4(0u, 0u, 0u, 0u);
             }
+            for (int i = lane; i < W_MAXREC; i += 32) me.live[i] = 0xffffffffu;     // slots without a record
+            if (lane < 4) me.ctr[lane] = 0;
+        }
+    } else if (worker && f.sync_early && f.write_mats) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");       // helpers write matrices in phase M
+    }
+    if (worker && geom) {
+        const int wl = warp * 32 + lane;     // this lane among the worker lanes
 
-            // ---- A: vertices.  A posed node's model matrix is computed here from its pose channels (the state
-            // tensor of the caller: reference envs/cartpole/renderer.py:125-138 + shader_context.py:47-84),
-            // other nodes' matrices are read from their matrix buffer; lane "vertex 0" of an instance parks
-            // the 3x3 part in shared memory for the normals of phase B.
-            {
-                float VP[16];
-                load_mat(f.vp + (size_t)scene * 16, VP);
+        // ---- M: instances.  A posed node's model matrix is computed here from its pose channels (the state
+        // tensor of the caller: reference envs/cartpole/renderer.py:125-138 + shader_context.py:47-84), other
+        // nodes' matrices are read from their matrix buffer; parked in shared memory for phases A and S.
+        {
+            const int TI = f.total_inst;
 #pragma unroll 1
-                for (int v = lane; v < f.total_verts; v += 32) {
-                    int ni = 0;
+            for (int it = wl; it < n_sc * TI; it += GW * 32) {
+                const int sl = fast_div(it, f.w_inst_magic);
+                const int gi = it - sl * TI;
+                int ni = 0;
 #pragma unroll 1
-                    for (int i = 1; i < f.n_nodes; ++i)
-                        if (v >= f.nodes[i].vert_begin) ni = i;
-                    const NodeDev &nd = f.nodes[ni];
-                    const int local = v - nd.vert_begin;
-                    const int inst = fast_div(local, nd.vert_magic);
-                    const int vert = local - inst * nd.n_verts;
-                    const size_t b = nd.shared ? (size_t)inst : (size_t)scene * nd.inst + inst;
-                    float M[16];
-                    if (nd.pose_idx >= 0) pose_matrix(f.poses[nd.pose_idx], b, M);
-                    else load_mat(nd.mats + b * 16, M);
-                    if (vert == 0) {
-                        float4 *mi = minst + (nd.inst_begin + inst) * 3;
+                for (int i = 1; i < f.n_nodes; ++i)
+                    if (gi >= f.nodes[i].inst_begin) ni = i;
+                const NodeDev &nd = f.nodes[ni];
+                const int inst = gi - nd.inst_begin;
+                const size_t b = nd.shared ? (size_t)inst : (size_t)(first_scene + sl) * nd.inst + inst;
+                float M[16];
+                if (nd.pose_idx >= 0) pose_matrix(f.poses[nd.pose_idx], b, M);
+                else load_mat(nd.mats + b * 16, M);
+                float4 *mi = wscene(smem_raw + sl * region, nblk).minst + gi * 4;
 #pragma unroll
-                        for (int j = 0; j < 3; ++j) mi[j] = make_float4(M[4 * j], M[4 * j + 1], M[4 * j + 2], M[4 * j + 3]);
-                        if (f.write_mats && nd.pose_idx >= 0) {
-                            float4 *o = reinterpret_cast<float4 *>(f.poses[nd.pose_idx].out_mats + b * 16);
+                for (int j = 0; j < 4; ++j) mi[j] = make_float4(M[4 * j], M[4 * j + 1], M[4 * j + 2], M[4 * j + 3]);
+                if (f.write_mats && nd.pose_idx >= 0) {
+                    float4 *o = reinterpret_cast<float4 *>(f.poses[nd.pose_idx].out_mats + b * 16);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) o[j] = make_float4(M[4 * j], M[4 * j + 1], M[4 * j + 2], M[4 * j + 3]);
-                        }
-                    }
-                    const float4 p = __ldg(nd.vpos + vert);
-                    float world[4], c[4];
-                    mat_vec4(M, p.x, p.y, p.z, 1.0f, world);
-                    mat_vec4(VP, world[0], world[1], world[2], world[3], c);
-                    int flags = 0;
-#pragma unroll
-                    for (int pl = 0; pl < 6; ++pl) {
-                        const float a = c[pl >> 1];
-                        const bool out = (pl & 1) ? (a > c[3]) : (a < -c[3]);
-                        flags |= out ? (1 << pl) : 0;
-                    }
-                    if (needs_clip(c)) flags |= VF_CLIP;
-                    int X = 0, Y = 0;
-                    float z = 0.0f;
-                    if (project_vertex(f, c, X, Y, z)) flags |= VF_PROJ;
-                    clipc[v] = make_float4(c[0], c[1], c[2], c[3]);
-                    proj[v] = make_int4(X, Y, __float_as_int(z), flags);
+                    for (int j = 0; j < 4; ++j) o[j] = make_float4(M[4 * j], M[4 * j + 1], M[4 * j + 2], M[4 * j + 3]);
                 }
             }
-            W_STAMP(1);
-            if (TMA_BG && BG_T == 0 && threadIdx.x == 0) issue_bg_stores(f, qctr, WARPS);      // the load has had phase A to arrive
-            __syncwarp();
+        }
+        group_sync<GW * 32>();
 
-            bool my_slow = false;
-            // setup + shade + bin one surviving triangle into record j
-            auto setup_live = [&](const NodeDev &nd, int inst, int tri, const int4 &q0, const int4 &q1,
-                                  const int4 &q2, int j) {
-                int X[3] = {q0.x, q1.x, q2.x}, Y[3] = {q0.y, q1.y, q2.y};
-                float z[3] = {__int_as_float(q0.z), __int_as_float(q1.z), __int_as_float(q2.z)};
-                const unsigned id = (unsigned)(nd.id_begin + inst * nd.n_tris + tri) + 1u;
-                Rec r;
-                BBox bb;
-                if (setup_snapped(f, X, Y, z, (nd.flags & PBR_MESH_TWO_SIDED) != 0, id, 0, f.H, r, bb)) {
-                    const size_t b = nd.shared ? (size_t)inst : (size_t)scene * nd.inst + inst;
-                    float n[3];
-                    const float4 n0 = __ldg(nd.tn + 3 * tri);
-                    xform_normal_cols(minst + (nd.inst_begin + inst) * 3, n0.x, n0.y, n0.z, n);
-                    r.col = shade(f, n, __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4)));
-                    my_slow |= (r.meta & M_SLOW) != 0u;
-                    recs[j] = r;
-                    // block box of the record, binned below with one lane per (record, block) pair
-                    live[j] = (unsigned)bb.bx0 | ((unsigned)bb.by0 << 8) | ((unsigned)bb.bx1 << 16) | ((unsigned)bb.by1 << 24);
-                } else {
-                    live[j] = 0xffffffffu;
-                }
-            };
-
-            if (split_bg) write_background_part(f, out_scene, HW, lane, 1);
-
-            // ---- B: classify triangle slots.  With <= 32 slots every lane keeps its own slot and
-            // goes straight to setup (record index = slot); otherwise survivors are compacted first
-            // so that the expensive setup runs on full warps.
-            int nlive = 0, nclip = 0;
-            const int S = f.total_slots;
-            const bool direct = S <= 32;
-            if (direct) live[lane] = 0xffffffffu;        // record index = slot: dead slots have no box
+        // ---- A: vertices (basic.vert:24-43)
+        {
+            const int TV = f.total_verts;
 #pragma unroll 1
-            for (int base = 0; base < S; base += 32) {
-                const int s = base + lane;
+            for (int it = wl; it < n_sc * TV; it += GW * 32) {
+                const int sl = fast_div(it, f.w_vert_magic);
+                const int v = it - sl * TV;
+                int ni = 0;
+#pragma unroll 1
+                for (int i = 1; i < f.n_nodes; ++i)
+                    if (v >= f.nodes[i].vert_begin) ni = i;
+                const NodeDev &nd = f.nodes[ni];
+                const int local = v - nd.vert_begin;
+                const int inst = fast_div(local, nd.vert_magic);
+                const int vert = local - inst * nd.n_verts;
+                const WScene sc = wscene(smem_raw + sl * region, nblk);
+                float M[16], VP[16];
+                {
+                    const float4 *mi = sc.minst + (nd.inst_begin + inst) * 4;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 a = mi[j];
+                        M[4 * j] = a.x; M[4 * j + 1] = a.y; M[4 * j + 2] = a.z; M[4 * j + 3] = a.w;
+                    }
+                }
+                load_mat(f.vp + (size_t)(first_scene + sl) * 16, VP);
+                const float4 p = __ldg(nd.vpos + vert);
+                float world[4], c[4];
+                mat_vec4(M, p.x, p.y, p.z, 1.0f, world);
+                mat_vec4(VP, world[0], world[1], world[2], world[3], c);
+                int flags = 0;
+#pragma unroll
+                for (int pl = 0; pl < 6; ++pl) {
+                    const float a = c[pl >> 1];
+                    const bool out = (pl & 1) ? (a > c[3]) : (a < -c[3]);
+                    flags |= out ? (1 << pl) : 0;
+                }
+                if (needs_clip(c)) flags |= VF_CLIP;
+                int X = 0, Y = 0;
+                float z = 0.0f;
+                if (project_vertex(f, c, X, Y, z)) flags |= VF_PROJ;
+                sc.clipc[v] = make_float4(c[0], c[1], c[2], c[3]);
+                sc.proj[v] = make_int4(X, Y, __float_as_int(z), flags);
+            }
+        }
+        W_STAMP(1);
+        if (TMA_BG && BG_T == 0 && threadIdx.x == 0) issue_bg_stores(f, qctr, WARPS);      // the load has had phase A to arrive
+        if (split_bg && active) write_background_part(f, out_scene, HW, lane, 1);
+        group_sync<GW * 32>();
+
+        // ---- B: classify triangle slots; survivors go to the CTA's live list as (scene, slot, record index)
+        {
+#pragma unroll 1
+            for (int base = warp * 32; base < n_sc * S; base += GW * 32) {
+                const int it = base + lane;
                 int cat = 0;            // 0 dead, 1 live, 2 clip
-                unsigned packed = 0;
-                if (s < S) {
+                int sl = 0, s = 0;
+                if (it < n_sc * S) {
+                    sl = fast_div(it, f.w_slot_magic);
+                    s = it - sl * S;
                     int ni = 0;
 #pragma unroll 1
                     for (int i = 1; i < f.n_nodes; ++i)
@@ -496,10 +552,10 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                     const int local = s - nd.slot_begin;
                     const int inst = fast_div(local, nd.tri_magic);
                     const int tri = local - inst * nd.n_tris;
-                    packed = pack_slot(ni, inst, tri);
                     const uint4 ti = __ldg(nd.tidx + tri);
                     const int vb = nd.vert_begin + inst * nd.n_verts;
-                    const int4 q0 = proj[vb + ti.x], q1 = proj[vb + ti.y], q2 = proj[vb + ti.z];
+                    const int4 *pj = wscene(smem_raw + sl * region, nblk).proj;
+                    const int4 q0 = pj[vb + ti.x], q1 = pj[vb + ti.y], q2 = pj[vb + ti.z];
                     const int f_and = q0.w & q1.w & q2.w, f_or = q0.w | q1.w | q2.w;
                     if (f_and & 0x3f) {
                         cat = 0;
@@ -511,38 +567,79 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                         const bool two_sided = (nd.flags & PBR_MESH_TWO_SIDED) != 0;
                         cat = (area2 < 0 || (two_sided && area2 > 0)) ? 1 : 0;
                     }
-                    if (direct && cat == 1) setup_live(nd, inst, tri, q0, q1, q2, s);
-                }
-                const unsigned bc = __ballot_sync(0xffffffffu, cat == 2);
-                if (cat == 2) clipl[nclip + __popc(bc & lt_mask)] = packed;
-                nclip += __popc(bc);
-                if (!direct) {
-                    const unsigned bl = __ballot_sync(0xffffffffu, cat == 1);
-                    if (cat == 1) live[nlive + __popc(bl & lt_mask)] = packed;
-                    nlive += __popc(bl);
-                }
-            }
-            __syncwarp();
-            if (!direct) {      // record index = position in the live list
-#pragma unroll 1
-                for (int base = 0; base < nlive; base += 32) {
-                    const int j = base + lane;
-                    if (j < nlive) {
-                        const WSlot ws = unpack_slot(live[j]);
-                        const NodeDev &nd = f.nodes[ws.ni];
-                        const uint4 ti = __ldg(nd.tidx + ws.tri);
-                        const int vb = nd.vert_begin + ws.inst * nd.n_verts;
-                        setup_live(nd, ws.inst, ws.tri, proj[vb + ti.x], proj[vb + ti.y], proj[vb + ti.z], j);
+                    if (cat == 2) {      // rare: the scene's own warp clips it later
+                        const WScene sc = wscene(smem_raw + sl * region, nblk);
+                        sc.clipl[atomicAdd(&sc.ctr[1], 1)] = pack_slot(ni, inst, tri);
                     }
                 }
-            } else {
-                nlive = S;
+                int j = s;
+                if (!direct && cat == 1) j = atomicAdd(&wscene(smem_raw + sl * region, nblk).ctr[2], 1);
+                const unsigned bl = __ballot_sync(0xffffffffu, cat == 1);
+                int pos = 0;
+                if (lane == 0 && bl) pos = atomicAdd(&qctr[2], __popc(bl));
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                if (cat == 1) livelist[pos + __popc(bl & lt_mask)] = ((unsigned)sl << 16) | ((unsigned)s << 8) | (unsigned)j;
             }
-            int nrec = nlive;
-            scene_slow = nclip > 0 || __any_sync(0xffffffffu, my_slow);     // (clipped fans: not tracked, assume so)
-            W_STAMP(2);
-            if (split_bg) write_background_part(f, out_scene, HW, lane, 2);
+        }
+        group_sync<GW * 32>();
 
+        // ---- S: set-up of the survivors: integer edge equations, depth plane, flat shade (basic.frag:31-38)
+        // -> 64-byte record + block box of the record
+        {
+            const int n_live = qctr[2];
+#pragma unroll 1
+            for (int it = wl; it < n_live; it += GW * 32) {
+                const unsigned e = livelist[it];
+                const int sl = (int)(e >> 16), s = (int)((e >> 8) & 255u), j = (int)(e & 255u);
+                int ni = 0;
+#pragma unroll 1
+                for (int i = 1; i < f.n_nodes; ++i)
+                    if (s >= f.nodes[i].slot_begin) ni = i;
+                const NodeDev &nd = f.nodes[ni];
+                const int local = s - nd.slot_begin;
+                const int inst = fast_div(local, nd.tri_magic);
+                const int tri = local - inst * nd.n_tris;
+                const uint4 ti = __ldg(nd.tidx + tri);
+                const int vb = nd.vert_begin + inst * nd.n_verts;
+                const WScene sc = wscene(smem_raw + sl * region, nblk);
+                const int4 q0 = sc.proj[vb + ti.x], q1 = sc.proj[vb + ti.y], q2 = sc.proj[vb + ti.z];
+                int X[3] = {q0.x, q1.x, q2.x}, Y[3] = {q0.y, q1.y, q2.y};
+                float z[3] = {__int_as_float(q0.z), __int_as_float(q1.z), __int_as_float(q2.z)};
+                const unsigned id = (unsigned)(nd.id_begin + inst * nd.n_tris + tri) + 1u;
+                Rec r;
+                BBox bb;
+                if (setup_snapped(f, X, Y, z, (nd.flags & PBR_MESH_TWO_SIDED) != 0, id, 0, f.H, r, bb)) {
+                    const size_t b = nd.shared ? (size_t)inst : (size_t)(first_scene + sl) * nd.inst + inst;
+                    float n[3];
+                    const float4 n0 = __ldg(nd.tn + 3 * tri);
+                    xform_normal_cols(sc.minst + (nd.inst_begin + inst) * 4, n0.x, n0.y, n0.z, n);
+                    r.col = shade(f, n, __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4)));
+                    if (r.meta & M_SLOW) sc.ctr[3] = 1;
+                    sc.recs[j] = r;
+                    // block box of the record, binned below with one lane per (record, block) pair
+                    sc.live[j] = (unsigned)bb.bx0 | ((unsigned)bb.by0 << 8) | ((unsigned)bb.bx1 << 16) | ((unsigned)bb.by1 << 24);
+                }
+            }
+        }
+        W_STAMP(2);
+        if (split_bg && active) write_background_part(f, out_scene, HW, lane, 2);
+        group_sync<GW * 32>();
+    }
+
+    // ---- per scene, by its own warp: binning, clipped fans, block list
+    if (active && geom) {
+        Rec *const recs = me.recs;
+        unsigned *const masks = me.masks;
+        unsigned short *const blist = me.blist;
+        unsigned *const live = me.live;
+        unsigned *const clipl = me.clipl;
+        int *const ovf_entry = &me.ctr[0];
+        const float4 *const clipc = me.clipc;
+        const int nclip = me.ctr[1];
+        const int nlive = direct ? S : me.ctr[2];
+        int nrec = nlive;
+        scene_slow = nclip > 0 || me.ctr[3] != 0;     // (clipped fans: not tracked, assume so)
+        {
             // ---- B2: bin.  One lane per (record, block of its box) pair instead of one lane per record
             // looping over its box: the boxes are small and uneven (1-8 blocks), a per-record loop runs as
             // long as the largest box while most lanes idle.
@@ -609,7 +706,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                         const size_t b = nd.shared ? (size_t)ws.inst : (size_t)scene * nd.inst + ws.inst;
                         float n[3];
                         const float4 n0 = __ldg(nd.tn + 3 * ws.tri);
-                        xform_normal_cols(minst + (nd.inst_begin + ws.inst) * 3, n0.x, n0.y, n0.z, n);
+                        xform_normal_cols(me.minst + (nd.inst_begin + ws.inst) * 4, n0.x, n0.y, n0.z, n);
                         col = __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4));
                         id = (unsigned)(nd.id_begin + ws.inst * nd.n_tris + ws.tri) + 1u;
                         two_sided = (nd.flags & PBR_MESH_TWO_SIDED) != 0;
@@ -724,7 +821,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         // bit 31: the static layer covers part of the block (looked up here, one lane per item, so
         // that the sweep does not start every item with a dependent global load)
         for (int i = lane; i < nlist; i += 32) {
-            unsigned it = ((unsigned)warp << 16) | blist[i] | (scene_slow ? 0x40000000u : 0u);
+            unsigned it = ((unsigned)warp << 16) | me.blist[i] | (scene_slow ? 0x40000000u : 0u);
             if (f.base_flags != nullptr) {
                 const int bb = (int)((it >> 8) & 255u) * f.nbx + (int)(it & 255u);
                 if (__ldg(f.base_flags + bb) != 0) it |= 0x80000000u;
@@ -766,7 +863,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         } else {
             i = next++;
             if (i >= nitems) break;
-            item = blist[i];
+            item = me.blist[i];
             if (f.base_flags != nullptr && __ldg(f.base_flags + (int)((item >> 8) & 255u) * f.nbx + (int)(item & 255u)) != 0)
                 item |= 0x80000000u;
         }
@@ -825,10 +922,10 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             __syncwarp();
             __threadfence_block();
         }
-        const int e = *ovf_entry;
+        const int e = me.ctr[0];
 #pragma unroll 1
         for (int i = 0; i + 1 < novf; ++i)
-            overflow_block(f, recs, masks, e, nblk, blist[nblk - 1 - i], f.out + (size_t)scene * scene_bytes_out, lane);
+            overflow_block(f, me.recs, me.masks, e, nblk, me.blist[nblk - 1 - i], f.out + (size_t)scene * scene_bytes_out, lane);
         __syncwarp();
         if (lane == 0) atomicAnd(f.ovf_busy + e / W_POOL_PER_SM, ~(1u << (e % W_POOL_PER_SM)));
     }
