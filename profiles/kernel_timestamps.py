@@ -11,10 +11,10 @@ sys.path.insert(0, '/root/repo')
 import numpy as np, torch
 from pybatchrender_b200.envs.cartpole import CartPoleRenderer
 from pybatchrender_b200 import _native
-import bench
+from pybatchrender_b200 import workloads
 N = 4096
 r = CartPoleRenderer(dict(num_scenes=N, tile_resolution=(64, 64), device='cuda'))
-st = [bench.cartpole_state(N, i, torch).cuda() for i in range(4)]
+st = [workloads.cartpole_state(N, i).cuda() for i in range(4)]
 outs = [torch.empty((N, 3, 64, 64), dtype=torch.uint8, device='cuda') for _ in range(5)]
 for i in range(20): r.step(st[i % 4], out=outs[i % 5])
 torch.cuda.synchronize()

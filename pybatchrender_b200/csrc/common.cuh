@@ -86,6 +86,8 @@ struct FrameDev {
     float amb[3], dcol[3], ldir[3];
     float s, oms;           // clamp(strength), 1 - clamp(strength)
     int write_mats;         // small-scene kernel: posed nodes also write their matrices to out_mats
+    int keys32;             // small-scene kernel: the static layer (if any) was drawn before every node of this frame,
+                            // so scenes without clipped / int64 records may use 32-bit depth keys (raster_block32)
     int sync_early;         // small-scene kernel: wait for the previous grid before the first write to `out`
                             // (the previous launch on this stream may still be writing the same buffer)
     PoseDev poses[MAX_FRAME_POSES];
@@ -125,15 +127,20 @@ constexpr int DEVSTAT_WARP_OVERFLOW = 1;   // small-scene kernel ran out of reco
 constexpr int DEVSTAT_STAGED_OVERFLOW = 2; // geometry pre-pass ran out of per-scene record capacity
 
 // record meta bits
-constexpr unsigned M_VALID = 1u << 16, M_SLOW = 1u << 17, M_SMOOTH = 1u << 18;
-constexpr unsigned M_NB0 = 1u << 19, M_NB1 = 1u << 20, M_NB2 = 1u << 21;
-constexpr unsigned M_TEX = 1u << 22;        // the record's SRec carries a texture part
+// byte 0: flags; bytes 1..3: 1 if edge 0 / 1 / 2 is not a top-left edge (its stored edge value carries a bias of
+// -1) -- a byte each so that the sweep gets them with one PRMT / shift instead of shift + mask
+constexpr unsigned M_VALID = 1u, M_SLOW = 2u, M_SMOOTH = 4u;
+constexpr unsigned M_TEX = 8u;              // the record's SRec carries a texture part
+constexpr unsigned M_NB0 = 1u << 8, M_NB1 = 1u << 16, M_NB2 = 1u << 24;
+__device__ __forceinline__ int meta_nb0(unsigned meta) { return (int)__byte_perm(meta, 0u, 0x4441u); }
+__device__ __forceinline__ int meta_nb1(unsigned meta) { return (int)__byte_perm(meta, 0u, 0x4442u); }
+__device__ __forceinline__ int meta_nb2(unsigned meta) { return (int)(meta >> 24); }
 
 struct __align__(16) Rec {
     int e[9];        // fast: Eo[3], A[3], B[3]        slow: X0,Y0,X1,Y1,X2,Y2,-,-,-
     unsigned col;    // packed RGBA8 (flat shading)
     unsigned id;     // 1 + draw index
-    unsigned meta;   // anchor block x (8) | anchor block y (8) | flags
+    unsigned meta;   // flags | edge bias bytes (M_*)
     float z0, dz1, dz2, invA;   // 16-byte aligned: one LDS.128
 };
 static_assert(sizeof(Rec) == 64, "Rec must be 64 bytes");
@@ -388,7 +395,7 @@ __device__ __forceinline__ bool setup_snapped(const FrameDev &f, int *X, int *Y,
     r.id = id;
     r.col = 0;
 
-    unsigned meta = M_VALID | (unsigned)bb.bx0 | ((unsigned)bb.by0 << 8);
+    unsigned meta = M_VALID;
     int dx[3], dy[3], bias[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -433,7 +440,7 @@ __device__ __forceinline__ long long slow_edge(const Rec &r, int i, int px, int 
     const int a = (i + 1) % 3, b = (i + 2) % 3;
     const int xa = r.e[2 * a], ya = r.e[2 * a + 1], xb = r.e[2 * b], yb = r.e[2 * b + 1];
     const long long F = (long long)(yb - ya) * (px - xa) - (long long)(xb - xa) * (py - ya);
-    const unsigned nb = (r.meta >> (19 + i)) & 1u;
+    const unsigned nb = (r.meta >> (8 + 8 * i)) & 1u;
     return F - (long long)nb;
 }
 
@@ -503,7 +510,7 @@ __device__ __noinline__ bool slow_cover(const Rec &r, int px, int py0, bool ok0,
     const long long G0 = slow_edge(r, 0, spx, spy1), G1 = slow_edge(r, 1, spx, spy1), G2 = slow_edge(r, 2, spx, spy1);
     cov0 = ok0 && ((F0 | F1 | F2) >= 0);
     cov1 = ok1 && ((G0 | G1 | G2) >= 0);
-    const long long nb0 = (meta >> 19) & 1, nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
+    const long long nb0 = meta_nb0(meta), nb1 = meta_nb1(meta), nb2 = meta_nb2(meta);
     f1a = (float)(F1 + nb1); f2a = (float)(F2 + nb2);
     f1b = (float)(G1 + nb1); f2b = (float)(G2 + nb2);
     f0a = (float)(F0 + nb0); f0b = (float)(G0 + nb0);
@@ -531,7 +538,7 @@ __device__ __forceinline__ FastCov fast_cover(const int4 &ea, const int4 &eb, co
     FastCov c;
     c.cov0 = ok0 && ((F0 | F1 | F2) >= 0);
     c.cov1 = ok1 && ((G0 | G1 | G2) >= 0);
-    const int nb0 = (meta >> 19) & 1, nb1 = (meta >> 20) & 1, nb2 = (meta >> 21) & 1;
+    const int nb0 = meta_nb0(meta), nb1 = meta_nb1(meta), nb2 = meta_nb2(meta);
     c.F0 = F0 + nb0; c.F1 = F1 + nb1; c.F2 = F2 + nb2;
     c.G0 = G0 + nb0; c.G1 = G1 + nb1; c.G2 = G2 + nb2;
     return c;
@@ -653,6 +660,44 @@ __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bm
             const float4 zq = *reinterpret_cast<const float4 *>(&r.z0);       // z0 dz1 dz2 invA
             raster_one<SMOOTH, CHECK_SLOW>(*f, r, SMOOTH ? reinterpret_cast<const SRec *>(srecs + (size_t)t * f->srec_stride) : nullptr,
                                ea, eb, ec, zq, px, py0, ok0, ok1, ps);
+        }
+    }
+}
+
+// The same sweep with 32-bit depth keys, for callers that can promise (a) no int64 records and no per-pixel
+// shading among `recs`, (b) the records are visited in draw order (ascending bit index == ascending draw id) and
+// (c) whatever the pixel state was initialised from was drawn before all of them.  Then "smaller (depth, id) wins"
+// is "strictly smaller depth wins": the id never has to be compared or carried, and a pixel was won by this sweep
+// iff its depth changed.  Saves 4 of the 10 compare / select instructions per covered (block, record) pair -- they
+// all go to the ALU pipe, which is what bounds the small-scene kernel.
+struct PixelState32 {
+    unsigned z0, z1;             // depth bits (non-negative floats order like unsigned integers)
+    unsigned c0, c1;             // packed RGBA8 of the current winner
+};
+
+template <int MWORDS>
+__device__ __forceinline__ void raster_block32(const Rec *recs, const unsigned *bmask, int px, int py0, bool ok0,
+                                               bool ok1, PixelState32 &ps) {
+#pragma unroll 1
+    for (int w = 0; w < MWORDS; ++w) {
+        unsigned m = bmask[w];
+#pragma unroll 1
+        while (m) {
+            const int t = w * 32 + __ffs(m) - 1;
+            m &= m - 1;
+            const Rec &r = recs[t];
+            const int4 ea = *reinterpret_cast<const int4 *>(&r.e[0]);         // Eo0 Eo1 Eo2 A0
+            const int4 eb = *reinterpret_cast<const int4 *>(&r.e[4]);         // A1 A2 B0 B1
+            const int4 ec = *reinterpret_cast<const int4 *>(&r.e[8]);         // B2 col id meta
+            const FastCov c = fast_cover(ea, eb, ec, px, py0, ok0, ok1);
+            if (!__any_sync(0xffffffffu, c.cov0 || c.cov1)) continue;
+            const float4 zq = *reinterpret_cast<const float4 *>(&r.z0);       // z0 dz1 dz2 invA
+            const float za = fmaf((float)c.F2 * zq.w, zq.z, fmaf((float)c.F1 * zq.w, zq.y, zq.x));
+            const float zc = fmaf((float)c.G2 * zq.w, zq.z, fmaf((float)c.G1 * zq.w, zq.y, zq.x));
+            const unsigned ka = __float_as_uint(za), kc = __float_as_uint(zc);
+            const bool w0 = c.cov0 & (ka < ps.z0), w1 = c.cov1 & (kc < ps.z1);
+            ps.z0 = w0 ? ka : ps.z0; ps.c0 = w0 ? (unsigned)ec.y : ps.c0;
+            ps.z1 = w1 ? kc : ps.z1; ps.c1 = w1 ? (unsigned)ec.y : ps.c1;
         }
     }
 }

@@ -357,6 +357,8 @@ struct NodeStats {
     long long slots = 0, verts = 0, insts = 0;
     bool any_smooth = false, any_textured = false, warp_ok = true;
     int skipped = 0;
+    long long skipped_id_end = 0;         // draw index past the last triangle of the skipped (static layer) nodes
+    long long active_id_begin = 1ll << 40;   // draw index of the first triangle of the active nodes
     int n_poses = 0;          // posed nodes among the active ones (all of them in f.poses when <= MAX_FRAME_POSES)
     bool poses_in_frame = false;
 };
@@ -392,8 +394,10 @@ static int fill_nodes(const pbr_frame_desc *d, int device, NodeMode mode, FrameD
         const bool in_base = (n.flags & PBR_NODE_IN_BASE) != 0;
         if ((mode == NODES_SKIP_BASE && in_base) || (mode == NODES_SHARED_ONLY && !(n.shared && in_base))) {
             st.skipped++;
+            if (ids > st.skipped_id_end) st.skipped_id_end = ids;
             continue;
         }
+        if (id_begin < st.active_id_begin) st.active_id_begin = id_begin;
         NodeDev &nd = f.nodes[f.n_nodes++];
         nd.tp = n.mesh->tp; nd.tn = n.mesh->tn; nd.vpos = n.mesh->vpos; nd.tidx = n.mesh->tidx;
         // basic.frag:31-32: base = mix(1, texel, clamp(useTexture)); without a bound image the node is untextured
@@ -685,6 +689,10 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         if (ns.n_poses > 0 && !ns.poses_in_frame)
             if (int rc = materialise_poses(d, stream)) return rc;
         f.write_mats = (ns.poses_in_frame && (d->flags & PBR_FRAME_WRITE_MATS)) ? 1 : 0;
+        // 32-bit depth keys are enough when ties against the static layer always go to the layer, i.e. when
+        // everything in it was drawn before the first node of this frame (CartPole: the rail is node 0)
+        static const bool no_k32 = getenv("PBR_B200_NO_KEYS32") != nullptr;       // A/B timing aid
+        f.keys32 = (!no_k32 && (!use_base || ns.skipped_id_end <= ns.active_id_begin)) ? 1 : 0;
         {   // programmatic launch chain: this launch may start while the previous small-scene launches on the
             // stream drain; it orders itself behind them when it writes memory they write (see raster_warp.cuh)
             const unsigned char *lo = f.out + (size_t)f.scene_begin * f.C * H * W;

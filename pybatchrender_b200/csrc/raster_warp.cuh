@@ -877,18 +877,40 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         const int px = bx * 8 + lx, py0 = by * 8 + ly;
         const bool ok0 = px < f.W && py0 < f.H, ok1 = px < f.W && py0 + 4 < f.H;
         const int b = by * f.nbx + bx;
-        PixelState ps;
-        ps.k0 = ps.k1 = KEY_CLEAR;
-        if (item & 0x80000000u) {                         // static layer covers part of this block
-            ps.k0 = __ldg(f.base_keys + (size_t)b * 64 + lane);
-            ps.k1 = __ldg(f.base_keys + (size_t)b * 64 + 32 + lane);
+        // winners of this block: did this sweep win the lane's pixels, and with which colour
+        bool won0, won1;
+        unsigned c0, c1;
+        if (f.keys32 && direct && !(item & 0x40000000u)) {
+            // no clipped / int64 records in this scene, records in draw order, static layer drawn first:
+            // 32-bit depth keys (see raster_block32)
+            PixelState32 q;
+            q.z0 = q.z1 = (unsigned)(KEY_CLEAR >> 32);
+            if (item & 0x80000000u) {                     // static layer covers part of this block
+                const unsigned *bk = reinterpret_cast<const unsigned *>(f.base_keys + (size_t)b * 64);
+                q.z0 = __ldg(bk + 2 * lane + 1);
+                q.z1 = __ldg(bk + 2 * (32 + lane) + 1);
+            }
+            q.c0 = q.c1 = 0u;
+            const unsigned zi0 = q.z0, zi1 = q.z1;
+            raster_block32<W_MW>(srecs, smasks + b * W_MW, px, py0, ok0, ok1, q);
+            won0 = q.z0 != zi0; won1 = q.z1 != zi1;
+            c0 = q.c0; c1 = q.c1;
+        } else {
+            PixelState ps;
+            ps.k0 = ps.k1 = KEY_CLEAR;
+            if (item & 0x80000000u) {
+                ps.k0 = __ldg(f.base_keys + (size_t)b * 64 + lane);
+                ps.k1 = __ldg(f.base_keys + (size_t)b * 64 + 32 + lane);
+            }
+            ps.c0 = ps.c1 = 0u;
+            const unsigned id0 = (unsigned)ps.k0, id1 = (unsigned)ps.k1;
+            if (WARPS > 1 && !(item & 0x40000000u))
+                raster_block<W_MW, false, false>(srecs, smasks + b * W_MW, px, py0, ok0, ok1, ps, &f);
+            else
+                raster_block<W_MW, false, true>(srecs, smasks + b * W_MW, px, py0, ok0, ok1, ps, &f);
+            won0 = key_changed(ps.k0, id0); won1 = key_changed(ps.k1, id1);
+            c0 = ps.c0; c1 = ps.c1;
         }
-        ps.c0 = ps.c1 = 0u;
-        const unsigned id0 = (unsigned)ps.k0, id1 = (unsigned)ps.k1;
-        if (WARPS > 1 && !(item & 0x40000000u))
-            raster_block<W_MW, false, false>(srecs, smasks + b * W_MW, px, py0, ok0, ok1, ps, &f);
-        else
-            raster_block<W_MW, false, true>(srecs, smasks + b * W_MW, px, py0, ok0, ok1, ps, &f);
         if (f.debug == 3) continue;
         if (LATE_WAIT && !stores_done) {                  // first patch of this warp: the background has to be there
             if (lane == 0)
@@ -898,18 +920,18 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             stores_done = true;
         }
         unsigned char *p = out_scene + py0 * f.W + px;
-        if (key_changed(ps.k0, id0)) {
-            p[0] = (unsigned char)(ps.c0 & 255u);
-            p[HW] = (unsigned char)((ps.c0 >> 8) & 255u);
-            p[2 * HW] = (unsigned char)((ps.c0 >> 16) & 255u);
-            if (f.C == 4) p[3 * HW] = (unsigned char)(ps.c0 >> 24);
+        if (won0) {
+            p[0] = (unsigned char)(c0 & 255u);
+            p[HW] = (unsigned char)((c0 >> 8) & 255u);
+            p[2 * HW] = (unsigned char)((c0 >> 16) & 255u);
+            if (f.C == 4) p[3 * HW] = (unsigned char)(c0 >> 24);
         }
-        if (key_changed(ps.k1, id1)) {
+        if (won1) {
             p += 4 * f.W;
-            p[0] = (unsigned char)(ps.c1 & 255u);
-            p[HW] = (unsigned char)((ps.c1 >> 8) & 255u);
-            p[2 * HW] = (unsigned char)((ps.c1 >> 16) & 255u);
-            if (f.C == 4) p[3 * HW] = (unsigned char)(ps.c1 >> 24);
+            p[0] = (unsigned char)(c1 & 255u);
+            p[HW] = (unsigned char)((c1 >> 8) & 255u);
+            p[2 * HW] = (unsigned char)((c1 >> 16) & 255u);
+            if (f.C == 4) p[3 * HW] = (unsigned char)(c1 >> 24);
         }
     }
     W_STAMP(6);
