@@ -81,7 +81,7 @@ struct WScene {
     Rec *recs;                // [W_MAXREC]
     unsigned *masks;          // [nblk][W_MW]
     unsigned short *blist;    // [nblk]
-    unsigned *live;           // [W_MAXREC] block box of each record (0xffffffff: none)
+    unsigned *live;           // [W_MAXREC] (spare)
     unsigned *clipl;          // [W_MAXREC] packed slots of the triangles that need clipping
     int *ctr;                 // [4] overflow pool entry, clipped triangles, records drawn (S > 32), has int64 records
     unsigned char **out_slot; // out[scene], for the sweep
@@ -100,6 +100,8 @@ __device__ __forceinline__ WScene wscene(unsigned char *base, int nblk) {
     s.out_slot = reinterpret_cast<unsigned char **>(s.ctr + 6);
     return s;
 }
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // named barrier 1 over the first THREADS threads of the CTA (the warps that share the geometry work)
 template <int THREADS_>
@@ -339,6 +341,9 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 #ifndef PBR_W_TRIGGER
 #define PBR_W_TRIGGER 1
 #endif
+#ifndef PBR_W_PREFETCH
+#define PBR_W_PREFETCH 1
+#endif
 template <int WARPS, bool TMA_BG>
 __global__ void __launch_bounds__(32 * (WARPS + (TMA_BG ? PBR_W_HELPERS : 0)), 32 / (WARPS + (TMA_BG ? PBR_W_HELPERS : 0)))
 raster_warp_kernel(const __grid_constant__ FrameDev f) {
@@ -444,7 +449,6 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 const int n16 = (int)(align16((size_t)nblk * W_MW * 4) / 16);
                 for (int i = lane; i < n16; i += 32) m4[i] = make_uint4(0u, 0u, 0u, 0u);
             }
-            for (int i = lane; i < W_MAXREC; i += 32) me.live[i] = 0xffffffffu;     // slots without a record
             if (lane < 4) me.ctr[lane] = 0;
         }
     } else if (worker && f.sync_early && f.write_mats) {
@@ -452,6 +456,26 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     }
     if (worker && geom) {
         const int wl = warp * 32 + lane;     // this lane among the worker lanes
+
+        // L1 is empty at kernel entry and every phase below starts with a load that the phase before it cannot
+        // issue (barrier in between): ask for those lines now -- the scenes' VP rows (phase A) and instance
+        // colours (phase S), the meshes' vertices, index triples and normals (phases A, B, S)
+        if (PBR_W_PREFETCH) {
+            int k = wl;
+            if (k < n_sc) {
+                prefetch_l1(f.vp + (size_t)(first_scene + k) * 16);
+            } else if ((k -= n_sc) < f.n_nodes * 8) {
+                const NodeDev &nd = f.nodes[k >> 3];
+                const int part = k & 7;
+                if (part == 0) prefetch_l1(nd.vpos);
+                else if (part <= 2) { if ((part - 1) * 8 < nd.n_tris) prefetch_l1(nd.tidx + (part - 1) * 8); }
+                else if ((part - 3) * 8 < 3 * nd.n_tris) prefetch_l1(nd.tn + (part - 3) * 8);
+            } else if ((k -= f.n_nodes * 8) < n_sc * f.n_nodes) {
+                const int sl = k / f.n_nodes;
+                const NodeDev &nd = f.nodes[k - sl * f.n_nodes];
+                prefetch_l1(nd.cols + (nd.shared ? (size_t)0 : (size_t)(first_scene + sl) * nd.inst) * 4);
+            }
+        }
 
         // ---- M: instances.  A posed node's model matrix is computed here from its pose channels (the state
         // tensor of the caller: reference envs/cartpole/renderer.py:125-138 + shader_context.py:47-84), other
@@ -584,7 +608,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         group_sync<GW * 32>();
 
         // ---- S: set-up of the survivors: integer edge equations, depth plane, flat shade (basic.frag:31-38)
-        // -> 64-byte record + block box of the record
+        // -> 64-byte record, binned into the per-block masks
         {
             const int n_live = qctr[2];
 #pragma unroll 1
@@ -616,8 +640,10 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                     r.col = shade(f, n, __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4)));
                     if (r.meta & M_SLOW) sc.ctr[3] = 1;
                     sc.recs[j] = r;
-                    // block box of the record, binned below with one lane per (record, block) pair
-                    sc.live[j] = (unsigned)bb.bx0 | ((unsigned)bb.by0 << 8) | ((unsigned)bb.bx1 << 16) | ((unsigned)bb.by1 << 24);
+                    // into the masks of the 8x8 blocks its box touches (edge-function reject per block): the
+                    // boxes are small (1-8 blocks) and the lanes of this phase are full, so a loop per lane
+                    // beats a second pass with one lane per (record, block) pair
+                    bin_record<W_MW>(r, bb, j, f.nbx, sc.masks);
                 }
             }
         }
@@ -631,7 +657,6 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         Rec *const recs = me.recs;
         unsigned *const masks = me.masks;
         unsigned short *const blist = me.blist;
-        unsigned *const live = me.live;
         unsigned *const clipl = me.clipl;
         int *const ovf_entry = &me.ctr[0];
         const float4 *const clipc = me.clipc;
@@ -640,51 +665,6 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         int nrec = nlive;
         scene_slow = nclip > 0 || me.ctr[3] != 0;     // (clipped fans: not tracked, assume so)
         {
-            // ---- B2: bin.  One lane per (record, block of its box) pair instead of one lane per record
-            // looping over its box: the boxes are small and uneven (1-8 blocks), a per-record loop runs as
-            // long as the largest box while most lanes idle.
-            __syncwarp();
-#pragma unroll 1
-            for (int base = 0; base < nlive; base += 32) {
-                const int j = base + lane;
-                const unsigned pk = j < nlive ? live[j] : 0xffffffffu;
-                const int cnt = pk == 0xffffffffu ? 0
-                                                  : ((int)((pk >> 16) & 255u) - (int)(pk & 255u) + 1) *
-                                                        ((int)(pk >> 24) - (int)((pk >> 8) & 255u) + 1);
-                int incl = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int o = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += o;
-                }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                const int start = incl - cnt;
-#pragma unroll 1
-                for (int pb = 0; pb < total; pb += 32) {
-                    const int p = pb + lane;
-                    int lo = 0;                       // last record whose first pair index is <= p
-#pragma unroll
-                    for (int step = 16; step >= 1; step >>= 1) {
-                        const int sv = __shfl_sync(0xffffffffu, start, lo + step);
-                        if (sv <= p) lo += step;
-                    }
-                    const unsigned rpk = __shfl_sync(0xffffffffu, pk, lo);
-                    const int rst = __shfl_sync(0xffffffffu, start, lo);
-                    if (p < total) {
-                        BBox bb;
-                        bb.bx0 = (int)(rpk & 255u); bb.by0 = (int)((rpk >> 8) & 255u);
-                        bb.bx1 = (int)((rpk >> 16) & 255u); bb.by1 = (int)(rpk >> 24);
-                        const int bw = bb.bx1 - bb.bx0 + 1, k = p - rst;
-                        const int yy = (int)__fdividef((float)k + 0.5f, (float)bw);     // exact: never within 1/512 of an integer
-                        const int bx = bb.bx0 + k - yy * bw, by = bb.by0 + yy;
-                        const int t = base + lo;
-                        const bool small = (bb.bx1 - bb.bx0) + (bb.by1 - bb.by0) <= 1;
-                        if (small || block_hit(recs[t], bb, bx, by))
-                            atomicOr(&masks[(by * f.nbx + bx) * W_MW + (t >> 5)], 1u << (t & 31));
-                    }
-                }
-            }
-
             // ---- B3: clipped triangles -> fan triangles in the spare record slots
             if (nclip > 0) {
                 int entry = -1;                          // warp-uniform
