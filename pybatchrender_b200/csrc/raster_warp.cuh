@@ -342,7 +342,12 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 #define PBR_W_TRIGGER 1
 #endif
 #ifndef PBR_W_PREFETCH
-#define PBR_W_PREFETCH 1
+#define PBR_W_PREFETCH 0
+#endif
+// Experiment: hold the CTA's bulk stores back until the geometry has issued its global loads (1: until the
+// vertices are done, 2: until the set-up is done) -- the loads queue behind the store burst on the SM's path to L2
+#ifndef PBR_W_BG_AFTER
+#define PBR_W_BG_AFTER 0
 #endif
 template <int WARPS, bool TMA_BG>
 __global__ void __launch_bounds__(32 * (WARPS + (TMA_BG ? PBR_W_HELPERS : 0)), 32 / (WARPS + (TMA_BG ? PBR_W_HELPERS : 0)))
@@ -375,7 +380,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     int *qctr = reinterpret_cast<int *>(smem_raw + f.w_qctr_off);
     unsigned *livelist = reinterpret_cast<unsigned *>(qctr) - WARPS * W_MAXSLOT; // [WARPS * W_MAXSLOT], just below the counters
     constexpr bool LATE_WAIT = TMA_BG && PBR_W_LATE_WAIT != 0;
-    if (threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; qctr[2] = 0; qctr[3] = 0; }
+    if (threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; qctr[2] = 0; qctr[3] = 0; qctr[6] = 0; }
     __syncthreads();          // counters initialised (all warps arrive together: cheap)
     // The thread that drives the TMA engine: lane 0 of the LAST helper warp when there is one.  Issuing the
     // CTA's bulk stores blocks the issuing thread for microseconds (time stamps: a scene warp that did it
@@ -397,6 +402,8 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         mbar_expect_tx(bg_bar, (unsigned)scene_bytes_out);
         tma_load(qctr + 8, f.base_color, (unsigned)scene_bytes_out, bg_bar);
         if (f.sync_early) asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (PBR_W_BG_AFTER != 0 && f.debug != 1)
+            while (atomicAdd(&qctr[6], 0) < PBR_W_BG_AFTER) __nanosleep(100);
         if (BG_T != 0) {
             if (PBR_W_BG_SERIAL) {
                 unsigned smid;
@@ -557,6 +564,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         if (TMA_BG && BG_T == 0 && threadIdx.x == 0) issue_bg_stores(f, qctr, WARPS);      // the load has had phase A to arrive
         if (split_bg && active) write_background_part(f, out_scene, HW, lane, 1);
         group_sync<GW * 32>();
+        if (PBR_W_BG_AFTER == 1 && threadIdx.x == 0) atomicExch(&qctr[6], 1);
 
         // ---- B: classify triangle slots; survivors go to the CTA's live list as (scene, slot, record index)
         {
@@ -650,6 +658,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         W_STAMP(2);
         if (split_bg && active) write_background_part(f, out_scene, HW, lane, 2);
         group_sync<GW * 32>();
+        if (PBR_W_BG_AFTER == 2 && threadIdx.x == 0) atomicExch(&qctr[6], 2);
     }
 
     // ---- per scene, by its own warp: binning, clipped fans, block list
