@@ -746,20 +746,33 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
             CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS_TMA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem_optin));
             CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS_TMA, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS_TMA_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem_optin));
+            CUDA_TRY(cudaFuncSetAttribute(raster_warp_kernel<W_WARPS_TMA_SMALL, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             st->attr_warp = true;
         }
-        // background by TMA (14 scenes + 2 helper warps per CTA + the image in shared memory) when 2 such CTAs fit an SM
+        // background by TMA (scenes + 2 helper warps per CTA + the image in shared memory): 14 scenes per CTA while two
+        // such CTAs fit an SM, else 6 scenes per CTA (three CTAs per SM at 84x84: a single CTA of 14 leaves the SM
+        // idle at every barrier between its shared geometry phases -- measured 143 vs 113 us per 16,384 scenes)
         static const int tma_mode = getenv("PBR_B200_WARP_TMA") ? atoi(getenv("PBR_B200_WARP_TMA")) : -1;   // 0 / 1 force, else auto
         const size_t tile_bytes = (size_t)f.C * H * W;
-        const size_t tma_smem = warp_smem_bytes(nbx * (H8 / 8), W_WARPS_TMA, tile_bytes);
+        const size_t two_per_sm = ((size_t)st->max_smem_optin + 1024 - 2 * 1024) / 2;
+        const size_t tma_big = warp_smem_bytes(nbx * (H8 / 8), W_WARPS_TMA, tile_bytes);
+        const size_t tma_small = warp_smem_bytes(nbx * (H8 / 8), W_WARPS_TMA_SMALL, tile_bytes);
+        const bool big = tma_big <= two_per_sm;
+        const size_t tma_smem = big ? tma_big : tma_small;
         const bool tma_ok = f.base_color != nullptr && (tile_bytes & 15) == 0 && tma_smem <= (size_t)st->max_smem_optin;
-        // measured: faster for 64x64 (0.348 vs 0.302 of the roofline) and 84x84 (0.55 vs 0.52), slower for
-        // 32x32 (the copy is cheap, the wide barrier is not) and 128x128 (the image crowds out the scenes)
-        const bool use_tma = tma_ok && (tma_mode == 1 || (tma_mode != 0 && tma_smem <= 136 * 1024 && tile_bytes >= 8192));
-        if (use_tma) {
+        // measured: faster for 64x64 and 84x84, slower for 32x32 (the copy is cheap, the wide barrier is not) and
+        // 128x128 (the image crowds out the scenes)
+        const bool use_tma = tma_ok && (tma_mode == 1 || (tma_mode != 0 && tma_smem <= two_per_sm && tile_bytes >= 8192 && tile_bytes <= 32768));
+        if (use_tma && big) {
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS_TMA - 1) / W_WARPS_TMA);
             f.w_qctr_off = (int)warp_qctr_offset(nbx * (H8 / 8), W_WARPS_TMA);
             CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS_TMA, true>, wgrid, 32 * (W_WARPS_TMA + PBR_W_HELPERS), tma_smem, stream, f));
+            COUNT_LAUNCH();
+        } else if (use_tma) {
+            const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS_TMA_SMALL - 1) / W_WARPS_TMA_SMALL);
+            f.w_qctr_off = (int)warp_qctr_offset(nbx * (H8 / 8), W_WARPS_TMA_SMALL);
+            CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS_TMA_SMALL, true>, wgrid, 32 * (W_WARPS_TMA_SMALL + PBR_W_HELPERS), tma_smem, stream, f));
             COUNT_LAUNCH();
         } else {
             static const size_t smem_pad = getenv("PBR_B200_WARP_SMEM_PAD") ? (size_t)atoi(getenv("PBR_B200_WARP_SMEM_PAD")) : 0;   // occupancy experiments

@@ -72,6 +72,7 @@ __host__ __device__ inline size_t warp_smem_bytes(int nblk, int warps, size_t tm
 #define PBR_W_WARPS_TMA 14
 #endif
 constexpr int W_WARPS_TMA = PBR_W_WARPS_TMA;      // scenes per CTA when the background goes through TMA (see kernel comment)
+constexpr int W_WARPS_TMA_SMALL = 6;              // ... for tiles whose image leaves room for only one CTA of W_WARPS_TMA per SM
 
 // views into one scene's shared-memory region (layout: warp_scene_bytes)
 struct WScene {
