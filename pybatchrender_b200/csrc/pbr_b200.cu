@@ -33,6 +33,7 @@
 #include "raster_general.cuh"
 #include "raster_warp.cuh"
 #include "raster_staged.cuh"
+#include "raster_binned.cuh"
 #include "transforms.cuh"
 
 using namespace pbr;
@@ -82,6 +83,12 @@ struct StreamScratch {
     size_t g_bcount_cap = 0, g_bidx_cap = 0;
     unsigned *g_bbox = nullptr;
     int *g_count = nullptr;
+    // block-list path (raster_binned.cuh): parked vertices, per-block counts / offsets, (block, record) pairs
+    float4 *b_vclip = nullptr;
+    int4 *b_vproj = nullptr;
+    int *b_cnt = nullptr, *b_off = nullptr;
+    unsigned *b_pairs = nullptr;
+    size_t b_vert_cap = 0, b_blk_cap = 0, b_pair_cap = 0;
     size_t g_rec_cap = 0;            // records allocated (all scenes of one launch)
     size_t g_scene_cap = 0;          // scenes allocated in g_count
     // clear-colour image [C,H,W]: copy source of the small-scene kernel's background when there is
@@ -109,6 +116,7 @@ struct DeviceState {
     unsigned *ovf_busy = nullptr;
     size_t ovf_mask_words = 0;           // mask words per entry currently allocated
     bool cap_worst_case = false;         // staged path: a frame overflowed its record lists -> size them for 6 per slot
+    bool attr_binned = false;
 };
 std::mutex g_mu;
 DeviceState g_dev[64];
@@ -634,6 +642,108 @@ static int launch_staged(FrameDev &f, DeviceState *st, void *stream) {
     return PBR_OK;
 }
 
+// Large scenes, block-list path (raster_binned.cuh): cull, vertices, triangles + block counts, scan, fill, one warp
+// per block -- in launches of as many scenes as the scratch budget holds.
+static int launch_binned(FrameDev &f, DeviceState *st, void *stream) {
+    StreamScratch *ss = &st->per_stream[stream];
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (st->status_host[1] != 0) {
+        st->status_host[1] = 0;
+        st->cap_worst_case = true;
+        return fail(PBR_EOVERFLOW, "pbr_render: an earlier large-scene frame on this device dropped triangles (record or block "
+                                   "lists too small); later frames take the band-based path with worst-case sizes -- render again");
+    }
+    const int H8 = ((f.H + 7) / 8) * 8;
+    f.BH = H8; f.nbands = 1; f.nbx = (f.W + 7) / 8; f.nby = H8 / 8;       // blocks of the whole tile
+    f.plane_stride = f.H * f.W; f.linear = 1;
+    const size_t nblk = (size_t)f.nbx * f.nby;
+    const size_t cap = ((size_t)f.total_slots + (size_t)f.total_slots / 2 + 64 + 3) & ~(size_t)3;
+    const size_t pairs_cap = 4 * cap + 4 * nblk;
+    const size_t tv = (size_t)f.total_verts;
+    const bool smooth = f.smooth != 0;
+    static const size_t budget_mb = getenv("PBR_B200_SCRATCH_MB") ? (size_t)atoll(getenv("PBR_B200_SCRATCH_MB")) : 4096;
+    const size_t per_scene = cap * (sizeof(Rec) + 4 + (smooth ? (size_t)f.srec_stride : 0)) + tv * 32 + nblk * 8 + 4 + pairs_cap * 4 +
+                             (size_t)f.total_inst + 4;
+    size_t per_launch = (budget_mb << 20) / per_scene;
+    if (per_launch < 1) per_launch = 1;
+    if (per_launch > (size_t)f.scene_count) per_launch = (size_t)f.scene_count;
+    if (per_launch > 65535) per_launch = 65535;                     // gridDim.y
+    auto grow = [&](void **p, size_t *have, size_t need_elems, size_t elem) -> cudaError_t {
+        if (need_elems <= *have) return cudaSuccess;
+        cudaError_t e = cudaStreamSynchronize(cs);
+        if (e != cudaSuccess) return e;
+        cudaFree(*p);
+        *p = nullptr; *have = 0;
+        e = cudaMalloc(p, need_elems * elem);
+        if (e == cudaSuccess) *have = need_elems;
+        return e;
+    };
+    if (per_launch * cap > ss->g_rec_cap || per_launch > ss->g_scene_cap || (smooth && per_launch * cap * (size_t)f.srec_stride > ss->g_srec_cap)) {
+        CUDA_TRY(cudaStreamSynchronize(cs));
+        cudaFree(ss->g_recs); cudaFree(ss->g_bbox); cudaFree(ss->g_count); cudaFree(ss->g_srecs);
+        ss->g_recs = nullptr; ss->g_bbox = nullptr; ss->g_count = nullptr; ss->g_srecs = nullptr;
+        ss->g_rec_cap = 0; ss->g_scene_cap = 0; ss->g_srec_cap = 0;
+        CUDA_TRY(cudaMalloc(&ss->g_recs, per_launch * cap * sizeof(Rec)));
+        CUDA_TRY(cudaMalloc(&ss->g_bbox, per_launch * cap * 4 + 64));
+        CUDA_TRY(cudaMalloc(&ss->g_count, per_launch * sizeof(int)));
+        ss->g_rec_cap = per_launch * cap; ss->g_scene_cap = per_launch;
+        if (smooth) {
+            CUDA_TRY(cudaMalloc(&ss->g_srecs, per_launch * cap * (size_t)f.srec_stride));
+            ss->g_srec_cap = per_launch * cap * (size_t)f.srec_stride;
+        }
+    }
+    CUDA_TRY(grow((void **)&ss->g_vis, &ss->g_vis_cap, per_launch * (size_t)f.total_inst, 1));
+    if (per_launch * tv > ss->b_vert_cap) {
+        CUDA_TRY(cudaStreamSynchronize(cs));
+        cudaFree(ss->b_vclip); cudaFree(ss->b_vproj);
+        ss->b_vclip = nullptr; ss->b_vproj = nullptr; ss->b_vert_cap = 0;
+        CUDA_TRY(cudaMalloc(&ss->b_vclip, per_launch * tv * sizeof(float4)));
+        CUDA_TRY(cudaMalloc(&ss->b_vproj, per_launch * tv * sizeof(int4)));
+        ss->b_vert_cap = per_launch * tv;
+    }
+    if (per_launch * (nblk + 1) > ss->b_blk_cap) {
+        CUDA_TRY(cudaStreamSynchronize(cs));
+        cudaFree(ss->b_cnt); cudaFree(ss->b_off);
+        ss->b_cnt = nullptr; ss->b_off = nullptr; ss->b_blk_cap = 0;
+        CUDA_TRY(cudaMalloc(&ss->b_cnt, per_launch * (nblk + 1) * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&ss->b_off, per_launch * (nblk + 1) * sizeof(int)));
+        ss->b_blk_cap = per_launch * (nblk + 1);
+    }
+    CUDA_TRY(grow((void **)&ss->b_pairs, &ss->b_pair_cap, per_launch * pairs_cap, sizeof(unsigned)));
+
+    StagedDev g;
+    g.vis = ss->g_vis; g.bcount = nullptr; g.bidx = nullptr;
+    g.recs = ss->g_recs; g.srecs = smooth ? ss->g_srecs : nullptr; g.bbox = ss->g_bbox; g.count = ss->g_count; g.cap = (int)cap;
+    BinnedDev bd;
+    bd.vclip = ss->b_vclip; bd.vproj = ss->b_vproj; bd.blk_cnt = ss->b_cnt; bd.blk_off = ss->b_off; bd.pairs = ss->b_pairs;
+    bd.pairs_cap = (int)pairs_cap; bd.total_verts = f.total_verts;
+    const int first = f.scene_begin, last = f.scene_begin + f.scene_count;
+    for (int s0 = first; s0 < last; s0 += (int)per_launch) {
+        const int n = (int)((size_t)(last - s0) < per_launch ? (size_t)(last - s0) : per_launch);
+        g.scene0 = s0;
+        CUDA_TRY(cudaMemsetAsync(ss->g_count, 0, (size_t)n * sizeof(int), cs));
+        CUDA_TRY(cudaMemsetAsync(ss->b_cnt, 0, (size_t)n * nblk * sizeof(int), cs));
+        cull_kernel<<<dim3((unsigned)((f.total_inst + 255) / 256), (unsigned)n), 256, 0, cs>>>(f, g);
+        COUNT_LAUNCH();
+        bin_xform_kernel<<<dim3((unsigned)((tv + B_THREADS - 1) / B_THREADS), (unsigned)n), B_THREADS, 0, cs>>>(f, g, bd);
+        COUNT_LAUNCH();
+        bin_tri_kernel<<<dim3((unsigned)((f.total_slots + B_THREADS - 1) / B_THREADS), (unsigned)n), B_THREADS, 0, cs>>>(f, g, bd);
+        COUNT_LAUNCH();
+        bin_scan_kernel<<<(unsigned)n, B_THREADS, 0, cs>>>(f, bd);
+        COUNT_LAUNCH();
+        bin_fill_kernel<<<dim3((unsigned)((cap + B_THREADS - 1) / B_THREADS), (unsigned)n), B_THREADS, 0, cs>>>(f, g, bd);
+        COUNT_LAUNCH();
+        const dim3 rgrid((unsigned)((nblk + B_WPB - 1) / B_WPB), (unsigned)n);
+        if (smooth)
+            raster_binned_kernel<true><<<rgrid, B_WPB * 32, 0, cs>>>(f, g, bd);
+        else
+            raster_binned_kernel<false><<<rgrid, B_WPB * 32, 0, cs>>>(f, g, bd);
+        COUNT_LAUNCH();
+        CUDA_TRY(cudaGetLastError());
+    }
+    return PBR_OK;
+}
+
 int pbr_render(const pbr_frame_desc *d, void *stream) {
     if (int rc = check_frame(d, "pbr_render", true)) return rc;
     if (d->scene_count == 0) return PBR_OK;
@@ -791,8 +901,14 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         if (int rc = materialise_poses(d, stream)) return rc;
     size_t smem_fused = 0;
     if (int rc = plan_general(f, st, &smem_fused)) return rc;
-    if (!(d->flags & PBR_FRAME_FORCE_FUSED) && (ns.slots > CH || f.nbands > 1))
+    if (!(d->flags & PBR_FRAME_FORCE_FUSED) && (ns.slots > CH || f.nbands > 1)) {
+        // block lists unless a frame overflowed them (then: band-based path, worst-case record capacity) or
+        // PBR_B200_LARGE=staged asks for the band-based path (A/B measurements)
+        static const bool want_staged = getenv("PBR_B200_LARGE") != nullptr && strcmp(getenv("PBR_B200_LARGE"), "staged") == 0;
+        const bool fits = ns.verts <= 0x7fffffffll / 64 && d->tile_w <= 2048 && d->tile_h <= 2048;
+        if (!want_staged && !st->cap_worst_case && fits) return launch_binned(f, st, stream);
         return launch_staged(f, st, stream);
+    }
     return launch_general(f, st, stream);
 }
 

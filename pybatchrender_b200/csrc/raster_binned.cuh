@@ -1,0 +1,393 @@
+// raster_binned.cuh -- the large-scene path: per-8x8-block record lists, one warp per block.
+//
+// Large scenes (hundreds to tens of thousands of triangle slots per scene, tiles of 128^2 .. 256^2 and up:
+// BASELINE configs 3 and 5, Steering-v0) go through six kernels per launch chunk:
+//
+//   cull_kernel       (raster_staged.cuh)  thread per (scene, instance): bounding sphere vs clip planes / pixel grid
+//   bin_xform_kernel  thread per (scene, instance, unique vertex): clip = VP*(M*v), outcodes, project + snap
+//                     (reference basic.vert:24-43) -- once per vertex, not once per triangle corner
+//   bin_tri_kernel    thread per (scene, triangle slot): reject / cull / needs-clip from the three parked vertices;
+//                     the survivors of the CTA are compacted in shared memory and set up on full warps (edge
+//                     equations, depth plane, flat shade or per-pixel shading inputs) -> 64-byte record appended to
+//                     the scene's list, and the 8x8 blocks it can touch are counted
+//   bin_scan_kernel   CTA per scene: exclusive prefix sum of the block counts = where each block's list starts
+//   bin_fill_kernel   thread per record: its index into the list of every block it can touch
+//   raster_binned_kernel  WARP per (scene, block): walks the block's list -- records gathered eight at a time into
+//                     shared memory -- with the depth|id keys and colours of its 64 pixels in registers, then writes
+//                     the finished block straight to out[scene]: no colour / depth tile in shared memory, no
+//                     per-band rescans of the scene's records, no CTA barrier in the sweep.
+//
+// Measured against the band-based path it replaces (raster_staged.cuh: CTA per band of rows, 128-record chunks
+// binned and swept behind CTA barriers, depth keys in shared memory) in profiles/README.md.
+#pragma once
+#include "raster_staged.cuh"
+
+namespace pbr {
+
+struct BinnedDev {
+    float4 *vclip;           // [scenes_in_launch][total_verts] clip-space positions
+    int4 *vproj;             // [scenes_in_launch][total_verts] snapped x, y, depth bits, flags (VF_*)
+    int *blk_cnt;            // [scenes_in_launch][nblk] records per block (count pass), then the fill cursors
+    int *blk_off;            // [scenes_in_launch][nblk + 1] start of each block's list in `pairs`
+    unsigned *pairs;         // [scenes_in_launch][pairs_cap] record indices, block after block
+    int pairs_cap;
+    int total_verts;
+};
+
+constexpr int BV_CLIP = 0x40, BV_PROJ = 0x80;       // vertex flags (bits 0..5: outside clip plane p)
+constexpr int B_THREADS = 256;
+constexpr int B_WPB = 8;                            // block-warps per CTA of the raster kernel
+constexpr int B_GATHER = 8;                         // records staged per round (8 x 64 B = one 16-byte load per lane)
+
+// ------------------------------------------------------------------------------------------------
+// vertices
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(B_THREADS) bin_xform_kernel(const __grid_constant__ FrameDev f,
+                                                              const __grid_constant__ StagedDev g,
+                                                              const __grid_constant__ BinnedDev bd) {
+    const int local_scene = blockIdx.y;
+    const int scene = g.scene0 + local_scene;
+    const int v = blockIdx.x * B_THREADS + threadIdx.x;
+    if (v >= bd.total_verts) return;
+    int ni = 0;
+#pragma unroll 1
+    for (int i = 1; i < f.n_nodes; ++i)
+        if (v >= f.nodes[i].vert_begin) ni = i;
+    const NodeDev &nd = f.nodes[ni];
+    const int local = v - nd.vert_begin;
+    const int inst = local / nd.n_verts;
+    const int vert = local - inst * nd.n_verts;
+    if (!g.vis[(size_t)local_scene * f.total_inst + nd.inst_begin + inst]) return;
+    const size_t b = nd.shared ? (size_t)inst : (size_t)scene * nd.inst + inst;
+    float M[16], VP[16];
+    const float4 *m4 = reinterpret_cast<const float4 *>(nd.mats + b * 16);
+    const int vp_row = f.vp_scene_override >= 0 ? f.vp_scene_override : scene;
+    const float4 *v4 = reinterpret_cast<const float4 *>(f.vp + (size_t)vp_row * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 a = __ldg(m4 + j), c = __ldg(v4 + j);
+        M[4 * j] = a.x; M[4 * j + 1] = a.y; M[4 * j + 2] = a.z; M[4 * j + 3] = a.w;
+        VP[4 * j] = c.x; VP[4 * j + 1] = c.y; VP[4 * j + 2] = c.z; VP[4 * j + 3] = c.w;
+    }
+    const float4 p = __ldg(nd.vpos + vert);
+    float world[4], c[4];
+    mat_vec4(M, p.x, p.y, p.z, 1.0f, world);
+    mat_vec4(VP, world[0], world[1], world[2], world[3], c);
+    int flags = 0;
+#pragma unroll
+    for (int pl = 0; pl < 6; ++pl) {
+        const float a = c[pl >> 1];
+        const bool out = (pl & 1) ? (a > c[3]) : (a < -c[3]);
+        flags |= out ? (1 << pl) : 0;
+    }
+    if (needs_clip(c)) flags |= BV_CLIP;
+    int X = 0, Y = 0;
+    float z = 0.0f;
+    if (project_vertex(f, c, X, Y, z)) flags |= BV_PROJ;
+    const size_t o = (size_t)local_scene * bd.total_verts + v;
+    bd.vclip[o] = make_float4(c[0], c[1], c[2], c[3]);
+    bd.vproj[o] = make_int4(X, Y, __float_as_int(z), flags);
+}
+
+// ------------------------------------------------------------------------------------------------
+// triangles
+// ------------------------------------------------------------------------------------------------
+// load_slot (raster_general.cuh) with the clip-space positions taken from the parked vertices
+__device__ __forceinline__ void load_slot_parked(const FrameDev &f, int scene, int slot, int ni, int inst, int tri,
+                                                 const float4 *vclip, SlotGeom &g) {
+    const NodeDev &nd = f.nodes[ni];
+    const int local = slot - nd.slot_begin;
+    const size_t b = nd.shared ? (size_t)inst : (size_t)scene * nd.inst + inst;
+    float M[16];
+    const float4 *m4 = reinterpret_cast<const float4 *>(nd.mats + b * 16);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float4 a = __ldg(m4 + j);
+        M[4 * j] = a.x; M[4 * j + 1] = a.y; M[4 * j + 2] = a.z; M[4 * j + 3] = a.w;
+    }
+    M[12] = M[13] = M[14] = M[15] = 0.0f;      // (the normal transform reads columns 0..2 only)
+    g.col = __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4));
+    g.two_sided = (nd.flags & PBR_MESH_TWO_SIDED) != 0;
+    g.node = &nd;
+    const bool textured = nd.tex != nullptr;
+    g.id = (unsigned)(nd.id_begin + local) + 1u;
+    const uint4 ti = __ldg(nd.tidx + tri);
+    g.flat = ti.w != 0u;
+    const unsigned vi[3] = {ti.x, ti.y, ti.z};
+    const int vb = nd.vert_begin + inst * nd.n_verts;
+    const float4 n0 = __ldg(nd.tn + 3 * tri);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float4 c = vclip[vb + vi[k]];
+        g.v[k].c[0] = c.x; g.v[k].c[1] = c.y; g.v[k].c[2] = c.z; g.v[k].c[3] = c.w;
+        const float4 n = (k == 0 || g.flat) ? n0 : __ldg(nd.tn + 3 * tri + k);
+        xform_normal(M, n.x, n.y, n.z, g.v[k].n);
+        float2 uv = make_float2(0.0f, 0.0f);
+        if (textured && nd.tuv != nullptr) uv = __ldg(nd.tuv + 3 * tri + k);
+        g.v[k].uv[0] = uv.x; g.v[k].uv[1] = uv.y;
+    }
+}
+
+// append the record to the scene's list and count it in every block it can touch
+__device__ __forceinline__ void bin_append(const FrameDev &f, const StagedDev &g, const BinnedDev &bd, int local_scene,
+                                           const Rec &r, const BBox &bb, const CVT *vin, const SlotGeom &sg,
+                                           const TriVary &tv) {
+    const int idx = atomicAdd(&g.count[local_scene], 1);
+    if (idx >= g.cap) {
+        atomicOr(f.status, DEVSTAT_STAGED_OVERFLOW);
+        f.status_host[1] = 1;            // host-mapped: the next large-scene call reports it and grows the lists
+        return;
+    }
+    const size_t o = (size_t)local_scene * g.cap + idx;
+    uint4 *dst = reinterpret_cast<uint4 *>(g.recs + o);
+    const uint4 *src = reinterpret_cast<const uint4 *>(&r);
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+    g.bbox[o] = (unsigned)bb.bx0 | ((unsigned)bb.by0 << 8) | ((unsigned)bb.bx1 << 16) | ((unsigned)bb.by1 << 24);
+    if (g.srecs != nullptr && (r.meta & M_SMOOTH)) write_srec(f, g.srecs + o * (size_t)f.srec_stride, vin, sg, tv);
+    int *cnt = bd.blk_cnt + (size_t)local_scene * (f.nbx * f.nby);
+    const bool small = (bb.bx1 - bb.bx0) + (bb.by1 - bb.by0) <= 1;       // <= 2 blocks: no reject test
+    for (int by = bb.by0; by <= bb.by1; ++by)
+        for (int bx = bb.bx0; bx <= bb.bx1; ++bx)
+            if (small || block_hit(r, bb, bx, by)) atomicAdd(&cnt[by * f.nbx + bx], 1);
+}
+
+__device__ __noinline__ void bin_clipped(const FrameDev &f, const StagedDev &g, const BinnedDev &bd, int local_scene,
+                                         SlotGeom sg) {
+    CVT poly[MAX_POLY];
+    const int n = clip_poly(sg.v, poly);
+    for (int k = 0; k + 2 < n; ++k) {
+        CVT tri[3] = {poly[0], poly[k + 1], poly[k + 2]};
+        Rec r;
+        TriVary tv;
+        BBox bb;
+        if (setup_tri(f, tri, sg, 0, f.H, r, bb, tv)) bin_append(f, g, bd, local_scene, r, bb, tri, sg, tv);
+    }
+}
+
+__global__ void __launch_bounds__(B_THREADS) bin_tri_kernel(const __grid_constant__ FrameDev f,
+                                                            const __grid_constant__ StagedDev g,
+                                                            const __grid_constant__ BinnedDev bd) {
+    __shared__ unsigned s_live[B_THREADS], s_clip[B_THREADS];
+    __shared__ int s_n[2];
+    const int local_scene = blockIdx.y;
+    const int scene = g.scene0 + local_scene;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int slot = blockIdx.x * B_THREADS + tid;
+    if (tid < 2) s_n[tid] = 0;
+    __syncthreads();
+    const float4 *vclip = bd.vclip + (size_t)local_scene * bd.total_verts;
+    const int4 *vproj = bd.vproj + (size_t)local_scene * bd.total_verts;
+
+    // ---- classify this thread's slot from its three parked vertices
+    int cat = 0;            // 0 dead, 1 live, 2 clip
+    if (slot < f.total_slots) {
+        int ni, inst, tri;
+        locate_slot(f, slot, ni, inst, tri);
+        const NodeDev &nd = f.nodes[ni];
+        if (g.vis[(size_t)local_scene * f.total_inst + nd.inst_begin + inst]) {
+            const uint4 ti = __ldg(nd.tidx + tri);
+            const int vb = nd.vert_begin + inst * nd.n_verts;
+            const int4 q0 = vproj[vb + ti.x], q1 = vproj[vb + ti.y], q2 = vproj[vb + ti.z];
+            const int f_and = q0.w & q1.w & q2.w, f_or = q0.w | q1.w | q2.w;
+            if (f_and & 0x3f) {
+                cat = 0;                                  // all three outside one plane of the tile frustum
+            } else if (f_or & BV_CLIP) {
+                cat = 2;
+            } else if (f_and & BV_PROJ) {
+                const long long area2 = (long long)(q1.x - q0.x) * (q2.y - q0.y) - (long long)(q2.x - q0.x) * (q1.y - q0.y);
+                const bool two_sided = (nd.flags & PBR_MESH_TWO_SIDED) != 0;
+                cat = (area2 < 0 || (two_sided && area2 > 0)) ? 1 : 0;
+                if (cat == 1) {     // no pixel centre inside the bounding box: the set-up would drop it anyway
+                    const int xmin = min(q0.x, min(q1.x, q2.x)), xmax = max(q0.x, max(q1.x, q2.x));
+                    const int ymin = min(q0.y, min(q1.y, q2.y)), ymax = max(q0.y, max(q1.y, q2.y));
+                    const int i0 = max(0, (xmin - 128 + 255) >> 8), i1 = min(f.W - 1, (xmax - 128) >> 8);
+                    const int j0 = max(0, (ymin - 128 + 255) >> 8), j1 = min(f.H - 1, (ymax - 128) >> 8);
+                    if (i0 > i1 || j0 > j1) cat = 0;
+                }
+            }
+        }
+    }
+    // ---- compact the survivors of the CTA
+    {
+        const unsigned lt = (1u << lane) - 1u;
+        const unsigned bl = __ballot_sync(0xffffffffu, cat == 1), bc = __ballot_sync(0xffffffffu, cat == 2);
+        int pl = 0, pc = 0;
+        if (lane == 0) {
+            if (bl) pl = atomicAdd(&s_n[0], __popc(bl));
+            if (bc) pc = atomicAdd(&s_n[1], __popc(bc));
+        }
+        pl = __shfl_sync(0xffffffffu, pl, 0);
+        pc = __shfl_sync(0xffffffffu, pc, 0);
+        if (cat == 1) s_live[pl + __popc(bl & lt)] = (unsigned)slot;
+        if (cat == 2) s_clip[pc + __popc(bc & lt)] = (unsigned)slot;
+    }
+    __syncthreads();
+    // ---- set-up on full warps
+    const int n_live = s_n[0], n_clip = s_n[1];
+    for (int i = tid; i < n_live; i += B_THREADS) {
+        const int s = (int)s_live[i];
+        int ni, inst, tri;
+        locate_slot(f, s, ni, inst, tri);
+        SlotGeom sg;
+        load_slot_parked(f, scene, s, ni, inst, tri, vclip, sg);
+        Rec r;
+        TriVary tv;
+        BBox bb;
+        if (setup_tri(f, sg.v, sg, 0, f.H, r, bb, tv)) bin_append(f, g, bd, local_scene, r, bb, sg.v, sg, tv);
+    }
+    for (int i = tid; i < n_clip; i += B_THREADS) {
+        const int s = (int)s_clip[i];
+        int ni, inst, tri;
+        locate_slot(f, s, ni, inst, tri);
+        SlotGeom sg;
+        load_slot_parked(f, scene, s, ni, inst, tri, vclip, sg);
+        bin_clipped(f, g, bd, local_scene, sg);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// block lists
+// ------------------------------------------------------------------------------------------------
+// CTA per scene: blk_off = exclusive prefix sum of blk_cnt; blk_cnt is zeroed (it becomes the fill cursor)
+__global__ void __launch_bounds__(B_THREADS) bin_scan_kernel(const __grid_constant__ FrameDev f,
+                                                             const __grid_constant__ BinnedDev bd) {
+    __shared__ int s_warp[B_THREADS / 32];
+    __shared__ int s_carry;
+    const int local_scene = blockIdx.x;
+    const int nblk = f.nbx * f.nby;
+    int *cnt = bd.blk_cnt + (size_t)local_scene * nblk;
+    int *off = bd.blk_off + (size_t)local_scene * (nblk + 1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblk; base += B_THREADS) {
+        const int i = base + tid;
+        const int c = i < nblk ? cnt[i] : 0;
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int before = s_carry;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        if (i < nblk) { off[i] = before + incl - c; cnt[i] = 0; }
+        __syncthreads();
+        if (tid == B_THREADS - 1) s_carry = before + incl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        off[nblk] = s_carry;
+        if (s_carry > bd.pairs_cap) {        // lists do not fit: flagged like a record overflow (the host then
+            atomicOr(f.status, DEVSTAT_STAGED_OVERFLOW);      // falls back to the band-based path with worst-case sizes)
+            f.status_host[1] = 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(B_THREADS) bin_fill_kernel(const __grid_constant__ FrameDev f,
+                                                             const __grid_constant__ StagedDev g,
+                                                             const __grid_constant__ BinnedDev bd) {
+    const int local_scene = blockIdx.y;
+    const int idx = blockIdx.x * B_THREADS + threadIdx.x;
+    if (idx >= min(g.count[local_scene], g.cap)) return;
+    const int nblk = f.nbx * f.nby;
+    const size_t o = (size_t)local_scene * g.cap + idx;
+    Rec r;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(g.recs + o);
+        uint4 *dst = reinterpret_cast<uint4 *>(&r);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+    }
+    const unsigned pb = g.bbox[o];
+    BBox bb;
+    bb.bx0 = (int)(pb & 255u); bb.by0 = (int)((pb >> 8) & 255u);
+    bb.bx1 = (int)((pb >> 16) & 255u); bb.by1 = (int)(pb >> 24);
+    int *cur = bd.blk_cnt + (size_t)local_scene * nblk;
+    const int *off = bd.blk_off + (size_t)local_scene * (nblk + 1);
+    unsigned *pairs = bd.pairs + (size_t)local_scene * bd.pairs_cap;
+    const bool small = (bb.bx1 - bb.bx0) + (bb.by1 - bb.by0) <= 1;
+    for (int by = bb.by0; by <= bb.by1; ++by)
+        for (int bx = bb.bx0; bx <= bb.bx1; ++bx)
+            if (small || block_hit(r, bb, bx, by)) {
+                const int blk = by * f.nbx + bx;
+                const int p = off[blk] + atomicAdd(&cur[blk], 1);
+                if (p < bd.pairs_cap) pairs[p] = (unsigned)idx;
+            }
+}
+
+// ------------------------------------------------------------------------------------------------
+// raster: one warp per (scene, 8x8 block)
+// ------------------------------------------------------------------------------------------------
+template <bool SMOOTH>
+__global__ void __launch_bounds__(B_WPB * 32) raster_binned_kernel(const __grid_constant__ FrameDev f,
+                                                                   const __grid_constant__ StagedDev g,
+                                                                   const __grid_constant__ BinnedDev bd) {
+    __shared__ __align__(16) Rec s_recs[B_WPB][B_GATHER];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int local_scene = blockIdx.y;
+    const int scene = g.scene0 + local_scene;
+    const int nblk = f.nbx * f.nby;
+    const int blk = blockIdx.x * B_WPB + warp;
+    if (blk >= nblk) return;                                  // (no CTA-wide barrier below)
+    const int by = blk / f.nbx, bx = blk - by * f.nbx;
+    const int px = bx * 8 + (lane & 7), py0 = by * 8 + (lane >> 3);
+    const bool ok0 = px < f.W && py0 < f.H, ok1 = px < f.W && py0 + 4 < f.H;
+    const int *off = bd.blk_off + (size_t)local_scene * (nblk + 1);
+    const int begin = min(off[blk], bd.pairs_cap), end = min(off[blk + 1], bd.pairs_cap);
+    const unsigned *pairs = bd.pairs + (size_t)local_scene * bd.pairs_cap;
+    const Rec *grecs = g.recs + (size_t)local_scene * g.cap;
+    const unsigned char *gsrecs = SMOOTH ? g.srecs + (size_t)local_scene * g.cap * f.srec_stride : nullptr;
+
+    PixelState ps;
+    ps.k0 = ps.k1 = KEY_CLEAR;
+    ps.c0 = ps.c1 = f.bg;
+    Rec *mine = s_recs[warp];
+#pragma unroll 1
+    for (int base = begin; base < end; base += B_GATHER) {
+        const int n = min(B_GATHER, end - base);
+        // gather: lane l fetches quarter (l & 3) of record (l >> 2) of this round -- one 16-byte load per lane
+        const int slot = lane >> 2;
+        unsigned ridx = 0;
+        if (slot < n) {
+            ridx = __ldg(pairs + base + slot);
+            reinterpret_cast<uint4 *>(mine + slot)[lane & 3] = __ldg(reinterpret_cast<const uint4 *>(grecs + ridx) + (lane & 3));
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int k = 0; k < n; ++k) {
+            const Rec &r = mine[k];
+            const int4 ea = *reinterpret_cast<const int4 *>(&r.e[0]);
+            const int4 eb = *reinterpret_cast<const int4 *>(&r.e[4]);
+            const int4 ec = *reinterpret_cast<const int4 *>(&r.e[8]);
+            const float4 zq = *reinterpret_cast<const float4 *>(&r.z0);
+            const SRec *sr = nullptr;
+            if (SMOOTH) {
+                const unsigned ri = __shfl_sync(0xffffffffu, ridx, k * 4);
+                sr = reinterpret_cast<const SRec *>(gsrecs + (size_t)ri * f.srec_stride);
+            }
+            raster_one<SMOOTH, true>(f, r, sr, ea, eb, ec, zq, px, py0, ok0, ok1, ps);
+        }
+        __syncwarp();
+    }
+    // the finished block, straight to out[scene] (background where nothing was drawn)
+    const int HW = f.H * f.W;
+    unsigned char *p = f.out + (size_t)scene * f.C * HW + (size_t)py0 * f.W + px;
+    if (ok0) {
+        p[0] = (unsigned char)(ps.c0 & 255u);
+        p[HW] = (unsigned char)((ps.c0 >> 8) & 255u);
+        p[2 * HW] = (unsigned char)((ps.c0 >> 16) & 255u);
+        if (f.C == 4) p[3 * HW] = (unsigned char)(ps.c0 >> 24);
+    }
+    if (ok1) {
+        p += 4 * f.W;
+        p[0] = (unsigned char)(ps.c1 & 255u);
+        p[HW] = (unsigned char)((ps.c1 >> 8) & 255u);
+        p[2 * HW] = (unsigned char)((ps.c1 >> 16) & 255u);
+        if (f.C == 4) p[3 * HW] = (unsigned char)(ps.c1 >> 24);
+    }
+}
+
+}  // namespace pbr
