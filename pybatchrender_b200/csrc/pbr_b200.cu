@@ -729,9 +729,12 @@ static int launch_binned(FrameDev &f, DeviceState *st, void *stream) {
         COUNT_LAUNCH();
         bin_tri_kernel<<<dim3((unsigned)((f.total_slots + B_THREADS - 1) / B_THREADS), (unsigned)n), B_THREADS, 0, cs>>>(f, g, bd);
         COUNT_LAUNCH();
+        const dim3 bgrid((unsigned)((cap + B_THREADS - 1) / B_THREADS), (unsigned)n);
+        bin_blocks_kernel<false><<<bgrid, B_THREADS, 0, cs>>>(f, g, bd);
+        COUNT_LAUNCH();
         bin_scan_kernel<<<(unsigned)n, B_THREADS, 0, cs>>>(f, bd);
         COUNT_LAUNCH();
-        bin_fill_kernel<<<dim3((unsigned)((cap + B_THREADS - 1) / B_THREADS), (unsigned)n), B_THREADS, 0, cs>>>(f, g, bd);
+        bin_blocks_kernel<true><<<bgrid, B_THREADS, 0, cs>>>(f, g, bd);
         COUNT_LAUNCH();
         const dim3 rgrid((unsigned)((nblk + B_WPB - 1) / B_WPB), (unsigned)n);
         if (smooth)

@@ -9,9 +9,10 @@
 //   bin_tri_kernel    thread per (scene, triangle slot): reject / cull / needs-clip from the three parked vertices;
 //                     the survivors of the CTA are compacted in shared memory and set up on full warps (edge
 //                     equations, depth plane, flat shade or per-pixel shading inputs) -> 64-byte record appended to
-//                     the scene's list, and the 8x8 blocks it can touch are counted
+//                     the scene's list
+//   bin_blocks_kernel<false>  thread per record: counts it in every 8x8 block it can touch
 //   bin_scan_kernel   CTA per scene: exclusive prefix sum of the block counts = where each block's list starts
-//   bin_fill_kernel   thread per record: its index into the list of every block it can touch
+//   bin_blocks_kernel<true>   thread per record: its index into the list of each of those blocks
 //   raster_binned_kernel  WARP per (scene, block): walks the block's list -- records gathered eight at a time into
 //                     shared memory -- with the depth|id keys and colours of its 64 pixels in registers, then writes
 //                     the finished block straight to out[scene]: no colour / depth tile in shared memory, no
@@ -128,7 +129,7 @@ __device__ __forceinline__ void load_slot_parked(const FrameDev &f, int scene, i
     }
 }
 
-// append the record to the scene's list and count it in every block it can touch
+// append the record to the scene's list (the blocks it can touch are counted by bin_blocks_kernel)
 __device__ __forceinline__ void bin_append(const FrameDev &f, const StagedDev &g, const BinnedDev &bd, int local_scene,
                                            const Rec &r, const BBox &bb, const CVT *vin, const SlotGeom &sg,
                                            const TriVary &tv) {
@@ -144,11 +145,6 @@ __device__ __forceinline__ void bin_append(const FrameDev &f, const StagedDev &g
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
     g.bbox[o] = (unsigned)bb.bx0 | ((unsigned)bb.by0 << 8) | ((unsigned)bb.bx1 << 16) | ((unsigned)bb.by1 << 24);
     if (g.srecs != nullptr && (r.meta & M_SMOOTH)) write_srec(f, g.srecs + o * (size_t)f.srec_stride, vin, sg, tv);
-    int *cnt = bd.blk_cnt + (size_t)local_scene * (f.nbx * f.nby);
-    const bool small = (bb.bx1 - bb.bx0) + (bb.by1 - bb.by0) <= 1;       // <= 2 blocks: no reject test
-    for (int by = bb.by0; by <= bb.by1; ++by)
-        for (int bx = bb.bx0; bx <= bb.bx1; ++bx)
-            if (small || block_hit(r, bb, bx, by)) atomicAdd(&cnt[by * f.nbx + bx], 1);
 }
 
 __device__ __noinline__ void bin_clipped(const FrameDev &f, const StagedDev &g, const BinnedDev &bd, int local_scene,
@@ -287,35 +283,71 @@ __global__ void __launch_bounds__(B_THREADS) bin_scan_kernel(const __grid_consta
     }
 }
 
-__global__ void __launch_bounds__(B_THREADS) bin_fill_kernel(const __grid_constant__ FrameDev f,
-                                                             const __grid_constant__ StagedDev g,
-                                                             const __grid_constant__ BinnedDev bd) {
+// Thread per record, run twice: FILL = false counts the record in every 8x8 block it can touch (block box of the
+// record + edge-function reject per block), FILL = true -- after the scan -- writes its index into those blocks'
+// lists.  Boxes of up to 4 blocks are walked by the record's own thread; larger ones (a near triangle can span the
+// whole tile: 256 .. 1024 blocks) are handed to the warp, whose lanes stride over the box together.
+template <bool FILL>
+__global__ void __launch_bounds__(B_THREADS) bin_blocks_kernel(const __grid_constant__ FrameDev f,
+                                                               const __grid_constant__ StagedDev g,
+                                                               const __grid_constant__ BinnedDev bd) {
     const int local_scene = blockIdx.y;
     const int idx = blockIdx.x * B_THREADS + threadIdx.x;
-    if (idx >= min(g.count[local_scene], g.cap)) return;
+    const int lane = threadIdx.x & 31;
+    const int total = min(g.count[local_scene], g.cap);
+    if (blockIdx.x * B_THREADS >= total) return;            // whole CTA past the end of the list
     const int nblk = f.nbx * f.nby;
-    const size_t o = (size_t)local_scene * g.cap + idx;
-    Rec r;
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(g.recs + o);
-        uint4 *dst = reinterpret_cast<uint4 *>(&r);
-        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
-    }
-    const unsigned pb = g.bbox[o];
-    BBox bb;
-    bb.bx0 = (int)(pb & 255u); bb.by0 = (int)((pb >> 8) & 255u);
-    bb.bx1 = (int)((pb >> 16) & 255u); bb.by1 = (int)(pb >> 24);
     int *cur = bd.blk_cnt + (size_t)local_scene * nblk;
     const int *off = bd.blk_off + (size_t)local_scene * (nblk + 1);
     unsigned *pairs = bd.pairs + (size_t)local_scene * bd.pairs_cap;
-    const bool small = (bb.bx1 - bb.bx0) + (bb.by1 - bb.by0) <= 1;
-    for (int by = bb.by0; by <= bb.by1; ++by)
-        for (int bx = bb.bx0; bx <= bb.bx1; ++bx)
-            if (small || block_hit(r, bb, bx, by)) {
-                const int blk = by * f.nbx + bx;
-                const int p = off[blk] + atomicAdd(&cur[blk], 1);
-                if (p < bd.pairs_cap) pairs[p] = (unsigned)idx;
-            }
+    auto visit = [&](const Rec &r, const BBox &bb, bool small, int bx, int by, unsigned ridx) {
+        if (small || block_hit(r, bb, bx, by)) {
+            const int blk = by * f.nbx + bx;
+            const int p = atomicAdd(&cur[blk], 1);
+            if (FILL && off[blk] + p < bd.pairs_cap) pairs[off[blk] + p] = ridx;
+        }
+    };
+    Rec r;
+    BBox bb;
+    bb.bx0 = bb.by0 = 0; bb.bx1 = bb.by1 = -1;
+    if (idx < total) {
+        const size_t o = (size_t)local_scene * g.cap + idx;
+        const uint4 *src = reinterpret_cast<const uint4 *>(g.recs + o);
+        uint4 *dst = reinterpret_cast<uint4 *>(&r);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+        const unsigned pb = g.bbox[o];
+        bb.bx0 = (int)(pb & 255u); bb.by0 = (int)((pb >> 8) & 255u);
+        bb.bx1 = (int)((pb >> 16) & 255u); bb.by1 = (int)(pb >> 24);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) r.e[i] = 0;
+        r.meta = 0;
+    }
+    const int bw = bb.bx1 - bb.bx0 + 1, bh = bb.by1 - bb.by0 + 1;
+    const int area = bw * bh;
+    if (area > 0 && area <= 4) {
+        const bool small = (bw - 1) + (bh - 1) <= 1;       // <= 2 blocks: no reject test
+        for (int by = bb.by0; by <= bb.by1; ++by)
+            for (int bx = bb.bx0; bx <= bb.bx1; ++bx) visit(r, bb, small, bx, by, (unsigned)idx);
+    }
+    unsigned big = __ballot_sync(0xffffffffu, area > 4);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        Rec q;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) q.e[i] = __shfl_sync(0xffffffffu, r.e[i], src);
+        q.meta = __shfl_sync(0xffffffffu, r.meta, src);
+        BBox qb;
+        qb.bx0 = __shfl_sync(0xffffffffu, bb.bx0, src); qb.by0 = __shfl_sync(0xffffffffu, bb.by0, src);
+        qb.bx1 = __shfl_sync(0xffffffffu, bb.bx1, src); qb.by1 = __shfl_sync(0xffffffffu, bb.by1, src);
+        const unsigned qidx = (unsigned)(blockIdx.x * B_THREADS + (threadIdx.x & ~31) + src);
+        const int qw = qb.bx1 - qb.bx0 + 1, qa = qw * (qb.by1 - qb.by0 + 1);
+        for (int k = lane; k < qa; k += 32) {
+            const int yy = k / qw;
+            visit(q, qb, false, qb.bx0 + k - yy * qw, qb.by0 + yy, qidx);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -344,6 +376,11 @@ __global__ void __launch_bounds__(B_WPB * 32) raster_binned_kernel(const __grid_
     PixelState ps;
     ps.k0 = ps.k1 = KEY_CLEAR;
     ps.c0 = ps.c1 = f.bg;
+    // SMOOTH: records shaded per pixel are not shaded when they win (most wins are overwritten again, and every
+    // one would cost a fragment-shader evaluation for the whole warp) -- the pixel remembers the record and the
+    // fragment shader runs once, after the sweep, for the final winner
+    constexpr unsigned NO_REC = 0xffffffffu;
+    unsigned win0 = NO_REC, win1 = NO_REC;
     Rec *mine = s_recs[warp];
 #pragma unroll 1
     for (int base = begin; base < end; base += B_GATHER) {
@@ -363,14 +400,55 @@ __global__ void __launch_bounds__(B_WPB * 32) raster_binned_kernel(const __grid_
             const int4 eb = *reinterpret_cast<const int4 *>(&r.e[4]);
             const int4 ec = *reinterpret_cast<const int4 *>(&r.e[8]);
             const float4 zq = *reinterpret_cast<const float4 *>(&r.z0);
-            const SRec *sr = nullptr;
+            bool w0, w1;
+            if (!((unsigned)ec.w & M_SLOW)) {
+                const FastCov c = fast_cover(ea, eb, ec, px, py0, ok0, ok1);
+                if (!__any_sync(0xffffffffu, c.cov0 || c.cov1)) continue;
+                depth_update(ps, (float)c.F1, (float)c.F2, (float)c.G1, (float)c.G2, c.cov0, c.cov1, zq, (unsigned)ec.z,
+                             (unsigned)ec.y, w0, w1);
+            } else {
+                bool cov0, cov1;
+                float f0a, f1a, f2a, f0b, f1b, f2b;
+                const bool any = slow_cover(r, px, py0, ok0, ok1, cov0, cov1, f1a, f2a, f1b, f2b, f0a, f0b);
+                if (!__any_sync(0xffffffffu, any)) continue;
+                depth_update(ps, f1a, f2a, f1b, f2b, cov0, cov1, zq, (unsigned)ec.z, (unsigned)ec.y, w0, w1);
+            }
             if (SMOOTH) {
                 const unsigned ri = __shfl_sync(0xffffffffu, ridx, k * 4);
-                sr = reinterpret_cast<const SRec *>(gsrecs + (size_t)ri * f.srec_stride);
+                const unsigned tag = ((unsigned)ec.w & M_SMOOTH) ? ri : NO_REC;
+                win0 = w0 ? tag : win0;
+                win1 = w1 ? tag : win1;
             }
-            raster_one<SMOOTH, true>(f, r, sr, ea, eb, ec, zq, px, py0, ok0, ok1, ps);
         }
         __syncwarp();
+    }
+    if (SMOOTH && __any_sync(0xffffffffu, win0 != NO_REC || win1 != NO_REC)) {
+        // fragment shader of the final winners (basic.frag:31-38 with interpolated normal / uv): every lane fetches
+        // the record and the shading inputs of its own two pixels
+        auto shade_final = [&](unsigned ri, bool second) -> unsigned {
+            const Rec *rp = grecs + ri;
+            const int4 ea = __ldg(reinterpret_cast<const int4 *>(&rp->e[0]));
+            const int4 eb = __ldg(reinterpret_cast<const int4 *>(&rp->e[4]));
+            const int4 ec = __ldg(reinterpret_cast<const int4 *>(&rp->e[8]));
+            const float invA = __ldg(&rp->invA);
+            const SRec *sr = reinterpret_cast<const SRec *>(gsrecs + (size_t)ri * f.srec_stride);
+            float f0, f1, f2;
+            if (!((unsigned)ec.w & M_SLOW)) {
+                const FastCov c = fast_cover(ea, eb, ec, px, py0, true, true);
+                f0 = (float)(second ? c.G0 : c.F0); f1 = (float)(second ? c.G1 : c.F1); f2 = (float)(second ? c.G2 : c.F2);
+            } else {
+                Rec r;
+                *reinterpret_cast<int4 *>(&r.e[0]) = ea; *reinterpret_cast<int4 *>(&r.e[4]) = eb;
+                *reinterpret_cast<int4 *>(&r.e[8]) = ec;
+                bool c0, c1;
+                float f0a, f1a, f2a, f0b, f1b, f2b;
+                slow_cover(r, px, py0, true, true, c0, c1, f1a, f2a, f1b, f2b, f0a, f0b);
+                f0 = second ? f0b : f0a; f1 = second ? f1b : f1a; f2 = second ? f2b : f2a;
+            }
+            return shade_pixel(f, *sr, ((unsigned)ec.w & M_TEX) != 0, f0, f1, f2, invA);
+        };
+        if (win0 != NO_REC) ps.c0 = shade_final(win0, false);
+        if (win1 != NO_REC) ps.c1 = shade_final(win1, true);
     }
     // the finished block, straight to out[scene] (background where nothing was drawn)
     const int HW = f.H * f.W;
