@@ -160,7 +160,7 @@ __device__ __noinline__ void bin_clipped(const FrameDev &f, const StagedDev &g, 
     }
 }
 
-__global__ void __launch_bounds__(B_THREADS) bin_tri_kernel(const __grid_constant__ FrameDev f,
+__global__ void __launch_bounds__(B_THREADS, 4) bin_tri_kernel(const __grid_constant__ FrameDev f,
                                                             const __grid_constant__ StagedDev g,
                                                             const __grid_constant__ BinnedDev bd) {
     __shared__ unsigned s_live[B_THREADS], s_clip[B_THREADS];
@@ -354,10 +354,10 @@ __global__ void __launch_bounds__(B_THREADS) bin_blocks_kernel(const __grid_cons
 // raster: one warp per (scene, 8x8 block)
 // ------------------------------------------------------------------------------------------------
 template <bool SMOOTH>
-__global__ void __launch_bounds__(B_WPB * 32) raster_binned_kernel(const __grid_constant__ FrameDev f,
+__global__ void __launch_bounds__(B_WPB * 32, 4) raster_binned_kernel(const __grid_constant__ FrameDev f,
                                                                    const __grid_constant__ StagedDev g,
                                                                    const __grid_constant__ BinnedDev bd) {
-    __shared__ __align__(16) Rec s_recs[B_WPB][B_GATHER];
+    __shared__ __align__(16) Rec s_recs[B_WPB][2][B_GATHER];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int local_scene = blockIdx.y;
     const int scene = g.scene0 + local_scene;
@@ -381,17 +381,28 @@ __global__ void __launch_bounds__(B_WPB * 32) raster_binned_kernel(const __grid_
     // fragment shader runs once, after the sweep, for the final winner
     constexpr unsigned NO_REC = 0xffffffffu;
     unsigned win0 = NO_REC, win1 = NO_REC;
-    Rec *mine = s_recs[warp];
+    // Records travel list -> shared memory eight at a time (lane l fetches quarter (l & 3) of record (l >> 2): one
+    // 16-byte load per lane per round), double buffered: the loads of round i + 1 are in flight while round i is
+    // swept, so the two dependent L2 round trips (index, then record) are not on the warp's critical path.
+    const int slot = lane >> 2;
+    unsigned ridx = 0, ridx_next = 0;
+    uint4 q_next = make_uint4(0u, 0u, 0u, 0u);
+    auto fetch = [&](int base) {
+        if (base + slot < end) {
+            ridx_next = __ldg(pairs + base + slot);
+            q_next = __ldg(reinterpret_cast<const uint4 *>(grecs + ridx_next) + (lane & 3));
+        }
+    };
+    fetch(begin);
+    int buf = 0;
 #pragma unroll 1
     for (int base = begin; base < end; base += B_GATHER) {
         const int n = min(B_GATHER, end - base);
-        // gather: lane l fetches quarter (l & 3) of record (l >> 2) of this round -- one 16-byte load per lane
-        const int slot = lane >> 2;
-        unsigned ridx = 0;
-        if (slot < n) {
-            ridx = __ldg(pairs + base + slot);
-            reinterpret_cast<uint4 *>(mine + slot)[lane & 3] = __ldg(reinterpret_cast<const uint4 *>(grecs + ridx) + (lane & 3));
-        }
+        Rec *mine = s_recs[warp][buf];
+        ridx = ridx_next;
+        if (slot < n) reinterpret_cast<uint4 *>(mine + slot)[lane & 3] = q_next;
+        fetch(base + B_GATHER);
+        buf ^= 1;
         __syncwarp();
 #pragma unroll 1
         for (int k = 0; k < n; ++k) {
@@ -420,7 +431,6 @@ __global__ void __launch_bounds__(B_WPB * 32) raster_binned_kernel(const __grid_
                 win1 = w1 ? tag : win1;
             }
         }
-        __syncwarp();
     }
     if (SMOOTH && __any_sync(0xffffffffu, win0 != NO_REC || win1 != NO_REC)) {
         // fragment shader of the final winners (basic.frag:31-38 with interpolated normal / uv): every lane fetches
