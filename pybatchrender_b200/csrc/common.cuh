@@ -179,7 +179,17 @@ __device__ __forceinline__ void lerp_extra(CVT &w, const CVT &vi, const CVT &vo,
 
 struct BBox {
     int bx0, by0, bx1, by1;   // 8x8-pixel blocks, inclusive
+    int px0, py0, px1, py1;   // pixels whose centres lie inside the triangle's bounding box, inclusive
 };
+// pixel box of a small triangle in one word: x0 (11 bits) | y0 (11) | width - 1 (5) | height - 1 (5); boxes wider or
+// higher than PBOX_MAX pixels (and anything the lane-per-record raster path must not take) are PBOX_NONE
+constexpr unsigned PBOX_NONE = 0xffffffffu;
+constexpr int PBOX_MAX = 4;
+__device__ __forceinline__ unsigned pack_pbox(const BBox &bb) {
+    const int w = bb.px1 - bb.px0 + 1, h = bb.py1 - bb.py0 + 1;
+    if (w > PBOX_MAX || h > PBOX_MAX) return PBOX_NONE;
+    return (unsigned)bb.px0 | ((unsigned)bb.py0 << 11) | ((unsigned)(w - 1) << 22) | ((unsigned)(h - 1) << 27);
+}
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
@@ -387,6 +397,7 @@ __device__ __forceinline__ bool setup_snapped(const FrameDev &f, int *X, int *Y,
     const int j0 = max(0, (ymin - 128 + 255) >> 8), j1 = min(band_h - 1, (ymax - 128) >> 8);
     if (i0 > i1 || j0 > j1) return false;
     bb.bx0 = i0 >> 3; bb.bx1 = i1 >> 3; bb.by0 = j0 >> 3; bb.by1 = j1 >> 3;
+    bb.px0 = i0; bb.px1 = i1; bb.py0 = j0; bb.py1 = j1;
 
     r.invA = 1.0f / (float)A2;
     r.z0 = z[0];

@@ -87,8 +87,8 @@ struct StreamScratch {
     float4 *b_vclip = nullptr;
     int4 *b_vproj = nullptr;
     int *b_cnt = nullptr, *b_off = nullptr;
-    unsigned *b_pairs = nullptr;
-    size_t b_vert_cap = 0, b_blk_cap = 0, b_pair_cap = 0;
+    unsigned *b_pairs = nullptr, *b_pbox = nullptr;
+    size_t b_vert_cap = 0, b_blk_cap = 0, b_pair_cap = 0, b_pbox_cap = 0;
     size_t g_rec_cap = 0;            // records allocated (all scenes of one launch)
     size_t g_scene_cap = 0;          // scenes allocated in g_count
     // clear-colour image [C,H,W]: copy source of the small-scene kernel's background when there is
@@ -662,7 +662,7 @@ static int launch_binned(FrameDev &f, DeviceState *st, void *stream) {
     const size_t tv = (size_t)f.total_verts;
     const bool smooth = f.smooth != 0;
     static const size_t budget_mb = getenv("PBR_B200_SCRATCH_MB") ? (size_t)atoll(getenv("PBR_B200_SCRATCH_MB")) : 4096;
-    const size_t per_scene = cap * (sizeof(Rec) + 4 + (smooth ? (size_t)f.srec_stride : 0)) + tv * 32 + nblk * 8 + 4 + pairs_cap * 4 +
+    const size_t per_scene = cap * (sizeof(Rec) + 8 + (smooth ? (size_t)f.srec_stride : 0)) + tv * 32 + nblk * 16 + 4 + pairs_cap * 4 +
                              (size_t)f.total_inst + 4;
     size_t per_launch = (budget_mb << 20) / per_scene;
     if (per_launch < 1) per_launch = 1;
@@ -701,28 +701,29 @@ static int launch_binned(FrameDev &f, DeviceState *st, void *stream) {
         CUDA_TRY(cudaMalloc(&ss->b_vproj, per_launch * tv * sizeof(int4)));
         ss->b_vert_cap = per_launch * tv;
     }
-    if (per_launch * (nblk + 1) > ss->b_blk_cap) {
+    if (per_launch * (2 * nblk + 1) > ss->b_blk_cap) {      // two lists per block
         CUDA_TRY(cudaStreamSynchronize(cs));
         cudaFree(ss->b_cnt); cudaFree(ss->b_off);
         ss->b_cnt = nullptr; ss->b_off = nullptr; ss->b_blk_cap = 0;
-        CUDA_TRY(cudaMalloc(&ss->b_cnt, per_launch * (nblk + 1) * sizeof(int)));
-        CUDA_TRY(cudaMalloc(&ss->b_off, per_launch * (nblk + 1) * sizeof(int)));
-        ss->b_blk_cap = per_launch * (nblk + 1);
+        CUDA_TRY(cudaMalloc(&ss->b_cnt, per_launch * (2 * nblk + 1) * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&ss->b_off, per_launch * (2 * nblk + 1) * sizeof(int)));
+        ss->b_blk_cap = per_launch * (2 * nblk + 1);
     }
     CUDA_TRY(grow((void **)&ss->b_pairs, &ss->b_pair_cap, per_launch * pairs_cap, sizeof(unsigned)));
+    CUDA_TRY(grow((void **)&ss->b_pbox, &ss->b_pbox_cap, per_launch * cap, sizeof(unsigned)));
 
     StagedDev g;
     g.vis = ss->g_vis; g.bcount = nullptr; g.bidx = nullptr;
     g.recs = ss->g_recs; g.srecs = smooth ? ss->g_srecs : nullptr; g.bbox = ss->g_bbox; g.count = ss->g_count; g.cap = (int)cap;
     BinnedDev bd;
-    bd.vclip = ss->b_vclip; bd.vproj = ss->b_vproj; bd.blk_cnt = ss->b_cnt; bd.blk_off = ss->b_off; bd.pairs = ss->b_pairs;
+    bd.vclip = ss->b_vclip; bd.vproj = ss->b_vproj; bd.blk_cnt = ss->b_cnt; bd.blk_off = ss->b_off; bd.pairs = ss->b_pairs; bd.pbox = ss->b_pbox;
     bd.pairs_cap = (int)pairs_cap; bd.total_verts = f.total_verts;
     const int first = f.scene_begin, last = f.scene_begin + f.scene_count;
     for (int s0 = first; s0 < last; s0 += (int)per_launch) {
         const int n = (int)((size_t)(last - s0) < per_launch ? (size_t)(last - s0) : per_launch);
         g.scene0 = s0;
         CUDA_TRY(cudaMemsetAsync(ss->g_count, 0, (size_t)n * sizeof(int), cs));
-        CUDA_TRY(cudaMemsetAsync(ss->b_cnt, 0, (size_t)n * nblk * sizeof(int), cs));
+        CUDA_TRY(cudaMemsetAsync(ss->b_cnt, 0, (size_t)n * 2 * nblk * sizeof(int), cs));
         cull_kernel<<<dim3((unsigned)((f.total_inst + 255) / 256), (unsigned)n), 256, 0, cs>>>(f, g);
         COUNT_LAUNCH();
         bin_xform_kernel<<<dim3((unsigned)((tv + B_THREADS - 1) / B_THREADS), (unsigned)n), B_THREADS, 0, cs>>>(f, g, bd);

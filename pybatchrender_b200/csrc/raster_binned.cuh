@@ -28,9 +28,11 @@ namespace pbr {
 struct BinnedDev {
     float4 *vclip;           // [scenes_in_launch][total_verts] clip-space positions
     int4 *vproj;             // [scenes_in_launch][total_verts] snapped x, y, depth bits, flags (VF_*)
-    int *blk_cnt;            // [scenes_in_launch][nblk] records per block (count pass), then the fill cursors
-    int *blk_off;            // [scenes_in_launch][nblk + 1] start of each block's list in `pairs`
+    // every block has two lists: [2*blk] big records (swept by the whole warp), [2*blk + 1] small ones (a lane each)
+    int *blk_cnt;            // [scenes_in_launch][2 * nblk] records per list (count pass), then the fill cursors
+    int *blk_off;            // [scenes_in_launch][2 * nblk + 1] start of each list in `pairs`
     unsigned *pairs;         // [scenes_in_launch][pairs_cap] record indices, block after block
+    unsigned *pbox;          // [scenes_in_launch][cap] packed pixel box of small records (pack_pbox), else PBOX_NONE
     int pairs_cap;
     int total_verts;
 };
@@ -129,7 +131,7 @@ __device__ __forceinline__ void load_slot_parked(const FrameDev &f, int scene, i
     }
 }
 
-// append the record to the scene's list (the blocks it can touch are counted by bin_blocks_kernel)
+// append the record to the scene's list and count it in the blocks it can touch
 __device__ __forceinline__ void bin_append(const FrameDev &f, const StagedDev &g, const BinnedDev &bd, int local_scene,
                                            const Rec &r, const BBox &bb, const CVT *vin, const SlotGeom &sg,
                                            const TriVary &tv) {
@@ -145,6 +147,20 @@ __device__ __forceinline__ void bin_append(const FrameDev &f, const StagedDev &g
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
     g.bbox[o] = (unsigned)bb.bx0 | ((unsigned)bb.by0 << 8) | ((unsigned)bb.bx1 << 16) | ((unsigned)bb.by1 << 24);
     if (g.srecs != nullptr && (r.meta & M_SMOOTH)) write_srec(f, g.srecs + o * (size_t)f.srec_stride, vin, sg, tv);
+    // small pixel box and int32 edge functions: the raster kernel gives the record a lane of its own
+    const unsigned pb = (r.meta & M_SLOW) ? PBOX_NONE : pack_pbox(bb);
+    bd.pbox[o] = pb;
+    // count it in the lists of the blocks it can touch; block boxes of more than 4 blocks are left to
+    // bin_blocks_kernel<false>, whose warps walk them together
+    const int bw = bb.bx1 - bb.bx0 + 1, bh = bb.by1 - bb.by0 + 1;
+    if (bw * bh <= 4) {
+        int *cnt = bd.blk_cnt + (size_t)local_scene * (2 * f.nbx * f.nby);
+        const int kind = pb != PBOX_NONE ? 1 : 0;
+        const bool small = (bw - 1) + (bh - 1) <= 1;       // <= 2 blocks: no reject test
+        for (int by = bb.by0; by <= bb.by1; ++by)
+            for (int bx = bb.bx0; bx <= bb.bx1; ++bx)
+                if (small || block_hit(r, bb, bx, by)) atomicAdd(&cnt[2 * (by * f.nbx + bx) + kind], 1);
+    }
 }
 
 __device__ __noinline__ void bin_clipped(const FrameDev &f, const StagedDev &g, const BinnedDev &bd, int local_scene,
@@ -250,7 +266,7 @@ __global__ void __launch_bounds__(B_THREADS) bin_scan_kernel(const __grid_consta
     __shared__ int s_warp[B_THREADS / 32];
     __shared__ int s_carry;
     const int local_scene = blockIdx.x;
-    const int nblk = f.nbx * f.nby;
+    const int nblk = 2 * f.nbx * f.nby;                 // lists, two per block
     int *cnt = bd.blk_cnt + (size_t)local_scene * nblk;
     int *off = bd.blk_off + (size_t)local_scene * (nblk + 1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -284,9 +300,10 @@ __global__ void __launch_bounds__(B_THREADS) bin_scan_kernel(const __grid_consta
 }
 
 // Thread per record, run twice: FILL = false counts the record in every 8x8 block it can touch (block box of the
-// record + edge-function reject per block), FILL = true -- after the scan -- writes its index into those blocks'
-// lists.  Boxes of up to 4 blocks are walked by the record's own thread; larger ones (a near triangle can span the
-// whole tile: 256 .. 1024 blocks) are handed to the warp, whose lanes stride over the box together.
+// record + edge-function reject per block) -- only records whose block box exceeds 4 blocks, the others were counted
+// by bin_tri_kernel when they were made; FILL = true -- after the scan -- writes every record's index into those
+// blocks' lists.  Boxes of up to 4 blocks are walked by the record's own thread; larger ones (a near triangle can
+// span the whole tile: 256 .. 1024 blocks) are handed to the warp, whose lanes stride over the box together.
 template <bool FILL>
 __global__ void __launch_bounds__(B_THREADS) bin_blocks_kernel(const __grid_constant__ FrameDev f,
                                                                const __grid_constant__ StagedDev g,
@@ -296,20 +313,21 @@ __global__ void __launch_bounds__(B_THREADS) bin_blocks_kernel(const __grid_cons
     const int lane = threadIdx.x & 31;
     const int total = min(g.count[local_scene], g.cap);
     if (blockIdx.x * B_THREADS >= total) return;            // whole CTA past the end of the list
-    const int nblk = f.nbx * f.nby;
-    int *cur = bd.blk_cnt + (size_t)local_scene * nblk;
-    const int *off = bd.blk_off + (size_t)local_scene * (nblk + 1);
+    const int nlist = 2 * f.nbx * f.nby;
+    int *cur = bd.blk_cnt + (size_t)local_scene * nlist;
+    const int *off = bd.blk_off + (size_t)local_scene * (nlist + 1);
     unsigned *pairs = bd.pairs + (size_t)local_scene * bd.pairs_cap;
-    auto visit = [&](const Rec &r, const BBox &bb, bool small, int bx, int by, unsigned ridx) {
+    auto visit = [&](const Rec &r, const BBox &bb, bool small, int bx, int by, int kind, unsigned ridx) {
         if (small || block_hit(r, bb, bx, by)) {
-            const int blk = by * f.nbx + bx;
-            const int p = atomicAdd(&cur[blk], 1);
-            if (FILL && off[blk] + p < bd.pairs_cap) pairs[off[blk] + p] = ridx;
+            const int l = 2 * (by * f.nbx + bx) + kind;
+            const int p = atomicAdd(&cur[l], 1);
+            if (FILL && off[l] + p < bd.pairs_cap) pairs[off[l] + p] = ridx;
         }
     };
     Rec r;
     BBox bb;
     bb.bx0 = bb.by0 = 0; bb.bx1 = bb.by1 = -1;
+    int kind = 0;
     if (idx < total) {
         const size_t o = (size_t)local_scene * g.cap + idx;
         const uint4 *src = reinterpret_cast<const uint4 *>(g.recs + o);
@@ -318,6 +336,7 @@ __global__ void __launch_bounds__(B_THREADS) bin_blocks_kernel(const __grid_cons
         const unsigned pb = g.bbox[o];
         bb.bx0 = (int)(pb & 255u); bb.by0 = (int)((pb >> 8) & 255u);
         bb.bx1 = (int)((pb >> 16) & 255u); bb.by1 = (int)(pb >> 24);
+        kind = bd.pbox[o] != PBOX_NONE ? 1 : 0;
     } else {
 #pragma unroll
         for (int i = 0; i < 9; ++i) r.e[i] = 0;
@@ -325,10 +344,10 @@ __global__ void __launch_bounds__(B_THREADS) bin_blocks_kernel(const __grid_cons
     }
     const int bw = bb.bx1 - bb.bx0 + 1, bh = bb.by1 - bb.by0 + 1;
     const int area = bw * bh;
-    if (area > 0 && area <= 4) {
-        const bool small = (bw - 1) + (bh - 1) <= 1;       // <= 2 blocks: no reject test
+    if (FILL && area > 0 && area <= 4) {                    // (counted by bin_tri_kernel already)
+        const bool small = (bw - 1) + (bh - 1) <= 1;
         for (int by = bb.by0; by <= bb.by1; ++by)
-            for (int bx = bb.bx0; bx <= bb.bx1; ++bx) visit(r, bb, small, bx, by, (unsigned)idx);
+            for (int bx = bb.bx0; bx <= bb.bx1; ++bx) visit(r, bb, small, bx, by, kind, (unsigned)idx);
     }
     unsigned big = __ballot_sync(0xffffffffu, area > 4);
     while (big) {
@@ -341,11 +360,12 @@ __global__ void __launch_bounds__(B_THREADS) bin_blocks_kernel(const __grid_cons
         BBox qb;
         qb.bx0 = __shfl_sync(0xffffffffu, bb.bx0, src); qb.by0 = __shfl_sync(0xffffffffu, bb.by0, src);
         qb.bx1 = __shfl_sync(0xffffffffu, bb.bx1, src); qb.by1 = __shfl_sync(0xffffffffu, bb.by1, src);
+        const int qkind = __shfl_sync(0xffffffffu, kind, src);
         const unsigned qidx = (unsigned)(blockIdx.x * B_THREADS + (threadIdx.x & ~31) + src);
         const int qw = qb.bx1 - qb.bx0 + 1, qa = qw * (qb.by1 - qb.by0 + 1);
         for (int k = lane; k < qa; k += 32) {
             const int yy = k / qw;
-            visit(q, qb, false, qb.bx0 + k - yy * qw, qb.by0 + yy, qidx);
+            visit(q, qb, false, qb.bx0 + k - yy * qw, qb.by0 + yy, qkind, qidx);
         }
     }
 }
@@ -355,9 +375,12 @@ __global__ void __launch_bounds__(B_THREADS) bin_blocks_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------------
 template <bool SMOOTH>
 __global__ void __launch_bounds__(B_WPB * 32, 4) raster_binned_kernel(const __grid_constant__ FrameDev f,
-                                                                   const __grid_constant__ StagedDev g,
-                                                                   const __grid_constant__ BinnedDev bd) {
+                                                                      const __grid_constant__ StagedDev g,
+                                                                      const __grid_constant__ BinnedDev bd) {
     __shared__ __align__(16) Rec s_recs[B_WPB][2][B_GATHER];
+    __shared__ unsigned long long s_key[B_WPB][64];        // small records: depth|id of the block's pixels
+    __shared__ unsigned s_col[B_WPB][64];                  // ... colour of the current winner
+    __shared__ unsigned s_tag[SMOOTH ? B_WPB : 1][64];     // ... its record index if it is shaded per pixel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int local_scene = blockIdx.y;
     const int scene = g.scene0 + local_scene;
@@ -367,8 +390,9 @@ __global__ void __launch_bounds__(B_WPB * 32, 4) raster_binned_kernel(const __gr
     const int by = blk / f.nbx, bx = blk - by * f.nbx;
     const int px = bx * 8 + (lane & 7), py0 = by * 8 + (lane >> 3);
     const bool ok0 = px < f.W && py0 < f.H, ok1 = px < f.W && py0 + 4 < f.H;
-    const int *off = bd.blk_off + (size_t)local_scene * (nblk + 1);
-    const int begin = min(off[blk], bd.pairs_cap), end = min(off[blk + 1], bd.pairs_cap);
+    const int *off = bd.blk_off + (size_t)local_scene * (2 * nblk + 1);
+    const int begin = min(off[2 * blk], bd.pairs_cap), end = min(off[2 * blk + 1], bd.pairs_cap);     // big records
+    const int send = min(off[2 * blk + 2], bd.pairs_cap);                                             // small: [end, send)
     const unsigned *pairs = bd.pairs + (size_t)local_scene * bd.pairs_cap;
     const Rec *grecs = g.recs + (size_t)local_scene * g.cap;
     const unsigned char *gsrecs = SMOOTH ? g.srecs + (size_t)local_scene * g.cap * f.srec_stride : nullptr;
@@ -431,6 +455,84 @@ __global__ void __launch_bounds__(B_WPB * 32, 4) raster_binned_kernel(const __gr
                 win1 = w1 ? tag : win1;
             }
         }
+    }
+    // ---- small records (pixel box <= 4 x 4, int32 edge functions): ONE LANE PER RECORD.  A triangle that can cover
+    // a handful of pixels would keep a whole warp busy for ~60 instructions in the sweep above; here 32 of them are
+    // evaluated at once, each lane walking the pixels of its record's box that lie in this block.  Visibility is
+    // resolved through the block's depth|id keys in shared memory (64-bit atomicMin: smaller (depth, id) wins,
+    // whatever the order), then the lanes whose key survived write their colour, and the warp merges the result
+    // with the keys of the big records in its registers.
+    if (send > end) {
+        s_key[warp][lane] = KEY_CLEAR;
+        s_key[warp][lane + 32] = KEY_CLEAR;
+        __syncwarp();
+        const int ox = bx * 8, oy = by * 8;
+#pragma unroll 1
+        for (int base = end; base < send; base += 32) {
+            const int i = base + lane;
+            const bool valid = i < send;
+            unsigned ridx = 0, hits = 0;
+            int4 ea = make_int4(0, 0, 0, 0), eb = ea, ec = ea;
+            float4 zq = make_float4(0.f, 0.f, 0.f, 0.f);
+            int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
+            if (valid) {
+                ridx = __ldg(pairs + i);
+                const unsigned pb = __ldg(bd.pbox + (size_t)local_scene * g.cap + ridx);
+                const Rec *rp = grecs + ridx;
+                ea = __ldg(reinterpret_cast<const int4 *>(&rp->e[0]));
+                eb = __ldg(reinterpret_cast<const int4 *>(&rp->e[4]));
+                ec = __ldg(reinterpret_cast<const int4 *>(&rp->e[8]));
+                zq = __ldg(reinterpret_cast<const float4 *>(&rp->z0));
+                const int bx0 = (int)(pb & 2047u), by0 = (int)((pb >> 11) & 2047u);
+                x0 = max(bx0, ox); x1 = min(bx0 + (int)((pb >> 22) & 31u), ox + 7);
+                y0 = max(by0, oy); y1 = min(by0 + (int)(pb >> 27), oy + 7);
+            }
+            const unsigned meta = (unsigned)ec.w;
+            const int nb1 = meta_nb1(meta), nb2 = meta_nb2(meta);
+            // biased edge values + depth of the sample at pixel (xx, yy): same integer / float operations as fast_cover
+            // and depth_update
+            auto sample = [&](int xx, int yy, unsigned long long &key) -> bool {
+                const unsigned rx = (unsigned)xx, ry = (unsigned)yy;
+                const int F0 = (int)((unsigned)ea.x + (unsigned)ea.w * rx + (unsigned)eb.z * ry);
+                const int F1 = (int)((unsigned)ea.y + (unsigned)eb.x * rx + (unsigned)eb.w * ry);
+                const int F2 = (int)((unsigned)ea.z + (unsigned)eb.y * rx + (unsigned)ec.x * ry);
+                if ((F0 | F1 | F2) < 0) return false;
+                const float z = fmaf((float)(F2 + nb2) * zq.w, zq.z, fmaf((float)(F1 + nb1) * zq.w, zq.y, zq.x));
+                key = make_key(z, (unsigned)ec.z);
+                return true;
+            };
+            {
+                unsigned bit = 1u;
+                for (int yy = y0; yy <= y1; ++yy)
+                    for (int xx = x0; xx <= x1; ++xx, bit <<= 1) {
+                        unsigned long long key;
+                        if (sample(xx, yy, key)) {
+                            atomicMin(&s_key[warp][(yy - oy) * 8 + (xx - ox)], key);
+                            hits |= bit;
+                        }
+                    }
+            }
+            __syncwarp();
+            if (hits) {
+                unsigned bit = 1u;
+                for (int yy = y0; yy <= y1; ++yy)
+                    for (int xx = x0; xx <= x1; ++xx, bit <<= 1)
+                        if (hits & bit) {
+                            unsigned long long key;
+                            sample(xx, yy, key);
+                            const int p = (yy - oy) * 8 + (xx - ox);
+                            if (s_key[warp][p] == key) {
+                                s_col[warp][p] = (unsigned)ec.y;
+                                if (SMOOTH) s_tag[warp][p] = (meta & M_SMOOTH) ? ridx : NO_REC;
+                            }
+                        }
+            }
+            __syncwarp();
+        }
+        // merge with the big records' keys (this lane's pixels are entries lane and lane + 32 of the block)
+        const unsigned long long k0 = s_key[warp][lane], k1 = s_key[warp][lane + 32];
+        if (ok0 && k0 < ps.k0) { ps.k0 = k0; ps.c0 = s_col[warp][lane]; if (SMOOTH) win0 = s_tag[warp][lane]; }
+        if (ok1 && k1 < ps.k1) { ps.k1 = k1; ps.c1 = s_col[warp][lane + 32]; if (SMOOTH) win1 = s_tag[warp][lane + 32]; }
     }
     if (SMOOTH && __any_sync(0xffffffffu, win0 != NO_REC || win1 != NO_REC)) {
         // fragment shader of the final winners (basic.frag:31-38 with interpolated normal / uv): every lane fetches
