@@ -181,13 +181,17 @@ struct BBox {
     int bx0, by0, bx1, by1;   // 8x8-pixel blocks, inclusive
     int px0, py0, px1, py1;   // pixels whose centres lie inside the triangle's bounding box, inclusive
 };
-// pixel box of a small triangle in one word: x0 (11 bits) | y0 (11) | width - 1 (5) | height - 1 (5); boxes wider or
-// higher than PBOX_MAX pixels (and anything the lane-per-record raster path must not take) are PBOX_NONE
+// pixel box of a small triangle in one word: x0 (11 bits) | y0 (11) | width - 1 (5) | height - 1 (5); boxes of more
+// than PBOX_AREA pixels or longer than PBOX_SIDE (and anything the lane-per-record raster path must not take) are
+// PBOX_NONE.  32 pixels = one bit each in the lane's hit mask.
 constexpr unsigned PBOX_NONE = 0xffffffffu;
-constexpr int PBOX_MAX = 4;
+#ifndef PBR_PBOX_AREA
+#define PBR_PBOX_AREA 32
+#endif
+constexpr int PBOX_AREA = PBR_PBOX_AREA, PBOX_SIDE = 16;
 __device__ __forceinline__ unsigned pack_pbox(const BBox &bb) {
     const int w = bb.px1 - bb.px0 + 1, h = bb.py1 - bb.py0 + 1;
-    if (w > PBOX_MAX || h > PBOX_MAX) return PBOX_NONE;
+    if (w > PBOX_SIDE || h > PBOX_SIDE || w * h > PBOX_AREA) return PBOX_NONE;
     return (unsigned)bb.px0 | ((unsigned)bb.py0 << 11) | ((unsigned)(w - 1) << 22) | ((unsigned)(h - 1) << 27);
 }
 
