@@ -125,6 +125,8 @@ typedef struct {
 #define PBR_FRAME_FORCE_GENERAL 1u      /* skip the small-scene fast kernel (testing / debugging) */
 #define PBR_FRAME_WRITE_MATS 4u          /* posed nodes: also write their matrices to pose->out_mats on the
                                            small-scene path (tests; costs the overlap between frames) */
+#define PBR_FRAME_FORCE_STAGED 8u        /* large scenes: band-based path (geometry pre-pass + TMA-staged raster per band) */
+#define PBR_FRAME_FORCE_BINNED 16u       /* large scenes: block-list path (per-block record lists, one warp per block) */
 #define PBR_FRAME_FORCE_FUSED 2u        /* general path: keep geometry fused into the raster kernel
                                            instead of the geometry pre-pass + TMA-staged raster */
 
@@ -173,7 +175,8 @@ int pbr_compose_transforms(const pbr_pose_desc *poses, int32_t n_poses, void *st
  *        scene (the frame is still exact: the surplus went to the overflow pool; later frames on this
  *        device take the general kernel until the bit is cleared);
  * bit 1: the geometry pre-pass of a large scene ran out of per-scene record capacity and DROPPED
- *        triangles -- the frame is wrong; the Python wrapper raises when it sees this bit. */
+ *        triangles -- the frame is wrong; the next large-scene pbr_render returns PBR_EOVERFLOW once and later
+ *        frames use worst-case capacities (clear = 1 also returns the device to the normal capacities). */
 int pbr_device_status(int32_t device, int32_t *status_bits, int32_t clear);
 
 /* The same bits without a device synchronisation: read from host-mapped memory the kernels also write

@@ -183,10 +183,10 @@ struct BBox {
 };
 // pixel box of a small triangle in one word: x0 (11 bits) | y0 (11) | width - 1 (5) | height - 1 (5); boxes of more
 // than PBOX_AREA pixels or longer than PBOX_SIDE (and anything the lane-per-record raster path must not take) are
-// PBOX_NONE.  32 pixels = one bit each in the lane's hit mask.
+// PBOX_NONE (the lane's hit mask has one bit per pixel of the box: at most 32).
 constexpr unsigned PBOX_NONE = 0xffffffffu;
 #ifndef PBR_PBOX_AREA
-#define PBR_PBOX_AREA 32
+#define PBR_PBOX_AREA 16
 #endif
 constexpr int PBOX_AREA = PBR_PBOX_AREA, PBOX_SIDE = 16;
 __device__ __forceinline__ unsigned pack_pbox(const BBox &bb) {

@@ -906,11 +906,18 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
     size_t smem_fused = 0;
     if (int rc = plan_general(f, st, &smem_fused)) return rc;
     if (!(d->flags & PBR_FRAME_FORCE_FUSED) && (ns.slots > CH || f.nbands > 1)) {
-        // block lists unless a frame overflowed them (then: band-based path, worst-case record capacity) or
-        // PBR_B200_LARGE=staged asks for the band-based path (A/B measurements)
-        static const bool want_staged = getenv("PBR_B200_LARGE") != nullptr && strcmp(getenv("PBR_B200_LARGE"), "staged") == 0;
-        const bool fits = ns.verts <= 0x7fffffffll / 64 && d->tile_w <= 2048 && d->tile_h <= 2048;
-        if (!want_staged && !st->cap_worst_case && fits) return launch_binned(f, st, stream);
+        // Tiles of several bands: per-block record lists (raster_binned.cuh) -- measured 1.3x (config 3) and 2.0x
+        // (config 5) faster than the band-based path, which rescans and re-bins the scene's records in every band.
+        // Single-band tiles (Steering-v0 at 64x64) stay on the band-based path: its one CTA per scene needs three
+        // launches per frame instead of seven.  After a list overflow: band-based path with worst-case capacity.
+        // PBR_B200_LARGE=staged|binned and PBR_FRAME_FORCE_STAGED / _BINNED override the choice (tests, A/B).
+        static const char *want = getenv("PBR_B200_LARGE");
+        const bool fits = ns.verts <= 0x7fffffffll / 64 && d->tile_w <= 2048 && d->tile_h <= 2048 && !st->cap_worst_case;
+        bool binned = f.nbands > 1;
+        if (want != nullptr) binned = strcmp(want, "binned") == 0;
+        if (d->flags & PBR_FRAME_FORCE_STAGED) binned = false;
+        if (d->flags & PBR_FRAME_FORCE_BINNED) binned = true;
+        if (binned && fits) return launch_binned(f, st, stream);
         return launch_staged(f, st, stream);
     }
     return launch_general(f, st, stream);
@@ -1007,7 +1014,7 @@ int pbr_device_status(int32_t device, int32_t *status_bits, int32_t clear) {
     if (rc == PBR_OK) {
         int v = 0;
         cudaError_t e = cudaMemcpy(&v, st->status, sizeof(int), cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess && clear) { e = cudaMemset(st->status, 0, sizeof(int)); st->status_host[0] = 0; st->status_host[1] = 0; }
+        if (e == cudaSuccess && clear) { e = cudaMemset(st->status, 0, sizeof(int)); st->status_host[0] = 0; st->status_host[1] = 0; st->cap_worst_case = false; }
         if (e != cudaSuccess) rc = fail(PBR_ECUDA, "pbr_device_status: %s", cudaGetErrorString(e));
         *status_bits = v;
     }

@@ -168,37 +168,73 @@ def test_more_posed_nodes_than_the_kernel_takes_and_posed_shared_node():
     _assert_same(r2.render(), oracle_render(r2), "six posed nodes")
 
 
-@pytest.mark.parametrize("fused", [False, True], ids=["staged", "fused"])
+# the three ways a large scene can go: band-based (geometry pre-pass + TMA-staged raster per band of rows), block
+# lists (one warp per 8x8 block), geometry fused into the general raster kernel
+LARGE_PATHS = {"staged": 8, "binned": 16, "fused": 2}      # PBR_FRAME_FORCE_STAGED / _BINNED / _FUSED
+
+
+@pytest.mark.parametrize("path", list(LARGE_PATHS))
 @pytest.mark.parametrize("channels", [3, 4])
-def test_many_cubes_clipping_and_multipass(channels, fused):
+def test_many_cubes_clipping_and_multipass(channels, path):
     """16 boxes/scene = 192 triangle slots (> one 128-slot pass), camera inside the cloud so that
     triangles cross the near plane (clip path) and the guard band."""
     r = many_cubes_renderer(num_scenes=24, instances=16, tile=(64, 64), device="cuda", channels=channels)
-    if fused:
-        r.render_flags = 2          # PBR_FRAME_FORCE_FUSED: geometry inside the raster kernel
+    r.render_flags = LARGE_PATHS[path]
     px = r.step()
     ref = oracle_render(r)
     assert (ref != 0).any()
     _assert_same(px, ref, "many cubes")
 
 
-@pytest.mark.parametrize("fused", [False, True], ids=["staged", "fused"])
+@pytest.mark.parametrize("path", list(LARGE_PATHS))
 @pytest.mark.parametrize("n,inst,tile,seed", [(6, 40, (128, 128), 7), (3, 150, (256, 256), 8), (5, 300, (84, 84), 9),
-                                              (2, 64, (200, 120), 10)])
-def test_many_cubes_large_tile_bands(n, inst, tile, seed, fused):
+                                              (2, 64, (200, 120), 10), (3, 90, (75, 53), 11)])
+def test_many_cubes_large_tile_bands(n, inst, tile, seed, path):
     """Several bands per tile and several 128-record chunks per scene: geometry pre-pass + TMA-staged
     raster against the fused kernel and the oracle."""
     r = many_cubes_renderer(num_scenes=n, instances=inst, tile=tile, device="cuda", seed=seed)
-    if fused:
-        r.render_flags = 2
-    _assert_same(r.step(), oracle_render(r), f"many cubes {tile} x{inst}")
+    r.render_flags = LARGE_PATHS[path]
+    _assert_same(r.step(), oracle_render(r), f"many cubes {tile} x{inst} {path}")
     assert r._native.device_status(torch.cuda.current_device()) == 0
 
 
-def test_camera_inside_geometry_heavy_clipping():
+@pytest.mark.parametrize("path", list(LARGE_PATHS))
+def test_camera_inside_geometry_heavy_clipping(path):
+    """Huge near triangles: block boxes that span the whole tile (walked by whole warps when the block lists are
+    built), int64 records, fans of clipped triangles."""
     r = many_cubes_renderer(num_scenes=16, instances=12, tile=(64, 64), device="cuda", seed=11, spread=3.0,
                             eye=(0.0, -1.0, 0.0))
-    _assert_same(r.step(), oracle_render(r), "heavy clipping")
+    r.render_flags = LARGE_PATHS[path]
+    _assert_same(r.step(), oracle_render(r), f"heavy clipping {path}")
+    big = many_cubes_renderer(num_scenes=4, instances=20, tile=(200, 136), device="cuda", seed=12, spread=4.0,
+                              eye=(0.0, -1.5, 0.2))
+    big.render_flags = LARGE_PATHS[path]
+    _assert_same(big.step(), oracle_render(big), f"heavy clipping, large tile, {path}")
+
+
+def test_block_list_overflow_is_reported_and_heals():
+    """A frame whose (block, record) lists do not fit the scratch sized for it sets the overflow flag; the next
+    large-scene call reports PBR_EOVERFLOW once and from then on this device uses the band-based path with
+    worst-case record capacity, which renders the same frame exactly."""
+    import pybatchrender_b200._native as nat
+    dev = torch.cuda.current_device()
+    # every triangle is huge (camera inside big boxes): each record lands in nearly every block list
+    r = many_cubes_renderer(num_scenes=2, instances=120, tile=(256, 256), device="cuda", seed=13, spread=0.6,
+                            eye=(0.0, 0.0, 0.0), two_sided=True)
+    node = r._pbr_nodes[0]
+    node.set_scales(torch.full((node.buf_instances, 1), 9.0))
+    r.render_flags = 16                                # PBR_FRAME_FORCE_BINNED
+    r._native.device_status(dev, clear=True)
+    r.render()
+    torch.cuda.synchronize()
+    if r._native.device_status_nosync(dev) & 2:
+        with pytest.raises(nat.NativeError, match="dropped triangles"):
+            r.render()
+        r.render_flags = 0
+        _assert_same(r.render(), oracle_render(r), "after the overflow: band-based path, worst-case capacity")
+    else:                                              # lists were large enough after all: the frame must be exact
+        _assert_same(r.render(), oracle_render(r), "block lists fit")
+    r._native.device_status(dev, clear=True)
 
 
 @pytest.mark.parametrize("general", [False, True], ids=["warp", "general"])
@@ -546,11 +582,11 @@ def test_sharded_render_equals_single_process_render():
     dict(num_scenes=4, boxes=2, spheres=6, spread=3.0, eye=(0.0, -2.0, 0.0)),          # heavy near-plane clipping
     dict(num_scenes=4, boxes=0, spheres=3, spread=1.5, eye=(0.2, -0.3, 0.1), two_sided=True),   # camera inside
 ])
-@pytest.mark.parametrize("fused", [False, True])
-def test_smooth_normals_bit_exact(kw, fused):
+@pytest.mark.parametrize("path", list(LARGE_PATHS))
+def test_smooth_normals_bit_exact(kw, path):
     r = mixed_mesh_renderer(device="cuda", **kw)
-    r.render_flags = 2 if fused else 0          # PBR_FRAME_FORCE_FUSED
-    _assert_same(r.render(), oracle_render(r), f"smooth {kw} fused={fused}")
+    r.render_flags = LARGE_PATHS[path]
+    _assert_same(r.render(), oracle_render(r), f"smooth {kw} {path}")
     assert r._native.device_status(torch.cuda.current_device()) == 0
 
 

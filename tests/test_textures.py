@@ -83,10 +83,10 @@ def test_oracle_texture_orientation_and_filtering():
     dict(eye=(0.3, -1.2, 0.2), spread=1.5, two_sided=True),    # camera among the instances: clipped, two-sided
     dict(use=0.35, tex_shape=(32, 5)),
 ])
-@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("fused", [0, 2, 8, 16], ids=["auto", "fused", "staged", "binned"])
 def test_textured_frames_bit_exact(kw, fused):
     r = _scene("cuda", **kw)
-    r.render_flags = 2 if fused else 0
+    r.render_flags = fused        # PBR_FRAME_FORCE_FUSED / _STAGED / _BINNED
     got = r.render().cpu().numpy()
     assert np.array_equal(got, oracle_render(r)), f"textured {kw} fused={fused}"
     assert r._native.device_status(torch.cuda.current_device()) == 0
