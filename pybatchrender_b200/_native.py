@@ -250,6 +250,19 @@ class NativeBase:
             pass
 
 
+def new_pose_struct(matbuf: torch.Tensor) -> "_PoseDesc":
+    """A pbr_pose_desc for one node: identity pose, matrices materialise into ``matbuf``."""
+    _cuda_f32(matbuf, "matbuf")
+    st = _PoseDesc()
+    for k in range(3):
+        st.pos[k].ptr, st.pos[k].stride, st.pos[k].constant = None, 0, 0.0
+        st.hpr[k].ptr, st.hpr[k].stride, st.hpr[k].constant = None, 0, 0.0
+    st.scale.ptr, st.scale.stride, st.scale.constant = None, 0, 1.0
+    st.out_mats = matbuf.data_ptr()
+    st.n_instances = int(matbuf.shape[0])
+    return st
+
+
 class Native:
     """Thin object the renderer holds; every method enqueues work on torch's current stream."""
 
@@ -311,6 +324,13 @@ class Native:
         dst.out_mats = out.data_ptr()
         dst.n_instances = n
 
+    def compose_structs(self, structs: list, device: torch.device) -> None:
+        """pbr_compose_transforms over ready-made pbr_pose_desc structures (``new_pose_struct``)."""
+        arr = (_PoseDesc * len(structs))(*structs)
+        with torch.cuda.device(device):
+            rc = self.lib.pbr_compose_transforms(arr, len(structs), _stream_ptr(device))
+        _check(rc, "pbr_compose_transforms")
+
     def compose(self, poses: list[dict], device: torch.device) -> None:
         """Write the matrices of several poses (see ``fill_pose``) in one launch."""
         arr = (_PoseDesc * len(poses))()
@@ -323,12 +343,10 @@ class Native:
     def _frame(self, *, num_scenes, tile_w, tile_h, channels, vp, nodes, out, bg, ambient, dir_dir, dir_col,
                strength, scene_begin=0, scene_count=None, flags=0, base=None):
         """nodes: list of (NativeMesh, matbuf, colbuf, instances_per_scene, shared[, in_base[, use_texture,
-        NativeTexture | None[, pose dict | None]]])."""
+        NativeTexture | None[, pose dict | pbr_pose_desc structure | None]]])."""
         _cuda_f32(vp, "viewbuf")
         nd = (_NodeDesc * max(1, len(nodes)))()
-        n_posed = sum(1 for item in nodes if len(item) > 8 and item[8] is not None)
-        poses = (_PoseDesc * max(1, n_posed))()
-        k_pose = 0
+        poses = []                     # pbr_pose_desc structures the node array points at (kept alive with it)
         for i, item in enumerate(nodes):
             mesh, mats, cols, inst, shared = item[:5]
             _cuda_f32(mats, "matbuf")
@@ -342,9 +360,12 @@ class Native:
             nd[i].texture = item[7].handle if len(item) > 7 and item[7] is not None else None
             nd[i].flags = PBR_NODE_IN_BASE if (len(item) > 5 and item[5]) else 0
             if len(item) > 8 and item[8] is not None:
-                self.fill_pose(poses[k_pose], item[8])
-                nd[i].pose = ctypes.pointer(poses[k_pose])
-                k_pose += 1
+                st = item[8]
+                if isinstance(st, dict):
+                    d, st = st, _PoseDesc()
+                    self.fill_pose(st, d)
+                poses.append(st)
+                nd[i].pose = ctypes.pointer(st)
         f = _FrameDesc()
         f.num_scenes = int(num_scenes)
         f.scene_begin = int(scene_begin)
@@ -362,6 +383,33 @@ class Native:
         f.flags = int(flags)
         f.base = base.handle if base is not None else None
         return f, (nd, poses)
+
+    def prepare(self, *, out, **kw):
+        """Build the native description of a frame once; ``render_cached`` enqueues it any number of times (with
+        another output buffer / scene window).  Valid while the tensors it points at are alive and the scene's
+        structure is unchanged -- the renderer keys it on its version counters."""
+        if not out.is_cuda or out.dtype != torch.uint8 or not out.is_contiguous():
+            raise NativeError("out must be a contiguous uint8 CUDA tensor")
+        f, keep = self._frame(out=out, **kw)
+        dev = out.device
+        return [f, ctypes.byref(f), keep, dev, dev.index if dev.index is not None else torch.cuda.current_device(),
+                int(kw["num_scenes"])]
+
+    def render_cached(self, prepared, out, scene_begin: int = 0, scene_count=None) -> None:
+        f, fref, _keep, dev, dev_index, n = prepared
+        if not out.is_cuda or out.dtype != torch.uint8 or not out.is_contiguous():
+            raise NativeError("out must be a contiguous uint8 CUDA tensor")
+        f.out = out.data_ptr()
+        f.scene_begin = scene_begin
+        f.scene_count = n - scene_begin if scene_count is None else scene_count
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if torch.cuda.current_device() == dev_index:
+            rc = self.lib.pbr_render(fref, stream)
+        else:
+            with torch.cuda.device(dev):
+                rc = self.lib.pbr_render(fref, stream)
+        if rc != 0:
+            _check(rc, "pbr_render")
 
     def render(self, *, out, **kw) -> None:
         if not out.is_cuda or out.dtype != torch.uint8 or not out.is_contiguous():

@@ -730,7 +730,8 @@ static int launch_binned(FrameDev &f, DeviceState *st, void *stream) {
         COUNT_LAUNCH();
         bin_tri_kernel<<<dim3((unsigned)((f.total_slots + B_THREADS - 1) / B_THREADS), (unsigned)n), B_THREADS, 0, cs>>>(f, g, bd);
         COUNT_LAUNCH();
-        const dim3 bgrid((unsigned)((cap + B_THREADS - 1) / B_THREADS), (unsigned)n);
+        // a quarter of the lists' capacity (grid-stride loop inside): they are rarely more than a third full
+        const dim3 bgrid((unsigned)((cap / 4 + B_THREADS - 1) / B_THREADS), (unsigned)n);
         bin_blocks_kernel<false><<<bgrid, B_THREADS, 0, cs>>>(f, g, bd);
         COUNT_LAUNCH();
         bin_scan_kernel<<<(unsigned)n, B_THREADS, 0, cs>>>(f, bd);
@@ -913,7 +914,8 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         // PBR_B200_LARGE=staged|binned and PBR_FRAME_FORCE_STAGED / _BINNED override the choice (tests, A/B).
         static const char *want = getenv("PBR_B200_LARGE");
         const bool fits = ns.verts <= 0x7fffffffll / 64 && d->tile_w <= 2048 && d->tile_h <= 2048 && !st->cap_worst_case;
-        bool binned = f.nbands > 1;
+        bool binned = f.nbands > 1 && ns.slots <= 20000;       // (Steering-v0, ~50k slots per scene, mostly culled:
+                                                               //  1.03 ms band-based vs 1.20 ms per 1024 scenes)
         if (want != nullptr) binned = strcmp(want, "binned") == 0;
         if (d->flags & PBR_FRAME_FORCE_STAGED) binned = false;
         if (d->flags & PBR_FRAME_FORCE_BINNED) binned = true;

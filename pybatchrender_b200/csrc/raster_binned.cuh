@@ -311,10 +311,8 @@ __global__ void __launch_bounds__(B_THREADS) bin_blocks_kernel(const __grid_cons
                                                                const __grid_constant__ StagedDev g,
                                                                const __grid_constant__ BinnedDev bd) {
     const int local_scene = blockIdx.y;
-    const int idx = blockIdx.x * B_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int total = min(g.count[local_scene], g.cap);
-    if (blockIdx.x * B_THREADS >= total) return;            // whole CTA past the end of the list
     const int nlist = 2 * f.nbx * f.nby;
     int *cur = bd.blk_cnt + (size_t)local_scene * nlist;
     const int *off = bd.blk_off + (size_t)local_scene * (nlist + 1);
@@ -326,6 +324,10 @@ __global__ void __launch_bounds__(B_THREADS) bin_blocks_kernel(const __grid_cons
             if (FILL && off[l] + p < bd.pairs_cap) pairs[off[l] + p] = ridx;
         }
     };
+    // (the grid covers a fraction of the list's capacity: the lists are usually far shorter than that)
+#pragma unroll 1
+    for (int cta_base = blockIdx.x * B_THREADS; cta_base < total; cta_base += gridDim.x * B_THREADS) {
+    const int idx = cta_base + threadIdx.x;
     Rec r;
     BBox bb;
     bb.bx0 = bb.by0 = 0; bb.bx1 = bb.by1 = -1;
@@ -363,12 +365,13 @@ __global__ void __launch_bounds__(B_THREADS) bin_blocks_kernel(const __grid_cons
         qb.bx0 = __shfl_sync(0xffffffffu, bb.bx0, src); qb.by0 = __shfl_sync(0xffffffffu, bb.by0, src);
         qb.bx1 = __shfl_sync(0xffffffffu, bb.bx1, src); qb.by1 = __shfl_sync(0xffffffffu, bb.by1, src);
         const int qkind = __shfl_sync(0xffffffffu, kind, src);
-        const unsigned qidx = (unsigned)(blockIdx.x * B_THREADS + (threadIdx.x & ~31) + src);
+        const unsigned qidx = (unsigned)(cta_base + (threadIdx.x & ~31) + src);
         const int qw = qb.bx1 - qb.bx0 + 1, qa = qw * (qb.by1 - qb.by0 + 1);
         for (int k = lane; k < qa; k += 32) {
             const int yy = k / qw;
             visit(q, qb, false, qb.bx0 + k - yy * qw, qb.by0 + yy, qkind, qidx);
         }
+    }
     }
 }
 

@@ -98,16 +98,21 @@ class CartPoleRenderer(PBRRenderer):
         if state.device != self.device:
             state = state.to(self.device, non_blocking=True)
         state = self._fit_batch(state)
-        x, theta = state[:, 0], state[:, 2]
 
         if self._native is not None:
             # cart = T(x, 0, 0); pole = T(x, pole_y, 0) . Ry(theta): bound to the state columns, evaluated by
             # the raster kernel itself -- no launch, no matrix buffer written or read
-            self.cart.set_pose(pos=(x, 0.0, 0.0))
-            self.pole.set_pose(pos=(x, self.pole_y, 0.0), hpr=(0.0, theta, 0.0))
+            if self.cart._pose is None or self.pole._pose is None:
+                x, theta = state[:, 0], state[:, 2]
+                self.cart.set_pose(pos=(x, 0.0, 0.0))
+                self.pole.set_pose(pos=(x, self.pole_y, 0.0), hpr=(0.0, theta, 0.0))
+            else:                      # every later step: re-point the two state columns, nothing else
+                self.cart.bind_pose_columns(state, {0: 0})
+                self.pole.bind_pose_columns(state, {0: 0, 4: 2})
             return
 
         # generic path (CPU): same sequence of setter calls as the reference
+        x, theta = state[:, 0], state[:, 2]
         self.cart_x_pos[:, :, 0] = x.unsqueeze(1)
         self.cart_pos[:, :, 0:1] = self.cart_x_pos
         self.cart.set_positions(self.cart_pos)

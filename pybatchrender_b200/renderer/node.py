@@ -116,6 +116,8 @@ class PBRNode(PBRShaderContext):
             dev, B = self.device, self.buf_instances
             self._matbuf = torch.zeros((B, 16), dtype=torch.float32, device=dev)
             self._pose = None              # dict(pos, hpr, scale) while the matrices are bound to pose channels
+            self._pose_struct = None       # native pbr_pose_desc owned by the node (created by the first set_pose)
+            self._pose_chans = None
             self._mirror_stale = False
             self.colbuf = torch.ones((B, 4), dtype=torch.float32, device=dev)
             self._set_shader_input("instancesPerScene", self.instances_per_scene)
@@ -150,21 +152,61 @@ class PBRNode(PBRShaderContext):
             self.set_hprs(torch.stack([col(c) for c in hpr], 1), lazy=True)
             self.set_scales(col(scale).reshape(-1, 1))
             return
-        for c in pos + hpr + (scale,):
-            if isinstance(c, torch.Tensor) and (c.dim() != 1 or c.shape[0] != self.buf_instances or not c.is_cuda
-                                                or c.dtype != torch.float32):
-                raise ValueError(f"set_pose: channel tensors must be 1-D float32 CUDA views of {self.buf_instances} elements")
+        # The node owns one native pose descriptor (pbr_pose_desc); a frame description points at it, so
+        # re-binding channels here is all a step has to do.  Channels that did not change are skipped.
+        chans = pos + hpr + (scale,)
+        prev = self._pose_chans
+        if self._pose_struct is None:
+            from .. import _native
+            self._pose_struct = _native.new_pose_struct(self._matbuf)
+        if self._pose is None:
+            self._touch()                  # the frame description changes shape: posed from now on
+        st, B = self._pose_struct, self.buf_instances
+        for k in range(7):
+            c = chans[k]
+            if prev is not None and c is prev[k]:
+                continue
+            dst = st.pos[k] if k < 3 else (st.hpr[k - 3] if k < 6 else st.scale)
+            if isinstance(c, torch.Tensor):
+                if c.dim() != 1 or c.shape[0] != B or not c.is_cuda or c.dtype != torch.float32:
+                    raise ValueError(f"set_pose: channel tensors must be 1-D float32 CUDA views of {B} elements")
+                dst.ptr, dst.stride, dst.constant = c.data_ptr(), c.stride(0), 0.0
+            else:
+                if prev is not None and isinstance(prev[k], (int, float)) and float(prev[k]) == float(c):
+                    continue
+                dst.ptr, dst.stride, dst.constant = None, 0, float(c)
+        self._pose_chans = chans           # keeps the channel tensors alive
         self._pose = dict(pos=pos, hpr=hpr, scale=scale)
         self._mirror_stale = True
-        self._touch()
+
+    def bind_pose_columns(self, state: torch.Tensor, columns: dict) -> None:
+        """Fast re-binding for renderers that feed columns of one ``[B, k]`` float32 state tensor every step
+        (CartPole: ``{0: 0, 4: 2}`` = pos.x <- state[:, 0], hpr.P <- state[:, 2]): channel index (0..2 position,
+        3..5 H/P/R, 6 scale) -> column.  Equivalent to ``set_pose`` with ``state[:, col]`` views for those channels
+        and everything else unchanged, without creating the views.  Needs a previous ``set_pose``."""
+        st = self._pose_struct
+        if st is None or self._pose is None:
+            raise RuntimeError("bind_pose_columns needs a pose bound with set_pose first")
+        if state.dim() != 2 or state.shape[0] != self.buf_instances or state.dtype != torch.float32 or not state.is_cuda:
+            raise ValueError(f"bind_pose_columns: state must be a [{self.buf_instances}, k] float32 CUDA tensor")
+        base, s0, s1 = state.data_ptr(), state.stride(0), state.stride(1)
+        for k, col in columns.items():
+            dst = st.pos[k] if k < 3 else (st.hpr[k - 3] if k < 6 else st.scale)
+            dst.ptr, dst.stride = base + 4 * s1 * col, s0
+        chans = list(self._pose_chans)
+        for k, col in columns.items():
+            chans[k] = (state, col)        # (tensor, column): resolved lazily by _pose_desc
+        self._pose_chans = tuple(chans)
+        self._pose_state = state           # keeps the tensor alive until the next binding
+        self._mirror_stale = True
 
     def _pose_desc(self):
-        """What the native layer needs to evaluate the pose (None: matrices come from matbuf)."""
-        return None if self._pose is None else dict(out=self._matbuf, **self._pose)
+        """The node's native pose descriptor (None: matrices come from matbuf)."""
+        return None if self._pose is None else self._pose_struct
 
     def _materialise_pose(self) -> None:
         if self._pose is not None:
-            self.base._native.compose([self._pose_desc()], self.device)
+            self.base._native.compose_structs([self._pose_struct], self.device)
 
     def _sync_mirrors(self) -> None:
         """Refresh transforms_b44 / rot3_b33 / scale_b11 from the bound pose (reference keeps them current on
@@ -175,7 +217,9 @@ class PBRNode(PBRShaderContext):
         self._materialise_pose()
         B = self.buf_instances
         T = self._matbuf.view(B, 4, 4).transpose(1, 2).contiguous()
-        sc = self._pose["scale"]
+        sc = self._pose_chans[6]
+        if isinstance(sc, tuple):
+            sc = sc[0][:, sc[1]]
         sc = sc.reshape(B, 1, 1).clone() if isinstance(sc, torch.Tensor) else torch.full(
             (B, 1, 1), float(sc), dtype=torch.float32, device=self.device)
         self._transforms_b44, self._scale_b11 = T, sc
@@ -186,6 +230,8 @@ class PBRNode(PBRShaderContext):
         if self.has_geometry and self._pose is not None:
             self._sync_mirrors()
             self._pose = None
+            self._pose_chans = None
+            self._touch()
 
     @property
     def matbuf(self) -> torch.Tensor:

@@ -87,6 +87,8 @@ class PBRRenderer:
         self.static_layer = True
         self._base = None
         self._base_sig = None
+        self._call_cache = None        # (key, prepared native frame description) of the last frame
+        self._out_shape = None
 
     # ------------------------------------------------------------------ scene construction
     def set_background_color(self, r: float, g: float, b: float, a: float = 1.0) -> None:
@@ -200,14 +202,15 @@ class PBRRenderer:
                 from .. import _native
                 n._native_texture = _native.NativeTexture(n.texture_image, self.device)
         return [(n._native_mesh, n._matbuf, n.colbuf, n.instances_per_scene, n.shared_across,
-                 in_base and n.shared_across, float(n.shader_inputs.get("useTexture", 0.0)), n._native_texture,
-                 n._pose_desc())
+                 in_base and n.shared_across and n._pose is None, float(n.shader_inputs.get("useTexture", 0.0)),
+                 n._native_texture, n._pose_desc())
                 for n in self._node_cache]
 
     def invalidate_static(self) -> None:
         """Force the static layer to be re-rendered (needed only if matbuf / colbuf / viewbuf of a
         shared node or the camera were written behind the API's back)."""
         self._base_sig = None
+        self._call_cache = None
 
     def _static_signature(self):
         cam = self._pbr_cam
@@ -215,7 +218,8 @@ class PBRRenderer:
             return None
         if self._node_cache is None:
             self._node_cache = self._drawable_nodes()
-        shared = [n for n in self._node_cache if n.shared_across]
+        # (a node bound to pose channels follows tensors that change behind the API: never part of the static layer)
+        shared = [n for n in self._node_cache if n.shared_across and n._pose is None]
         if not shared or len(shared) == len(self._node_cache) and self.num_scenes < 2:
             return None
         return (tuple((id(n), getattr(n, "_version", 0)) for n in shared), id(cam), getattr(cam, "_version", 0),
@@ -223,21 +227,42 @@ class PBRRenderer:
                 int(self.cfg.num_channels), self._scene_version)
 
     # ------------------------------------------------------------------ rendering
+    def _frame_key(self, flags: int):
+        """Everything a cached native frame description depends on (tensor *contents* do not: the library reads
+        matrices, colours, VP rows and pose channels on the device when the frame executes)."""
+        if self._node_cache is None:
+            self._node_cache = self._drawable_nodes()
+        cam = self._pbr_cam
+        return (self._scene_version, flags | self.render_flags, self.static_layer, id(cam), cam._version, cam.uniform,
+                self._light_params(), self._background_color, tuple(self.cfg.tile_resolution), int(self.cfg.num_channels),
+                tuple(n._version for n in self._node_cache))
+
     def render(self, out: torch.Tensor | None = None, scene_begin: int = 0, scene_count: int | None = None,
                flags: int = 0) -> torch.Tensor:
         """Rasterise the current scene state into ``out`` (allocated if None) and return it."""
-        if self._native is None:
+        native = self._native
+        if native is None:
             raise RuntimeError(
                 "PBRRenderer: rendering needs a CUDA device and libpbr_b200.so (cfg.device is "
                 f"{self.cfg.device!r}); there is no CPU fallback")
         if self._pbr_cam is None:
             self.add_camera()
-        W, H = int(self.cfg.tile_resolution[0]), int(self.cfg.tile_resolution[1])
-        C, N = int(self.cfg.num_channels), self.num_scenes
+        shape = self._out_shape
+        if shape is None:
+            W, H = int(self.cfg.tile_resolution[0]), int(self.cfg.tile_resolution[1])
+            shape = self._out_shape = (self.num_scenes, int(self.cfg.num_channels), H, W)
         if out is None:
-            out = torch.empty((N, C, H, W), dtype=torch.uint8, device=self.device)
-        elif tuple(out.shape) != (N, C, H, W):
-            raise ValueError(f"out must have shape {(N, C, H, W)}, got {tuple(out.shape)}")
+            out = torch.empty(shape, dtype=torch.uint8, device=self.device)
+        elif out.shape != shape:
+            raise ValueError(f"out must have shape {shape}, got {tuple(out.shape)}")
+        # ---- fast path: nothing but tensor contents (and the output buffer) changed since the last frame -- the
+        # native frame description built then is still right, only `out` and the scene window are patched in
+        key = self._frame_key(flags)
+        call = self._call_cache
+        if call is not None and call[0] == key:
+            native.render_cached(call[1], out, scene_begin, scene_count)
+            return out
+        N, C, H, W = shape
         amb, ddir, dcol, strength = self._light_params()
         common = dict(num_scenes=N, tile_w=W, tile_h=H, channels=C, vp=self._pbr_cam.viewbuf,
                       bg=self._background_color, ambient=amb, dir_dir=ddir, dir_col=dcol, strength=strength)
@@ -248,12 +273,14 @@ class PBRRenderer:
                 from .. import _native
                 self._base = _native.NativeBase(self.device)
             if sig != self._base_sig:
-                self._native.base_render(self._base, nodes=self._native_nodes(in_base=True), scene_begin=0,
-                                         scene_count=1, **common)
+                native.base_render(self._base, nodes=self._native_nodes(in_base=True), scene_begin=0,
+                                   scene_count=1, **common)
                 self._base_sig = sig
             base = self._base
-        self._native.render(nodes=self._native_nodes(in_base=base is not None), out=out, scene_begin=scene_begin,
-                            scene_count=scene_count, flags=flags | self.render_flags, base=base, **common)
+        prepared = native.prepare(nodes=self._native_nodes(in_base=base is not None), out=out, flags=flags | self.render_flags,
+                                  base=base, **common)
+        native.render_cached(prepared, out, scene_begin, scene_count)
+        self._call_cache = (key, prepared)
         return out
 
     def _step(self, *args, **kwargs):

@@ -129,7 +129,7 @@ def test_pose_matrices_equal_the_reference_under_stubs():
 
 def test_more_posed_nodes_than_the_kernel_takes_and_posed_shared_node():
     """Six posed single-triangle-pair nodes (> MAX_FRAME_POSES = 4: the library materialises them with the pose
-    kernel first) and a posed shared node that goes into the static layer."""
+    kernel first) and a posed shared node (which stays out of the static layer)."""
     from pybatchrender_b200 import PBRRenderer, meshes
     n = 40
     r = PBRRenderer(dict(num_scenes=n, tile_resolution=(64, 64), device="cuda"))
@@ -148,8 +148,8 @@ def test_more_posed_nodes_than_the_kernel_takes_and_posed_shared_node():
         node.set_colors(torch.tensor(np.concatenate([rng.uniform(0.2, 1, (node.buf_instances, 3)),
                                                      np.ones((node.buf_instances, 1))], 1), dtype=torch.float32))
         node.set_pose(pos=(c[:, i], c[:, i + 1], 0.3 * i), hpr=(c[:, i + 2], 0.4, c[:, i + 3]), scale=1.0 + 0.25 * i)
-    _assert_same(r.render(), oracle_render(r), "three posed nodes (one in the static layer)")
-    assert r._base_sig is not None
+    _assert_same(r.render(), oracle_render(r), "three posed nodes (one shared)")
+    assert r._base_sig is None          # a posed node follows tensors that change behind the API: never in the static layer
     r.static_layer = False
     _assert_same(r.render(), oracle_render(r), "three posed nodes, no static layer")
     # > MAX_FRAME_POSES posed nodes in the frame
@@ -420,6 +420,48 @@ def test_graph_replay_over_state_and_output_rings_like_the_bench():
     for b in range(2):
         r._step(states[ring - 2 + b])
         _assert_same(outs[b], oracle_render(r, n_threads=host_threads()), f"two-buffer ping-pong, buffer {b}")
+
+
+def test_cached_frame_description_tracks_every_change():
+    """``render`` reuses the native frame description of the previous frame while nothing but tensor contents
+    changed; every setter that changes what the description says must invalidate it."""
+    n = 48
+    r = _cartpole(n)
+    st = [cartpole_states(n, seed=70 + i).cuda() for i in range(3)]
+    a = r.step(st[0])
+    assert r._call_cache is not None
+    _assert_same(a, oracle_render(r), "first frame")
+    b = r.step(st[1])                                    # same description, other state tensor, new output
+    assert b.data_ptr() != a.data_ptr()
+    _assert_same(b, oracle_render(r), "cached description, new state")
+    st[1][:, 0] += 0.25                                  # contents of the bound tensor change in place
+    _assert_same(r.render(), oracle_render(r), "in-place state update")
+    r.cart.set_colors(torch.rand(n, 4).cuda())           # node contents through a setter
+    _assert_same(r.render(), oracle_render(r), "colours")
+    r._pbr_light.set_ambient((0.4, 0.1, 0.3))
+    _assert_same(r.render(), oracle_render(r), "light")
+    r.set_background_color(0.1, 0.2, 0.3)
+    _assert_same(r.render(), oracle_render(r), "background")
+    r._pbr_cam.set_positions(torch.tensor([4.0, 6.0, 2.5]))
+    r._pbr_cam.look_at(torch.tensor([0.0, 0.0, 0.2]))
+    _assert_same(r.render(), oracle_render(r), "camera")
+    r.rail.set_positions(torch.tensor([[0.0, 0.1, -0.05]]))            # shared node: static layer re-rendered
+    _assert_same(r.render(), oracle_render(r), "shared node")
+    r.pole.set_hprs(torch.zeros(n, 3))                   # a generic setter ends the pose binding of that node
+    assert r.pole._pose is None
+    _assert_same(r.render(), oracle_render(r), "binding ended")
+    r.step(st[2])                                        # ... and CartPole's _step binds it again
+    assert r.pole._pose is not None
+    _assert_same(r.render(), oracle_render(r), "bound again")
+    out = torch.full((n, 3, 64, 64), 9, dtype=torch.uint8, device="cuda")
+    r.render(out=out, scene_begin=5, scene_count=7)      # scene window through the cached description
+    full = r.render()
+    assert torch.equal(out[5:12], full[5:12]) and (out[:5] == 9).all() and (out[12:] == 9).all()
+    extra = r.add_node("models/box", instances_per_scene=1, model_scale=(0.3, 0.3, 0.3))     # scene structure
+    extra.set_positions(torch.tensor(np.random.default_rng(0).uniform(-1, 1, (n, 3)), dtype=torch.float32))
+    _assert_same(r.render(), oracle_render(r), "node added")
+    extra.np.removeNode()
+    _assert_same(r.render(), oracle_render(r), "node removed")
 
 
 def test_errors_are_loud():
