@@ -118,7 +118,9 @@ struct DeviceState {
     bool cap_worst_case = false;         // staged path: a frame overflowed its record lists -> size them for 6 per slot
     bool attr_binned = false;
 };
-std::mutex g_mu;
+// one lock per device: calls only enqueue work, and calls for different GPUs (one host thread per device is the
+// expected multi-GPU driver inside one process) do not wait for each other
+std::mutex g_mu[64];
 DeviceState g_dev[64];
 
 int device_state(int device, DeviceState **out) {
@@ -757,7 +759,7 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
 
     FrameDev f;
     fill_uniforms(d, f);
-    std::lock_guard<std::mutex> lock(g_mu);
+    std::lock_guard<std::mutex> lock(g_mu[device & 63]);
     DeviceState *st = nullptr;
     if (int rc = device_state(device, &st)) return rc;
     f.status = st->status;
@@ -930,7 +932,7 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
 int pbr_debug_pool(void *dst, size_t bytes) {
     int device = 0;
     cudaGetDevice(&device);
-    std::lock_guard<std::mutex> lock(g_mu);
+    std::lock_guard<std::mutex> lock(g_mu[device & 63]);
     DeviceState *st = nullptr;
     if (int rc = device_state(device, &st)) return rc;
     CUDA_TRY(cudaDeviceSynchronize());
@@ -966,7 +968,7 @@ int pbr_base_render(pbr_base_t b, const pbr_frame_desc *d, void *stream) {
 
     FrameDev f;
     fill_uniforms(d, f);
-    std::lock_guard<std::mutex> lock(g_mu);
+    std::lock_guard<std::mutex> lock(g_mu[device & 63]);
     DeviceState *st = nullptr;
     if (int rc = device_state(device, &st)) return rc;
     f.status = st->status;
@@ -1007,7 +1009,7 @@ int pbr_base_render(pbr_base_t b, const pbr_frame_desc *d, void *stream) {
 
 int pbr_device_status(int32_t device, int32_t *status_bits, int32_t clear) {
     if (!status_bits) return fail(PBR_EINVAL, "pbr_device_status: NULL output");
-    std::lock_guard<std::mutex> lock(g_mu);
+    std::lock_guard<std::mutex> lock(g_mu[device & 63]);
     int prev = 0;
     CUDA_TRY(cudaGetDevice(&prev));
     CUDA_TRY(cudaSetDevice(device));
@@ -1048,7 +1050,7 @@ unsigned long long pbr_kernel_launches(void) { return g_launches.load(std::memor
 int pbr_device_status_nosync(int32_t device, int32_t *status_bits) {
     if (!status_bits) return fail(PBR_EINVAL, "pbr_device_status_nosync: NULL output");
     if (device < 0 || device >= 64) return fail(PBR_EINVAL, "pbr_device_status_nosync: bad device %d", device);
-    std::lock_guard<std::mutex> lock(g_mu);
+    std::lock_guard<std::mutex> lock(g_mu[device & 63]);
     const DeviceState &st = g_dev[device];
     *status_bits = st.status_host ? ((st.status_host[0] ? DEVSTAT_WARP_OVERFLOW : 0) | (st.status_host[1] ? DEVSTAT_STAGED_OVERFLOW : 0)) : 0;
     return PBR_OK;

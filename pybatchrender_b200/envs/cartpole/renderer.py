@@ -33,6 +33,9 @@ _PARTS = {
 _RAIL_RGBA = (0.2, 0.2, 0.2, 1.0)
 _POLE_RGBA = (1.0, 0.7, 0.2, 1.0)
 _CART_RGBA_RAMP = ((0.6, 0.8, 1.0, 1.0), (1.0, 0.6, 0.8, 1.0))
+# pose channel (0..2 position, 3..5 H/P/R) <- state column: x drives both nodes, theta the pole's P angle
+_CART_COLUMNS = ((0, 0),)
+_POLE_COLUMNS = ((0, 0), (4, 2))
 
 
 class CartPoleRenderer(PBRRenderer):
@@ -94,10 +97,13 @@ class CartPoleRenderer(PBRRenderer):
     def _step(self, state_batch: torch.Tensor | None = None):
         if state_batch is None:
             return
-        state = torch.as_tensor(state_batch, dtype=torch.float32).detach()
+        state = state_batch
+        if not (isinstance(state, torch.Tensor) and state.dtype == torch.float32 and not state.requires_grad):
+            state = torch.as_tensor(state_batch, dtype=torch.float32).detach()
         if state.device != self.device:
             state = state.to(self.device, non_blocking=True)
-        state = self._fit_batch(state)
+        if state.shape[0] != self.num_scenes:
+            state = self._fit_batch(state)
 
         if self._native is not None:
             # cart = T(x, 0, 0); pole = T(x, pole_y, 0) . Ry(theta): bound to the state columns, evaluated by
@@ -107,8 +113,8 @@ class CartPoleRenderer(PBRRenderer):
                 self.cart.set_pose(pos=(x, 0.0, 0.0))
                 self.pole.set_pose(pos=(x, self.pole_y, 0.0), hpr=(0.0, theta, 0.0))
             else:                      # every later step: re-point the two state columns, nothing else
-                self.cart.bind_pose_columns(state, {0: 0})
-                self.pole.bind_pose_columns(state, {0: 0, 4: 2})
+                self.cart.bind_pose_columns(state, _CART_COLUMNS)
+                self.pole.bind_pose_columns(state, _POLE_COLUMNS)
             return
 
         # generic path (CPU): same sequence of setter calls as the reference

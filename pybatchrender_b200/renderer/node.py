@@ -118,6 +118,7 @@ class PBRNode(PBRShaderContext):
             self._pose = None              # dict(pos, hpr, scale) while the matrices are bound to pose channels
             self._pose_struct = None       # native pbr_pose_desc owned by the node (created by the first set_pose)
             self._pose_chans = None
+            self._pose_cols = None
             self._mirror_stale = False
             self.colbuf = torch.ones((B, 4), dtype=torch.float32, device=dev)
             self._set_shader_input("instancesPerScene", self.instances_per_scene)
@@ -155,7 +156,7 @@ class PBRNode(PBRShaderContext):
         # The node owns one native pose descriptor (pbr_pose_desc); a frame description points at it, so
         # re-binding channels here is all a step has to do.  Channels that did not change are skipped.
         chans = pos + hpr + (scale,)
-        prev = self._pose_chans
+        prev = self._pose_chans if self._pose_cols is None else None      # (columns were re-pointed since: rewrite all)
         if self._pose_struct is None:
             from .. import _native
             self._pose_struct = _native.new_pose_struct(self._matbuf)
@@ -176,28 +177,28 @@ class PBRNode(PBRShaderContext):
                     continue
                 dst.ptr, dst.stride, dst.constant = None, 0, float(c)
         self._pose_chans = chans           # keeps the channel tensors alive
+        self._pose_cols = None
         self._pose = dict(pos=pos, hpr=hpr, scale=scale)
         self._mirror_stale = True
 
-    def bind_pose_columns(self, state: torch.Tensor, columns: dict) -> None:
+    def bind_pose_columns(self, state: torch.Tensor, columns) -> None:
         """Fast re-binding for renderers that feed columns of one ``[B, k]`` float32 state tensor every step
-        (CartPole: ``{0: 0, 4: 2}`` = pos.x <- state[:, 0], hpr.P <- state[:, 2]): channel index (0..2 position,
-        3..5 H/P/R, 6 scale) -> column.  Equivalent to ``set_pose`` with ``state[:, col]`` views for those channels
-        and everything else unchanged, without creating the views.  Needs a previous ``set_pose``."""
+        (CartPole: ``((0, 0), (4, 2))`` = pos.x <- state[:, 0], hpr.P <- state[:, 2]): pairs of (channel index:
+        0..2 position, 3..5 H/P/R, 6 scale; column).  Equivalent to ``set_pose`` with ``state[:, col]`` views for
+        those channels and everything else unchanged, without creating the views.  Needs a previous ``set_pose``."""
         st = self._pose_struct
         if st is None or self._pose is None:
             raise RuntimeError("bind_pose_columns needs a pose bound with set_pose first")
-        if state.dim() != 2 or state.shape[0] != self.buf_instances or state.dtype != torch.float32 or not state.is_cuda:
+        if isinstance(columns, dict):
+            columns = tuple(columns.items())
+        shape = state.shape
+        if len(shape) != 2 or shape[0] != self.buf_instances or state.dtype != torch.float32 or not state.is_cuda:
             raise ValueError(f"bind_pose_columns: state must be a [{self.buf_instances}, k] float32 CUDA tensor")
-        base, s0, s1 = state.data_ptr(), state.stride(0), state.stride(1)
-        for k, col in columns.items():
+        base, (s0, s1) = state.data_ptr(), state.stride()
+        for k, col in columns:
             dst = st.pos[k] if k < 3 else (st.hpr[k - 3] if k < 6 else st.scale)
             dst.ptr, dst.stride = base + 4 * s1 * col, s0
-        chans = list(self._pose_chans)
-        for k, col in columns.items():
-            chans[k] = (state, col)        # (tensor, column): resolved lazily by _pose_desc
-        self._pose_chans = tuple(chans)
-        self._pose_state = state           # keeps the tensor alive until the next binding
+        self._pose_cols = (state, columns)     # keeps the tensor alive; mirrors resolve channels through it
         self._mirror_stale = True
 
     def _pose_desc(self):
@@ -218,8 +219,10 @@ class PBRNode(PBRShaderContext):
         B = self.buf_instances
         T = self._matbuf.view(B, 4, 4).transpose(1, 2).contiguous()
         sc = self._pose_chans[6]
-        if isinstance(sc, tuple):
-            sc = sc[0][:, sc[1]]
+        if self._pose_cols is not None:
+            for k, col in self._pose_cols[1]:
+                if k == 6:
+                    sc = self._pose_cols[0][:, col]
         sc = sc.reshape(B, 1, 1).clone() if isinstance(sc, torch.Tensor) else torch.full(
             (B, 1, 1), float(sc), dtype=torch.float32, device=self.device)
         self._transforms_b44, self._scale_b11 = T, sc
@@ -231,6 +234,7 @@ class PBRNode(PBRShaderContext):
             self._sync_mirrors()
             self._pose = None
             self._pose_chans = None
+            self._pose_cols = None
             self._touch()
 
     @property

@@ -233,9 +233,10 @@ class PBRRenderer:
         if self._node_cache is None:
             self._node_cache = self._drawable_nodes()
         cam = self._pbr_cam
-        return (self._scene_version, flags | self.render_flags, self.static_layer, id(cam), cam._version, cam.uniform,
-                self._light_params(), self._background_color, tuple(self.cfg.tile_resolution), int(self.cfg.num_channels),
-                tuple(n._version for n in self._node_cache))
+        L = self._pbr_light
+        return (self._scene_version, flags | self.render_flags, self.static_layer, cam, cam._version,
+                None if L is None else (L.ambient, L.dir_dir, L.dir_col, L.strength), self._background_color, self._out_shape,
+                [n._version for n in self._node_cache])
 
     def render(self, out: torch.Tensor | None = None, scene_begin: int = 0, scene_count: int | None = None,
                flags: int = 0) -> torch.Tensor:
