@@ -132,7 +132,12 @@ def _check(rc: int, what: str) -> None:
         raise NativeError(f"{what} failed ({rc}): {msg.decode(errors='replace') if msg else ''}")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)     # a plain C call: ~0.2 us instead of ~6 us
+
+
 def _stream_ptr(device: torch.device) -> int:
+    if _raw_stream is not None:
+        return _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
     return int(torch.cuda.current_stream(device).cuda_stream)
 
 
@@ -402,7 +407,7 @@ class Native:
         f.out = out.data_ptr()
         f.scene_begin = scene_begin
         f.scene_count = n - scene_begin if scene_count is None else scene_count
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _raw_stream(dev_index) if _raw_stream is not None else torch.cuda.current_stream(dev).cuda_stream
         if torch.cuda.current_device() == dev_index:
             rc = self.lib.pbr_render(fref, stream)
         else:
