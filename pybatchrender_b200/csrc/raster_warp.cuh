@@ -82,7 +82,7 @@ struct WScene {
     Rec *recs;                // [W_MAXREC]
     unsigned *masks;          // [nblk][W_MW]
     unsigned short *blist;    // [nblk]
-    unsigned *live;           // [W_MAXREC] (spare)
+    unsigned *live;           // [W_MAXREC] flat colour of each record, parked by the shade lanes of phase S
     unsigned *clipl;          // [W_MAXREC] packed slots of the triangles that need clipping
     int *ctr;                 // [4] overflow pool entry, clipped triangles, records drawn (S > 32), has int64 records
     unsigned char **out_slot; // out[scene], for the sweep
@@ -341,6 +341,10 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 // frame has completed" for whatever follows on the stream (copies, torch kernels: ordinary, fully ordered launches).
 #ifndef PBR_W_TRIGGER
 #define PBR_W_TRIGGER 1
+#endif
+// phase S with two lanes per triangle (edges / shade) instead of one
+#ifndef PBR_W_SPLIT_SETUP
+#define PBR_W_SPLIT_SETUP 1
 #endif
 #ifndef PBR_W_PREFETCH
 #define PBR_W_PREFETCH 0
@@ -616,12 +620,20 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         }
         group_sync<GW * 32>();
 
-        // ---- S: set-up of the survivors: integer edge equations, depth plane, flat shade (basic.frag:31-38)
-        // -> 64-byte record, binned into the per-block masks
+        // ---- S: set-up of the survivors.  Two lanes per triangle, in different warps: "edges" (integer edge
+        // equations, depth plane -> 64-byte record, binned into the per-block masks) and "shade" (flat colour:
+        // normal through the model matrix, ambient + Lambert, basic.frag:31-38 -> parked in live[], copied into
+        // the record by the scene's warp behind the barrier).  The phase is a dependent chain per lane and only
+        // ~150 of the CTA's 480 worker lanes have a triangle: splitting it shortens the chain by a third.
         {
             const int n_live = qctr[2];
+            const int n_work = PBR_W_SPLIT_SETUP ? 2 * n_live : n_live;
 #pragma unroll 1
-            for (int it = wl; it < n_live; it += GW * 32) {
+            for (int it0 = wl; it0 < n_work; it0 += GW * 32) {
+                // (roles are contiguous ranges of the work items, so whole warps share a role)
+                const bool do_shade = !PBR_W_SPLIT_SETUP || it0 >= n_live;
+                const bool do_edges = !PBR_W_SPLIT_SETUP || it0 < n_live;
+                const int it = (PBR_W_SPLIT_SETUP && it0 >= n_live) ? it0 - n_live : it0;
                 const unsigned e = livelist[it];
                 const int sl = (int)(e >> 16), s = (int)((e >> 8) & 255u), j = (int)(e & 255u);
                 int ni = 0;
@@ -632,27 +644,30 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 const int local = s - nd.slot_begin;
                 const int inst = fast_div(local, nd.tri_magic);
                 const int tri = local - inst * nd.n_tris;
-                const uint4 ti = __ldg(nd.tidx + tri);
-                const int vb = nd.vert_begin + inst * nd.n_verts;
                 const WScene sc = wscene(smem_raw + sl * region, nblk);
-                const int4 q0 = sc.proj[vb + ti.x], q1 = sc.proj[vb + ti.y], q2 = sc.proj[vb + ti.z];
-                int X[3] = {q0.x, q1.x, q2.x}, Y[3] = {q0.y, q1.y, q2.y};
-                float z[3] = {__int_as_float(q0.z), __int_as_float(q1.z), __int_as_float(q2.z)};
-                const unsigned id = (unsigned)(nd.id_begin + inst * nd.n_tris + tri) + 1u;
-                Rec r;
-                BBox bb;
-                if (setup_snapped(f, X, Y, z, (nd.flags & PBR_MESH_TWO_SIDED) != 0, id, 0, f.H, r, bb)) {
+                if (do_shade) {
                     const size_t b = nd.shared ? (size_t)inst : (size_t)(first_scene + sl) * nd.inst + inst;
                     float n[3];
                     const float4 n0 = __ldg(nd.tn + 3 * tri);
                     xform_normal_cols(sc.minst + (nd.inst_begin + inst) * 4, n0.x, n0.y, n0.z, n);
-                    r.col = shade(f, n, __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4)));
-                    if (r.meta & M_SLOW) sc.ctr[3] = 1;
-                    sc.recs[j] = r;
-                    // into the masks of the 8x8 blocks its box touches (edge-function reject per block): the
-                    // boxes are small (1-8 blocks) and the lanes of this phase are full, so a loop per lane
-                    // beats a second pass with one lane per (record, block) pair
-                    bin_record<W_MW>(r, bb, j, f.nbx, sc.masks);
+                    sc.live[j] = shade(f, n, __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4)));
+                }
+                if (do_edges) {
+                    const uint4 ti = __ldg(nd.tidx + tri);
+                    const int vb = nd.vert_begin + inst * nd.n_verts;
+                    const int4 q0 = sc.proj[vb + ti.x], q1 = sc.proj[vb + ti.y], q2 = sc.proj[vb + ti.z];
+                    int X[3] = {q0.x, q1.x, q2.x}, Y[3] = {q0.y, q1.y, q2.y};
+                    float z[3] = {__int_as_float(q0.z), __int_as_float(q1.z), __int_as_float(q2.z)};
+                    const unsigned id = (unsigned)(nd.id_begin + inst * nd.n_tris + tri) + 1u;
+                    Rec r;
+                    BBox bb;
+                    if (setup_snapped(f, X, Y, z, (nd.flags & PBR_MESH_TWO_SIDED) != 0, id, 0, f.H, r, bb)) {
+                        if (r.meta & M_SLOW) sc.ctr[3] = 1;
+                        sc.recs[j] = r;                    // (colour: filled in from live[] behind the barrier)
+                        // into the masks of the 8x8 blocks its box touches (edge-function reject per block): the
+                        // boxes are small (1-8 blocks), a loop per lane beats a pass with a lane per (record, block)
+                        bin_record<W_MW>(r, bb, j, f.nbx, sc.masks);
+                    }
                 }
             }
         }
@@ -674,6 +689,8 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         const int nlive = direct ? S : me.ctr[2];
         int nrec = nlive;
         scene_slow = nclip > 0 || me.ctr[3] != 0;     // (clipped fans: not tracked, assume so)
+        for (int j = lane; j < nlive; j += 32) recs[j].col = me.live[j];       // flat colours of phase S
+        __syncwarp();
         {
             // ---- B3: clipped triangles -> fan triangles in the spare record slots
             if (nclip > 0) {
