@@ -33,7 +33,8 @@ for k, nm in enumerate(names):
     v = rel[:, w, k]
     print(f"{nm:26s} mean {v.mean():6.2f}  p10 {np.percentile(v,10):6.2f}  p50 {np.percentile(v,50):6.2f}  p90 {np.percentile(v,90):6.2f}  max {v.max():6.2f} us")
 # per-SM end time
-sm = buf[:, 0, 7].astype(int)
+sm = (buf[:, 0, 7] & 0xffffffff).astype(int)
+wslot = (buf[:, :, 7] >> 32).astype(int)
 end = rel[:, :, 6].max(1)
 per_sm = {}
 for s_, e in zip(sm, end): per_sm[s_] = max(per_sm.get(s_, 0), e)
@@ -69,3 +70,13 @@ print('queue - setup histogram (us):', np.histogram(d, bins=[0,0.5,1,1.5,2,3,4,5
 c = 100
 print('cta 100 per warp setup-A:', np.round(rel[c, :14, 2] - rel[c, :14, 1], 2).tolist())
 print('cta 100 per warp queue-setup:', np.round(rel[c, :14, 3] - rel[c, :14, 2], 2).tolist())
+
+# ---- do CTAs in high hardware warp slots run their geometry faster than those in low slots?
+hi = wslot[:, 0] >= 16
+geo = rel[:, :14, 5].max(1) - rel[:, :, 0].min(1)          # entry -> barrier release
+swp = rel[:, :, 6].max(1) - rel[:, :14, 5].max(1)
+life = rel[:, :, 6].max(1) - rel[:, :, 0].min(1)
+for name, sel in (("warp slots 0-15 ", ~hi), ("warp slots 16-31", hi)):
+    if sel.any():
+        print(f"CTAs in {name}: {int(sel.sum()):4d}  geometry {geo[sel].mean():5.2f} us  sweep {swp[sel].mean():5.2f} us  lifetime {life[sel].mean():5.2f} us")
+print("warp slot of warp 0, first CTAs:", wslot[:12, 0].tolist())

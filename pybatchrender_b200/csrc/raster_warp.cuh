@@ -364,7 +364,12 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     unsigned long long *tdump = reinterpret_cast<unsigned long long *>(f.ovf_recs) + ((size_t)blockIdx.x * 16 + warp) * 8;
 #define W_STAMP(k) do { if (lane == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tdump[k] = t_; } } while (0)
     W_STAMP(0);
-    if (lane == 0) { unsigned smid_; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_)); tdump[7] = smid_; }
+    if (lane == 0) {
+        unsigned smid_, wid_;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid_));        // hardware warp slot
+        tdump[7] = smid_ | ((unsigned long long)wid_ << 32);
+    }
 #else
 #define W_STAMP(k) do { } while (0)
 #endif
