@@ -20,10 +20,11 @@ for i in range(20): r.step(st[i % 4], out=outs[i % 5])
 torch.cuda.synchronize()
 lib = ctypes.CDLL(os.environ['PBR_B200_LIB'])
 nc = (N + 13) // 14
-buf = np.zeros((nc, 16, 8), dtype=np.uint64)
+buf = np.zeros((nc, 16, 16), dtype=np.uint64)
 rc = lib.pbr_debug_pool(buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(buf.nbytes))
 assert rc == 0
 t = buf[:, :, :7].astype(np.int64)
+tf = buf[:, :, 8:14].astype(np.int64)
 t0 = t[:, :, 0].min()
 rel = (t - t0) / 1000.0
 names = ['entry', 'after A (vertices)', 'after setup', 'before tma wait/queue', 'after tma wait', 'after barrier', 'sweep done']
@@ -80,3 +81,17 @@ for name, sel in (("warp slots 0-15 ", ~hi), ("warp slots 16-31", hi)):
     if sel.any():
         print(f"CTAs in {name}: {int(sel.sum()):4d}  geometry {geo[sel].mean():5.2f} us  sweep {swp[sel].mean():5.2f} us  lifetime {life[sel].mean():5.2f} us")
 print("warp slot of warp 0, first CTAs:", wslot[:12, 0].tolist())
+
+# ---- fine-grained phases (stamps 8..13 of each warp), relative to the CTA's own entry
+ent = t[:, :, 0].min(1, keepdims=True)
+names2 = ['entry barrier', 'M barrier', 'A barrier', 'B barrier', 'S barrier', 'tail: colours + clipped done']
+prev = np.zeros(nc)
+for k, nm in enumerate(names2):
+    v = (tf[:, :14, k] - ent) / 1000.0
+    m = v.mean(1)
+    print(f"  {nm:30s} mean {m.mean():6.2f} us after CTA entry  (+{(m - prev).mean():5.2f})   slowest warp {v.max(1).mean():6.2f}")
+    prev = m
+q = (t[:, :14, 3] - ent) / 1000.0
+print(f"  {'block list built (stamp 3)':30s} mean {q.mean():6.2f} us after CTA entry  (+{(q.mean(1) - prev).mean():5.2f})")
+bq = (t[:, :14, 5] - ent) / 1000.0
+print(f"  {'pre-sweep barrier released':30s} mean {bq.mean():6.2f} us after CTA entry")

@@ -361,7 +361,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
 #ifdef PBR_W_TIMING
-    unsigned long long *tdump = reinterpret_cast<unsigned long long *>(f.ovf_recs) + ((size_t)blockIdx.x * 16 + warp) * 8;
+    unsigned long long *tdump = reinterpret_cast<unsigned long long *>(f.ovf_recs) + ((size_t)blockIdx.x * 16 + warp) * 16;
 #define W_STAMP(k) do { if (lane == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tdump[k] = t_; } } while (0)
     W_STAMP(0);
     if (lane == 0) {
@@ -392,6 +392,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     constexpr bool LATE_WAIT = TMA_BG && PBR_W_LATE_WAIT != 0;
     if (threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; qctr[2] = 0; qctr[3] = 0; qctr[6] = 0; }
     __syncthreads();          // counters initialised (all warps arrive together: cheap)
+    W_STAMP(8);
     // The thread that drives the TMA engine: lane 0 of the LAST helper warp when there is one.  Issuing the
     // CTA's bulk stores blocks the issuing thread for microseconds (time stamps: a scene warp that did it
     // reached the sweep 3.5 us after its 13 neighbours, and the whole CTA waited for it at the barrier), so
@@ -524,6 +525,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             }
         }
         group_sync<GW * 32>();
+        W_STAMP(9);
 
         // ---- A: vertices (basic.vert:24-43)
         {
@@ -574,6 +576,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         if (TMA_BG && BG_T == 0 && threadIdx.x == 0) issue_bg_stores(f, qctr, WARPS);      // the load has had phase A to arrive
         if (split_bg && active) write_background_part(f, out_scene, HW, lane, 1);
         group_sync<GW * 32>();
+        W_STAMP(10);
         if (PBR_W_BG_AFTER == 1 && threadIdx.x == 0) atomicExch(&qctr[6], 1);
 
         // ---- B: classify triangle slots; survivors go to the CTA's live list as (scene, slot, record index)
@@ -624,6 +627,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             }
         }
         group_sync<GW * 32>();
+        W_STAMP(11);
 
         // ---- S: set-up of the survivors.  Two lanes per triangle, in different warps: "edges" (integer edge
         // equations, depth plane -> 64-byte record, binned into the per-block masks) and "shade" (flat colour:
@@ -679,6 +683,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         W_STAMP(2);
         if (split_bg && active) write_background_part(f, out_scene, HW, lane, 2);
         group_sync<GW * 32>();
+        W_STAMP(12);
         if (PBR_W_BG_AFTER == 2 && threadIdx.x == 0) atomicExch(&qctr[6], 2);
     }
 
@@ -789,6 +794,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 }
             }
             __syncwarp();     // records + masks complete; background stores ordered before patches
+            W_STAMP(13);
 
             // ---- list of this scene's non-empty blocks
             if (f.debug != 2) {
