@@ -685,10 +685,23 @@ __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bm
 // is "strictly smaller depth wins": the id never has to be compared or carried, and a pixel was won by this sweep
 // iff its depth changed.  Saves 4 of the 10 compare / select instructions per covered (block, record) pair -- they
 // all go to the ALU pipe, which is what bounds the small-scene kernel.
+#ifndef PBR_SWEEP_PAIRS
+#define PBR_SWEEP_PAIRS 1
+#endif
 struct PixelState32 {
     unsigned z0, z1;             // depth bits (non-negative floats order like unsigned integers)
     unsigned c0, c1;             // packed RGBA8 of the current winner
 };
+
+// one record of the 32-bit sweep: depth of both pixels, strict less-than, select
+__device__ __forceinline__ void update32(PixelState32 &ps, const FastCov &c, const int4 &ec, const float4 &zq) {
+    const float za = fmaf((float)c.F2 * zq.w, zq.z, fmaf((float)c.F1 * zq.w, zq.y, zq.x));
+    const float zc = fmaf((float)c.G2 * zq.w, zq.z, fmaf((float)c.G1 * zq.w, zq.y, zq.x));
+    const unsigned ka = __float_as_uint(za), kc = __float_as_uint(zc);
+    const bool w0 = c.cov0 & (ka < ps.z0), w1 = c.cov1 & (kc < ps.z1);
+    ps.z0 = w0 ? ka : ps.z0; ps.c0 = w0 ? (unsigned)ec.y : ps.c0;
+    ps.z1 = w1 ? kc : ps.z1; ps.c1 = w1 ? (unsigned)ec.y : ps.c1;
+}
 
 template <int MWORDS>
 __device__ __forceinline__ void raster_block32(const Rec *recs, const unsigned *bmask, int px, int py0, bool ok0,
@@ -696,6 +709,28 @@ __device__ __forceinline__ void raster_block32(const Rec *recs, const unsigned *
 #pragma unroll 1
     for (int w = 0; w < MWORDS; ++w) {
         unsigned m = bmask[w];
+#if PBR_SWEEP_PAIRS
+        // two records per iteration: their loads and edge functions are independent, so the warp has twice the
+        // instructions in flight between dependent ones (with 4 register words of pixel state instead of 6 this
+        // fits 64 registers; the depth updates stay in draw order)
+#pragma unroll 1
+        while (m & (m - 1)) {
+            const int t1 = w * 32 + __ffs(m) - 1;
+            m &= m - 1;
+            const int t2 = w * 32 + __ffs(m) - 1;
+            m &= m - 1;
+            const Rec &r1 = recs[t1], &r2 = recs[t2];
+            const int4 ea1 = *reinterpret_cast<const int4 *>(&r1.e[0]), ea2 = *reinterpret_cast<const int4 *>(&r2.e[0]);
+            const int4 eb1 = *reinterpret_cast<const int4 *>(&r1.e[4]), eb2 = *reinterpret_cast<const int4 *>(&r2.e[4]);
+            const int4 ec1 = *reinterpret_cast<const int4 *>(&r1.e[8]), ec2 = *reinterpret_cast<const int4 *>(&r2.e[8]);
+            const FastCov c1 = fast_cover(ea1, eb1, ec1, px, py0, ok0, ok1);
+            const FastCov c2 = fast_cover(ea2, eb2, ec2, px, py0, ok0, ok1);
+            const bool any1 = __any_sync(0xffffffffu, c1.cov0 || c1.cov1);
+            const bool any2 = __any_sync(0xffffffffu, c2.cov0 || c2.cov1);
+            if (any1) update32(ps, c1, ec1, *reinterpret_cast<const float4 *>(&r1.z0));
+            if (any2) update32(ps, c2, ec2, *reinterpret_cast<const float4 *>(&r2.z0));
+        }
+#endif
 #pragma unroll 1
         while (m) {
             const int t = w * 32 + __ffs(m) - 1;
@@ -706,13 +741,7 @@ __device__ __forceinline__ void raster_block32(const Rec *recs, const unsigned *
             const int4 ec = *reinterpret_cast<const int4 *>(&r.e[8]);         // B2 col id meta
             const FastCov c = fast_cover(ea, eb, ec, px, py0, ok0, ok1);
             if (!__any_sync(0xffffffffu, c.cov0 || c.cov1)) continue;
-            const float4 zq = *reinterpret_cast<const float4 *>(&r.z0);       // z0 dz1 dz2 invA
-            const float za = fmaf((float)c.F2 * zq.w, zq.z, fmaf((float)c.F1 * zq.w, zq.y, zq.x));
-            const float zc = fmaf((float)c.G2 * zq.w, zq.z, fmaf((float)c.G1 * zq.w, zq.y, zq.x));
-            const unsigned ka = __float_as_uint(za), kc = __float_as_uint(zc);
-            const bool w0 = c.cov0 & (ka < ps.z0), w1 = c.cov1 & (kc < ps.z1);
-            ps.z0 = w0 ? ka : ps.z0; ps.c0 = w0 ? (unsigned)ec.y : ps.c0;
-            ps.z1 = w1 ? kc : ps.z1; ps.c1 = w1 ? (unsigned)ec.y : ps.c1;
+            update32(ps, c, ec, *reinterpret_cast<const float4 *>(&r.z0));   // z0 dz1 dz2 invA
         }
     }
 }
