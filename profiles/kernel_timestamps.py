@@ -95,3 +95,8 @@ q = (t[:, :14, 3] - ent) / 1000.0
 print(f"  {'block list built (stamp 3)':30s} mean {q.mean():6.2f} us after CTA entry  (+{(q.mean(1) - prev).mean():5.2f})")
 bq = (t[:, :14, 5] - ent) / 1000.0
 print(f"  {'pre-sweep barrier released':30s} mean {bq.mean():6.2f} us after CTA entry")
+
+print("per warp index, mean us after CTA entry: entry-barrier, M, A, B, S barriers")
+for w in range(15):
+    v = (tf[:, w, :5] - ent) / 1000.0
+    print(f"  warp {w:2d}: " + "  ".join(f"{v[:, k].mean():6.2f}" for k in range(5)))
