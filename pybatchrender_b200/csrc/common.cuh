@@ -104,9 +104,19 @@ static_assert(sizeof(FrameDev) <= 8192, "FrameDev is a kernel parameter");
 __device__ __forceinline__ float pose_chan(const pbr_channel &c, size_t b) {
     return c.ptr ? __ldg(c.ptr + b * (size_t)c.stride) : c.constant;
 }
+// one out-of-line copy of sincosf per kernel: inlined three times (with its large-argument path) it was 600 SASS
+// instructions of straight-line code that a CTA runs once -- the geometry phases pay for instruction fetch, not issue
+__device__ __noinline__ float2 pose_sincos(float x) {
+    float sn, cs;
+    sincosf(x, &sn, &cs);
+    return make_float2(sn, cs);
+}
 __device__ __forceinline__ void pose_angle(const pbr_channel &c, size_t b, float &sn, float &cs) {
     sn = 0.0f; cs = 1.0f;
-    if (c.ptr != nullptr || c.constant != 0.0f) sincosf(pose_chan(c, b), &sn, &cs);
+    if (c.ptr != nullptr || c.constant != 0.0f) {
+        const float2 v = pose_sincos(pose_chan(c, b));
+        sn = v.x; cs = v.y;
+    }
 }
 __device__ __forceinline__ void pose_matrix(const PoseDev &d, size_t b, float *M) {
     float sh, ch, sp, cp, sr, cr;
