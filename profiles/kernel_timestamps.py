@@ -100,3 +100,6 @@ print("per warp index, mean us after CTA entry: entry-barrier, M, A, B, S barrie
 for w in range(15):
     v = (tf[:, w, :5] - ent) / 1000.0
     print(f"  warp {w:2d}: " + "  ".join(f"{v[:, k].mean():6.2f}" for k in range(5)))
+
+stg = (buf[:, :14, 14].astype(np.int64) - t[:, :, 0].min(1, keepdims=True)) / 1000.0
+print(f"stage-in barrier released {stg.mean():.2f} us after CTA entry (p10 {np.percentile(stg,10):.2f}, p90 {np.percentile(stg,90):.2f})")
