@@ -45,7 +45,6 @@ struct NodeDev {
     unsigned tri_magic;   // floor(2^32 / n_tris) + 1   (x / n_tris == __umulhi(x, magic) for x * n_tris < 2^32)
     unsigned vert_magic;  // floor(2^32 / n_verts) + 1
     int pose_idx;         // >= 0: matrices come from FrameDev::poses[pose_idx] instead of mats
-    int stage_vert, stage_tri;   // small-scene kernel: where this node's mesh sits in the CTA's stage-in area
 };
 
 struct Rec;
@@ -77,8 +76,6 @@ struct FrameDev {
     int w_region;           // small-scene kernel: bytes of one scene's shared-memory region
     int w_qctr_off;         // ... and offset of the CTA's queue counters (after the regions, the queue and the live list)
     unsigned w_inst_magic, w_vert_magic, w_slot_magic;   // div_magic of total_inst / total_verts / total_slots
-    int w_stage_off;        // byte offset of the CTA's stage-in area (raster_warp.cuh: WStage)
-    int w_sum_verts, w_sum_tris;   // unique vertices / triangles summed over the frame's nodes
     int plane_stride;       // bytes between colour planes in shared memory (multiple of 16)
     int linear;             // 1: the shared colour tile is a byte image of out[scene]
     int smooth;             // 1: some triangles are shaded per pixel (SMOOTH kernel instantiations)
@@ -93,7 +90,6 @@ struct FrameDev {
                             // so scenes without clipped / int64 records may use 32-bit depth keys (raster_block32)
     int sync_early;         // small-scene kernel: wait for the previous grid before the first write to `out`
                             // (the previous launch on this stream may still be writing the same buffer)
-    int n_frame_poses;      // entries of poses[] in use
     PoseDev poses[MAX_FRAME_POSES];
     NodeDev nodes[PBR_MAX_NODES];
 };
@@ -115,34 +111,26 @@ __device__ __noinline__ float2 pose_sincos(float x) {
     sincosf(x, &sn, &cs);
     return make_float2(sn, cs);
 }
-// pose from its seven channel values (v: pos xyz, hpr, scale).  An angle channel that is the constant 0 skips sincosf.
-__device__ __forceinline__ void pose_angle_value(const pbr_channel &c, float x, float &sn, float &cs) {
+__device__ __forceinline__ void pose_angle(const pbr_channel &c, size_t b, float &sn, float &cs) {
     sn = 0.0f; cs = 1.0f;
     if (c.ptr != nullptr || c.constant != 0.0f) {
-        const float2 v = pose_sincos(x);
+        const float2 v = pose_sincos(pose_chan(c, b));
         sn = v.x; cs = v.y;
     }
 }
-__device__ __forceinline__ void pose_matrix_values(const PoseDev &d, const float *v, float *M) {
+__device__ __forceinline__ void pose_matrix(const PoseDev &d, size_t b, float *M) {
     float sh, ch, sp, cp, sr, cr;
-    pose_angle_value(d.hpr[0], v[3], sh, ch);
-    pose_angle_value(d.hpr[1], v[4], sp, cp);
-    pose_angle_value(d.hpr[2], v[5], sr, cr);
-    const float s = v[6];
+    pose_angle(d.hpr[0], b, sh, ch);
+    pose_angle(d.hpr[1], b, sp, cp);
+    pose_angle(d.hpr[2], b, sr, cr);
+    const float s = pose_chan(d.scale, b);
     const float r00 = ch * cp, r01 = ch * sp * sr - sh * cr, r02 = ch * sp * cr + sh * sr;
     const float r10 = sh * cp, r11 = sh * sp * sr + ch * cr, r12 = sh * sp * cr - ch * sr;
     const float r20 = -sp, r21 = cp * sr, r22 = cp * cr;
     M[0] = r00 * s; M[1] = r10 * s; M[2] = r20 * s; M[3] = 0.0f;
     M[4] = r01 * s; M[5] = r11 * s; M[6] = r21 * s; M[7] = 0.0f;
     M[8] = r02 * s; M[9] = r12 * s; M[10] = r22 * s; M[11] = 0.0f;
-    M[12] = v[0]; M[13] = v[1]; M[14] = v[2]; M[15] = 1.0f;
-}
-__device__ __forceinline__ void pose_matrix(const PoseDev &d, size_t b, float *M) {
-    float v[7];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { v[k] = pose_chan(d.pos[k], b); v[3 + k] = pose_chan(d.hpr[k], b); }
-    v[6] = pose_chan(d.scale, b);
-    pose_matrix_values(d, v, M);
+    M[12] = pose_chan(d.pos[0], b); M[13] = pose_chan(d.pos[1], b); M[14] = pose_chan(d.pos[2], b); M[15] = 1.0f;
 }
 
 constexpr int DEVSTAT_WARP_OVERFLOW = 1;   // small-scene kernel ran out of record slots

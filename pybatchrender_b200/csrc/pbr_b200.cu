@@ -365,7 +365,6 @@ enum NodeMode { NODES_ALL = 0, NODES_SKIP_BASE = 1, NODES_SHARED_ONLY = 2 };
 
 struct NodeStats {
     long long slots = 0, verts = 0, insts = 0;
-    long long sum_verts = 0, sum_tris = 0;       // unique vertices / triangles of the active nodes' meshes
     bool any_smooth = false, any_textured = false, warp_ok = true;
     int skipped = 0;
     long long skipped_id_end = 0;         // draw index past the last triangle of the skipped (static layer) nodes
@@ -436,8 +435,6 @@ static int fill_nodes(const pbr_frame_desc *d, int device, NodeMode mode, FrameD
         nd.bsphere = make_float4(n.mesh->bsphere[0], n.mesh->bsphere[1], n.mesh->bsphere[2], n.mesh->bsphere[3]);
         nd.inst_begin = (int)st.insts;
         st.insts += n.instances_per_scene;
-        nd.stage_vert = (int)st.sum_verts; nd.stage_tri = (int)st.sum_tris;
-        st.sum_verts += n.mesh->n_verts; st.sum_tris += n.mesh->n_tris;
         nd.tri_magic = div_magic((unsigned)n.mesh->n_tris);
         nd.vert_magic = div_magic((unsigned)n.mesh->n_verts);
         st.slots += ntri;
@@ -446,7 +443,6 @@ static int fill_nodes(const pbr_frame_desc *d, int device, NodeMode mode, FrameD
         if (n.instances_per_scene >= 8192 || n.mesh->n_tris >= 8192) st.warp_ok = false;
     }
     st.poses_in_frame = st.n_poses > 0 && st.n_poses <= MAX_FRAME_POSES;
-    f.n_frame_poses = st.poses_in_frame ? st.n_poses : 0;
     if (!st.poses_in_frame)
         for (int i = 0; i < f.n_nodes; ++i) f.nodes[i].pose_idx = -1;
     f.smooth = st.any_smooth ? 1 : 0;
@@ -773,11 +769,8 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
     const int W = f.W, H = f.H;
     const int nbx = (W + 7) / 8;
     const int H8 = ((H + 7) / 8) * 8;
-    auto stage_bytes = [&](const NodeStats &ns, int warps) {
-        return (size_t)warp_stage_layout(warps, (int)ns.insts, (int)ns.sum_verts, (int)ns.sum_tris, nbx * (H8 / 8)).end;
-    };
+    const size_t warp_smem = warp_smem_bytes(nbx * (H8 / 8), W_WARPS);
     auto warp_eligible = [&](const NodeStats &ns) {
-        const size_t warp_smem = warp_smem_bytes(nbx * (H8 / 8), W_WARPS, 0, stage_bytes(ns, W_WARPS));
         // once a scene overflowed the small-scene kernel's record slots (too many clipped fan
         // triangles; sticky flag in host-mapped memory) this device keeps to the general kernel
         return ns.warp_ok && !ns.any_smooth && st->status_host[0] == 0 && !(d->flags & PBR_FRAME_FORCE_GENERAL) && ns.slots <= W_MAXSLOT && ns.verts <= W_MAXVERT && ns.insts <= W_MAXINST &&
@@ -805,7 +798,6 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         f.w_inst_magic = div_magic((unsigned)f.total_inst);
         f.w_vert_magic = div_magic((unsigned)f.total_verts);
         f.w_slot_magic = div_magic((unsigned)f.total_slots);
-        f.w_sum_verts = (int)ns.sum_verts; f.w_sum_tris = (int)ns.sum_tris;
         // w_qctr_off is set where the kernel variant (scenes per CTA) is chosen
         f.plane_stride = H * W;
         f.linear = 1;
@@ -881,8 +873,8 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         static const int tma_mode = getenv("PBR_B200_WARP_TMA") ? atoi(getenv("PBR_B200_WARP_TMA")) : -1;   // 0 / 1 force, else auto
         const size_t tile_bytes = (size_t)f.C * H * W;
         const size_t two_per_sm = ((size_t)st->max_smem_optin + 1024 - 2 * 1024) / 2;
-        const size_t tma_big = warp_smem_bytes(nbx * (H8 / 8), W_WARPS_TMA, tile_bytes, stage_bytes(ns, W_WARPS_TMA));
-        const size_t tma_small = warp_smem_bytes(nbx * (H8 / 8), W_WARPS_TMA_SMALL, tile_bytes, stage_bytes(ns, W_WARPS_TMA_SMALL));
+        const size_t tma_big = warp_smem_bytes(nbx * (H8 / 8), W_WARPS_TMA, tile_bytes);
+        const size_t tma_small = warp_smem_bytes(nbx * (H8 / 8), W_WARPS_TMA_SMALL, tile_bytes);
         const bool big = tma_big <= two_per_sm;
         const size_t tma_smem = big ? tma_big : tma_small;
         const bool tma_ok = f.base_color != nullptr && (tile_bytes & 15) == 0 && tma_smem <= (size_t)st->max_smem_optin;
@@ -892,21 +884,17 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         if (use_tma && big) {
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS_TMA - 1) / W_WARPS_TMA);
             f.w_qctr_off = (int)warp_qctr_offset(nbx * (H8 / 8), W_WARPS_TMA);
-            f.w_stage_off = (int)warp_stage_offset(nbx * (H8 / 8), W_WARPS_TMA, tile_bytes);
             CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS_TMA, true>, wgrid, 32 * (W_WARPS_TMA + PBR_W_HELPERS), tma_smem, stream, f));
             COUNT_LAUNCH();
         } else if (use_tma) {
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS_TMA_SMALL - 1) / W_WARPS_TMA_SMALL);
             f.w_qctr_off = (int)warp_qctr_offset(nbx * (H8 / 8), W_WARPS_TMA_SMALL);
-            f.w_stage_off = (int)warp_stage_offset(nbx * (H8 / 8), W_WARPS_TMA_SMALL, tile_bytes);
             CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS_TMA_SMALL, true>, wgrid, 32 * (W_WARPS_TMA_SMALL + PBR_W_HELPERS), tma_smem, stream, f));
             COUNT_LAUNCH();
         } else {
             static const size_t smem_pad = getenv("PBR_B200_WARP_SMEM_PAD") ? (size_t)atoi(getenv("PBR_B200_WARP_SMEM_PAD")) : 0;   // occupancy experiments
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS - 1) / W_WARPS);
             f.w_qctr_off = (int)warp_qctr_offset(nbx * (H8 / 8), W_WARPS);
-            f.w_stage_off = (int)warp_stage_offset(nbx * (H8 / 8), W_WARPS, 0);
-            const size_t warp_smem = warp_smem_bytes(nbx * (H8 / 8), W_WARPS, 0, stage_bytes(ns, W_WARPS));
             CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS, false>, wgrid, 32 * W_WARPS, warp_smem + smem_pad, stream, f));
             COUNT_LAUNCH();
         }

@@ -37,7 +37,7 @@ namespace pbr {
 constexpr int W_MAXREC = 48;     // records per scene (triangle slots that survive + clipped fans); < 64 (mask bits)
 constexpr int W_MAXSLOT = 36;    // eligibility: leaves >= 12 spare records for clipped fans
 constexpr int W_MAXVERT = 48;    // (instance, vertex) pairs per scene
-constexpr int W_MAXINST = 8;     // instances per scene (their model matrices are parked in shared memory)
+constexpr int W_MAXINST = 16;    // instances per scene (their 3x3 model matrices are parked in shared memory)
 constexpr int W_GEOM_BYTES = W_MAXVERT * 32 + W_MAXINST * 64;    // parked vertices (clip + projected) and matrices
 constexpr int W_MW = 2;          // mask words per block (64 record bits)
 #ifndef W_WARPS
@@ -63,33 +63,10 @@ __host__ __device__ inline size_t warp_scene_bytes(int nblk) {
 __host__ __device__ inline size_t warp_qctr_offset(int nblk, int warps) {
     return (size_t)warps * warp_scene_bytes(nblk) + align16((size_t)warps * nblk * 4) + align16((size_t)warps * W_MAXSLOT * 4);
 }
-// The CTA's stage-in area: everything the geometry phases read from global memory, fetched in ONE round of loads at
-// kernel entry (a global load takes ~1.5 us next to the frame's bulk stores; five phases that each began with one
-// spent most of their time waiting).  Per scene: VP (4 x 16 B), per instance 7 pose channel values (32 B) and the
-// colour (16 B); per node: unique vertices, index triples and face normals of its mesh; the static layer's block flags.
-struct WStage {
-    int vp, pose, cols, vpos, tidx, tn0, flags, end;      // byte offsets from the start of the area
-};
-__host__ __device__ inline WStage warp_stage_layout(int warps, int total_inst, int sum_verts, int sum_tris, int nblk) {
-    WStage o;
-    size_t p = 0;
-    o.vp = (int)p;    p += (size_t)warps * 64;
-    o.pose = (int)p;  p += (size_t)warps * total_inst * 32;
-    o.cols = (int)p;  p += (size_t)warps * total_inst * 16;
-    o.vpos = (int)p;  p += (size_t)sum_verts * 16;
-    o.tidx = (int)p;  p += (size_t)sum_tris * 16;
-    o.tn0 = (int)p;   p += (size_t)sum_tris * 16;
-    o.flags = (int)p; p += align16((size_t)nblk);
-    o.end = (int)p;
-    return o;
-}
 // shared memory of a CTA of `warps` scenes: scene regions + block queue + counters (+ mbarrier and the
 // background image when the background is written by TMA)
-__host__ __device__ inline size_t warp_stage_offset(int nblk, int warps, size_t tma_tile_bytes) {
-    return warp_qctr_offset(nblk, warps) + 32 + (tma_tile_bytes ? align16(tma_tile_bytes) : 0);
-}
-__host__ __device__ inline size_t warp_smem_bytes(int nblk, int warps, size_t tma_tile_bytes, size_t stage_bytes) {
-    return warp_stage_offset(nblk, warps, tma_tile_bytes) + stage_bytes;
+__host__ __device__ inline size_t warp_smem_bytes(int nblk, int warps, size_t tma_tile_bytes = 0) {
+    return warp_qctr_offset(nblk, warps) + 16 + (tma_tile_bytes ? 16 + align16(tma_tile_bytes) : 0);
 }
 #ifndef PBR_W_WARPS_TMA
 #define PBR_W_WARPS_TMA 14
@@ -495,91 +472,33 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     } else if (worker && f.sync_early && f.write_mats) {
         asm volatile("griddepcontrol.wait;" ::: "memory");       // helpers write matrices in phase M
     }
-    // the CTA's stage-in area (see WStage)
-    const WStage so = warp_stage_layout(WARPS, f.total_inst, f.w_sum_verts, f.w_sum_tris, nblk);
-    unsigned char *const stage = smem_raw + f.w_stage_off;
-    float4 *const s_vp = reinterpret_cast<float4 *>(stage + so.vp);          // [WARPS][4]
-    float4 *const s_pose = reinterpret_cast<float4 *>(stage + so.pose);      // [WARPS][total_inst][2]
-    float4 *const s_cols = reinterpret_cast<float4 *>(stage + so.cols);      // [WARPS][total_inst]
-    float4 *const s_vpos = reinterpret_cast<float4 *>(stage + so.vpos);      // [sum_verts]
-    uint4 *const s_tidx = reinterpret_cast<uint4 *>(stage + so.tidx);        // [sum_tris]
-    float4 *const s_tn0 = reinterpret_cast<float4 *>(stage + so.tn0);        // [sum_tris] normal of corner 0
-    unsigned char *const s_flags = stage + so.flags;                         // [nblk] static layer covers the block
     if (worker && geom) {
         const int wl = warp * 32 + lane;     // this lane among the worker lanes
 
-        // ---- stage-in: every global load of the geometry phases, issued now, in one round (see WStage)
-        {
-            const int TI = f.total_inst;
-            const int n_inst = n_sc * TI, n_vp = n_sc * 4;
-            const int n_mesh = f.w_sum_verts + 2 * f.w_sum_tris;
-            const int n_flag = f.base_flags != nullptr ? (nblk + 15) / 16 : 0;
-            const int n_all = n_inst + n_vp + n_mesh + n_flag;
-#pragma unroll 1
-            for (int it = wl; it < n_all; it += GW * 32) {
-                if (it < n_inst) {                   // an instance: matrix (or pose channel values) and colour
-                    const int sl = fast_div(it, f.w_inst_magic);
-                    const int gi = it - sl * TI;
-                    int ni = 0;
-#pragma unroll 1
-                    for (int i = 1; i < f.n_nodes; ++i)
-                        if (gi >= f.nodes[i].inst_begin) ni = i;
-                    const NodeDev &nd = f.nodes[ni];
-                    const int inst = gi - nd.inst_begin;
-                    const size_t b = nd.shared ? (size_t)inst : (size_t)(first_scene + sl) * nd.inst + inst;
-                    const float4 col = __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4));
-                    if (nd.pose_idx >= 0) {
-                        const PoseDev &d = f.poses[nd.pose_idx];
-                        float v[8];
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) { v[k] = pose_chan(d.pos[k], b); v[3 + k] = pose_chan(d.hpr[k], b); }
-                        v[6] = pose_chan(d.scale, b); v[7] = 0.0f;
-                        s_pose[it * 2] = make_float4(v[0], v[1], v[2], v[3]);
-                        s_pose[it * 2 + 1] = make_float4(v[4], v[5], v[6], v[7]);
-                    } else {
-                        const float4 *m4 = reinterpret_cast<const float4 *>(nd.mats + b * 16);
-                        const float4 c0 = __ldg(m4), c1 = __ldg(m4 + 1), c2 = __ldg(m4 + 2), c3 = __ldg(m4 + 3);
-                        float4 *mi = wscene(smem_raw + sl * region, nblk).minst + gi * 4;
-                        mi[0] = c0; mi[1] = c1; mi[2] = c2; mi[3] = c3;
-                    }
-                    s_cols[it] = col;
-                } else if (it < n_inst + n_vp) {     // a column of a scene's VP
-                    const int k = it - n_inst;
-                    s_vp[k] = __ldg(reinterpret_cast<const float4 *>(f.vp + (size_t)(first_scene + (k >> 2)) * 16) + (k & 3));
-                } else if (it < n_inst + n_vp + n_mesh) {      // mesh data of the nodes
-                    int k = it - n_inst - n_vp;
-                    const int which = k < f.w_sum_verts ? 0 : (k < f.w_sum_verts + f.w_sum_tris ? 1 : 2);
-                    k -= which == 0 ? 0 : (which == 1 ? f.w_sum_verts : f.w_sum_verts + f.w_sum_tris);
-                    int ni = 0;
-#pragma unroll 1
-                    for (int i = 1; i < f.n_nodes; ++i)
-                        if (k >= (which == 0 ? f.nodes[i].stage_vert : f.nodes[i].stage_tri)) ni = i;
-                    const NodeDev &nd = f.nodes[ni];
-                    if (which == 0) s_vpos[k] = __ldg(nd.vpos + (k - nd.stage_vert));
-                    else if (which == 1) s_tidx[k] = __ldg(nd.tidx + (k - nd.stage_tri));
-                    else s_tn0[k] = __ldg(nd.tn + 3 * (k - nd.stage_tri));
-                } else {                             // 16 block flags of the static layer
-                    const int k = it - n_inst - n_vp - n_mesh;
-                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                    if (16 * k + 16 <= nblk) {
-                        // (base_flags is cudaMalloc'ed: 16-byte aligned)
-                        v = __ldg(reinterpret_cast<const uint4 *>(f.base_flags) + k);
-                    } else {
-                        unsigned char tmp[16];
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) tmp[q] = 16 * k + q < nblk ? __ldg(f.base_flags + 16 * k + q) : (unsigned char)0;
-                        v = *reinterpret_cast<const uint4 *>(tmp);
-                    }
-                    reinterpret_cast<uint4 *>(s_flags)[k] = v;
-                }
+        // L1 is empty at kernel entry and every phase below starts with a load that the phase before it cannot
+        // issue (barrier in between): ask for those lines now -- the scenes' VP rows (phase A) and instance
+        // colours (phase S), the meshes' vertices, index triples and normals (phases A, B, S)
+        if (PBR_W_PREFETCH) {
+            int k = wl;
+            if (k < n_sc) {
+                prefetch_l1(f.vp + (size_t)(first_scene + k) * 16);
+            } else if ((k -= n_sc) < f.n_nodes * 8) {
+                const NodeDev &nd = f.nodes[k >> 3];
+                const int part = k & 7;
+                if (part == 0) prefetch_l1(nd.vpos);
+                else if (part <= 2) { if ((part - 1) * 8 < nd.n_tris) prefetch_l1(nd.tidx + (part - 1) * 8); }
+                else if ((part - 3) * 8 < 3 * nd.n_tris) prefetch_l1(nd.tn + (part - 3) * 8);
+            } else if ((k -= f.n_nodes * 8) < n_sc * f.n_nodes) {
+                const int sl = k / f.n_nodes;
+                const NodeDev &nd = f.nodes[k - sl * f.n_nodes];
+                prefetch_l1(nd.cols + (nd.shared ? (size_t)0 : (size_t)(first_scene + sl) * nd.inst) * 4);
             }
         }
-        group_sync<GW * 32>();
-        W_STAMP(14);
 
-        // ---- M: posed instances: model matrix from the staged pose channel values (the state tensor of the caller:
-        // reference envs/cartpole/renderer.py:125-138 + shader_context.py:47-84), parked beside the loaded ones
-        if (f.n_frame_poses > 0) {
+        // ---- M: instances.  A posed node's model matrix is computed here from its pose channels (the state
+        // tensor of the caller: reference envs/cartpole/renderer.py:125-138 + shader_context.py:47-84), other
+        // nodes' matrices are read from their matrix buffer; parked in shared memory for phases A and S.
+        {
             const int TI = f.total_inst;
 #pragma unroll 1
             for (int it = wl; it < n_sc * TI; it += GW * 32) {
@@ -590,24 +509,22 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 for (int i = 1; i < f.n_nodes; ++i)
                     if (gi >= f.nodes[i].inst_begin) ni = i;
                 const NodeDev &nd = f.nodes[ni];
-                if (nd.pose_idx < 0) continue;
-                const float4 a = s_pose[it * 2], c = s_pose[it * 2 + 1];
-                const float v[7] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z};
+                const int inst = gi - nd.inst_begin;
+                const size_t b = nd.shared ? (size_t)inst : (size_t)(first_scene + sl) * nd.inst + inst;
                 float M[16];
-                pose_matrix_values(f.poses[nd.pose_idx], v, M);
+                if (nd.pose_idx >= 0) pose_matrix(f.poses[nd.pose_idx], b, M);
+                else load_mat(nd.mats + b * 16, M);
                 float4 *mi = wscene(smem_raw + sl * region, nblk).minst + gi * 4;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) mi[j] = make_float4(M[4 * j], M[4 * j + 1], M[4 * j + 2], M[4 * j + 3]);
-                if (f.write_mats) {
-                    const int inst = gi - nd.inst_begin;
-                    const size_t b = nd.shared ? (size_t)inst : (size_t)(first_scene + sl) * nd.inst + inst;
+                if (f.write_mats && nd.pose_idx >= 0) {
                     float4 *o = reinterpret_cast<float4 *>(f.poses[nd.pose_idx].out_mats + b * 16);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) o[j] = make_float4(M[4 * j], M[4 * j + 1], M[4 * j + 2], M[4 * j + 3]);
                 }
             }
-            group_sync<GW * 32>();
         }
+        group_sync<GW * 32>();
         W_STAMP(9);
 
         // ---- A: vertices (basic.vert:24-43)
@@ -635,14 +552,8 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                         M[4 * j] = a.x; M[4 * j + 1] = a.y; M[4 * j + 2] = a.z; M[4 * j + 3] = a.w;
                     }
                 }
-                {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 a = s_vp[sl * 4 + j];
-                        VP[4 * j] = a.x; VP[4 * j + 1] = a.y; VP[4 * j + 2] = a.z; VP[4 * j + 3] = a.w;
-                    }
-                }
-                const float4 p = s_vpos[nd.stage_vert + vert];
+                load_mat(f.vp + (size_t)(first_scene + sl) * 16, VP);
+                const float4 p = __ldg(nd.vpos + vert);
                 float world[4], c[4];
                 mat_vec4(M, p.x, p.y, p.z, 1.0f, world);
                 mat_vec4(VP, world[0], world[1], world[2], world[3], c);
@@ -686,7 +597,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                     const int local = s - nd.slot_begin;
                     const int inst = fast_div(local, nd.tri_magic);
                     const int tri = local - inst * nd.n_tris;
-                    const uint4 ti = s_tidx[nd.stage_tri + tri];
+                    const uint4 ti = __ldg(nd.tidx + tri);
                     const int vb = nd.vert_begin + inst * nd.n_verts;
                     const int4 *pj = wscene(smem_raw + sl * region, nblk).proj;
                     const int4 q0 = pj[vb + ti.x], q1 = pj[vb + ti.y], q2 = pj[vb + ti.z];
@@ -744,13 +655,14 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 const int tri = local - inst * nd.n_tris;
                 const WScene sc = wscene(smem_raw + sl * region, nblk);
                 if (do_shade) {
+                    const size_t b = nd.shared ? (size_t)inst : (size_t)(first_scene + sl) * nd.inst + inst;
                     float n[3];
-                    const float4 n0 = s_tn0[nd.stage_tri + tri];
+                    const float4 n0 = __ldg(nd.tn + 3 * tri);
                     xform_normal_cols(sc.minst + (nd.inst_begin + inst) * 4, n0.x, n0.y, n0.z, n);
-                    sc.live[j] = shade(f, n, s_cols[sl * f.total_inst + nd.inst_begin + inst]);
+                    sc.live[j] = shade(f, n, __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4)));
                 }
                 if (do_edges) {
-                    const uint4 ti = s_tidx[nd.stage_tri + tri];
+                    const uint4 ti = __ldg(nd.tidx + tri);
                     const int vb = nd.vert_begin + inst * nd.n_verts;
                     const int4 q0 = sc.proj[vb + ti.x], q1 = sc.proj[vb + ti.y], q2 = sc.proj[vb + ti.z];
                     int X[3] = {q0.x, q1.x, q2.x}, Y[3] = {q0.y, q1.y, q2.y};
@@ -930,7 +842,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             unsigned it = ((unsigned)warp << 16) | me.blist[i] | (scene_slow ? 0x40000000u : 0u);
             if (f.base_flags != nullptr) {
                 const int bb = (int)((it >> 8) & 255u) * f.nbx + (int)(it & 255u);
-                if (s_flags[bb] != 0) it |= 0x80000000u;
+                if (__ldg(f.base_flags + bb) != 0) it |= 0x80000000u;
             }
             queue[qbase + i] = it;
         }
