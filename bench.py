@@ -413,26 +413,39 @@ def timed_run(wl: Workload, K: int, W: int, barrier, native):
                     wl.step(i)
             return g, native.kernel_launches() - l0
 
-        g_full, l_full = capture(STATE_RING)
-        tail = K % STATE_RING
-        g_tail, l_tail = capture(tail) if tail else (None, 0)
+        if K <= 256:
+            # short runs (the driver's --steps 20): ONE graph of exactly K steps, so that no host-side graph launch
+            # falls inside the timed region (with 8 ranks on one host a late second launch showed as 19.3 us per step)
+            g_all, l_all = capture(K)
 
-        def run_steps(k):
-            # exactly k steps: whole graphs, then the tail graph (k % STATE_RING == tail by construction)
-            for _ in range(k // STATE_RING):
+            def run_steps(k):
+                g_all.replay()
+            for _ in range(max(2, (W + K - 1) // K)):
+                g_all.replay()
+            launches = l_all
+            for i in range(K):
+                last[i % wl.out_ring] = i
+        else:
+            g_full, l_full = capture(STATE_RING)
+            tail = K % STATE_RING
+            g_tail, l_tail = capture(tail) if tail else (None, 0)
+
+            def run_steps(k):
+                # exactly k steps: whole graphs, then the tail graph (k % STATE_RING == tail by construction)
+                for _ in range(k // STATE_RING):
+                    g_full.replay()
+                if k % STATE_RING:
+                    g_tail.replay()
+            # warm-up: >= W steps and, whatever W is, at least two replays of every graph that is timed
+            for _ in range(max(2, (W + STATE_RING - 1) // STATE_RING)):
                 g_full.replay()
-            if k % STATE_RING:
-                g_tail.replay()
-        # warm-up: >= W steps and, whatever W is, at least two replays of every graph that is timed
-        for _ in range(max(2, (W + STATE_RING - 1) // STATE_RING)):
-            g_full.replay()
-        if g_tail is not None:
-            for _ in range(2):
-                g_tail.replay()
-        launches = (K // STATE_RING) * l_full + (l_tail if tail else 0)
-        # what each ring buffer holds at the end: the full graph ran (in the warm-up at least), then the tail graph
-        for i in list(range(STATE_RING)) + list(range(tail)):
-            last[i % wl.out_ring] = i
+            if g_tail is not None:
+                for _ in range(2):
+                    g_tail.replay()
+            launches = (K // STATE_RING) * l_full + (l_tail if tail else 0)
+            # what each ring buffer holds at the end: the full graph ran (in the warm-up at least), then the tail graph
+            for i in list(range(STATE_RING)) + list(range(tail)):
+                last[i % wl.out_ring] = i
     else:
         for i in range(max(3, W)):
             wl.step(i)
@@ -611,8 +624,9 @@ def measure_config(config, K, W, dev, rank, world, distributed, barrier, native,
                    "parallelism": f"scene-sharded x{world}, no collective",
                    "l2": f"output ring of {wl.out_ring} x {wl.frame_bytes / 1e6:.1f} MB (> 126 MB L2 in flight)"
                          + (f"; state ring of {STATE_RING}" if wl.states is not None else ""),
-                   "launch": (f"CUDA graphs of {STATE_RING} steps, each replayed before the timed region; one kernel "
-                              "per step, consecutive frames overlap through programmatic dependent launch")
+                   "launch": ((f"one CUDA graph of the {K} timed steps" if K <= 256 else f"CUDA graphs of {STATE_RING} steps")
+                              + ", replayed before the timed region; one kernel per step, consecutive frames overlap "
+                                "through programmatic dependent launch")
                    if wl.use_graphs else "eager: instance cull + geometry pre-pass + staged raster per launch chunk"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic,
