@@ -864,6 +864,9 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     }
     const int nitems = WARPS > 1 ? qctr[0] : nlist;
     const int lx = lane & 7, ly = lane >> 3;
+    const int tileW = f.W, tileH = f.H, tileNbx = f.nbx;
+    const bool rgba = f.C == 4;
+    const bool keys32 = f.keys32 != 0 && direct;
     int next = 0;
 #pragma unroll 1
     while (true) {
@@ -895,12 +898,12 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         unsigned char *out_scene = *reinterpret_cast<unsigned char *const *>(sreg + region - 8);
 
         const int px = bx * 8 + lx, py0 = by * 8 + ly;
-        const bool ok0 = px < f.W && py0 < f.H, ok1 = px < f.W && py0 + 4 < f.H;
-        const int b = by * f.nbx + bx;
+        const bool ok0 = px < tileW && py0 < tileH, ok1 = px < tileW && py0 + 4 < tileH;
+        const int b = by * tileNbx + bx;
         // winners of this block: did this sweep win the lane's pixels, and with which colour
         bool won0, won1;
         unsigned c0, c1;
-        if (f.keys32 && direct && !(item & 0x40000000u)) {
+        if (keys32 && !(item & 0x40000000u)) {
             // no clipped / int64 records in this scene, records in draw order, static layer drawn first:
             // 32-bit depth keys (see raster_block32)
             PixelState32 q;
@@ -939,19 +942,21 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             __threadfence_block();
             stores_done = true;
         }
-        unsigned char *p = out_scene + py0 * f.W + px;
+        // (tile width / channel count from locals: read through `f` they are re-loaded after every byte store,
+        // which the compiler cannot prove not to alias the frame description)
+        unsigned char *p = out_scene + py0 * tileW + px;
         if (won0) {
             p[0] = (unsigned char)(c0 & 255u);
             p[HW] = (unsigned char)((c0 >> 8) & 255u);
             p[2 * HW] = (unsigned char)((c0 >> 16) & 255u);
-            if (f.C == 4) p[3 * HW] = (unsigned char)(c0 >> 24);
+            if (rgba) p[3 * HW] = (unsigned char)(c0 >> 24);
         }
         if (won1) {
-            p += 4 * f.W;
+            p += 4 * tileW;
             p[0] = (unsigned char)(c1 & 255u);
             p[HW] = (unsigned char)((c1 >> 8) & 255u);
             p[2 * HW] = (unsigned char)((c1 >> 16) & 255u);
-            if (f.C == 4) p[3 * HW] = (unsigned char)(c1 >> 24);
+            if (rgba) p[3 * HW] = (unsigned char)(c1 >> 24);
         }
     }
     W_STAMP(6);
