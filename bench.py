@@ -471,7 +471,9 @@ def timed_run(wl: Workload, K: int, W: int, barrier, native):
 def roofline_leg(wl: Workload, K: int):
     """The raster kernel(s) alone on resident inputs: average launch time over the same number of steps."""
     import torch
-    reps = max(1, K // STATE_RING)
+    # (at least 8 replays = 128 launches: the first launch of a chain has no frame ahead of it to overlap with, and the
+    # figure wanted here is the kernel's average duration, not the start-up of a short chain)
+    reps = max(8, K // STATE_RING)
     if wl.use_graphs:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):

@@ -103,3 +103,21 @@ for w in range(15):
 
 stg = (buf[:, :14, 14].astype(np.int64) - t[:, :, 0].min(1, keepdims=True)) / 1000.0
 print(f"stage-in barrier released {stg.mean():.2f} us after CTA entry (p10 {np.percentile(stg,10):.2f}, p90 {np.percentile(stg,90):.2f})")
+
+# ---- are the two CTAs of an SM in step (both in geometry, then both in the sweep) or staggered?
+ent1 = rel[:, :, 0].min(1); bar1 = rel[:, :14, 5].max(1); end1 = rel[:, :, 6].max(1)
+by_sm = {}
+for c in range(nc): by_sm.setdefault(int(sm[c]), []).append(c)
+d_ent, ovl = [], []
+for s_, cs in by_sm.items():
+    if len(cs) != 2: continue
+    a, b = cs
+    d_ent.append(abs(ent1[a] - ent1[b]))
+    # share of a's sweep during which b is in its geometry (and the reverse)
+    for x, y in ((a, b), (b, a)):
+        lo, hi2 = max(bar1[x], ent1[y]), min(end1[x], bar1[y])
+        ovl.append(max(0.0, hi2 - lo) / max(1e-9, end1[x] - bar1[x]))
+d_ent = np.array(d_ent)
+print(f"entry offset between the two CTAs of an SM: mean {d_ent.mean():.2f} us p10 {np.percentile(d_ent,10):.2f} p50 {np.percentile(d_ent,50):.2f} p90 {np.percentile(d_ent,90):.2f}; "
+      f"share of a sweep spent beside the other CTA's geometry (same frame only): {np.mean(ovl):.2f}")
+print("entry times of the last frame's CTAs (us after the first): p10 %.2f p50 %.2f p90 %.2f max %.2f" % tuple(np.percentile(ent1, [10, 50, 90, 100])))

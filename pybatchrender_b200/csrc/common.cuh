@@ -698,6 +698,9 @@ __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bm
 #ifndef PBR_SWEEP_PAIRS
 #define PBR_SWEEP_PAIRS 0
 #endif
+#ifndef PBR_SWEEP_PREFETCH
+#define PBR_SWEEP_PREFETCH 0
+#endif
 struct PixelState32 {
     unsigned z0, z1;             // depth bits (non-negative floats order like unsigned integers)
     unsigned c0, c1;             // packed RGBA8 of the current winner
@@ -741,6 +744,47 @@ __device__ __forceinline__ void raster_block32(const Rec *recs, const unsigned *
             if (any2) update32(ps, c2, ec2, *reinterpret_cast<const float4 *>(&r2.z0));
         }
 #endif
+#if PBR_SWEEP_PREFETCH
+        // the next record's edge words are loaded while this one is evaluated (two copies of the body, the
+        // record registers ping-pong between them: no moves)
+        if (m == 0u) continue;
+        const Rec *ra = recs + (w * 32 + __ffs(m) - 1), *rb = ra;
+        m &= m - 1;
+        int4 aa = *reinterpret_cast<const int4 *>(&ra->e[0]), ab = *reinterpret_cast<const int4 *>(&ra->e[4]),
+             ac = *reinterpret_cast<const int4 *>(&ra->e[8]);
+        int4 ba, bb, bc;
+#pragma unroll 1
+        while (true) {
+            bool more = m != 0u;
+            if (more) {
+                rb = recs + (w * 32 + __ffs(m) - 1);
+                m &= m - 1;
+                ba = *reinterpret_cast<const int4 *>(&rb->e[0]);
+                bb = *reinterpret_cast<const int4 *>(&rb->e[4]);
+                bc = *reinterpret_cast<const int4 *>(&rb->e[8]);
+            }
+            {
+                const FastCov c = fast_cover(aa, ab, ac, px, py0, ok0, ok1);
+                if (__any_sync(0xffffffffu, c.cov0 || c.cov1))
+                    update32(ps, c, ac, *reinterpret_cast<const float4 *>(&ra->z0));
+            }
+            if (!more) break;
+            more = m != 0u;
+            if (more) {
+                ra = recs + (w * 32 + __ffs(m) - 1);
+                m &= m - 1;
+                aa = *reinterpret_cast<const int4 *>(&ra->e[0]);
+                ab = *reinterpret_cast<const int4 *>(&ra->e[4]);
+                ac = *reinterpret_cast<const int4 *>(&ra->e[8]);
+            }
+            {
+                const FastCov c = fast_cover(ba, bb, bc, px, py0, ok0, ok1);
+                if (__any_sync(0xffffffffu, c.cov0 || c.cov1))
+                    update32(ps, c, bc, *reinterpret_cast<const float4 *>(&rb->z0));
+            }
+            if (!more) break;
+        }
+#else
 #pragma unroll 1
         while (m) {
             const int t = w * 32 + __ffs(m) - 1;
@@ -753,6 +797,7 @@ __device__ __forceinline__ void raster_block32(const Rec *recs, const unsigned *
             if (!__any_sync(0xffffffffu, c.cov0 || c.cov1)) continue;
             update32(ps, c, ec, *reinterpret_cast<const float4 *>(&r.z0));   // z0 dz1 dz2 invA
         }
+#endif
     }
 }
 
