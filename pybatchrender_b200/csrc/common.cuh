@@ -496,9 +496,21 @@ __device__ __forceinline__ bool block_hit(const Rec &r, const BBox &bb, int bx, 
 }
 
 // set record t's bit in every block its triangle can touch.  masks: [nblk][MWORDS]
+// Record t of a mask word is bit 31 - (t & 31): the record that is drawn first is the HIGHEST set bit, which one FLO
+// finds (ffs is BREV + FLO, both on the quarter-rate XU pipe), and the bit index times the record size is subtracted
+// from the address of the word's record 31.
+__device__ __forceinline__ unsigned rec_bit(int t) { return 0x80000000u >> (t & 31); }
+// pops the first record of a mask word: returns 31 - (its index in the word)
+__device__ __forceinline__ int pop_rec(unsigned &m) {
+    int p;
+    asm("bfind.u32 %0, %1;" : "=r"(p) : "r"(m));      // (31 - __clz(m) is rewritten into clz arithmetic again)
+    m ^= 1u << p;
+    return p;
+}
+
 template <int MWORDS>
 __device__ __forceinline__ void bin_record(const Rec &r, const BBox &bb, int t, int nbx, unsigned *masks) {
-    const unsigned bit = 1u << (t & 31);
+    const unsigned bit = rec_bit(t);
     const int word = t >> 5;
     const bool small = (bb.bx1 - bb.bx0) + (bb.by1 - bb.by0) <= 1;       // <= 2 blocks: no reject test
     for (int by = bb.by0; by <= bb.by1; ++by)
@@ -675,8 +687,7 @@ __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bm
         unsigned m = bmask[w];
 #pragma unroll 1
         while (m) {
-            const int t = w * 32 + __ffs(m) - 1;
-            m &= m - 1;
+            const int t = w * 32 + 31 - pop_rec(m);
             const Rec &r = recs[t];
             // the whole record in four 128-bit shared loads, issued back to back
             const int4 ea = *reinterpret_cast<const int4 *>(&r.e[0]);         // Eo0 Eo1 Eo2 A0
@@ -690,17 +701,11 @@ __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bm
 }
 
 // The same sweep with 32-bit depth keys, for callers that can promise (a) no int64 records and no per-pixel
-// shading among `recs`, (b) the records are visited in draw order (ascending bit index == ascending draw id) and
+// shading among `recs`, (b) the records are visited in draw order (ascending record index == ascending draw id) and
 // (c) whatever the pixel state was initialised from was drawn before all of them.  Then "smaller (depth, id) wins"
 // is "strictly smaller depth wins": the id never has to be compared or carried, and a pixel was won by this sweep
 // iff its depth changed.  Saves 4 of the 10 compare / select instructions per covered (block, record) pair -- they
 // all go to the ALU pipe, which is what bounds the small-scene kernel.
-#ifndef PBR_SWEEP_PAIRS
-#define PBR_SWEEP_PAIRS 0
-#endif
-#ifndef PBR_SWEEP_PREFETCH
-#define PBR_SWEEP_PREFETCH 0
-#endif
 struct PixelState32 {
     unsigned z0, z1;             // depth bits (non-negative floats order like unsigned integers)
     unsigned c0, c1;             // packed RGBA8 of the current winner
@@ -719,77 +724,15 @@ __device__ __forceinline__ void update32(PixelState32 &ps, const FastCov &c, con
 template <int MWORDS>
 __device__ __forceinline__ void raster_block32(const Rec *recs, const unsigned *bmask, int px, int py0, bool ok0,
                                                bool ok1, PixelState32 &ps) {
+    // (measured slower, see profiles/README.md: two records per iteration, and loading the next record's words
+    // while this one is evaluated -- the loop is bound by what it issues, not by its shared-memory loads)
 #pragma unroll 1
     for (int w = 0; w < MWORDS; ++w) {
         unsigned m = bmask[w];
-#if PBR_SWEEP_PAIRS
-        // two records per iteration: their loads and edge functions are independent, so the warp has twice the
-        // instructions in flight between dependent ones (with 4 register words of pixel state instead of 6 this
-        // fits 64 registers; the depth updates stay in draw order).  Measured: 17.10 vs 16.87 us per frame -- off.
-#pragma unroll 1
-        while (m & (m - 1)) {
-            const int t1 = w * 32 + __ffs(m) - 1;
-            m &= m - 1;
-            const int t2 = w * 32 + __ffs(m) - 1;
-            m &= m - 1;
-            const Rec &r1 = recs[t1], &r2 = recs[t2];
-            const int4 ea1 = *reinterpret_cast<const int4 *>(&r1.e[0]), ea2 = *reinterpret_cast<const int4 *>(&r2.e[0]);
-            const int4 eb1 = *reinterpret_cast<const int4 *>(&r1.e[4]), eb2 = *reinterpret_cast<const int4 *>(&r2.e[4]);
-            const int4 ec1 = *reinterpret_cast<const int4 *>(&r1.e[8]), ec2 = *reinterpret_cast<const int4 *>(&r2.e[8]);
-            const FastCov c1 = fast_cover(ea1, eb1, ec1, px, py0, ok0, ok1);
-            const FastCov c2 = fast_cover(ea2, eb2, ec2, px, py0, ok0, ok1);
-            const bool any1 = __any_sync(0xffffffffu, c1.cov0 || c1.cov1);
-            const bool any2 = __any_sync(0xffffffffu, c2.cov0 || c2.cov1);
-            if (any1) update32(ps, c1, ec1, *reinterpret_cast<const float4 *>(&r1.z0));
-            if (any2) update32(ps, c2, ec2, *reinterpret_cast<const float4 *>(&r2.z0));
-        }
-#endif
-#if PBR_SWEEP_PREFETCH
-        // the next record's edge words are loaded while this one is evaluated (two copies of the body, the
-        // record registers ping-pong between them: no moves)
-        if (m == 0u) continue;
-        const Rec *ra = recs + (w * 32 + __ffs(m) - 1), *rb = ra;
-        m &= m - 1;
-        int4 aa = *reinterpret_cast<const int4 *>(&ra->e[0]), ab = *reinterpret_cast<const int4 *>(&ra->e[4]),
-             ac = *reinterpret_cast<const int4 *>(&ra->e[8]);
-        int4 ba, bb, bc;
-#pragma unroll 1
-        while (true) {
-            bool more = m != 0u;
-            if (more) {
-                rb = recs + (w * 32 + __ffs(m) - 1);
-                m &= m - 1;
-                ba = *reinterpret_cast<const int4 *>(&rb->e[0]);
-                bb = *reinterpret_cast<const int4 *>(&rb->e[4]);
-                bc = *reinterpret_cast<const int4 *>(&rb->e[8]);
-            }
-            {
-                const FastCov c = fast_cover(aa, ab, ac, px, py0, ok0, ok1);
-                if (__any_sync(0xffffffffu, c.cov0 || c.cov1))
-                    update32(ps, c, ac, *reinterpret_cast<const float4 *>(&ra->z0));
-            }
-            if (!more) break;
-            more = m != 0u;
-            if (more) {
-                ra = recs + (w * 32 + __ffs(m) - 1);
-                m &= m - 1;
-                aa = *reinterpret_cast<const int4 *>(&ra->e[0]);
-                ab = *reinterpret_cast<const int4 *>(&ra->e[4]);
-                ac = *reinterpret_cast<const int4 *>(&ra->e[8]);
-            }
-            {
-                const FastCov c = fast_cover(ba, bb, bc, px, py0, ok0, ok1);
-                if (__any_sync(0xffffffffu, c.cov0 || c.cov1))
-                    update32(ps, c, bc, *reinterpret_cast<const float4 *>(&rb->z0));
-            }
-            if (!more) break;
-        }
-#else
+        const char *const last = reinterpret_cast<const char *>(recs + w * 32 + 31);       // record of bit 0
 #pragma unroll 1
         while (m) {
-            const int t = w * 32 + __ffs(m) - 1;
-            m &= m - 1;
-            const Rec &r = recs[t];
+            const Rec &r = *reinterpret_cast<const Rec *>(last + pop_rec(m) * -(int)sizeof(Rec));
             const int4 ea = *reinterpret_cast<const int4 *>(&r.e[0]);         // Eo0 Eo1 Eo2 A0
             const int4 eb = *reinterpret_cast<const int4 *>(&r.e[4]);         // A1 A2 B0 B1
             const int4 ec = *reinterpret_cast<const int4 *>(&r.e[8]);         // B2 col id meta
@@ -797,7 +740,6 @@ __device__ __forceinline__ void raster_block32(const Rec *recs, const unsigned *
             if (!__any_sync(0xffffffffu, c.cov0 || c.cov1)) continue;
             update32(ps, c, ec, *reinterpret_cast<const float4 *>(&r.z0));   // z0 dz1 dz2 invA
         }
-#endif
     }
 }
 

@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(THREADS) raster_staged_kernel(const __grid_con
             const int y0 = max(bb.by0, band_by0), y1 = min(bb.by1, band_by0 + f.nby - 1);
             if (y0 <= y1) {
                 const Rec &r = recs[tid];
-                const unsigned bit = 1u << (tid & 31);
+                const unsigned bit = rec_bit(tid);
                 const int word = tid >> 5;
                 const bool small = (bb.bx1 - bb.bx0) + (bb.by1 - bb.by0) <= 1;
                 for (int by = y0; by <= y1; ++by)
