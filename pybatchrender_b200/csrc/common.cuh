@@ -504,7 +504,9 @@ __device__ __forceinline__ unsigned rec_bit(int t) { return 0x80000000u >> (t & 
 __device__ __forceinline__ int pop_rec(unsigned &m) {
     int p;
     asm("bfind.u32 %0, %1;" : "=r"(p) : "r"(m));      // (31 - __clz(m) is rewritten into clz arithmetic again)
-    m ^= 1u << p;
+    unsigned below;
+    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(below) : "r"(0), "r"(p));      // bits 0 .. p-1
+    m &= below;
     return p;
 }
 
@@ -726,20 +728,29 @@ __device__ __forceinline__ void raster_block32(const Rec *recs, const unsigned *
                                                bool ok1, PixelState32 &ps) {
     // (measured slower, see profiles/README.md: two records per iteration, and loading the next record's words
     // while this one is evaluated -- the loop is bound by what it issues, not by its shared-memory loads)
+    static_assert(MWORDS == 2, "the block's two mask words are read with one 64-bit load");
+    const uint2 mm = *reinterpret_cast<const uint2 *>(bmask);
+    unsigned m = mm.x, m_next = mm.y;
+    // the records are in shared memory: one 32-bit address per word, the loads take it plus an immediate
+    unsigned last = (unsigned)__cvta_generic_to_shared(recs + 31);                           // record of bit 0
 #pragma unroll 1
-    for (int w = 0; w < MWORDS; ++w) {
-        unsigned m = bmask[w];
-        const char *const last = reinterpret_cast<const char *>(recs + w * 32 + 31);       // record of bit 0
+    while (true) {
 #pragma unroll 1
         while (m) {
-            const Rec &r = *reinterpret_cast<const Rec *>(last + pop_rec(m) * -(int)sizeof(Rec));
-            const int4 ea = *reinterpret_cast<const int4 *>(&r.e[0]);         // Eo0 Eo1 Eo2 A0
-            const int4 eb = *reinterpret_cast<const int4 *>(&r.e[4]);         // A1 A2 B0 B1
-            const int4 ec = *reinterpret_cast<const int4 *>(&r.e[8]);         // B2 col id meta
+            const unsigned a = last + (unsigned)(pop_rec(m) * -(int)sizeof(Rec));
+            int4 ea, eb, ec;                                                  // Eo0 Eo1 Eo2 A0 | A1 A2 B0 B1 | B2 col id meta
+            asm("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(ea.x), "=r"(ea.y), "=r"(ea.z), "=r"(ea.w) : "r"(a));
+            asm("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4+16];" : "=r"(eb.x), "=r"(eb.y), "=r"(eb.z), "=r"(eb.w) : "r"(a));
+            asm("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4+32];" : "=r"(ec.x), "=r"(ec.y), "=r"(ec.z), "=r"(ec.w) : "r"(a));
             const FastCov c = fast_cover(ea, eb, ec, px, py0, ok0, ok1);
             if (!__any_sync(0xffffffffu, c.cov0 || c.cov1)) continue;
-            update32(ps, c, ec, *reinterpret_cast<const float4 *>(&r.z0));   // z0 dz1 dz2 invA
+            float4 zq;                                                        // z0 dz1 dz2 invA
+            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+48];" : "=f"(zq.x), "=f"(zq.y), "=f"(zq.z), "=f"(zq.w) : "r"(a));
+            update32(ps, c, ec, zq);
         }
+        if (m_next == 0u) break;
+        m = m_next; m_next = 0u;
+        last += 32u * (unsigned)sizeof(Rec);
     }
 }
 

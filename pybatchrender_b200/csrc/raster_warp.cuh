@@ -840,12 +840,15 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     W_STAMP(4);
     if (WARPS > 1) {
         int qbase = 0;
+        const unsigned wide_keys = (f.keys32 != 0 && direct) ? 0u : 0x20000000u;
         if (lane == 0 && nlist > 0) qbase = atomicAdd(&qctr[0], nlist);
         qbase = __shfl_sync(0xffffffffu, qbase, 0);
         // bit 31: the static layer covers part of the block (looked up here, one lane per item, so
         // that the sweep does not start every item with a dependent global load)
         for (int i = lane; i < nlist; i += 32) {
-            unsigned it = ((unsigned)warp << 16) | me.blist[i] | (scene_slow ? 0x40000000u : 0u);
+            // bit 30: the scene has int64 / clipped records; bit 29: sweep it with 64-bit keys (that, or the frame's
+            // draw order does not allow 32-bit ones)
+            unsigned it = ((unsigned)warp << 16) | me.blist[i] | (scene_slow ? 0x60000000u : 0u) | wide_keys;
             if (f.base_flags != nullptr) {
                 const int bb = (int)((it >> 8) & 255u) * f.nbx + (int)(it & 255u);
                 if (__ldg(f.base_flags + bb) != 0) it |= 0x80000000u;
@@ -871,10 +874,15 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     const int tileW = f.W, tileH = f.H, tileNbx = f.nbx;
     const bool rgba = f.C == 4;
     const bool keys32 = f.keys32 != 0 && direct;
+    const unsigned pop_addr = smem_u32(&qctr[1]);
     int next = 0;
     int ahead = 0;                                        // PBR_W_POP_AHEAD: lane 0 holds the next item's index
-    if (PBR_W_POP_AHEAD && WARPS > 1 && lane == 0)
-        asm volatile("atom.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(ahead) : "r"(smem_u32(&qctr[1])) : "memory");
+    // (atom.inc with a bound below 2^32 - 1 stays one ATOMS.INC; ptxas rewrites a single-lane atom.add, and inc with
+    // bound 0xffffffff, into leader election + popc + ATOMS.ADD, ~20 instructions.  A predicated atom in the asm
+    // block instead of the branch: ptxas turns it back into the branch.)
+#define PBR_W_POP(dst)                                                                                              \
+    if (lane == 0) asm volatile("atom.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(dst) : "r"(pop_addr) : "memory")
+    if (PBR_W_POP_AHEAD && WARPS > 1) PBR_W_POP(ahead);
 #pragma unroll 1
     while (true) {
         int i;
@@ -885,27 +893,23 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             i = __shfl_sync(0xffffffffu, ahead, 0);
             if (i >= nitems) break;
             item = queue[i];
-            if (lane == 0)
-                asm volatile("atom.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(ahead) : "r"(smem_u32(&qctr[1])) : "memory");
+            PBR_W_POP(ahead);
         } else if (WARPS > 1) {
-            i = 0;
             // (measured on one box: popping two items per atomic 27.1 us, static round robin without any
-            // atomic 27.2 us, this single pop 25.3 us -- the dynamic balance is worth its ~30 instructions)
-            // atom.inc with a bound below 2^32 - 1 stays one ATOMS.INC; ptxas rewrites a single-lane
-            // atom.add (and inc with bound 0xffffffff) into leader election + popc + ATOMS.ADD (~20 instr)
-            if (lane == 0)
-                asm volatile("atom.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(i) : "r"(smem_u32(&qctr[1])) : "memory");
+            // atomic 27.2 us, this single pop 25.3 us -- the dynamic balance is worth its instructions)
+            i = 0;
+            PBR_W_POP(i);
             i = __shfl_sync(0xffffffffu, i, 0);
             if (i >= nitems) break;
             item = queue[i];
         } else {
             i = next++;
             if (i >= nitems) break;
-            item = me.blist[i];
+            item = me.blist[i] | (scene_slow ? 0x60000000u : 0u) | ((f.keys32 != 0 && direct) ? 0u : 0x20000000u);
             if (f.base_flags != nullptr && __ldg(f.base_flags + (int)((item >> 8) & 255u) * f.nbx + (int)(item & 255u)) != 0)
                 item |= 0x80000000u;
         }
-        const int w = (int)((item >> 16) & 0x3fffu);
+        const int w = (int)((item >> 16) & 0x1fffu);
         const int bx = (int)(item & 255u), by = (int)((item >> 8) & 255u);
         const unsigned char *sreg = smem_raw + w * region;
         const Rec *srecs = reinterpret_cast<const Rec *>(sreg + (size_t)W_GEOM_BYTES);
@@ -918,7 +922,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         // winners of this block: did this sweep win the lane's pixels, and with which colour
         bool won0, won1;
         unsigned c0, c1;
-        if (keys32 && !(item & 0x40000000u)) {
+        if (!(item & 0x20000000u)) {
             // no clipped / int64 records in this scene, records in draw order, static layer drawn first:
             // 32-bit depth keys (see raster_block32)
             PixelState32 q;
@@ -949,7 +953,9 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             won0 = key_changed(ps.k0, id0); won1 = key_changed(ps.k1, id1);
             c0 = ps.c0; c1 = ps.c1;
         }
-        if (f.debug == 3) continue;
+#ifdef PBR_W_TIMING
+        if (f.debug == 3) continue;                       // (profiling aid: sweep without the patches)
+#endif
         if (LATE_WAIT && !stores_done) {                  // first patch of this warp: the background has to be there
             if (lane == 0)
                 while (atomicAdd(&qctr[3], 0) == 0) __nanosleep(40);
@@ -957,23 +963,26 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             __threadfence_block();
             stores_done = true;
         }
-        // (tile width / channel count from locals: read through `f` they are re-loaded after every byte store,
-        // which the compiler cannot prove not to alias the frame description)
-        unsigned char *p = out_scene + py0 * tileW + px;
+        // The lane's two pixels, three (four) planes each.  One 64-bit address per pixel; the planes are reached by
+        // adding the plane size to it (tile width / plane size / channel count from locals: read through `f` they
+        // are re-loaded after every byte store, which the compiler cannot prove not to alias the frame description).
+        unsigned char *p = out_scene + (py0 * tileW + px);
         if (won0) {
-            p[0] = (unsigned char)(c0 & 255u);
-            p[HW] = (unsigned char)((c0 >> 8) & 255u);
-            p[2 * HW] = (unsigned char)((c0 >> 16) & 255u);
-            if (rgba) p[3 * HW] = (unsigned char)(c0 >> 24);
+            unsigned char *q = p;
+            *q = (unsigned char)c0; q += HW;
+            *q = (unsigned char)(c0 >> 8); q += HW;
+            *q = (unsigned char)(c0 >> 16);
+            if (rgba) { q += HW; *q = (unsigned char)(c0 >> 24); }
         }
         if (won1) {
-            p += 4 * tileW;
-            p[0] = (unsigned char)(c1 & 255u);
-            p[HW] = (unsigned char)((c1 >> 8) & 255u);
-            p[2 * HW] = (unsigned char)((c1 >> 16) & 255u);
-            if (rgba) p[3 * HW] = (unsigned char)(c1 >> 24);
+            unsigned char *q = p + 4 * tileW;
+            *q = (unsigned char)c1; q += HW;
+            *q = (unsigned char)(c1 >> 8); q += HW;
+            *q = (unsigned char)(c1 >> 16);
+            if (rgba) { q += HW; *q = (unsigned char)(c1 >> 24); }
         }
     }
+#undef PBR_W_POP
     W_STAMP(6);
     if (PBR_W_TRIGGER == 3) asm volatile("griddepcontrol.launch_dependents;");
     // blocks with records in the overflow pool: swept by the scene's own warp, then the entry is released
