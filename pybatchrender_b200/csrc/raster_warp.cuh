@@ -87,18 +87,26 @@ struct WScene {
     int *ctr;                 // [4] overflow pool entry, clipped triangles, records drawn (S > 32), has int64 records
     unsigned char **out_slot; // out[scene], for the sweep
 };
+// (the parts whose size depends on the tile -- block masks, block list -- come last: everything else sits at a
+// constant offset from the region's base)
+constexpr int W_OFF_RECS = W_GEOM_BYTES;
+constexpr int W_OFF_LIVE = W_OFF_RECS + W_MAXREC * (int)sizeof(Rec);
+constexpr int W_OFF_CLIPL = W_OFF_LIVE + W_MAXREC * 4;
+constexpr int W_OFF_CTR = W_OFF_CLIPL + W_MAXREC * 4;
+constexpr int W_OFF_OUT = W_OFF_CTR + 24;
+constexpr int W_OFF_MASKS = W_OFF_CTR + 32;
 __device__ __forceinline__ WScene wscene(unsigned char *base, int nblk) {
     WScene s;
     s.clipc = reinterpret_cast<float4 *>(base);
     s.proj = reinterpret_cast<int4 *>(base + (size_t)W_MAXVERT * 16);
     s.minst = reinterpret_cast<float4 *>(base + (size_t)W_MAXVERT * 32);
-    s.recs = reinterpret_cast<Rec *>(base + (size_t)W_GEOM_BYTES);
-    s.masks = reinterpret_cast<unsigned *>(s.recs + W_MAXREC);
-    s.blist = reinterpret_cast<unsigned short *>(s.masks + align16((size_t)nblk * W_MW * 4) / 4);
-    s.live = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(s.blist) + align16((size_t)nblk * 2));
-    s.clipl = s.live + W_MAXREC;
-    s.ctr = reinterpret_cast<int *>(s.clipl + W_MAXREC);
-    s.out_slot = reinterpret_cast<unsigned char **>(s.ctr + 6);
+    s.recs = reinterpret_cast<Rec *>(base + W_OFF_RECS);
+    s.live = reinterpret_cast<unsigned *>(base + W_OFF_LIVE);
+    s.clipl = reinterpret_cast<unsigned *>(base + W_OFF_CLIPL);
+    s.ctr = reinterpret_cast<int *>(base + W_OFF_CTR);
+    s.out_slot = reinterpret_cast<unsigned char **>(base + W_OFF_OUT);
+    s.masks = reinterpret_cast<unsigned *>(base + W_OFF_MASKS);
+    s.blist = reinterpret_cast<unsigned short *>(base + W_OFF_MASKS + align16((size_t)nblk * W_MW * 4));
     return s;
 }
 
@@ -912,9 +920,9 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         const int w = (int)((item >> 16) & 0x1fffu);
         const int bx = (int)(item & 255u), by = (int)((item >> 8) & 255u);
         const unsigned char *sreg = smem_raw + w * region;
-        const Rec *srecs = reinterpret_cast<const Rec *>(sreg + (size_t)W_GEOM_BYTES);
-        const unsigned *smasks = reinterpret_cast<const unsigned *>(srecs + W_MAXREC);
-        unsigned char *out_scene = *reinterpret_cast<unsigned char *const *>(sreg + region - 8);
+        const Rec *srecs = reinterpret_cast<const Rec *>(sreg + W_OFF_RECS);
+        const unsigned *smasks = reinterpret_cast<const unsigned *>(sreg + W_OFF_MASKS);
+        unsigned char *out_scene = *reinterpret_cast<unsigned char *const *>(sreg + W_OFF_OUT);
 
         const int px = bx * 8 + lx, py0 = by * 8 + ly;
         const bool ok0 = px < tileW && py0 < tileH, ok1 = px < tileW && py0 + 4 < tileH;
@@ -967,19 +975,22 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         // adding the plane size to it (tile width / plane size / channel count from locals: read through `f` they
         // are re-loaded after every byte store, which the compiler cannot prove not to alias the frame description).
         unsigned char *p = out_scene + (py0 * tileW + px);
-        if (won0) {
-            unsigned char *q = p;
-            *q = (unsigned char)c0; q += HW;
-            *q = (unsigned char)(c0 >> 8); q += HW;
-            *q = (unsigned char)(c0 >> 16);
-            if (rgba) { q += HW; *q = (unsigned char)(c0 >> 24); }
-        }
-        if (won1) {
-            unsigned char *q = p + 4 * tileW;
-            *q = (unsigned char)c1; q += HW;
-            *q = (unsigned char)(c1 >> 8); q += HW;
-            *q = (unsigned char)(c1 >> 16);
-            if (rgba) { q += HW; *q = (unsigned char)(c1 >> 24); }
+        if (!rgba) {                                      // (one uniform branch, not a predicated fourth store per pixel)
+            if (won0) {
+                unsigned char *q = p;
+                *q = (unsigned char)c0; q += HW;
+                *q = (unsigned char)(c0 >> 8); q += HW;
+                *q = (unsigned char)(c0 >> 16);
+            }
+            if (won1) {
+                unsigned char *q = p + 4 * tileW;
+                *q = (unsigned char)c1; q += HW;
+                *q = (unsigned char)(c1 >> 8); q += HW;
+                *q = (unsigned char)(c1 >> 16);
+            }
+        } else {
+            if (won0) put_pixel(out_scene, HW, 4, tileW, px, py0, c0);
+            if (won1) put_pixel(out_scene, HW, 4, tileW, px, py0 + 4, c1);
         }
     }
 #undef PBR_W_POP
