@@ -724,15 +724,15 @@ __device__ __forceinline__ void update32(PixelState32 &ps, const FastCov &c, con
 }
 
 template <int MWORDS>
-__device__ __forceinline__ void raster_block32(const Rec *recs, const unsigned *bmask, int px, int py0, bool ok0,
+__device__ __forceinline__ void raster_block32(unsigned recs_saddr, unsigned bmask_saddr, int px, int py0, bool ok0,
                                                bool ok1, PixelState32 &ps) {
     // (measured slower, see profiles/README.md: two records per iteration, and loading the next record's words
     // while this one is evaluated -- the loop is bound by what it issues, not by its shared-memory loads)
     static_assert(MWORDS == 2, "the block's two mask words are read with one 64-bit load");
-    const uint2 mm = *reinterpret_cast<const uint2 *>(bmask);
-    unsigned m = mm.x, m_next = mm.y;
-    // the records are in shared memory: one 32-bit address per word, the loads take it plus an immediate
-    unsigned last = (unsigned)__cvta_generic_to_shared(recs + 31);                           // record of bit 0
+    // records and masks by their 32-bit shared-memory addresses: the loads take a register plus an immediate
+    unsigned m, m_next;
+    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(m), "=r"(m_next) : "r"(bmask_saddr));
+    unsigned last = recs_saddr + 31u * (unsigned)sizeof(Rec);                                // record of bit 0
 #pragma unroll 1
     while (true) {
 #pragma unroll 1

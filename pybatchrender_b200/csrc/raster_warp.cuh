@@ -82,7 +82,7 @@ struct WScene {
     Rec *recs;                // [W_MAXREC]
     unsigned *masks;          // [nblk][W_MW]
     unsigned short *blist;    // [nblk]
-    unsigned *live;           // [W_MAXREC] flat colour of each record, parked by the shade lanes of phase S
+    unsigned *live;           // [W_MAXREC] (spare)
     unsigned *clipl;          // [W_MAXREC] packed slots of the triangles that need clipping
     int *ctr;                 // [4] overflow pool entry, clipped triangles, records drawn (S > 32), has int64 records
     unsigned char **out_slot; // out[scene], for the sweep
@@ -478,7 +478,8 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         if (geom) {
             {   // masks are 8 bytes per block, region padded to 16 bytes: clear with 128-bit stores
                 uint4 *m4 = reinterpret_cast<uint4 *>(me.masks);
-                const int n16 = (int)(align16((size_t)nblk * W_MW * 4) / 16);
+                const int n16 = (nblk * W_MW * 4 + 15) >> 4;
+#pragma unroll 1
                 for (int i = lane; i < n16; i += 32) m4[i] = make_uint4(0u, 0u, 0u, 0u);
             }
             if (lane < 4) me.ctr[lane] = 0;
@@ -645,8 +646,8 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
 
         // ---- S: set-up of the survivors.  Two lanes per triangle, in different warps: "edges" (integer edge
         // equations, depth plane -> 64-byte record, binned into the per-block masks) and "shade" (flat colour:
-        // normal through the model matrix, ambient + Lambert, basic.frag:31-38 -> parked in live[], copied into
-        // the record by the scene's warp behind the barrier).  The phase is a dependent chain per lane and only
+        // normal through the model matrix, ambient + Lambert, basic.frag:31-38 -> the record's colour word, which
+        // the edge lane leaves alone).  The phase is a dependent chain per lane and only
         // ~150 of the CTA's 480 worker lanes have a triangle: splitting it shortens the chain by a third.
         {
             const int n_live = qctr[2];
@@ -673,7 +674,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                     float n[3];
                     const float4 n0 = __ldg(nd.tn + 3 * tri);
                     xform_normal_cols(sc.minst + (nd.inst_begin + inst) * 4, n0.x, n0.y, n0.z, n);
-                    sc.live[j] = shade(f, n, __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4)));
+                    sc.recs[j].col = shade(f, n, __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4)));
                 }
                 if (do_edges) {
                     const uint4 ti = __ldg(nd.tidx + tri);
@@ -686,7 +687,13 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                     BBox bb;
                     if (setup_snapped(f, X, Y, z, (nd.flags & PBR_MESH_TWO_SIDED) != 0, id, 0, f.H, r, bb)) {
                         if (r.meta & M_SLOW) sc.ctr[3] = 1;
-                        sc.recs[j] = r;                    // (colour: filled in from live[] behind the barrier)
+                        // (every field but the colour, which the shade lane of this triangle writes)
+                        Rec *const d = sc.recs + j;
+                        *reinterpret_cast<int4 *>(&d->e[0]) = make_int4(r.e[0], r.e[1], r.e[2], r.e[3]);
+                        *reinterpret_cast<int4 *>(&d->e[4]) = make_int4(r.e[4], r.e[5], r.e[6], r.e[7]);
+                        d->e[8] = r.e[8];
+                        *reinterpret_cast<uint2 *>(&d->id) = make_uint2(r.id, r.meta);
+                        *reinterpret_cast<float4 *>(&d->z0) = make_float4(r.z0, r.dz1, r.dz2, r.invA);
                         // into the masks of the 8x8 blocks its box touches (edge-function reject per block): the
                         // boxes are small (1-8 blocks), a loop per lane beats a pass with a lane per (record, block)
                         bin_record<W_MW>(r, bb, j, f.nbx, sc.masks);
@@ -713,8 +720,6 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         const int nlive = direct ? S : me.ctr[2];
         int nrec = nlive;
         scene_slow = nclip > 0 || me.ctr[3] != 0;     // (clipped fans: not tracked, assume so)
-        for (int j = lane; j < nlive; j += 32) recs[j].col = me.live[j];       // flat colours of phase S
-        __syncwarp();
         {
             // ---- B3: clipped triangles -> fan triangles in the spare record slots
             if (nclip > 0) {
@@ -879,10 +884,11 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     }
     const int nitems = WARPS > 1 ? qctr[0] : nlist;
     const int lx = lane & 7, ly = lane >> 3;
-    const int tileW = f.W, tileH = f.H, tileNbx = f.nbx;
+    const int tileW = f.W, tileH = f.H, tileH4 = f.H - 4, tileNbx = f.nbx;
     const bool rgba = f.C == 4;
     const bool keys32 = f.keys32 != 0 && direct;
     const unsigned pop_addr = smem_u32(&qctr[1]);
+    const unsigned smem_base = smem_u32(smem_raw);
     int next = 0;
     int ahead = 0;                                        // PBR_W_POP_AHEAD: lane 0 holds the next item's index
     // (atom.inc with a bound below 2^32 - 1 stays one ATOMS.INC; ptxas rewrites a single-lane atom.add, and inc with
@@ -925,7 +931,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         unsigned char *out_scene = *reinterpret_cast<unsigned char *const *>(sreg + W_OFF_OUT);
 
         const int px = bx * 8 + lx, py0 = by * 8 + ly;
-        const bool ok0 = px < tileW && py0 < tileH, ok1 = px < tileW && py0 + 4 < tileH;
+        const bool ok0 = px < tileW && py0 < tileH, ok1 = px < tileW && py0 < tileH4;
         const int b = by * tileNbx + bx;
         // winners of this block: did this sweep win the lane's pixels, and with which colour
         bool won0, won1;
@@ -936,13 +942,15 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             PixelState32 q;
             q.z0 = q.z1 = (unsigned)(KEY_CLEAR >> 32);
             if (item & 0x80000000u) {                     // static layer covers part of this block
+                asm volatile("" ::: "memory");            // (a branch, not ten predicated-off instructions per item)
                 const unsigned *bk = reinterpret_cast<const unsigned *>(f.base_keys + (size_t)b * 64);
                 q.z0 = __ldg(bk + 2 * lane + 1);
                 q.z1 = __ldg(bk + 2 * (32 + lane) + 1);
             }
             q.c0 = q.c1 = 0u;
             const unsigned zi0 = q.z0, zi1 = q.z1;
-            raster_block32<W_MW>(srecs, smasks + b * W_MW, px, py0, ok0, ok1, q);
+            raster_block32<W_MW>(smem_base + w * region + W_OFF_RECS, smem_base + w * region + W_OFF_MASKS + b * (W_MW * 4),
+                                 px, py0, ok0, ok1, q);
             won0 = q.z0 != zi0; won1 = q.z1 != zi1;
             c0 = q.c0; c1 = q.c1;
         } else {
