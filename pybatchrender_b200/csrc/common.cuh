@@ -515,6 +515,35 @@ __device__ __forceinline__ void bin_record(const Rec &r, const BBox &bb, int t, 
     const unsigned bit = rec_bit(t);
     const int word = t >> 5;
     const bool small = (bb.bx1 - bb.bx0) + (bb.by1 - bb.by0) <= 1;       // <= 2 blocks: no reject test
+    if (!small && !(r.meta & M_SLOW)) {
+        // block_hit() for every block of the box, stepped: the largest value of each edge function over a block's
+        // pixel centres is taken at a fixed corner, so it moves by 8 A per block to the right and 8 B per block down
+        // (the same wrapping 32-bit arithmetic as block_hit: identical bits)
+        unsigned row[3], sx[3], sy[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int A = r.e[3 + i], B = r.e[6 + i];
+            row[i] = (unsigned)r.e[i] + (unsigned)A * (unsigned)(bb.bx0 * 8 + (A > 0 ? 7 : 0)) +
+                     (unsigned)B * (unsigned)(bb.by0 * 8 + (B > 0 ? 7 : 0));
+            sx[i] = 8u * (unsigned)A;
+            sy[i] = 8u * (unsigned)B;
+        }
+        unsigned *mrow = masks + (bb.by0 * nbx + bb.bx0) * MWORDS + word;
+#pragma unroll 1
+        for (int by = bb.by0; by <= bb.by1; ++by) {
+            unsigned f0 = row[0], f1 = row[1], f2 = row[2];
+            unsigned *m = mrow;
+#pragma unroll 1
+            for (int bx = bb.bx0; bx <= bb.bx1; ++bx) {
+                if ((int)(f0 | f1 | f2) >= 0) atomicOr(m, bit);
+                f0 += sx[0]; f1 += sx[1]; f2 += sx[2];
+                m += MWORDS;
+            }
+            row[0] += sy[0]; row[1] += sy[1]; row[2] += sy[2];
+            mrow += nbx * MWORDS;
+        }
+        return;
+    }
     for (int by = bb.by0; by <= bb.by1; ++by)
         for (int bx = bb.bx0; bx <= bb.bx1; ++bx)
             if (small || block_hit(r, bb, bx, by)) atomicOr(&masks[(by * nbx + bx) * MWORDS + word], bit);

@@ -884,12 +884,12 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         if (use_tma && big) {
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS_TMA - 1) / W_WARPS_TMA);
             f.w_qctr_off = (int)warp_qctr_offset(nbx * (H8 / 8), W_WARPS_TMA);
-            CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS_TMA, true>, wgrid, 32 * (W_WARPS_TMA + PBR_W_HELPERS), tma_smem, stream, f));
+            CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS_TMA, true>, wgrid, 32 * (W_WARPS_TMA + w_helpers(W_WARPS_TMA)), tma_smem, stream, f));
             COUNT_LAUNCH();
         } else if (use_tma) {
             const unsigned wgrid = (unsigned)((f.scene_count + W_WARPS_TMA_SMALL - 1) / W_WARPS_TMA_SMALL);
             f.w_qctr_off = (int)warp_qctr_offset(nbx * (H8 / 8), W_WARPS_TMA_SMALL);
-            CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS_TMA_SMALL, true>, wgrid, 32 * (W_WARPS_TMA_SMALL + PBR_W_HELPERS), tma_smem, stream, f));
+            CUDA_TRY(launch_dependent(raster_warp_kernel<W_WARPS_TMA_SMALL, true>, wgrid, 32 * (W_WARPS_TMA_SMALL + w_helpers(W_WARPS_TMA_SMALL)), tma_smem, stream, f));
             COUNT_LAUNCH();
         } else {
             static const size_t smem_pad = getenv("PBR_B200_WARP_SMEM_PAD") ? (size_t)atoi(getenv("PBR_B200_WARP_SMEM_PAD")) : 0;   // occupancy experiments

@@ -73,6 +73,7 @@ __host__ __device__ inline size_t warp_smem_bytes(int nblk, int warps, size_t tm
 #endif
 constexpr int W_WARPS_TMA = PBR_W_WARPS_TMA;      // scenes per CTA when the background goes through TMA (see kernel comment)
 constexpr int W_WARPS_TMA_SMALL = 6;              // ... for tiles whose image leaves room for only one CTA of W_WARPS_TMA per SM
+__host__ __device__ constexpr int w_helpers(int warps);                // helper warps (no scene of their own) of a TMA CTA with `warps` scenes
 
 // views into one scene's shared-memory region (layout: warp_scene_bytes)
 struct WScene {
@@ -312,6 +313,11 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 #ifndef PBR_W_HELPERS
 #define PBR_W_HELPERS 2
 #endif
+// ... and with the 6-scene CTAs (three per SM): measured at 84x84 x 16,384 scenes 102.8 us with 2 helpers, 101.0 with 3,
+// 99.5 with 4 (the 14-scene CTAs get slower with more: 15.30 / 15.79 / 15.70 us at 64x64 x 4096, 56 registers per thread)
+#ifndef PBR_W_HELPERS_SMALL
+#define PBR_W_HELPERS_SMALL 4
+#endif
 #ifndef PBR_W_BG_HELPER
 #define PBR_W_BG_HELPER 1
 #endif
@@ -368,8 +374,10 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 #ifndef PBR_W_BG_AFTER
 #define PBR_W_BG_AFTER 0
 #endif
+__host__ __device__ constexpr int w_helpers(int warps) { return warps <= W_WARPS_TMA_SMALL ? PBR_W_HELPERS_SMALL : PBR_W_HELPERS; }
 template <int WARPS, bool TMA_BG>
-__global__ void __launch_bounds__(32 * (WARPS + (TMA_BG ? PBR_W_HELPERS : 0)), 32 / (WARPS + (TMA_BG ? PBR_W_HELPERS : 0)))
+__global__ void __launch_bounds__(32 * (WARPS + (TMA_BG ? w_helpers(WARPS) : 0)),
+                                  (WARPS + (TMA_BG ? w_helpers(WARPS) : 0)) > 16 ? 2 : 32 / (WARPS + (TMA_BG ? w_helpers(WARPS) : 0)))
 raster_warp_kernel(const __grid_constant__ FrameDev f) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -413,7 +421,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     // it must not be a warp that has geometry to do.  It loads the image, waits for it, issues the
     // stores and waits for them while the other warps do geometry.  (When the frame before this one may still
     // be writing the same memory -- f.sync_early -- it first waits for that grid to complete.)
-    constexpr int HELP = TMA_BG ? PBR_W_HELPERS : 0;
+    constexpr int HELP = TMA_BG ? w_helpers(WARPS) : 0;
     constexpr bool BG_HELP = TMA_BG && HELP > 0 && PBR_W_BG_HELPER != 0;
     constexpr int BG_T = BG_HELP ? (WARPS + HELP - 1) * 32 : 0;
     // the warps that share the geometry work: the scene warps and the helpers that do not drive the TMA engine
