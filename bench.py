@@ -468,27 +468,32 @@ def timed_run(wl: Workload, K: int, W: int, barrier, native):
     return e0.elapsed_time(e1), launches, last
 
 
+ROOFLINE_LAUNCHES = 128
+
+
 def roofline_leg(wl: Workload, K: int):
-    """The raster kernel(s) alone on resident inputs: average launch time over the same number of steps."""
+    """The raster kernel(s) alone on resident inputs: average duration of a launch, CUDA events on the launching stream.
+
+    Small-scene configurations (one kernel per frame, consecutive launches overlap through programmatic dependent
+    launch): ONE graph of max(K, 128) launches, replayed twice untimed, then timed -- elapsed / launches.  The first
+    launch of a chain has no frame ahead of it to overlap with (it alone takes ~23 us), so a chain of 16-20 launches
+    reads 3-5 % slower than the kernel runs in steady state; `roofline.launches_timed` says how many were averaged."""
     import torch
-    # (at least 8 replays = 128 launches: the first launch of a chain has no frame ahead of it to overlap with, and the
-    # figure wanted here is the kernel's average duration, not the start-up of a short chain)
-    reps = max(8, K // STATE_RING)
     if wl.use_graphs:
+        n = max(K, ROOFLINE_LAUNCHES)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            for i in range(STATE_RING):
+            for i in range(n):
                 wl.raster_only(i)
-        for _ in range(3):
+        for _ in range(2):
             g.replay()
         torch.cuda.synchronize()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record()
-        for _ in range(reps):
-            g.replay()
+        g.replay()
         r1.record()
         torch.cuda.synchronize()
-        return r0.elapsed_time(r1) / (reps * STATE_RING)
+        return r0.elapsed_time(r1) / n
     n = max(2, min(K, 20))
     for i in range(2):
         wl.raster_only(i)
@@ -637,6 +642,8 @@ def measure_config(config, K, W, dev, rank, world, distributed, barrier, native,
                                      "launches cycling the output ring (profiles/)" if traffic is not None
                      else "not captured for this configuration",
                      "kernel": wl.kernel, "kernel_ms": raster_ms,
+                     "launches_timed": max(K, ROOFLINE_LAUNCHES) if wl.use_graphs else max(2, min(K, 20)),
+                     "frac_over_timed_steps": (c["algo"] * per_rank / (ms / K * 1e-3) / 1e9 / peak) if launches == K else None,
                      "algorithmic_bytes_per_launch": c["algo"] * per_rank, "peak_source": peak_src},
         "gpu_launches": launches,
     })

@@ -121,3 +121,12 @@ d_ent = np.array(d_ent)
 print(f"entry offset between the two CTAs of an SM: mean {d_ent.mean():.2f} us p10 {np.percentile(d_ent,10):.2f} p50 {np.percentile(d_ent,50):.2f} p90 {np.percentile(d_ent,90):.2f}; "
       f"share of a sweep spent beside the other CTA's geometry (same frame only): {np.mean(ovl):.2f}")
 print("entry times of the last frame's CTAs (us after the first): p10 %.2f p50 %.2f p90 %.2f max %.2f" % tuple(np.percentile(ent1, [10, 50, 90, 100])))
+
+# ---- what releases the pre-sweep barrier: the slowest scene warp, or the TMA thread waiting for the CTA's bulk stores?
+tw = buf.shape[1] - 1                                    # the TMA thread's warp is the last one
+t_tma = (t[:, tw, 4] - ent[:, 0]) / 1000.0               # its bulk stores have completed (stamp 4)
+t_tma0 = (t[:, tw, 3] - ent[:, 0]) / 1000.0              # it starts to wait for them (stamp 3)
+t_scn = (t[:, :14, 4].max(1) - ent[:, 0]) / 1000.0       # the slowest scene warp has its block list
+print(f"TMA thread: starts to wait for the stores {t_tma0.mean():.2f} us after CTA entry, stores complete {t_tma.mean():.2f} "
+      f"(p10 {np.percentile(t_tma,10):.2f}, p90 {np.percentile(t_tma,90):.2f}); slowest scene warp ready {t_scn.mean():.2f}; "
+      f"CTAs whose barrier waits for the stores: {int((t_tma > t_scn).sum())} of {nc}")

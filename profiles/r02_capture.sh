@@ -2,6 +2,8 @@
 # One gpurun call: every raw profile of round 2 (final build).  Summaries are made locally by profiles/r02_summarise.py.
 set -x
 O=gpurun_out
+python bench.py --steps 200 --warmup 20 > $O/r02s_bench.json 2> $O/r02s_bench.err
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras > $O/r02s_bench20.json 2>> $O/r02s_bench.err
 ncu --set full --clock-control none --import-source on -k regex:raster_warp -s 6 -c 1 -o $O/r02z_warp -f python bench.py --no-cpu-baseline --no-extras --no-verify --steps 16 --warmup 3 > $O/r02z_warp.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/r02z_launches.csv python bench.py --no-cpu-baseline --no-extras --no-verify --steps 64 --warmup 3 > /dev/null 2>&1
 ncu --replay-mode range --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none python profiles/traffic_range.py 16 > $O/r02z_traffic.log 2>&1

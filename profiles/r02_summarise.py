@@ -48,10 +48,15 @@ def lines_of(rep, n=24):
 out = ["# Round 2, final: raster_warp_kernel<14, true> on CartPole 4096 x 64^2 (B200) -- pose computed in the kernel, geometry shared",
        "# by the CTA (named barriers), 32-bit depth keys, frames chained by programmatic dependent launch",
        "# command: ncu --set full --clock-control none --import-source on -k regex:raster_warp -s 6 -c 1 python bench.py --no-cpu-baseline --no-extras --no-verify --steps 16 --warmup 3",
-       "# (one launch profiled in isolation: serialised, cold caches -- its 25 us are not the 16.8 us of the chained launches in the bench)", ""]
+       "# (one launch profiled in isolation: serialised, cold caches -- its ~23 us are not the ~15 us per frame of the chained launches in",
+       "# the bench line below: there the next frame's CTAs start as the SM slots of this one free up)", ""]
 bench = os.path.join(G, "r02s_bench.json")
 if os.path.exists(bench):
     out += ["## bench.py line of the same build (python bench.py --steps 200 --warmup 20)", open(bench).read().strip().splitlines()[-1], ""]
+bench20 = os.path.join(G, "r02s_bench20.json")
+if os.path.exists(bench20):
+    out += ["## ... and with the driver's flags (python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras)",
+            open(bench20).read().strip().splitlines()[-1], ""]
 out += ["## key metrics (one launch = 4096 scenes)"] + metrics(os.path.join(G, "r02z_warp.ncu-rep")) + [""]
 out += ["## launch list of `bench.py --no-cpu-baseline --no-extras --no-verify --steps 64 --warmup 3` (ncu --metrics gpu__time_duration.sum,",
         "## first 300 launches of the process, serialised by ncu; raw file r02z_launches.csv): the step is ONE kernel"] + shares(os.path.join(G, "r02z_launches.csv")) + [""]
@@ -59,7 +64,7 @@ out += ["## instruction mix by phase (profiles/ncu_segments.py, executions per s
 out += ["## DRAM traffic over a RANGE of 16 consecutive launches cycling the 4-buffer output ring",
         "## (ncu --replay-mode range --metrics dram__bytes_read.sum,dram__bytes_write.sum python profiles/traffic_range.py 16)"]
 out += [l.rstrip() for l in open(os.path.join(G, "r02z_traffic.log")).read().splitlines()[-8:]]
-out += ["-> (751.48 + 1.65) MB / 16 launches = 47.07 MB per launch against 51.25 MB algorithmic (12,512 B x 4096): 0.92 -- every pixel",
+out += ["-> (751.59 + 1.55) MB / 16 launches = 47.07 MB per launch against 51.25 MB algorithmic (12,512 B x 4096): 0.92 -- every pixel",
         "   byte reaches DRAM once (the rest of the last frames is still in the 126 MB L2 when the range ends), reads ~ 0.1 MB per launch"]
 open(os.path.join(P, "r02z_raster_warp_ncu.txt"), "w").write("\n".join(out) + "\n")
 
