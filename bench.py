@@ -459,6 +459,11 @@ def timed_run(wl: Workload, K: int, W: int, barrier, native):
     barrier()
     l0 = native.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if wl.use_graphs:
+        # ~0.2 ms of device-side delay ahead of the start event: the host enqueues the event and the graph while it
+        # runs, so the events bracket the K steps on the device and not the host's launch latency (with 8 ranks on one
+        # host that latency showed as +1 us per step at K = 20); torch's own spin kernel, not one of ours
+        torch.cuda._sleep(400_000)
     e0.record()
     run_steps(K)
     e1.record()
@@ -633,7 +638,8 @@ def measure_config(config, K, W, dev, rank, world, distributed, barrier, native,
                          + (f"; state ring of {STATE_RING}" if wl.states is not None else ""),
                    "launch": ((f"one CUDA graph of the {K} timed steps" if K <= 256 else f"CUDA graphs of {STATE_RING} steps")
                               + ", replayed before the timed region; one kernel per step, consecutive frames overlap "
-                                "through programmatic dependent launch")
+                                "through programmatic dependent launch; a 0.2 ms device-side delay ahead of the start event "
+                                "keeps the host's launch latency out of the timed region")
                    if wl.use_graphs else "eager: instance cull + geometry pre-pass + staged raster per launch chunk"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic,

@@ -518,6 +518,7 @@ static int plan_general(FrameDev &f, DeviceState *st, size_t *smem_out) {
     f.BH = BH;
     f.nbands = (H + BH - 1) / BH;
     f.nbx = nbx;
+    f.nbx_magic = div_magic((unsigned)nbx);
     f.nby = BH / 8;
     if (f.nbx > 256 || f.nby > 256) return fail(PBR_EUNSUPPORTED, "pbr_render: more than 256 blocks per band side");
     f.plane_stride = (int)align16((size_t)BH * W);
@@ -657,6 +658,7 @@ static int launch_binned(FrameDev &f, DeviceState *st, void *stream) {
     }
     const int H8 = ((f.H + 7) / 8) * 8;
     f.BH = H8; f.nbands = 1; f.nbx = (f.W + 7) / 8; f.nby = H8 / 8;       // blocks of the whole tile
+    f.nbx_magic = div_magic((unsigned)f.nbx);
     f.plane_stride = f.H * f.W; f.linear = 1;
     const size_t nblk = (size_t)f.nbx * f.nby;
     const size_t cap = ((size_t)f.total_slots + (size_t)f.total_slots / 2 + 64 + 3) & ~(size_t)3;

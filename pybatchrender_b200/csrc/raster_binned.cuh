@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(B_WPB * 32, 4) raster_binned_kernel(const __gr
     const int nblk = f.nbx * f.nby;
     const int blk = blockIdx.x * B_WPB + warp;
     if (blk >= nblk) return;                                  // (no CTA-wide barrier below)
-    const int by = blk / f.nbx, bx = blk - by * f.nbx;
+    const int by = fast_div(blk, f.nbx_magic), bx = blk - by * f.nbx;
     const int px = bx * 8 + (lane & 7), py0 = by * 8 + (lane >> 3);
     const bool ok0 = px < f.W && py0 < f.H, ok1 = px < f.W && py0 + 4 < f.H;
     const int *off = bd.blk_off + (size_t)local_scene * (2 * nblk + 1);

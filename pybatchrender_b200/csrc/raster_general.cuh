@@ -192,7 +192,7 @@ __device__ __forceinline__ Smem carve(unsigned char *base, int C, int plane_stri
 
 template <bool SMOOTH>
 __device__ __forceinline__ void general_block(const FrameDev &f, const Smem &s, int b, int band_h, int lane) {
-    const int bx = b % f.nbx, by = b / f.nbx;
+    const int by = fast_div(b, f.nbx_magic), bx = b - by * f.nbx;
     const int px = bx * 8 + (lane & 7);
     const int py0 = by * 8 + (lane >> 3), py1 = py0 + 4;
     const bool ok0 = px < f.W && py0 < band_h, ok1 = px < f.W && py1 < band_h;

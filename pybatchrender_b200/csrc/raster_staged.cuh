@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(THREADS) raster_staged_kernel(const __grid_con
             i = __shfl_sync(0xffffffffu, i, 0);
             if (i >= nlist) break;
             const int b = s.blist[i];
-            const int bxl = b % f.nbx, byl = b / f.nbx;
+            const int byl = fast_div(b, f.nbx_magic), bxl = b - byl * f.nbx;
             const int px = bxl * 8 + (lane & 7);
             const int py0 = band_y0 + byl * 8 + (lane >> 3), py1 = py0 + 4;      // tile-global rows
             const bool ok0 = px < f.W && py0 < band_y0 + band_h, ok1 = px < f.W && py1 < band_y0 + band_h;
