@@ -737,6 +737,11 @@ __device__ __forceinline__ void raster_block(const Rec *recs, const unsigned *bm
 // is "strictly smaller depth wins": the id never has to be compared or carried, and a pixel was won by this sweep
 // iff its depth changed.  Saves 4 of the 10 compare / select instructions per covered (block, record) pair -- they
 // all go to the ALU pipe, which is what bounds the small-scene kernel.
+// skip the depth part of a (record, block) pair when no lane is covered?  The block reject test of the binning leaves
+// few such pairs: the vote and its branch cost more than they save
+#ifndef PBR_SWEEP_EARLY_OUT
+#define PBR_SWEEP_EARLY_OUT 1
+#endif
 struct PixelState32 {
     unsigned z0, z1;             // depth bits (non-negative floats order like unsigned integers)
     unsigned c0, c1;             // packed RGBA8 of the current winner
@@ -772,7 +777,9 @@ __device__ __forceinline__ void raster_block32(unsigned recs_saddr, unsigned bma
             asm("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4+16];" : "=r"(eb.x), "=r"(eb.y), "=r"(eb.z), "=r"(eb.w) : "r"(a));
             asm("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4+32];" : "=r"(ec.x), "=r"(ec.y), "=r"(ec.z), "=r"(ec.w) : "r"(a));
             const FastCov c = fast_cover(ea, eb, ec, px, py0, ok0, ok1);
+#if PBR_SWEEP_EARLY_OUT
             if (!__any_sync(0xffffffffu, c.cov0 || c.cov1)) continue;
+#endif
             float4 zq;                                                        // z0 dz1 dz2 invA
             asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+48];" : "=f"(zq.x), "=f"(zq.y), "=f"(zq.z), "=f"(zq.w) : "r"(a));
             update32(ps, c, ec, zq);

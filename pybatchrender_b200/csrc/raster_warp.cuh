@@ -339,6 +339,10 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 // (Round 2: with the frames chained -- the CTAs of the next frame arrive while this one sweeps -- the early barrier no longer
 // pays: 16.82 us per frame with the late wait, 16.54 without, 84x84 113.6 vs 111.7 us per 16,384 scenes.  Off.)
 // the sweep pops the item after the current one before it sweeps the current one (16.54 -> 16.51 us; 84x84: 111.5 -> 110.3)
+// blocks with at least this many records are swept first (0: in list order)
+#ifndef PBR_W_HEAVY
+#define PBR_W_HEAVY 4
+#endif
 #ifndef PBR_W_POP_AHEAD
 #define PBR_W_POP_AHEAD 1
 #endif
@@ -412,7 +416,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     int *qctr = reinterpret_cast<int *>(smem_raw + f.w_qctr_off);
     unsigned *livelist = reinterpret_cast<unsigned *>(qctr) - WARPS * W_MAXSLOT; // [WARPS * W_MAXSLOT], just below the counters
     constexpr bool LATE_WAIT = TMA_BG && PBR_W_LATE_WAIT != 0;
-    if (threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; qctr[2] = 0; qctr[3] = 0; qctr[6] = 0; }
+    if (threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; qctr[2] = 0; qctr[3] = 0; qctr[6] = 0; qctr[7] = 0; }
     __syncthreads();          // counters initialised (all warps arrive together: cheap)
     W_STAMP(8);
     // The thread that drives the TMA engine: lane 0 of the LAST helper warp when there is one.  Issuing the
@@ -453,6 +457,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     // blocks for the shared sweep; novf: 0 = no overflow pool entry claimed, else 1 + number of blocks
     // that have records in the pool (swept by overflow_block after the shared sweep)
     int nlist = 0, novf = 0;
+    int nlight = 0;                          // PBR_W_HEAVY: blocks with few records, listed from the back of blist
     bool scene_slow = false;                 // the scene has int64 (slow-path) records: its items say so (bit 30)
     if (TMA_BG && BG_T == 0 && f.debug == 1 && threadIdx.x == 0) issue_bg_stores(f, qctr, WARPS);
 
@@ -836,9 +841,22 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                             const int by = fast_div(b, f.nbx_magic);
                             packed = (by << 8) | (b - by * f.nbx);
                         }
-                        const unsigned bal = __ballot_sync(0xffffffffu, nz);
-                        if (nz) blist[nlist + __popc(bal & lt_mask)] = (unsigned short)packed;
-                        nlist += __popc(bal);
+                        if (PBR_W_HEAVY > 0) {
+                            // blocks with many records to the front of the list, the others to its back: the queue hands
+                            // out the expensive items first, so that the warps of the CTA finish their sweeps together
+                            bool heavy = false;
+                            if (nz) heavy = __popc(masks[b * W_MW]) + __popc(masks[b * W_MW + 1]) >= PBR_W_HEAVY;
+                            const unsigned hbal = __ballot_sync(0xffffffffu, nz && heavy);
+                            const unsigned lbal = __ballot_sync(0xffffffffu, nz && !heavy);
+                            if (nz && heavy) blist[nlist + __popc(hbal & lt_mask)] = (unsigned short)packed;
+                            if (nz && !heavy) blist[nblk - 1 - nlight - __popc(lbal & lt_mask)] = (unsigned short)packed;
+                            nlist += __popc(hbal);
+                            nlight += __popc(lbal);
+                        } else {
+                            const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                            if (nz) blist[nlist + __popc(bal & lt_mask)] = (unsigned short)packed;
+                            nlist += __popc(bal);
+                        }
                     }
                 } else {
                     const int both = overflow_lists(f, masks, blist, *ovf_entry, nblk, lane);
@@ -860,21 +878,25 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     if (TMA_BG && warp == BG_T / 32) __syncwarp();       // lane 0 spun on the mbarrier / the bulk group: reconverge
     W_STAMP(4);
     if (WARPS > 1) {
-        int qbase = 0;
+        int qbase = 0, lbase = 0;
         const unsigned wide_keys = (f.keys32 != 0 && direct) ? 0u : 0x20000000u;
         if (lane == 0 && nlist > 0) qbase = atomicAdd(&qctr[0], nlist);
+        if (PBR_W_HEAVY > 0 && lane == 0 && nlight > 0) lbase = atomicAdd(&qctr[7], nlight);
         qbase = __shfl_sync(0xffffffffu, qbase, 0);
+        if (PBR_W_HEAVY > 0) lbase = __shfl_sync(0xffffffffu, lbase, 0);
         // bit 31: the static layer covers part of the block (looked up here, one lane per item, so
         // that the sweep does not start every item with a dependent global load)
-        for (int i = lane; i < nlist; i += 32) {
+        // (light items fill the queue from its back)
+        for (int i = lane; i < nlist + nlight; i += 32) {
             // bit 30: the scene has int64 / clipped records; bit 29: sweep it with 64-bit keys (that, or the frame's
             // draw order does not allow 32-bit ones)
-            unsigned it = ((unsigned)warp << 16) | me.blist[i] | (scene_slow ? 0x60000000u : 0u) | wide_keys;
+            const bool light = i >= nlist;
+            unsigned it = ((unsigned)warp << 16) | me.blist[light ? nblk - 1 - (i - nlist) : i] | (scene_slow ? 0x60000000u : 0u) | wide_keys;
             if (f.base_flags != nullptr) {
                 const int bb = (int)((it >> 8) & 255u) * f.nbx + (int)(it & 255u);
                 if (__ldg(f.base_flags + bb) != 0) it |= 0x80000000u;
             }
-            queue[qbase + i] = it;
+            queue[light ? WARPS * nblk - 1 - (lbase + i - nlist) : qbase + i] = it;
         }
         __syncthreads();                                  // every scene of the CTA is set up and queued
     }
@@ -890,7 +912,9 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         }
         if (warp == BG_T / 32) { __syncwarp(); stores_done = true; }
     }
-    const int nitems = WARPS > 1 ? qctr[0] : nlist;
+    const int nheavy = WARPS > 1 ? qctr[0] : nlist;      // items handed out from the front of the queue / list ...
+    const int nitems = nheavy + (PBR_W_HEAVY > 0 ? (WARPS > 1 ? qctr[7] : nlight) : 0);       // ... then those from its back
+    const int qlast = (WARPS > 1 ? WARPS * nblk : nblk) - 1 + nheavy;
     const int lx = lane & 7, ly = lane >> 3;
     const int tileW = f.W, tileH = f.H, tileH4 = f.H - 4, tileNbx = f.nbx;
     const bool rgba = f.C == 4;
@@ -914,7 +938,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             // read at the top of the next turn); the last pop of every warp runs past the end of the queue
             i = __shfl_sync(0xffffffffu, ahead, 0);
             if (i >= nitems) break;
-            item = queue[i];
+            item = queue[(PBR_W_HEAVY > 0 && i >= nheavy) ? qlast - i : i];
             PBR_W_POP(ahead);
         } else if (WARPS > 1) {
             // (measured on one box: popping two items per atomic 27.1 us, static round robin without any
@@ -923,11 +947,11 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             PBR_W_POP(i);
             i = __shfl_sync(0xffffffffu, i, 0);
             if (i >= nitems) break;
-            item = queue[i];
+            item = queue[(PBR_W_HEAVY > 0 && i >= nheavy) ? qlast - i : i];
         } else {
             i = next++;
             if (i >= nitems) break;
-            item = me.blist[i] | (scene_slow ? 0x60000000u : 0u) | ((f.keys32 != 0 && direct) ? 0u : 0x20000000u);
+            item = me.blist[(PBR_W_HEAVY > 0 && i >= nheavy) ? qlast - i : i] | (scene_slow ? 0x60000000u : 0u) | ((f.keys32 != 0 && direct) ? 0u : 0x20000000u);
             if (f.base_flags != nullptr && __ldg(f.base_flags + (int)((item >> 8) & 255u) * f.nbx + (int)(item & 255u)) != 0)
                 item |= 0x80000000u;
         }
