@@ -664,13 +664,16 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         // ~150 of the CTA's 480 worker lanes have a triangle: splitting it shortens the chain by a third.
         {
             const int n_live = qctr[2];
-            const int n_work = PBR_W_SPLIT_SETUP ? 2 * n_live : n_live;
+            // (roles are contiguous ranges of the work items and the shade range starts at a warp boundary, so that no
+            // warp runs both chains: the warp at the boundary used to reach the barrier 0.3 us after the others)
+            const int shade0 = (n_live + 31) & ~31;
+            const int n_work = PBR_W_SPLIT_SETUP ? shade0 + n_live : n_live;
 #pragma unroll 1
             for (int it0 = wl; it0 < n_work; it0 += GW * 32) {
-                // (roles are contiguous ranges of the work items, so whole warps share a role)
-                const bool do_shade = !PBR_W_SPLIT_SETUP || it0 >= n_live;
-                const bool do_edges = !PBR_W_SPLIT_SETUP || it0 < n_live;
-                const int it = (PBR_W_SPLIT_SETUP && it0 >= n_live) ? it0 - n_live : it0;
+                const bool do_shade = !PBR_W_SPLIT_SETUP || it0 >= shade0;
+                const bool do_edges = !PBR_W_SPLIT_SETUP || it0 < shade0;
+                const int it = (PBR_W_SPLIT_SETUP && it0 >= shade0) ? it0 - shade0 : it0;
+                if (PBR_W_SPLIT_SETUP && it >= n_live) continue;              // the gap between the two ranges
                 const unsigned e = livelist[it];
                 const int sl = (int)(e >> 16), s = (int)((e >> 8) & 255u), j = (int)(e & 255u);
                 int ni = 0;
