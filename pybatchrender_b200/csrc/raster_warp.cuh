@@ -552,16 +552,15 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 }
             }
         }
-        group_sync<GW * 32>();
-        W_STAMP(9);
-
-        // ---- A: vertices (basic.vert:24-43)
+        // ---- A: vertices (basic.vert:24-43).  The global loads of a lane's first vertex -- its scene's VP rows and the
+        // object-space position -- are issued ahead of the barrier behind phase M: they are in flight while the pose
+        // lanes finish (only the model matrix, which comes out of shared memory, depends on phase M)
         {
             const int TV = f.total_verts;
-#pragma unroll 1
-            for (int it = wl; it < n_sc * TV; it += GW * 32) {
-                const int sl = fast_div(it, f.w_vert_magic);
-                const int v = it - sl * TV;
+            const int n_a = n_sc * TV;
+            auto decode = [&](int it, int &sl, int &v, int &mi_off, const float4 *&vp) {
+                sl = fast_div(it, f.w_vert_magic);
+                v = it - sl * TV;
                 int ni = 0;
 #pragma unroll 1
                 for (int i = 1; i < f.n_nodes; ++i)
@@ -569,19 +568,37 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 const NodeDev &nd = f.nodes[ni];
                 const int local = v - nd.vert_begin;
                 const int inst = fast_div(local, nd.vert_magic);
-                const int vert = local - inst * nd.n_verts;
+                mi_off = (nd.inst_begin + inst) * 4;
+                vp = nd.vpos + (local - inst * nd.n_verts);
+            };
+            int sl = 0, v = 0, mi_off = 0;
+            const float4 *vp = nullptr;
+            float VP[16];
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (wl < n_a) {
+                decode(wl, sl, v, mi_off, vp);
+                load_mat(f.vp + (size_t)(first_scene + sl) * 16, VP);
+                p = __ldg(vp);
+            }
+            group_sync<GW * 32>();
+            W_STAMP(9);
+#pragma unroll 1
+            for (int it = wl; it < n_a; it += GW * 32) {
+                if (it != wl) {
+                    decode(it, sl, v, mi_off, vp);
+                    load_mat(f.vp + (size_t)(first_scene + sl) * 16, VP);
+                    p = __ldg(vp);
+                }
                 const WScene sc = wscene(smem_raw + sl * region, nblk);
-                float M[16], VP[16];
+                float M[16];
                 {
-                    const float4 *mi = sc.minst + (nd.inst_begin + inst) * 4;
+                    const float4 *mi = sc.minst + mi_off;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float4 a = mi[j];
                         M[4 * j] = a.x; M[4 * j + 1] = a.y; M[4 * j + 2] = a.z; M[4 * j + 3] = a.w;
                     }
                 }
-                load_mat(f.vp + (size_t)(first_scene + sl) * 16, VP);
-                const float4 p = __ldg(nd.vpos + vert);
                 float world[4], c[4];
                 mat_vec4(M, p.x, p.y, p.z, 1.0f, world);
                 mat_vec4(VP, world[0], world[1], world[2], world[3], c);
