@@ -19,6 +19,7 @@ struct PoseDev {
     pbr_channel pos[3], hpr[3], scale;
     float *out_mats;      // [B,16]: written only when the frame asks for it (PBR_FRAME_WRITE_MATS)
 };
+constexpr int MAX_FRAME_PF = 4;      // prefetch ranges per frame (32 lanes = 4 ranges x 8 lines)
 constexpr int MAX_FRAME_POSES = 4;   // posed nodes per frame handled in-kernel; more are materialised by compose_kernel
 
 struct NodeDev {
@@ -90,6 +91,11 @@ struct FrameDev {
                             // so scenes without clipped / int64 records may use 32-bit depth keys (raster_block32)
     int sync_early;         // small-scene kernel: wait for the previous grid before the first write to `out`
                             // (the previous launch on this stream may still be writing the same buffer)
+    // small-scene kernel: per-scene inputs a CTA asks the L2 for on behalf of a later CTA (see PBR_W_PF_DIST):
+    // base address of scene 0's row and bytes per scene
+    int n_pf;
+    const unsigned char *pf_ptr[MAX_FRAME_PF];
+    int pf_row[MAX_FRAME_PF];
     PoseDev poses[MAX_FRAME_POSES];
     NodeDev nodes[PBR_MAX_NODES];
 };

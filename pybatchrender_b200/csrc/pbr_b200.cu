@@ -812,6 +812,29 @@ int pbr_render(const pbr_frame_desc *d, void *stream) {
         // everything in it was drawn before the first node of this frame (CartPole: the rail is node 0)
         static const bool no_k32 = getenv("PBR_B200_NO_KEYS32") != nullptr;       // A/B timing aid
         f.keys32 = (!no_k32 && (!use_base || ns.skipped_id_end <= ns.active_id_begin)) ? 1 : 0;
+        {   // per-scene inputs worth an L2 prefetch by an earlier CTA: the pose channels (rows of the caller's state
+            // tensor -- channels that point into the same rows count once), the VP rows, the instance colours
+            f.n_pf = 0;
+            auto add = [&](const void *ptr, long long row_bytes) {
+                if (ptr == nullptr || row_bytes <= 0 || row_bytes > 64) return;
+                const unsigned char *q = static_cast<const unsigned char *>(ptr);
+                for (int k = 0; k < f.n_pf; ++k)
+                    if (f.pf_row[k] == (int)row_bytes && q - f.pf_ptr[k] < row_bytes && f.pf_ptr[k] - q < row_bytes) {
+                        if (q < f.pf_ptr[k]) f.pf_ptr[k] = q;
+                        return;
+                    }
+                if (f.n_pf < MAX_FRAME_PF) { f.pf_ptr[f.n_pf] = q; f.pf_row[f.n_pf] = (int)row_bytes; ++f.n_pf; }
+            };
+            for (int i = 0; i < f.n_nodes; ++i) {
+                const NodeDev &nd = f.nodes[i];
+                if (nd.shared || nd.pose_idx < 0) continue;
+                const pbr_channel *ch = f.poses[nd.pose_idx].pos;       // pos[3], hpr[3], scale: seven in a row
+                for (int k = 0; k < 7; ++k) add(ch[k].ptr, (long long)nd.inst * ch[k].stride * 4);
+            }
+            if (f.vp_scene_override < 0) add(f.vp, 64);
+            for (int i = 0; i < f.n_nodes; ++i)
+                if (!f.nodes[i].shared) add(f.nodes[i].cols, (long long)f.nodes[i].inst * 16);
+        }
         {   // programmatic launch chain: this launch may start while the previous small-scene launches on the
             // stream drain; it orders itself behind them when it writes memory they write (see raster_warp.cuh)
             const unsigned char *lo = f.out + (size_t)f.scene_begin * f.C * H * W;

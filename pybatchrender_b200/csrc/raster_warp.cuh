@@ -340,6 +340,10 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 // pays: 16.82 us per frame with the late wait, 16.54 without, 84x84 113.6 vs 111.7 us per 16,384 scenes.  Off.)
 // the sweep pops the item after the current one before it sweeps the current one (16.54 -> 16.51 us; 84x84: 111.5 -> 110.3)
 // blocks with at least this many records are swept first (0: in list order)
+// a CTA asks the L2 for the per-scene inputs of the CTA this many places behind it (0: off)
+#ifndef PBR_W_PF_DIST
+#define PBR_W_PF_DIST 32
+#endif
 #ifndef PBR_W_HEAVY
 #define PBR_W_HEAVY 4
 #endif
@@ -520,6 +524,24 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 const int sl = k / f.n_nodes;
                 const NodeDev &nd = f.nodes[k - sl * f.n_nodes];
                 prefetch_l1(nd.cols + (nd.shared ? (size_t)0 : (size_t)(first_scene + sl) * nd.inst) * 4);
+            }
+        }
+
+        // The per-scene inputs of a CTA -- pose channel values (the caller's state), VP rows, instance colours -- are
+        // read once per frame and miss the L2 (50 MB of frames pass through it between two reads of a line): the first
+        // load of phase M alone takes 1.5 us.  The CTAs of a frame enter the SMs over ~15 us in index order, so the last
+        // worker warp of each CTA asks the L2 for the rows of the CTA PBR_W_PF_DIST places behind it, which enters a few
+        // microseconds later: lane = (range, 128-byte line), the ranges listed by the host.  (L1 prefetch of the CTA's
+        // own lines at entry was measured slower: 17.31 vs 16.78 us, the 8 KB of L1 beside 219 KB of shared memory do
+        // not hold them.)
+        if (PBR_W_PF_DIST > 0 && warp == GW - 1 && (lane >> 3) < f.n_pf) {
+            const int t_first = first_scene + PBR_W_PF_DIST * WARPS;
+            const int t_n = min(WARPS, f.scene_begin + f.scene_count - t_first);
+            if (t_n > 0) {
+                const int r = lane >> 3;
+                const size_t a0 = reinterpret_cast<size_t>(f.pf_ptr[r]) + (size_t)t_first * f.pf_row[r];
+                const size_t a = (a0 & ~(size_t)127) + (size_t)(lane & 7) * 128;
+                if (a < a0 + (size_t)t_n * f.pf_row[r]) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
             }
         }
 
