@@ -59,14 +59,16 @@ __host__ __device__ inline size_t warp_scene_bytes(int nblk) {
     return (size_t)W_GEOM_BYTES + (size_t)W_MAXREC * sizeof(Rec) + align16((size_t)nblk * W_MW * 4) +
            align16((size_t)nblk * 2) + 2 * W_MAXREC * 4 + 32;
 }
-// offset of the CTA's counters: behind the scene regions, the block queue and the live list
+// offset of the CTA's counters: behind the scene regions, the block queue, the block table and the live list
 __host__ __device__ inline size_t warp_qctr_offset(int nblk, int warps) {
-    return (size_t)warps * warp_scene_bytes(nblk) + align16((size_t)warps * nblk * 4) + align16((size_t)warps * W_MAXSLOT * 4);
+    return (size_t)warps * warp_scene_bytes(nblk) + align16((size_t)warps * nblk * 4) + align16((size_t)nblk * 4) +
+           align16((size_t)warps * W_MAXSLOT * 4);
 }
 // shared memory of a CTA of `warps` scenes: scene regions + block queue + counters (+ mbarrier and the
 // background image when the background is written by TMA)
 __host__ __device__ inline size_t warp_smem_bytes(int nblk, int warps, size_t tma_tile_bytes = 0) {
-    return warp_qctr_offset(nblk, warps) + 16 + (tma_tile_bytes ? 16 + align16(tma_tile_bytes) : 0);
+    // (eight counter words -- [4], [5] are the mbarrier of the TMA build, [6], [7] are used by every build -- then the image)
+    return warp_qctr_offset(nblk, warps) + 32 + (tma_tile_bytes ? align16(tma_tile_bytes) : 0);
 }
 #ifndef PBR_W_WARPS_TMA
 #define PBR_W_WARPS_TMA 14
@@ -417,6 +419,9 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     const WScene me = wscene(smem_raw + warp * region, nblk);
     if (lane == 0 && !helper) *me.out_slot = f.out + (size_t)scene * scene_bytes_out;
     unsigned *queue = reinterpret_cast<unsigned *>(smem_raw + WARPS * region);   // [WARPS * nblk]
+    // [nblk] what an item says about its block, the same for every scene: bits 0-7 bx, 8-15 by, bit 31 the static layer
+    // covers part of it (a global load) -- looked up once per CTA instead of once per (scene, block)
+    unsigned *const btab = queue + align16((size_t)WARPS * nblk * 4) / 4;
     int *qctr = reinterpret_cast<int *>(smem_raw + f.w_qctr_off);
     unsigned *livelist = reinterpret_cast<unsigned *>(qctr) - WARPS * W_MAXSLOT; // [WARPS * W_MAXSLOT], just below the counters
     constexpr bool LATE_WAIT = TMA_BG && PBR_W_LATE_WAIT != 0;
@@ -543,6 +548,14 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 const size_t a = (a0 & ~(size_t)127) + (size_t)(lane & 7) * 128;
                 if (a < a0 + (size_t)t_n * f.pf_row[r]) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
             }
+        }
+
+        // (filled by the worker lanes with the highest indices: the first warp has the pose chain to run; the readers
+        // are behind the phase barriers)
+        for (int b = GW * 32 - 1 - wl; b < nblk; b += GW * 32) {
+            const int by = fast_div(b, f.nbx_magic);
+            btab[b] = (unsigned)((by << 8) | (b - by * f.nbx)) |
+                      ((f.base_flags != nullptr && __ldg(f.base_flags + b) != 0) ? 0x80000000u : 0u);
         }
 
         // ---- M: instances.  A posed node's model matrix is computed here from its pose channels (the state
@@ -870,35 +883,46 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             __syncwarp();     // records + masks complete; background stores ordered before patches
             W_STAMP(13);
 
-            // ---- list of this scene's non-empty blocks
+            // ---- this scene's non-empty blocks: straight into the CTA's queue (several warps per CTA, no pool entry),
+            // else into the scene's own list.  Item: bit 31 the static layer covers part of the block, bit 30 the scene
+            // has int64 / clipped records, bit 29 sweep it with 64-bit keys (that, or the frame's draw order does not
+            // allow 32-bit ones), bits 16.. the scene's warp, bits 8-15 by, 0-7 bx.  Blocks with many records go to the
+            // front of the queue, the others fill it from the back: the queue hands out the expensive items first.
             if (f.debug != 2) {
-                if (novf == 0) {
+                if (novf == 0 && WARPS > 1) {
+                    const unsigned tag = ((unsigned)warp << 16) | (scene_slow ? 0x60000000u : 0u) |
+                                         ((f.keys32 != 0 && direct) ? 0u : 0x20000000u);
 #pragma unroll 1
                     for (int b0 = 0; b0 < nblk; b0 += 32) {
                         const int b = b0 + lane;
-                        bool nz = false;
-                        int packed = 0;
+                        bool nz = false, heavy = true;
                         if (b < nblk) {
-                            nz = (masks[b * W_MW] | masks[b * W_MW + 1]) != 0u;
-                            const int by = fast_div(b, f.nbx_magic);
-                            packed = (by << 8) | (b - by * f.nbx);
+                            const uint2 m = *reinterpret_cast<const uint2 *>(masks + b * W_MW);
+                            nz = (m.x | m.y) != 0u;
+                            if (PBR_W_HEAVY > 0) heavy = __popc(m.x) + __popc(m.y) >= PBR_W_HEAVY;
                         }
-                        if (PBR_W_HEAVY > 0) {
-                            // blocks with many records to the front of the list, the others to its back: the queue hands
-                            // out the expensive items first, so that the warps of the CTA finish their sweeps together
-                            bool heavy = false;
-                            if (nz) heavy = __popc(masks[b * W_MW]) + __popc(masks[b * W_MW + 1]) >= PBR_W_HEAVY;
-                            const unsigned hbal = __ballot_sync(0xffffffffu, nz && heavy);
-                            const unsigned lbal = __ballot_sync(0xffffffffu, nz && !heavy);
-                            if (nz && heavy) blist[nlist + __popc(hbal & lt_mask)] = (unsigned short)packed;
-                            if (nz && !heavy) blist[nblk - 1 - nlight - __popc(lbal & lt_mask)] = (unsigned short)packed;
-                            nlist += __popc(hbal);
-                            nlight += __popc(lbal);
-                        } else {
-                            const unsigned bal = __ballot_sync(0xffffffffu, nz);
-                            if (nz) blist[nlist + __popc(bal & lt_mask)] = (unsigned short)packed;
-                            nlist += __popc(bal);
+                        const unsigned hbal = __ballot_sync(0xffffffffu, nz && heavy);
+                        const unsigned lbal = PBR_W_HEAVY > 0 ? __ballot_sync(0xffffffffu, nz && !heavy) : 0u;
+                        if ((hbal | lbal) == 0u) continue;
+                        int hb = 0, lb = 0;
+                        if (lane == 0) {
+                            if (hbal) hb = atomicAdd(&qctr[0], __popc(hbal));
+                            if (lbal) lb = atomicAdd(&qctr[7], __popc(lbal));
                         }
+                        hb = __shfl_sync(0xffffffffu, hb, 0);
+                        if (PBR_W_HEAVY > 0) lb = __shfl_sync(0xffffffffu, lb, 0);
+                        if (nz)
+                            queue[heavy ? hb + __popc(hbal & lt_mask) : WARPS * nblk - 1 - (lb + __popc(lbal & lt_mask))] =
+                                tag | btab[b];
+                    }
+                } else if (novf == 0) {
+#pragma unroll 1
+                    for (int b0 = 0; b0 < nblk; b0 += 32) {
+                        const int b = b0 + lane;
+                        const bool nz = b < nblk && (masks[b * W_MW] | masks[b * W_MW + 1]) != 0u;
+                        const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                        if (nz) blist[nlist + __popc(bal & lt_mask)] = (unsigned short)(btab[b] & 0xffffu);
+                        nlist += __popc(bal);
                     }
                 } else {
                     const int both = overflow_lists(f, masks, blist, *ovf_entry, nblk, lane);
@@ -920,25 +944,14 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     if (TMA_BG && warp == BG_T / 32) __syncwarp();       // lane 0 spun on the mbarrier / the bulk group: reconverge
     W_STAMP(4);
     if (WARPS > 1) {
-        int qbase = 0, lbase = 0;
-        const unsigned wide_keys = (f.keys32 != 0 && direct) ? 0u : 0x20000000u;
-        if (lane == 0 && nlist > 0) qbase = atomicAdd(&qctr[0], nlist);
-        if (PBR_W_HEAVY > 0 && lane == 0 && nlight > 0) lbase = atomicAdd(&qctr[7], nlight);
-        qbase = __shfl_sync(0xffffffffu, qbase, 0);
-        if (PBR_W_HEAVY > 0) lbase = __shfl_sync(0xffffffffu, lbase, 0);
-        // bit 31: the static layer covers part of the block (looked up here, one lane per item, so
-        // that the sweep does not start every item with a dependent global load)
-        // (light items fill the queue from its back)
-        for (int i = lane; i < nlist + nlight; i += 32) {
-            // bit 30: the scene has int64 / clipped records; bit 29: sweep it with 64-bit keys (that, or the frame's
-            // draw order does not allow 32-bit ones)
-            const bool light = i >= nlist;
-            unsigned it = ((unsigned)warp << 16) | me.blist[light ? nblk - 1 - (i - nlist) : i] | (scene_slow ? 0x60000000u : 0u) | wide_keys;
-            if (f.base_flags != nullptr) {
-                const int bb = (int)((it >> 8) & 255u) * f.nbx + (int)(it & 255u);
-                if (__ldg(f.base_flags + bb) != 0) it |= 0x80000000u;
+        if (nlist > 0) {                                  // (a scene with a pool entry: the front of its own list)
+            int qbase = 0;
+            if (lane == 0) qbase = atomicAdd(&qctr[0], nlist);
+            qbase = __shfl_sync(0xffffffffu, qbase, 0);
+            for (int i = lane; i < nlist; i += 32) {
+                const int packed = me.blist[i];
+                queue[qbase + i] = ((unsigned)warp << 16) | 0x60000000u | btab[(packed >> 8) * f.nbx + (packed & 255)];
             }
-            queue[light ? WARPS * nblk - 1 - (lbase + i - nlist) : qbase + i] = it;
         }
         __syncthreads();                                  // every scene of the CTA is set up and queued
     }
