@@ -117,26 +117,23 @@ __device__ __noinline__ float2 pose_sincos(float x) {
     sincosf(x, &sn, &cs);
     return make_float2(sn, cs);
 }
-__device__ __forceinline__ void pose_angle(const pbr_channel &c, size_t b, float &sn, float &cs) {
-    sn = 0.0f; cs = 1.0f;
-    if (c.ptr != nullptr || c.constant != 0.0f) {
-        const float2 v = pose_sincos(pose_chan(c, b));
-        sn = v.x; cs = v.y;
-    }
-}
 __device__ __forceinline__ void pose_matrix(const PoseDev &d, size_t b, float *M) {
-    float sh, ch, sp, cp, sr, cr;
-    pose_angle(d.hpr[0], b, sh, ch);
-    pose_angle(d.hpr[1], b, sp, cp);
-    pose_angle(d.hpr[2], b, sr, cr);
+    // every channel value first -- seven independent loads in flight together -- then the trigonometry (the calls are
+    // out of line: a load behind one of them would wait for its own round trip)
+    const float ah = pose_chan(d.hpr[0], b), ap = pose_chan(d.hpr[1], b), ar = pose_chan(d.hpr[2], b);
     const float s = pose_chan(d.scale, b);
+    const float tx = pose_chan(d.pos[0], b), ty = pose_chan(d.pos[1], b), tz = pose_chan(d.pos[2], b);
+    float sh = 0.0f, ch = 1.0f, sp = 0.0f, cp = 1.0f, sr = 0.0f, cr = 1.0f;
+    if (d.hpr[0].ptr != nullptr || d.hpr[0].constant != 0.0f) { const float2 v = pose_sincos(ah); sh = v.x; ch = v.y; }
+    if (d.hpr[1].ptr != nullptr || d.hpr[1].constant != 0.0f) { const float2 v = pose_sincos(ap); sp = v.x; cp = v.y; }
+    if (d.hpr[2].ptr != nullptr || d.hpr[2].constant != 0.0f) { const float2 v = pose_sincos(ar); sr = v.x; cr = v.y; }
     const float r00 = ch * cp, r01 = ch * sp * sr - sh * cr, r02 = ch * sp * cr + sh * sr;
     const float r10 = sh * cp, r11 = sh * sp * sr + ch * cr, r12 = sh * sp * cr - ch * sr;
     const float r20 = -sp, r21 = cp * sr, r22 = cp * cr;
     M[0] = r00 * s; M[1] = r10 * s; M[2] = r20 * s; M[3] = 0.0f;
     M[4] = r01 * s; M[5] = r11 * s; M[6] = r21 * s; M[7] = 0.0f;
     M[8] = r02 * s; M[9] = r12 * s; M[10] = r22 * s; M[11] = 0.0f;
-    M[12] = pose_chan(d.pos[0], b); M[13] = pose_chan(d.pos[1], b); M[14] = pose_chan(d.pos[2], b); M[15] = 1.0f;
+    M[12] = tx; M[13] = ty; M[14] = tz; M[15] = 1.0f;
 }
 
 constexpr int DEVSTAT_WARP_OVERFLOW = 1;   // small-scene kernel ran out of record slots
