@@ -22,4 +22,4 @@ timeout 300 compute-sanitizer --tool racecheck python -c "import __graft_entry__
 timeout 300 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" > $O/r02z_memcheck.log 2>&1
 timeout 300 compute-sanitizer --tool memcheck python profiles/staged_workloads.py 3 16 1 > $O/r02z_memcheck_binned.log 2>&1
 timeout 300 compute-sanitizer --tool racecheck python profiles/staged_workloads.py 5 4 1 > $O/r02z_racecheck_binned.log 2>&1
-tail -3 $O/r02z_racecheck.log $O/r02z_memcheck.log $O/r02z_memcheck_binned.log $O/r02z_racecheck_binned.log
+for f in $O/r02z_racecheck.log $O/r02z_memcheck.log $O/r02z_memcheck_binned.log $O/r02z_racecheck_binned.log; do tail -n 3 $f; done
