@@ -113,7 +113,6 @@ __device__ __forceinline__ WScene wscene(unsigned char *base, int nblk) {
     return s;
 }
 
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // named barrier 1 over the first THREADS threads of the CTA (the warps that share the geometry work)
 template <int THREADS_>
@@ -299,8 +298,9 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 // TMA_BG: the background / static-layer image of every scene of the CTA is written by the TMA engine
 // instead of by the warps: one bulk load brings the C*H*W image (L2 resident, shared by all scenes)
 // into shared memory once per CTA, then one bulk store per scene sends it to out[scene]; the TMA
-// thread (lane 0 of the first helper warp) waits for the stores behind the CTA barrier that precedes
-// the sweep and raises a flag that every warp checks before its first pixel patch (PBR_W_LATE_WAIT);
+// thread (lane 0 of the last helper warp) waits for the stores ahead of the CTA barrier that precedes
+// the sweep (they complete ~5.4 us after the CTA's entry, the slowest scene warp is ready at ~9 us; a flag checked
+// before every warp's first pixel patch instead -- round 1 -- costs more under chained frames: 16.82 vs 16.54 us);
 // the CTAs of an SM take turns at issuing their stores (PBR_W_BG_SERIAL).  The warps issue
 // no background instruction at all (the copy was ~9 % of their instructions and the source of the
 // lg_throttle stalls).  The image costs C*H*W bytes of shared memory per CTA, which is why this
@@ -334,12 +334,10 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 #ifndef PBR_W_BG_SERIAL
 #define PBR_W_BG_SERIAL 2
 #endif
-// The barrier before the sweep only waits for the geometry of the CTA's scenes; the CTA's bulk stores are
-// waited for by the TMA thread *after* it, which then raises a flag (qctr[3]).  A sweeping warp evaluates
-// its first item and looks at the flag just before its first pixel patch: the CTA whose turn at the write
-// path comes second does one item per warp of useful work while its stores drain.
-// (Round 2: with the frames chained -- the CTAs of the next frame arrive while this one sweeps -- the early barrier no longer
-// pays: 16.82 us per frame with the late wait, 16.54 without, 84x84 113.6 vs 111.7 us per 16,384 scenes.  Off.)
+// (Round 1 let the barrier before the sweep wait for the geometry only and had the TMA thread raise a flag behind it that
+// every warp checked before its first pixel patch.  With the frames chained -- the CTAs of the next frame arrive while
+// this one sweeps -- that no longer pays: 16.82 us per frame with the flag, 16.54 with the TMA thread simply waiting for
+// its stores ahead of the barrier, 84x84 113.6 vs 111.7 us per 16,384 scenes.  Removed.)
 // the sweep pops the item after the current one before it sweeps the current one (16.54 -> 16.51 us; 84x84: 111.5 -> 110.3)
 // blocks with at least this many records are swept first (0: in list order)
 // a CTA asks the L2 for the per-scene inputs of the CTA this many places behind it (0: off)
@@ -351,9 +349,6 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 #endif
 #ifndef PBR_W_POP_AHEAD
 #define PBR_W_POP_AHEAD 1
-#endif
-#ifndef PBR_W_LATE_WAIT
-#define PBR_W_LATE_WAIT 0
 #endif
 // Programmatic launch chain.  The kernel is launched with programmatic stream serialisation and triggers its
 // dependents (PBR_W_TRIGGER: 1 = at entry, 2 = behind the pre-sweep barrier, 3 = at the end of the sweep, 0 = never):
@@ -375,14 +370,6 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 // phase S with two lanes per triangle (edges / shade) instead of one
 #ifndef PBR_W_SPLIT_SETUP
 #define PBR_W_SPLIT_SETUP 1
-#endif
-#ifndef PBR_W_PREFETCH
-#define PBR_W_PREFETCH 0
-#endif
-// Experiment: hold the CTA's bulk stores back until the geometry has issued its global loads (1: until the
-// vertices are done, 2: until the set-up is done) -- the loads queue behind the store burst on the SM's path to L2
-#ifndef PBR_W_BG_AFTER
-#define PBR_W_BG_AFTER 0
 #endif
 __host__ __device__ constexpr int w_helpers(int warps) { return warps <= W_WARPS_TMA_SMALL ? PBR_W_HELPERS_SMALL : PBR_W_HELPERS; }
 template <int WARPS, bool TMA_BG>
@@ -424,8 +411,9 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     unsigned *const btab = queue + align16((size_t)WARPS * nblk * 4) / 4;
     int *qctr = reinterpret_cast<int *>(smem_raw + f.w_qctr_off);
     unsigned *livelist = reinterpret_cast<unsigned *>(qctr) - WARPS * W_MAXSLOT; // [WARPS * W_MAXSLOT], just below the counters
-    constexpr bool LATE_WAIT = TMA_BG && PBR_W_LATE_WAIT != 0;
-    if (threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; qctr[2] = 0; qctr[3] = 0; qctr[6] = 0; qctr[7] = 0; }
+    // counters: [0] items queued from the front, [1] items popped, [2] live triangles, [7] items queued from the back
+    // ([4], [5]: the mbarrier of the TMA build)
+    if (threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; qctr[2] = 0; qctr[7] = 0; }
     __syncthreads();          // counters initialised (all warps arrive together: cheap)
     W_STAMP(8);
     // The thread that drives the TMA engine: lane 0 of the LAST helper warp when there is one.  Issuing the
@@ -448,8 +436,6 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         mbar_expect_tx(bg_bar, (unsigned)scene_bytes_out);
         tma_load(qctr + 8, f.base_color, (unsigned)scene_bytes_out, bg_bar);
         if (f.sync_early) asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (PBR_W_BG_AFTER != 0 && f.debug != 1)
-            while (atomicAdd(&qctr[6], 0) < PBR_W_BG_AFTER) __nanosleep(100);
         if (BG_T != 0) {
             if (PBR_W_BG_SERIAL) {
                 unsigned smid;
@@ -511,26 +497,6 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     }
     if (worker && geom) {
         const int wl = warp * 32 + lane;     // this lane among the worker lanes
-
-        // L1 is empty at kernel entry and every phase below starts with a load that the phase before it cannot
-        // issue (barrier in between): ask for those lines now -- the scenes' VP rows (phase A) and instance
-        // colours (phase S), the meshes' vertices, index triples and normals (phases A, B, S)
-        if (PBR_W_PREFETCH) {
-            int k = wl;
-            if (k < n_sc) {
-                prefetch_l1(f.vp + (size_t)(first_scene + k) * 16);
-            } else if ((k -= n_sc) < f.n_nodes * 8) {
-                const NodeDev &nd = f.nodes[k >> 3];
-                const int part = k & 7;
-                if (part == 0) prefetch_l1(nd.vpos);
-                else if (part <= 2) { if ((part - 1) * 8 < nd.n_tris) prefetch_l1(nd.tidx + (part - 1) * 8); }
-                else if ((part - 3) * 8 < 3 * nd.n_tris) prefetch_l1(nd.tn + (part - 3) * 8);
-            } else if ((k -= f.n_nodes * 8) < n_sc * f.n_nodes) {
-                const int sl = k / f.n_nodes;
-                const NodeDev &nd = f.nodes[k - sl * f.n_nodes];
-                prefetch_l1(nd.cols + (nd.shared ? (size_t)0 : (size_t)(first_scene + sl) * nd.inst) * 4);
-            }
-        }
 
         // The per-scene inputs of a CTA -- pose channel values (the caller's state), VP rows, instance colours -- are
         // read once per frame and miss the L2 (50 MB of frames pass through it between two reads of a line): the first
@@ -657,7 +623,6 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         if (split_bg && active) write_background_part(f, out_scene, HW, lane, 1);
         group_sync<GW * 32>();
         W_STAMP(10);
-        if (PBR_W_BG_AFTER == 1 && threadIdx.x == 0) atomicExch(&qctr[6], 1);
 
         // ---- B: classify triangle slots; survivors go to the CTA's live list as (scene, slot, record index)
         {
@@ -773,7 +738,6 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         if (split_bg && active) write_background_part(f, out_scene, HW, lane, 2);
         group_sync<GW * 32>();
         W_STAMP(12);
-        if (PBR_W_BG_AFTER == 2 && threadIdx.x == 0) atomicExch(&qctr[6], 2);
     }
 
     // ---- per scene, by its own warp: binning, clipped fans, block list
@@ -937,7 +901,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     // ---- D: raster.  One (scene, block) item at a time; with several warps per CTA the items of
     // all its scenes sit in one queue so that light scenes help heavy ones.
     W_STAMP(3);
-    if (TMA_BG && !LATE_WAIT && threadIdx.x == BG_T) {
+    if (TMA_BG && threadIdx.x == BG_T) {
         tma_wait_all();                                  // background written before any pixel patch
         if (PBR_W_BG_SERIAL == 1 && BG_T != 0) atomicAdd(f.bg_done + bg_sm, 1u);      // next CTA of this SM: your turn
     }
@@ -957,23 +921,12 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     }
     if (PBR_W_TRIGGER == 2) asm volatile("griddepcontrol.launch_dependents;");
     W_STAMP(5);
-    bool stores_done = !LATE_WAIT;                        // this warp has seen the CTA's bulk stores complete
-    if (LATE_WAIT) {
-        if (threadIdx.x == BG_T) {
-            tma_wait_all();
-            if (PBR_W_BG_SERIAL == 1 && BG_T != 0) atomicAdd(f.bg_done + bg_sm, 1u);
-            __threadfence_block();
-            atomicExch(&qctr[3], 1);                      // (atomics on both sides: a flag, not a data race)
-        }
-        if (warp == BG_T / 32) { __syncwarp(); stores_done = true; }
-    }
     const int nheavy = WARPS > 1 ? qctr[0] : nlist;      // items handed out from the front of the queue / list ...
     const int nitems = nheavy + (PBR_W_HEAVY > 0 ? (WARPS > 1 ? qctr[7] : nlight) : 0);       // ... then those from its back
     const int qlast = (WARPS > 1 ? WARPS * nblk : nblk) - 1 + nheavy;
     const int lx = lane & 7, ly = lane >> 3;
     const int tileW = f.W, tileH = f.H, tileH4 = f.H - 4, tileNbx = f.nbx;
     const bool rgba = f.C == 4;
-    const bool keys32 = f.keys32 != 0 && direct;
     const unsigned pop_addr = smem_u32(&qctr[1]);
     const unsigned smem_base = smem_u32(smem_raw);
     int next = 0;
@@ -1059,13 +1012,6 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
 #ifdef PBR_W_TIMING
         if (f.debug == 3) continue;                       // (profiling aid: sweep without the patches)
 #endif
-        if (LATE_WAIT && !stores_done) {                  // first patch of this warp: the background has to be there
-            if (lane == 0)
-                while (atomicAdd(&qctr[3], 0) == 0) __nanosleep(40);
-            __syncwarp();
-            __threadfence_block();
-            stores_done = true;
-        }
         // The lane's two pixels, three (four) planes each.  One 64-bit address per pixel; the planes are reached by
         // adding the plane size to it (tile width / plane size / channel count from locals: read through `f` they
         // are re-loaded after every byte store, which the compiler cannot prove not to alias the frame description).
@@ -1093,12 +1039,6 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     if (PBR_W_TRIGGER == 3) asm volatile("griddepcontrol.launch_dependents;");
     // blocks with records in the overflow pool: swept by the scene's own warp, then the entry is released
     if (novf > 0) {
-        if (LATE_WAIT && !stores_done) {
-            if (lane == 0)
-                while (atomicAdd(&qctr[3], 0) == 0) __nanosleep(40);
-            __syncwarp();
-            __threadfence_block();
-        }
         const int e = me.ctr[0];
 #pragma unroll 1
         for (int i = 0; i + 1 < novf; ++i)
