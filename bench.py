@@ -44,6 +44,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 STATE_RING = 16
+GRAPH_STEPS = 128       # steps per CUDA graph of runs longer than 256 steps (multiple of STATE_RING and of the output ring)
 
 # name, scenes (global for strong scaling, per GPU for weak), tile, algorithmic bytes per scene-frame
 CONFIGS = {
@@ -431,25 +432,27 @@ def timed_run(wl: Workload, K: int, W: int, barrier, native):
             for i in range(K):
                 last[i % wl.out_ring] = i
         else:
-            g_full, l_full = capture(STATE_RING)
-            tail = K % STATE_RING
+            # long runs: graphs of GRAPH_STEPS steps (a multiple of the state and output rings) plus a tail graph; the
+            # first launch of every replay has no frame ahead of it to overlap with (+ ~7 us per replay boundary)
+            g_full, l_full = capture(GRAPH_STEPS)
+            tail = K % GRAPH_STEPS
             g_tail, l_tail = capture(tail) if tail else (None, 0)
 
             def run_steps(k):
-                # exactly k steps: whole graphs, then the tail graph (k % STATE_RING == tail by construction)
-                for _ in range(k // STATE_RING):
+                # exactly k steps: whole graphs, then the tail graph (k % GRAPH_STEPS == tail by construction)
+                for _ in range(k // GRAPH_STEPS):
                     g_full.replay()
-                if k % STATE_RING:
+                if k % GRAPH_STEPS:
                     g_tail.replay()
             # warm-up: >= W steps and, whatever W is, at least two replays of every graph that is timed
-            for _ in range(max(2, (W + STATE_RING - 1) // STATE_RING)):
+            for _ in range(max(2, (W + GRAPH_STEPS - 1) // GRAPH_STEPS)):
                 g_full.replay()
             if g_tail is not None:
                 for _ in range(2):
                     g_tail.replay()
-            launches = (K // STATE_RING) * l_full + (l_tail if tail else 0)
+            launches = (K // GRAPH_STEPS) * l_full + (l_tail if tail else 0)
             # what each ring buffer holds at the end: the full graph ran (in the warm-up at least), then the tail graph
-            for i in list(range(STATE_RING)) + list(range(tail)):
+            for i in list(range(GRAPH_STEPS)) + list(range(tail)):
                 last[i % wl.out_ring] = i
     else:
         for i in range(max(3, W)):
@@ -485,12 +488,12 @@ def roofline_leg(wl: Workload, K: int):
     """The raster kernel(s) alone on resident inputs: average duration of a launch, CUDA events on the launching stream.
 
     Small-scene configurations (one kernel per frame, consecutive launches overlap through programmatic dependent
-    launch): ONE graph of max(K, 128) launches, replayed twice untimed, then timed -- elapsed / launches.  The first
+    launch): ONE graph of 128 ... 256 launches (K clamped to that range), replayed twice untimed, then timed -- elapsed / launches.  The first
     launch of a chain has no frame ahead of it to overlap with (it alone takes ~23 us), so a chain of 16-20 launches
     reads 3-5 % slower than the kernel runs in steady state; `roofline.launches_timed` says how many were averaged."""
     import torch
     if wl.use_graphs:
-        n = max(K, ROOFLINE_LAUNCHES)
+        n = min(max(K, ROOFLINE_LAUNCHES), 2 * ROOFLINE_LAUNCHES)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             for i in range(n):
@@ -641,7 +644,7 @@ def measure_config(config, K, W, dev, rank, world, distributed, barrier, native,
                    "parallelism": f"scene-sharded x{world}, no collective",
                    "l2": f"output ring of {wl.out_ring} x {wl.frame_bytes / 1e6:.1f} MB (> 126 MB L2 in flight)"
                          + (f"; state ring of {STATE_RING}" if wl.states is not None else ""),
-                   "launch": ((f"one CUDA graph of the {K} timed steps" if K <= 256 else f"CUDA graphs of {STATE_RING} steps")
+                   "launch": ((f"one CUDA graph of the {K} timed steps" if K <= 256 else f"CUDA graphs of {GRAPH_STEPS} steps")
                               + ", replayed before the timed region; one kernel per step, consecutive frames overlap "
                                 "through programmatic dependent launch; a 0.2 ms device-side delay ahead of the start event "
                                 "keeps the host's launch latency out of the timed region")
@@ -653,7 +656,7 @@ def measure_config(config, K, W, dev, rank, world, distributed, barrier, native,
                                      "launches cycling the output ring (profiles/)" if traffic is not None
                      else "not captured for this configuration",
                      "kernel": wl.kernel, "kernel_ms": raster_ms,
-                     "launches_timed": max(K, ROOFLINE_LAUNCHES) if wl.use_graphs else max(2, min(K, 20)),
+                     "launches_timed": min(max(K, ROOFLINE_LAUNCHES), 2 * ROOFLINE_LAUNCHES) if wl.use_graphs else max(2, min(K, 20)),
                      "frac_over_timed_steps": (c["algo"] * per_rank / (ms / K * 1e-3) / 1e9 / peak) if launches == K else None,
                      "algorithmic_bytes_per_launch": c["algo"] * per_rank, "peak_source": peak_src},
         "gpu_launches": launches,
