@@ -39,6 +39,15 @@ struct BinnedDev {
 
 constexpr int BV_CLIP = 0x40, BV_PROJ = 0x80;       // vertex flags (bits 0..5: outside clip plane p)
 constexpr int B_THREADS = 256;
+// resident CTAs per SM the triangle and raster kernels are compiled for (register budget 65536 / (256 * n)); measured on
+// configs 3 / 5 (ms per 1024 scenes): (4, 4) 0.352 / 2.325, (5, 4) 0.345 / 2.297, (4, 5) 0.362 / 2.400, (5, 5) 0.350 / 2.384,
+// (6, 6) 0.375 / 2.530
+#ifndef PBR_B_TRI_OCC
+#define PBR_B_TRI_OCC 5
+#endif
+#ifndef PBR_B_RASTER_OCC
+#define PBR_B_RASTER_OCC 4
+#endif
 constexpr int B_WPB = 8;                            // block-warps per CTA of the raster kernel
 constexpr int B_GATHER = 8;                         // records staged per round (8 x 64 B = one 16-byte load per lane)
 
@@ -178,7 +187,7 @@ __device__ __noinline__ void bin_clipped(const FrameDev &f, const StagedDev &g, 
     }
 }
 
-__global__ void __launch_bounds__(B_THREADS, 4) bin_tri_kernel(const __grid_constant__ FrameDev f,
+__global__ void __launch_bounds__(B_THREADS, PBR_B_TRI_OCC) bin_tri_kernel(const __grid_constant__ FrameDev f,
                                                             const __grid_constant__ StagedDev g,
                                                             const __grid_constant__ BinnedDev bd) {
     __shared__ unsigned s_live[B_THREADS], s_clip[B_THREADS];
@@ -379,7 +388,7 @@ __global__ void __launch_bounds__(B_THREADS) bin_blocks_kernel(const __grid_cons
 // raster: one warp per (scene, 8x8 block)
 // ------------------------------------------------------------------------------------------------
 template <bool SMOOTH>
-__global__ void __launch_bounds__(B_WPB * 32, 4) raster_binned_kernel(const __grid_constant__ FrameDev f,
+__global__ void __launch_bounds__(B_WPB * 32, PBR_B_RASTER_OCC) raster_binned_kernel(const __grid_constant__ FrameDev f,
                                                                       const __grid_constant__ StagedDev g,
                                                                       const __grid_constant__ BinnedDev bd) {
     __shared__ __align__(16) Rec s_recs[B_WPB][2][B_GATHER];
