@@ -529,8 +529,12 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         // nodes' matrices are read from their matrix buffer; parked in shared memory for phases A and S.
         {
             const int TI = f.total_inst;
+            // (work items start at the third-last worker warp: the first warps have a vertex each in phase A, whose
+            // loads they issue ahead of the barrier, and the last two fill the block table and prefetch -- the pose
+            // chain is the longest thing between kernel entry and the first barrier and shares its warp with nothing)
+            const int wlm = wl - (GW > 3 ? (GW - 3) * 32 : 0) + (wl < (GW > 3 ? (GW - 3) * 32 : 0) ? GW * 32 : 0);
 #pragma unroll 1
-            for (int it = wl; it < n_sc * TI; it += GW * 32) {
+            for (int it = wlm; it < n_sc * TI; it += GW * 32) {
                 const int sl = fast_div(it, f.w_inst_magic);
                 const int gi = it - sl * TI;
                 int ni = 0;
