@@ -505,7 +505,8 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         // microseconds later: lane = (range, 128-byte line), the ranges listed by the host.  (L1 prefetch of the CTA's
         // own lines at entry was measured slower: 17.31 vs 16.78 us, the 8 KB of L1 beside 219 KB of shared memory do
         // not hold them.)
-        if (PBR_W_PF_DIST > 0 && warp == GW - 1 && (lane >> 3) < f.n_pf) {
+        constexpr int PW = GW > 1 ? GW - 1 : 0;          // the warp that runs the pose chain of phase M: the last worker
+        if (PBR_W_PF_DIST > 0 && warp == (GW > 2 ? GW - 2 : 0) && (lane >> 3) < f.n_pf) {
             const int t_first = first_scene + PBR_W_PF_DIST * WARPS;
             const int t_n = min(WARPS, f.scene_begin + f.scene_count - t_first);
             if (t_n > 0) {
@@ -516,9 +517,10 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
             }
         }
 
-        // (filled by the worker lanes with the highest indices: the first warp has the pose chain to run; the readers
-        // are behind the phase barriers)
-        for (int b = GW * 32 - 1 - wl; b < nblk; b += GW * 32) {
+        // (filled by the worker lanes with the highest indices below the pose warp; the readers are behind the phase
+        // barriers)
+        for (int b = (PW > 0 ? PW : 1) * 32 - 1 - wl; b < nblk; b += (PW > 0 ? PW : 1) * 32) {
+            if (b < 0) break;                             // (the pose warp)
             const int by = fast_div(b, f.nbx_magic);
             btab[b] = (unsigned)((by << 8) | (b - by * f.nbx)) |
                       ((f.base_flags != nullptr && __ldg(f.base_flags + b) != 0) ? 0x80000000u : 0u);
@@ -529,10 +531,10 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
         // nodes' matrices are read from their matrix buffer; parked in shared memory for phases A and S.
         {
             const int TI = f.total_inst;
-            // (work items start at the third-last worker warp: the first warps have a vertex each in phase A, whose
-            // loads they issue ahead of the barrier, and the last two fill the block table and prefetch -- the pose
-            // chain is the longest thing between kernel entry and the first barrier and shares its warp with nothing)
-            const int wlm = wl - (GW > 3 ? (GW - 3) * 32 : 0) + (wl < (GW > 3 ? (GW - 3) * 32 : 0) ? GW * 32 : 0);
+            // (work items start at the last worker warp -- with the TMA build a helper: no scene of its own to prepare, no
+            // vertex in phase A whose loads it would issue first, and the block table and the prefetch are with the
+            // warps before it: the pose chain is the longest thing between kernel entry and the first barrier)
+            const int wlm = wl - PW * 32 + (wl < PW * 32 ? GW * 32 : 0);
 #pragma unroll 1
             for (int it = wlm; it < n_sc * TI; it += GW * 32) {
                 const int sl = fast_div(it, f.w_inst_magic);
