@@ -36,7 +36,7 @@ namespace pbr {
 
 constexpr int W_MAXREC = 48;     // records per scene (triangle slots that survive + clipped fans); < 64 (mask bits)
 constexpr int W_MAXSLOT = 36;    // eligibility: leaves >= 12 spare records for clipped fans
-constexpr int W_MAXVERT = 48;    // (instance, vertex) pairs per scene
+constexpr int W_MAXVERT = 48;    // (instance, vertex) pairs per scene (< 256: the live list names a corner in a byte)
 constexpr int W_MAXINST = 16;    // instances per scene (their 3x3 model matrices are parked in shared memory)
 constexpr int W_GEOM_BYTES = W_MAXVERT * 32 + W_MAXINST * 64;    // parked vertices (clip + projected) and matrices
 constexpr int W_MW = 2;          // mask words per block (64 record bits)
@@ -57,12 +57,12 @@ static_assert(6 * W_MAXSLOT - W_MAXREC <= W_OVF_MAXREC, "overflow pool too small
 // shared memory of one scene
 __host__ __device__ inline size_t warp_scene_bytes(int nblk) {
     return (size_t)W_GEOM_BYTES + (size_t)W_MAXREC * sizeof(Rec) + align16((size_t)nblk * W_MW * 4) +
-           align16((size_t)nblk * 2) + 2 * W_MAXREC * 4 + 32;
+           align16((size_t)nblk * 2) + W_MAXREC * 4 + 32;
 }
 // offset of the CTA's counters: behind the scene regions, the block queue, the block table and the live list
 __host__ __device__ inline size_t warp_qctr_offset(int nblk, int warps) {
     return (size_t)warps * warp_scene_bytes(nblk) + align16((size_t)warps * nblk * 4) + align16((size_t)nblk * 4) +
-           align16((size_t)warps * W_MAXSLOT * 4);
+           align16((size_t)warps * W_MAXSLOT * 12);
 }
 // shared memory of a CTA of `warps` scenes: scene regions + block queue + counters (+ mbarrier and the
 // background image when the background is written by TMA)
@@ -85,7 +85,6 @@ struct WScene {
     Rec *recs;                // [W_MAXREC]
     unsigned *masks;          // [nblk][W_MW]
     unsigned short *blist;    // [nblk]
-    unsigned *live;           // [W_MAXREC] (spare)
     unsigned *clipl;          // [W_MAXREC] packed slots of the triangles that need clipping
     int *ctr;                 // [4] overflow pool entry, clipped triangles, records drawn (S > 32), has int64 records
     unsigned char **out_slot; // out[scene], for the sweep
@@ -93,8 +92,7 @@ struct WScene {
 // (the parts whose size depends on the tile -- block masks, block list -- come last: everything else sits at a
 // constant offset from the region's base)
 constexpr int W_OFF_RECS = W_GEOM_BYTES;
-constexpr int W_OFF_LIVE = W_OFF_RECS + W_MAXREC * (int)sizeof(Rec);
-constexpr int W_OFF_CLIPL = W_OFF_LIVE + W_MAXREC * 4;
+constexpr int W_OFF_CLIPL = W_OFF_RECS + W_MAXREC * (int)sizeof(Rec);
 constexpr int W_OFF_CTR = W_OFF_CLIPL + W_MAXREC * 4;
 constexpr int W_OFF_OUT = W_OFF_CTR + 24;
 constexpr int W_OFF_MASKS = W_OFF_CTR + 32;
@@ -104,7 +102,6 @@ __device__ __forceinline__ WScene wscene(unsigned char *base, int nblk) {
     s.proj = reinterpret_cast<int4 *>(base + (size_t)W_MAXVERT * 16);
     s.minst = reinterpret_cast<float4 *>(base + (size_t)W_MAXVERT * 32);
     s.recs = reinterpret_cast<Rec *>(base + W_OFF_RECS);
-    s.live = reinterpret_cast<unsigned *>(base + W_OFF_LIVE);
     s.clipl = reinterpret_cast<unsigned *>(base + W_OFF_CLIPL);
     s.ctr = reinterpret_cast<int *>(base + W_OFF_CTR);
     s.out_slot = reinterpret_cast<unsigned char **>(base + W_OFF_OUT);
@@ -410,7 +407,11 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     // covers part of it (a global load) -- looked up once per CTA instead of once per (scene, block)
     unsigned *const btab = queue + align16((size_t)WARPS * nblk * 4) / 4;
     int *qctr = reinterpret_cast<int *>(smem_raw + f.w_qctr_off);
-    unsigned *livelist = reinterpret_cast<unsigned *>(qctr) - WARPS * W_MAXSLOT; // [WARPS * W_MAXSLOT], just below the counters
+    // live list, just below the counters: three words per surviving triangle -- (scene, slot, record index), the parked
+    // vertices of its corners (a byte each) + the two-sided bit, the draw id: what the set-up's edge lanes need, so that they
+    // neither search the node nor load the index triple again
+    unsigned *livelist = reinterpret_cast<unsigned *>(qctr) - 3 * WARPS * W_MAXSLOT;
+    unsigned *const live_v = livelist + WARPS * W_MAXSLOT, *const live_id = live_v + WARPS * W_MAXSLOT;
     // counters: [0] items queued from the front, [1] items popped, [2] live triangles, [7] items queued from the back
     // ([4], [5]: the mbarrier of the TMA build)
     if (threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; qctr[2] = 0; qctr[7] = 0; }
@@ -637,6 +638,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 const int it = base + lane;
                 int cat = 0;            // 0 dead, 1 live, 2 clip
                 int sl = 0, s = 0;
+                unsigned pv = 0, pid = 0;
                 if (it < n_sc * S) {
                     sl = fast_div(it, f.w_slot_magic);
                     s = it - sl * S;
@@ -662,6 +664,9 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                                                 (long long)(q2.x - q0.x) * (q1.y - q0.y);
                         const bool two_sided = (nd.flags & PBR_MESH_TWO_SIDED) != 0;
                         cat = (area2 < 0 || (two_sided && area2 > 0)) ? 1 : 0;
+                        pv = (unsigned)(vb + ti.x) | ((unsigned)(vb + ti.y) << 8) | ((unsigned)(vb + ti.z) << 16) |
+                             (two_sided ? 1u << 24 : 0u);
+                        pid = (unsigned)(nd.id_begin + inst * nd.n_tris + tri) + 1u;
                     }
                     if (cat == 2) {      // rare: the scene's own warp clips it later
                         const WScene sc = wscene(smem_raw + sl * region, nblk);
@@ -674,7 +679,12 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 int pos = 0;
                 if (lane == 0 && bl) pos = atomicAdd(&qctr[2], __popc(bl));
                 pos = __shfl_sync(0xffffffffu, pos, 0);
-                if (cat == 1) livelist[pos + __popc(bl & lt_mask)] = ((unsigned)sl << 16) | ((unsigned)s << 8) | (unsigned)j;
+                if (cat == 1) {
+                    const int at = pos + __popc(bl & lt_mask);
+                    livelist[at] = ((unsigned)sl << 16) | ((unsigned)s << 8) | (unsigned)j;
+                    live_v[at] = pv;
+                    live_id[at] = pid;
+                }
             }
         }
         group_sync<GW * 32>();
@@ -699,16 +709,16 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 if (PBR_W_SPLIT_SETUP && it >= n_live) continue;              // the gap between the two ranges
                 const unsigned e = livelist[it];
                 const int sl = (int)(e >> 16), s = (int)((e >> 8) & 255u), j = (int)(e & 255u);
-                int ni = 0;
-#pragma unroll 1
-                for (int i = 1; i < f.n_nodes; ++i)
-                    if (s >= f.nodes[i].slot_begin) ni = i;
-                const NodeDev &nd = f.nodes[ni];
-                const int local = s - nd.slot_begin;
-                const int inst = fast_div(local, nd.tri_magic);
-                const int tri = local - inst * nd.n_tris;
                 const WScene sc = wscene(smem_raw + sl * region, nblk);
                 if (do_shade) {
+                    int ni = 0;
+#pragma unroll 1
+                    for (int i = 1; i < f.n_nodes; ++i)
+                        if (s >= f.nodes[i].slot_begin) ni = i;
+                    const NodeDev &nd = f.nodes[ni];
+                    const int local = s - nd.slot_begin;
+                    const int inst = fast_div(local, nd.tri_magic);
+                    const int tri = local - inst * nd.n_tris;
                     const size_t b = nd.shared ? (size_t)inst : (size_t)(first_scene + sl) * nd.inst + inst;
                     float n[3];
                     const float4 n0 = __ldg(nd.tn + 3 * tri);
@@ -716,15 +726,15 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                     sc.recs[j].col = shade(f, n, __ldg(reinterpret_cast<const float4 *>(nd.cols + b * 4)));
                 }
                 if (do_edges) {
-                    const uint4 ti = __ldg(nd.tidx + tri);
-                    const int vb = nd.vert_begin + inst * nd.n_verts;
-                    const int4 q0 = sc.proj[vb + ti.x], q1 = sc.proj[vb + ti.y], q2 = sc.proj[vb + ti.z];
+                    const unsigned pv = live_v[it];
+                    const unsigned id = live_id[it];
+                    const bool two_sided = (pv >> 24) != 0u;
+                    const int4 q0 = sc.proj[pv & 255u], q1 = sc.proj[(pv >> 8) & 255u], q2 = sc.proj[(pv >> 16) & 255u];
                     int X[3] = {q0.x, q1.x, q2.x}, Y[3] = {q0.y, q1.y, q2.y};
                     float z[3] = {__int_as_float(q0.z), __int_as_float(q1.z), __int_as_float(q2.z)};
-                    const unsigned id = (unsigned)(nd.id_begin + inst * nd.n_tris + tri) + 1u;
                     Rec r;
                     BBox bb;
-                    if (setup_snapped(f, X, Y, z, (nd.flags & PBR_MESH_TWO_SIDED) != 0, id, 0, f.H, r, bb)) {
+                    if (setup_snapped(f, X, Y, z, two_sided, id, 0, f.H, r, bb)) {
                         if (r.meta & M_SLOW) sc.ctr[3] = 1;
                         // (every field but the colour, which the shade lane of this triangle writes)
                         Rec *const d = sc.recs + j;
