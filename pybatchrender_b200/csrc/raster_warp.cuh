@@ -59,10 +59,10 @@ __host__ __device__ inline size_t warp_scene_bytes(int nblk) {
     return (size_t)W_GEOM_BYTES + (size_t)W_MAXREC * sizeof(Rec) + align16((size_t)nblk * W_MW * 4) +
            align16((size_t)nblk * 2) + W_MAXREC * 4 + 32;
 }
-// offset of the CTA's counters: behind the scene regions, the block queue, the block table and the live list
+// offset of the CTA's counters: behind the scene regions, the block queue, the block table, the slot table and the live list
 __host__ __device__ inline size_t warp_qctr_offset(int nblk, int warps) {
     return (size_t)warps * warp_scene_bytes(nblk) + align16((size_t)warps * nblk * 4) + align16((size_t)nblk * 4) +
-           align16((size_t)warps * W_MAXSLOT * 12);
+           align16((size_t)W_MAXSLOT * 12) + align16((size_t)warps * W_MAXSLOT * 12);
 }
 // shared memory of a CTA of `warps` scenes: scene regions + block queue + counters (+ mbarrier and the
 // background image when the background is written by TMA)
@@ -406,6 +406,12 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     // [nblk] what an item says about its block, the same for every scene: bits 0-7 bx, 8-15 by, bit 31 the static layer
     // covers part of it (a global load) -- looked up once per CTA instead of once per (scene, block)
     unsigned *const btab = queue + align16((size_t)WARPS * nblk * 4) / 4;
+    // [3][W_MAXSLOT] what a triangle slot means, the same for every scene of the frame: the parked vertices of its
+    // corners (a byte each) + the two-sided bit, its draw id, its (node, instance, triangle) -- decoded once per CTA
+    // (node search, two divides, the load of the index triple) instead of once per (scene, slot) in phase B and again
+    // in phase S
+    unsigned *const stab_v = btab + align16((size_t)nblk * 4) / 4, *const stab_id = stab_v + W_MAXSLOT,
+                   *const stab_slot = stab_id + W_MAXSLOT;
     int *qctr = reinterpret_cast<int *>(smem_raw + f.w_qctr_off);
     // live list, just below the counters: three words per surviving triangle -- (scene, slot, record index), the parked
     // vertices of its corners (a byte each) + the two-sided bit, the draw id: what the set-up's edge lanes need, so that they
@@ -527,6 +533,26 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                       ((f.base_flags != nullptr && __ldg(f.base_flags + b) != 0) ? 0x80000000u : 0u);
         }
 
+        if (warp == (PW > 3 ? PW - 3 : 0)) {
+#pragma unroll 1
+            for (int s = lane; s < S && s < W_MAXSLOT; s += 32) {
+                int ni = 0;
+#pragma unroll 1
+                for (int i = 1; i < f.n_nodes; ++i)
+                    if (s >= f.nodes[i].slot_begin) ni = i;
+                const NodeDev &nd = f.nodes[ni];
+                const int local = s - nd.slot_begin;
+                const int inst = fast_div(local, nd.tri_magic);
+                const int tri = local - inst * nd.n_tris;
+                const uint4 ti = __ldg(nd.tidx + tri);
+                const int vb = nd.vert_begin + inst * nd.n_verts;
+                stab_v[s] = (unsigned)(vb + ti.x) | ((unsigned)(vb + ti.y) << 8) | ((unsigned)(vb + ti.z) << 16) |
+                            ((nd.flags & PBR_MESH_TWO_SIDED) ? 1u << 24 : 0u);
+                stab_id[s] = (unsigned)(nd.id_begin + inst * nd.n_tris + tri) + 1u;
+                stab_slot[s] = pack_slot(ni, inst, tri);
+            }
+        }
+
         // ---- M: instances.  A posed node's model matrix is computed here from its pose channels (the state
         // tensor of the caller: reference envs/cartpole/renderer.py:125-138 + shader_context.py:47-84), other
         // nodes' matrices are read from their matrix buffer; parked in shared memory for phases A and S.
@@ -642,18 +668,9 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 if (it < n_sc * S) {
                     sl = fast_div(it, f.w_slot_magic);
                     s = it - sl * S;
-                    int ni = 0;
-#pragma unroll 1
-                    for (int i = 1; i < f.n_nodes; ++i)
-                        if (s >= f.nodes[i].slot_begin) ni = i;
-                    const NodeDev &nd = f.nodes[ni];
-                    const int local = s - nd.slot_begin;
-                    const int inst = fast_div(local, nd.tri_magic);
-                    const int tri = local - inst * nd.n_tris;
-                    const uint4 ti = __ldg(nd.tidx + tri);
-                    const int vb = nd.vert_begin + inst * nd.n_verts;
+                    pv = stab_v[s];
                     const int4 *pj = wscene(smem_raw + sl * region, nblk).proj;
-                    const int4 q0 = pj[vb + ti.x], q1 = pj[vb + ti.y], q2 = pj[vb + ti.z];
+                    const int4 q0 = pj[pv & 255u], q1 = pj[(pv >> 8) & 255u], q2 = pj[(pv >> 16) & 255u];
                     const int f_and = q0.w & q1.w & q2.w, f_or = q0.w | q1.w | q2.w;
                     if (f_and & 0x3f) {
                         cat = 0;
@@ -662,15 +679,13 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                     } else if (f_and & VF_PROJ) {
                         const long long area2 = (long long)(q1.x - q0.x) * (q2.y - q0.y) -
                                                 (long long)(q2.x - q0.x) * (q1.y - q0.y);
-                        const bool two_sided = (nd.flags & PBR_MESH_TWO_SIDED) != 0;
+                        const bool two_sided = (pv >> 24) != 0u;
                         cat = (area2 < 0 || (two_sided && area2 > 0)) ? 1 : 0;
-                        pv = (unsigned)(vb + ti.x) | ((unsigned)(vb + ti.y) << 8) | ((unsigned)(vb + ti.z) << 16) |
-                             (two_sided ? 1u << 24 : 0u);
-                        pid = (unsigned)(nd.id_begin + inst * nd.n_tris + tri) + 1u;
+                        pid = stab_id[s];
                     }
                     if (cat == 2) {      // rare: the scene's own warp clips it later
                         const WScene sc = wscene(smem_raw + sl * region, nblk);
-                        sc.clipl[atomicAdd(&sc.ctr[1], 1)] = pack_slot(ni, inst, tri);
+                        sc.clipl[atomicAdd(&sc.ctr[1], 1)] = stab_slot[s];
                     }
                 }
                 int j = s;
@@ -711,14 +726,9 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 const int sl = (int)(e >> 16), s = (int)((e >> 8) & 255u), j = (int)(e & 255u);
                 const WScene sc = wscene(smem_raw + sl * region, nblk);
                 if (do_shade) {
-                    int ni = 0;
-#pragma unroll 1
-                    for (int i = 1; i < f.n_nodes; ++i)
-                        if (s >= f.nodes[i].slot_begin) ni = i;
-                    const NodeDev &nd = f.nodes[ni];
-                    const int local = s - nd.slot_begin;
-                    const int inst = fast_div(local, nd.tri_magic);
-                    const int tri = local - inst * nd.n_tris;
+                    const WSlot ws = unpack_slot(stab_slot[s]);
+                    const NodeDev &nd = f.nodes[ws.ni];
+                    const int inst = ws.inst, tri = ws.tri;
                     const size_t b = nd.shared ? (size_t)inst : (size_t)(first_scene + sl) * nd.inst + inst;
                     float n[3];
                     const float4 n0 = __ldg(nd.tn + 3 * tri);
