@@ -85,14 +85,14 @@ print("warp slot of warp 0, first CTAs:", wslot[:12, 0].tolist())
 # ---- fine-grained phases (stamps 8..13 of each warp), relative to the CTA's own entry
 ent = t[:, :, 0].min(1, keepdims=True)
 names2 = ['entry barrier', 'M barrier', 'A barrier', 'B barrier', 'S barrier', 'tail: colours + clipped done']
-prev = np.zeros(nc)
+prev = np.zeros(nc - 1)
 for k, nm in enumerate(names2):
-    v = (tf[:, :14, k] - ent) / 1000.0
+    v = (tf[:-1, :14, k] - ent[:-1]) / 1000.0             # (the last CTA may have warps without a scene: no stamp)
     m = v.mean(1)
     print(f"  {nm:30s} mean {m.mean():6.2f} us after CTA entry  (+{(m - prev).mean():5.2f})   slowest warp {v.max(1).mean():6.2f}")
     prev = m
-q = (t[:, :14, 3] - ent) / 1000.0
-print(f"  {'block list built (stamp 3)':30s} mean {q.mean():6.2f} us after CTA entry  (+{(q.mean(1) - prev).mean():5.2f})")
+q = (t[:-1, :14, 3] - ent[:-1]) / 1000.0
+print(f"  {'block list built (stamp 3)':30s} mean {q.mean():6.2f} us after CTA entry  (+{(q.mean(1) - prev).mean():5.2f})   slowest warp {q.max(1).mean():6.2f}")
 bq = (t[:, :14, 5] - ent) / 1000.0
 print(f"  {'pre-sweep barrier released':30s} mean {bq.mean():6.2f} us after CTA entry")
 

@@ -368,6 +368,67 @@ __device__ __noinline__ void issue_bg_stores(const FrameDev &f, int *qctr, int w
 #ifndef PBR_W_SPLIT_SETUP
 #define PBR_W_SPLIT_SETUP 1
 #endif
+// A scene's non-empty blocks into the CTA's queue: blocks with many records from the front, the others from the back
+// (qctr[0]: front count in the low half of the word, back count in the high half).  ROUNDS > 0: tiles of up to 32 x ROUNDS
+// blocks -- every round's ballots stay in registers and ONE atomic per scene reserves both ranges (an atomic or two per
+// 32 blocks made the 14 scene warps of a CTA queue up behind each other: 14.18 -> 13.83 us per frame); ROUNDS == 0: any
+// tile, one atomic per 32 blocks.
+template <int ROUNDS>
+__device__ __forceinline__ void queue_blocks(const unsigned *masks, int nblk, int lane, unsigned lt_mask, int *qctr,
+                                             unsigned *queue, const unsigned *btab, unsigned tag, int qcap) {
+    auto classify = [&](int b, bool &nz, bool &heavy) {
+        nz = false; heavy = true;
+        if (b < nblk) {
+            const uint2 m = *reinterpret_cast<const uint2 *>(masks + b * W_MW);
+            nz = (m.x | m.y) != 0u;
+            if (PBR_W_HEAVY > 0) heavy = __popc(m.x) + __popc(m.y) >= PBR_W_HEAVY;
+        }
+    };
+    if (ROUNDS > 0) {
+        constexpr int R = ROUNDS > 0 ? ROUNDS : 1;
+        unsigned hbal[R], lbal[R];
+        bool nz[R], hv[R];
+        int nh = 0, nl = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            classify(r * 32 + lane, nz[r], hv[r]);
+            hbal[r] = __ballot_sync(0xffffffffu, nz[r] && hv[r]);
+            lbal[r] = PBR_W_HEAVY > 0 ? __ballot_sync(0xffffffffu, nz[r] && !hv[r]) : 0u;
+            nh += __popc(hbal[r]);
+            nl += __popc(lbal[r]);
+        }
+        if (nh + nl == 0) return;
+        unsigned base = 0;
+        if (lane == 0) base = (unsigned)atomicAdd(&qctr[0], nh | (nl << 16));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        int hb = (int)(base & 0xffffu), lb = (int)(base >> 16);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (nz[r])
+                queue[hv[r] ? hb + __popc(hbal[r] & lt_mask) : qcap - 1 - (lb + __popc(lbal[r] & lt_mask))] =
+                    tag | btab[r * 32 + lane];
+            hb += __popc(hbal[r]);
+            lb += __popc(lbal[r]);
+        }
+    } else {
+#pragma unroll 1
+        for (int b0 = 0; b0 < nblk; b0 += 32) {
+            const int b = b0 + lane;
+            bool nz, heavy;
+            classify(b, nz, heavy);
+            const unsigned hbal = __ballot_sync(0xffffffffu, nz && heavy);
+            const unsigned lbal = PBR_W_HEAVY > 0 ? __ballot_sync(0xffffffffu, nz && !heavy) : 0u;
+            if ((hbal | lbal) == 0u) continue;
+            unsigned base = 0;
+            if (lane == 0) base = (unsigned)atomicAdd(&qctr[0], __popc(hbal) | (__popc(lbal) << 16));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (nz)
+                queue[heavy ? (int)(base & 0xffffu) + __popc(hbal & lt_mask)
+                            : qcap - 1 - ((int)(base >> 16) + __popc(lbal & lt_mask))] = tag | btab[b];
+        }
+    }
+}
+
 __host__ __device__ constexpr int w_helpers(int warps) { return warps <= W_WARPS_TMA_SMALL ? PBR_W_HELPERS_SMALL : PBR_W_HELPERS; }
 template <int WARPS, bool TMA_BG>
 __global__ void __launch_bounds__(32 * (WARPS + (TMA_BG ? w_helpers(WARPS) : 0)),
@@ -418,9 +479,9 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     // neither search the node nor load the index triple again
     unsigned *livelist = reinterpret_cast<unsigned *>(qctr) - 3 * WARPS * W_MAXSLOT;
     unsigned *const live_v = livelist + WARPS * W_MAXSLOT, *const live_id = live_v + WARPS * W_MAXSLOT;
-    // counters: [0] items queued from the front, [1] items popped, [2] live triangles, [7] items queued from the back
-    // ([4], [5]: the mbarrier of the TMA build)
-    if (threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; qctr[2] = 0; qctr[7] = 0; }
+    // counters: [0] items queued from the front (low half) and from the back (high half) of the queue, [1] items popped,
+    // [2] live triangles ([4], [5]: the mbarrier of the TMA build)
+    if (threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; qctr[2] = 0; }
     __syncthreads();          // counters initialised (all warps arrive together: cheap)
     W_STAMP(8);
     // The thread that drives the TMA engine: lane 0 of the LAST helper warp when there is one.  Issuing the
@@ -882,29 +943,10 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
                 if (novf == 0 && WARPS > 1) {
                     const unsigned tag = ((unsigned)warp << 16) | (scene_slow ? 0x60000000u : 0u) |
                                          ((f.keys32 != 0 && direct) ? 0u : 0x20000000u);
-#pragma unroll 1
-                    for (int b0 = 0; b0 < nblk; b0 += 32) {
-                        const int b = b0 + lane;
-                        bool nz = false, heavy = true;
-                        if (b < nblk) {
-                            const uint2 m = *reinterpret_cast<const uint2 *>(masks + b * W_MW);
-                            nz = (m.x | m.y) != 0u;
-                            if (PBR_W_HEAVY > 0) heavy = __popc(m.x) + __popc(m.y) >= PBR_W_HEAVY;
-                        }
-                        const unsigned hbal = __ballot_sync(0xffffffffu, nz && heavy);
-                        const unsigned lbal = PBR_W_HEAVY > 0 ? __ballot_sync(0xffffffffu, nz && !heavy) : 0u;
-                        if ((hbal | lbal) == 0u) continue;
-                        int hb = 0, lb = 0;
-                        if (lane == 0) {
-                            if (hbal) hb = atomicAdd(&qctr[0], __popc(hbal));
-                            if (lbal) lb = atomicAdd(&qctr[7], __popc(lbal));
-                        }
-                        hb = __shfl_sync(0xffffffffu, hb, 0);
-                        if (PBR_W_HEAVY > 0) lb = __shfl_sync(0xffffffffu, lb, 0);
-                        if (nz)
-                            queue[heavy ? hb + __popc(hbal & lt_mask) : WARPS * nblk - 1 - (lb + __popc(lbal & lt_mask))] =
-                                tag | btab[b];
-                    }
+                    // (separate copies for two and four rounds: skipping unused rounds at run time costs more than it saves)
+                    if (nblk <= 64) queue_blocks<2>(masks, nblk, lane, lt_mask, qctr, queue, btab, tag, WARPS * nblk);
+                    else if (nblk <= 128) queue_blocks<4>(masks, nblk, lane, lt_mask, qctr, queue, btab, tag, WARPS * nblk);
+                    else queue_blocks<0>(masks, nblk, lane, lt_mask, qctr, queue, btab, tag, WARPS * nblk);
                 } else if (novf == 0) {
 #pragma unroll 1
                     for (int b0 = 0; b0 < nblk; b0 += 32) {
@@ -936,7 +978,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     if (WARPS > 1) {
         if (nlist > 0) {                                  // (a scene with a pool entry: the front of its own list)
             int qbase = 0;
-            if (lane == 0) qbase = atomicAdd(&qctr[0], nlist);
+            if (lane == 0) qbase = atomicAdd(&qctr[0], nlist) & 0xffff;
             qbase = __shfl_sync(0xffffffffu, qbase, 0);
             for (int i = lane; i < nlist; i += 32) {
                 const int packed = me.blist[i];
@@ -947,8 +989,8 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     }
     if (PBR_W_TRIGGER == 2) asm volatile("griddepcontrol.launch_dependents;");
     W_STAMP(5);
-    const int nheavy = WARPS > 1 ? qctr[0] : nlist;      // items handed out from the front of the queue / list ...
-    const int nitems = nheavy + (PBR_W_HEAVY > 0 ? (WARPS > 1 ? qctr[7] : nlight) : 0);       // ... then those from its back
+    const int nheavy = WARPS > 1 ? (qctr[0] & 0xffff) : nlist;       // items handed out from the front of the queue / list ...
+    const int nitems = nheavy + (WARPS > 1 ? (int)((unsigned)qctr[0] >> 16) : nlight);     // ... then those from its back
     const int qlast = (WARPS > 1 ? WARPS * nblk : nblk) - 1 + nheavy;
     const int lx = lane & 7, ly = lane >> 3;
     const int tileW = f.W, tileH = f.H, tileH4 = f.H - 4, tileNbx = f.nbx;
