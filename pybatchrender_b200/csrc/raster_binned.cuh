@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(B_THREADS) bin_xform_kernel(const __grid_const
         if (v >= f.nodes[i].vert_begin) ni = i;
     const NodeDev &nd = f.nodes[ni];
     const int local = v - nd.vert_begin;
-    const int inst = local / nd.n_verts;
+    const int inst = (bd.total_verts < 65536 && nd.n_verts < 65536) ? fast_div(local, nd.vert_magic) : local / nd.n_verts;
     const int vert = local - inst * nd.n_verts;
     if (!g.vis[(size_t)local_scene * f.total_inst + nd.inst_begin + inst]) return;
     const size_t b = nd.shared ? (size_t)inst : (size_t)scene * nd.inst + inst;
