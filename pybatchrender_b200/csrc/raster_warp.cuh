@@ -481,7 +481,9 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     unsigned *const live_v = livelist + WARPS * W_MAXSLOT, *const live_id = live_v + WARPS * W_MAXSLOT;
     // counters: [0] items queued from the front (low half) and from the back (high half) of the queue, [1] items popped,
     // [2] live triangles ([4], [5]: the mbarrier of the TMA build)
-    if (threadIdx.x == 0) { qctr[0] = 0; qctr[1] = 0; qctr[2] = 0; }
+    // (the pop counter starts behind the warps' first items: warp w begins with item w -- sixteen first pops on one
+    // counter would queue up behind each other for ~0.4 us at the start of every sweep)
+    if (threadIdx.x == 0) { qctr[0] = 0; qctr[1] = (PBR_W_POP_AHEAD && WARPS > 1) ? (int)(blockDim.x >> 5) : 0; qctr[2] = 0; }
     __syncthreads();          // counters initialised (all warps arrive together: cheap)
     W_STAMP(8);
     // The thread that drives the TMA engine: lane 0 of the LAST helper warp when there is one.  Issuing the
@@ -1004,7 +1006,7 @@ raster_warp_kernel(const __grid_constant__ FrameDev f) {
     // block instead of the branch: ptxas turns it back into the branch.)
 #define PBR_W_POP(dst)                                                                                              \
     if (lane == 0) asm volatile("atom.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(dst) : "r"(pop_addr) : "memory")
-    if (PBR_W_POP_AHEAD && WARPS > 1) PBR_W_POP(ahead);
+    if (PBR_W_POP_AHEAD && WARPS > 1) ahead = warp;      // (lane 0's copy is the one that counts)
 #pragma unroll 1
     while (true) {
         int i;
