@@ -64,7 +64,7 @@ out += ["## instruction mix by phase (profiles/ncu_segments.py, executions per s
 out += ["## DRAM traffic over a RANGE of 16 consecutive launches cycling the 4-buffer output ring",
         "## (ncu --replay-mode range --metrics dram__bytes_read.sum,dram__bytes_write.sum python profiles/traffic_range.py 16)"]
 out += [l.rstrip() for l in open(os.path.join(G, "r02z_traffic.log")).read().splitlines()[-8:]]
-out += ["-> (755.52 + 2.33) MB / 16 launches = 47.37 MB per launch against 51.25 MB algorithmic (12,512 B x 4096): 0.92 -- every pixel",
+out += ["-> (756.45 + 2.33) MB / 16 launches = 47.42 MB per launch against 51.25 MB algorithmic (12,512 B x 4096): 0.92 -- every pixel",
         "   byte reaches DRAM once (the rest of the last frames is still in the 126 MB L2 when the range ends), reads ~ 0.1 MB per launch"]
 open(os.path.join(P, "r02z_raster_warp_ncu.txt"), "w").write("\n".join(out) + "\n")
 
