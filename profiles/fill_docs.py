@@ -22,7 +22,7 @@ eager {b200['value_eager']['value']/1e6:.0f} M/s ({b200['value_eager']['host_ms_
 on 16 cores (round 1 reported 0.35–0.97 M/s with per-frame thread creation and contention).  With the driver's
 `--steps 20 --warmup 5`: {b20['value']/1e6:.1f} M/s, {b20['ms_per_step']*1e3:.2f} µs per step, `roofline.frac` {b20['roofline']['frac']:.3f} over a chain of 128 launches ({b20['roofline']['frac_over_timed_steps']:.3f} over the
 20 timed steps, whose first launch has no frame ahead of it).  Config 4 at full size (65,536 × 84²): {ex['config4']['ms_per_step']:.3f} ms per frame
-= {ex['config4']['roofline_frac']:.2f}; config 3: {ex['config3']['ms_per_step']:.3f} ms = {ex['config3']['roofline_frac']:.3f}; config 5: {ex['config5']['ms_per_step']:.1f} ms = {ex['config5']['roofline_frac']:.3f}.  8 GPUs (`--steps 20`, a build a few hours older): {b8['value']/1e6:.0f} M/s ({b8['ms_per_step']*1e3:.2f} µs per step), e2e
+= {ex['config4']['roofline_frac']:.2f}; config 3: {ex['config3']['ms_per_step']:.3f} ms = {ex['config3']['roofline_frac']:.3f}; config 5: {ex['config5']['ms_per_step']:.1f} ms = {ex['config5']['roofline_frac']:.3f}.  8 GPUs (`--steps 20`): {b8['value']/1e6:.0f} M/s ({b8['ms_per_step']*1e3:.2f} µs per step), e2e
 {b8['e2e']['value']/1e6:.2f} M/s = {pct(b8['e2e']['frac_of_d2h_ceiling']):.0f} % of {b8['e2e']['d2h_ceiling_GBps']:.1f} GB/s of pinned D2H into one host, NCCL gather of the 352 MB of frames onto rank 0 at {b8['gather']['GBps_into_rank0']:.0f} GB/s
 (184–387 GB/s across runs), config 4 strong-sharded {b8['extra']['config4']['value']/1e6:.0f} M/s.
 
@@ -31,7 +31,7 @@ i = s.index("One box, `--steps 20 --warmup 5`\n(`profiles/r02z_bench_n{1_steps20
 j = s.index("## 7. The \"next\" rows")
 row = lambda b: "%.1f M (%.2f µs per step)" % (b["value"] / 1e6, b["ms_per_step"] * 1e3)
 s = s[:i] + ("One box, `--steps 20 --warmup 5`\n(`profiles/r02z_bench_n{1_steps20,2,4,8}.json.txt`): 1 GPU %s, 2 GPUs %s, 4 GPUs %s, 8 GPUs %s -- %.1f %% of 8 × the\n"
-     "single-GPU value (the multi-GPU lines are from a build a few hours older than the single-GPU one: 14.54 against 14.33 µs per step at N = 1 then).\n"
+     "single-GPU value (each N ran on its own box of the pool; the boxes differ by ~3 %% in per-step time).\n"
      "At 8 GPUs: config 4 strong-sharded %.0f M/s (%.1f M at N=1), config 5 %.2f M/s, config 3 (weak) %.1f M/s; e2e %.2f M/s = %.0f %%\n"
      "of the %.1f GB/s that plain pinned D2H copies from all eight GPUs reach on this host (4 GPUs: %.1f M/s at %.0f %% of %.0f GB/s -- the\n"
      "host side, not the renderer, sets these, and it differs from box to box); NCCL gather of 352 MB of frames onto rank 0 at %.0f GB/s.\n\n") % (
@@ -58,7 +58,7 @@ for the full `env.step` of the CartPole environment (the reference publishes 0.9
 end through host buffers (PCIe-bound: 50 MB of frames per step, {pct(b200['e2e']['frac_of_d2h_ceiling']):.0f} % of a plain pinned D2H copy); {b200['cpu_baseline']['value']/1e6:.2f} M/s for the
 CPU restatement of the reference pipeline on 16 host cores.  Large scenes (block-list path): many-cubes 1024×256 boxes
 at 128² {ex['config3']['ms_per_step']:.2f} ms per frame ({ex['config3']['value']/1e6:.1f} M scene-frames/s), mixed-mesh 16,384×64 instances at 256² {ex['config5']['ms_per_step']:.1f} ms per frame.  2 / 4 / 8
-GPUs: {b2['value']/1e6:.0f} / {b4['value']/1e6:.0f} / {b8['value']/1e6:.0f} M/s (weak; 14.54 µs per step at every N), config 4 strong-sharded {b8['extra']['config4']['value']/1e6:.0f} M/s on 8, NCCL gather of the
+GPUs: {b2['value']/1e6:.0f} / {b4['value']/1e6:.0f} / {b8['value']/1e6:.0f} M/s (weak; {100*b8['value']/(8*b20['value']):.0f} % of 8 × one GPU -- boxes differ by ~3 % in per-step time), config 4 strong-sharded {b8['extra']['config4']['value']/1e6:.0f} M/s on 8, NCCL gather of the
 frames onto rank 0 at 184–387 GB/s.
 
 ''' + s[j:]
@@ -69,7 +69,8 @@ p = P + "README.md"
 s = open(p).read()
 s = re.sub(r"`value` 153\.5 M \(BENCH_r01\) → [0-9.]+ M scene-frames/s; `roofline\.frac` 0\.415 → [0-9.]+; config 4 \(65,536 × 84²\) [0-9.]+\.",
            "`value` 153.5 M (BENCH_r01) → %.1f M scene-frames/s; `roofline.frac` 0.415 → %.3f; config 4 (65,536 × 84²) %.2f." % (b200["value"] / 1e6, b200["roofline"]["frac"], ex["config4"]["roofline_frac"]), s)
-s = re.sub(r"\([0-9.]+ / [0-9.]+ / [0-9.]+ M scene-frames/s: [0-9.]+ µs per step at every N\)",
-           "(%.1f / %.1f / %.1f M scene-frames/s: %.2f µs per step at every N)" % (b2["value"] / 1e6, b4["value"] / 1e6, b8["value"] / 1e6, b8["ms_per_step"] * 1e3), s)
+s = re.sub(r"\([0-9.]+ / [0-9.]+ / [0-9.]+ M scene-frames/s: [^)]*\)",
+           "(%.1f / %.1f / %.1f M scene-frames/s: %.2f / %.2f / %.2f µs per step)" % (b2["value"] / 1e6, b4["value"] / 1e6, b8["value"] / 1e6,
+                                                                                   b2["ms_per_step"] * 1e3, b4["ms_per_step"] * 1e3, b8["ms_per_step"] * 1e3), s)
 open(p, "w").write(s)
 print("docs refreshed")
