@@ -1,34 +1,40 @@
-// raster_warp.cuh -- the small-scene raster kernel: ONE WARP per scene for geometry, the warps of
-// a CTA share the raster work of their scenes; no colour tile in shared memory.
+// raster_warp.cuh -- the small-scene raster kernel: a CTA owns a few scenes (14, 6 or 4), its warps share
+// their geometry phase by phase and their raster work through one queue; no colour tile in shared memory.
 //
 // Target: CartPole-class scenes (a few instances of small flat-shaded meshes, <= 36 triangle slots).
-// A scene costs only a few thousand warp instructions and ~2 % of its pixels are covered, so the
-// design goals are (a) as many resident warps per SM as possible -- the per-scene shared-memory
-// footprint is ~6 KB (records, masks, parked vertices), so 28-32 scenes share an SM and the whole
-// 4096-scene batch is a single wave; (b) no wasted memory traffic: the background (or the
-// pre-rendered static layer) goes straight to out[scene] -- by TMA bulk stores from one shared-memory
-// copy per CTA, or as 128-bit stores by the warps -- and only covered pixels are patched afterwards
-// (the lines are still dirty in L2, DRAM sees each byte once); (c) balance:
-// scenes differ a lot in raster work, so the non-empty 8x8 blocks of the CTA's scenes go into one
-// queue that all warps of the CTA drain.
+// A scene costs ~2.7 k warp instructions and ~2 % of its pixels are covered, so the design goals are
+// (a) as many resident scenes per SM as possible -- the per-scene shared-memory footprint is ~6.4 KB
+// (records, masks, parked vertices), 28 scenes share an SM and the whole 4096-scene batch is one wave;
+// (b) no wasted memory traffic: the background (or the pre-rendered static layer) goes straight to
+// out[scene] -- by TMA bulk stores from one shared-memory copy per CTA, or as 128-bit stores by the warps --
+// and only covered pixels are patched afterwards (the lines are still dirty in L2, DRAM sees each byte
+// once); (c) balance: scenes differ a lot in raster work, so the non-empty 8x8 blocks of the CTA's scenes go
+// into one queue that all warps of the CTA drain; (d) one launch per frame, frames chained by programmatic
+// dependent launch: the next frame's CTAs start on an SM as this frame's leave it.
 //
-// Per CTA (TMA build): lane 0 of the first helper warp loads the background image into shared memory and,
-// when its CTA's turn on this SM has come, issues one bulk store per scene; it waits for them behind the
-// pre-sweep barrier.
-// Per warp / scene:
-//   0  background the clear colour / static layer image over out[scene] (128-bit stores; TMA build: none)
-//   A  vertices   lanes = (instance, unique vertex): clip = VP*(M*v), outcodes, project + snap,
-//                 parked in shared memory                                        (basic.vert:24-43)
-//   B  setup      lanes = triangle slots: trivial reject / needs-clip / back-face cull from the
-//                 parked vertices; survivors: integer edge equations, depth plane, flat shade
-//                 (basic.frag:31-38) -> 64-byte record, binned into per-8x8-block 64-bit masks
-//                 (with > 32 slots survivors are first compacted with ballots)
-//   B3 clip       lanes = triangles crossing the near plane / guard band: Sutherland-Hodgman, fan
-//                 triangles appended to the spare record slots, then to the per-SM overflow pool
+// Per CTA (TMA build): lane 0 of the last helper warp loads the background image into shared memory and,
+// when its CTA's turn on this SM has come, issues one bulk store per scene; it waits for them ahead of the
+// pre-sweep barrier.  Otherwise idle lanes build two tables that are the same for every scene of the frame:
+// the block table (packed block coordinates, "the static layer covers part of it") and the slot table (what a
+// triangle slot means: corner vertices, draw id, node / instance / triangle); one warp asks the L2 for the
+// per-scene inputs of the CTA 32 places behind this one.
+// Geometry, by the worker warps of the CTA over (scene, item) pairs of all its scenes, a named barrier
+// between the phases:
+//   M  instances  pose channels (the caller's state) -> model matrix, or the matrix buffer     (node.py:110-178)
+//   A  vertices   lanes = (scene, instance, unique vertex): clip = VP*(M*v), outcodes, project + snap,
+//                 parked in shared memory                                               (basic.vert:24-43)
+//   B  classify   lanes = (scene, triangle slot): trivial reject / needs-clip / back-face cull from the
+//                 parked vertices; survivors are compacted into the CTA's live list
+//   S  set-up     two lanes per survivor in different warps: integer edge equations + depth plane -> 64-byte
+//                 record, binned into per-8x8-block 64-bit masks | flat shade (basic.frag:31-38) -> its colour
+// then per scene, by its own warp:
+//   B3 clip       triangles crossing the near plane / guard band: Sutherland-Hodgman, fan triangles appended
+//                 to the spare record slots, then to the per-SM overflow pool
+//   Q  queue      the scene's non-empty blocks into the CTA's queue (one atomic per scene)
 // Per CTA:
-//   D  raster     warps pull (scene, block) items from the shared queue; every lane owns 2 pixels
-//                 of the block and keeps their (depth|id) key and colour in registers across the
-//                 block's records; winners are written straight to out[scene]
+//   D  raster     warps pull (scene, block) items from the shared queue; every lane owns 2 pixels of the
+//                 block and keeps their depth key (32 bits when draw order allows, else depth|id) and colour
+//                 in registers across the block's records; winners are written straight to out[scene]
 #pragma once
 #include "common.cuh"
 
