@@ -3,7 +3,7 @@
 //
 // Target: CartPole-class scenes (a few instances of small flat-shaded meshes, <= 36 triangle slots).
 // A scene costs ~2.7 k warp instructions and ~2 % of its pixels are covered, so the design goals are
-// (a) as many resident scenes per SM as possible -- the per-scene shared-memory footprint is ~6.4 KB
+// (a) as many resident scenes per SM as possible -- the per-scene shared-memory footprint is ~6.2 KB
 // (records, masks, parked vertices), 28 scenes share an SM and the whole 4096-scene batch is one wave;
 // (b) no wasted memory traffic: the background (or the pre-rendered static layer) goes straight to
 // out[scene] -- by TMA bulk stores from one shared-memory copy per CTA, or as 128-bit stores by the warps --
