@@ -38,7 +38,10 @@ struct BinnedDev {
 };
 
 constexpr int BV_CLIP = 0x40, BV_PROJ = 0x80;       // vertex flags (bits 0..5: outside clip plane p)
-constexpr int B_THREADS = 256;
+#ifndef PBR_B_THREADS
+#define PBR_B_THREADS 256
+#endif
+constexpr int B_THREADS = PBR_B_THREADS;
 // resident CTAs per SM the triangle and raster kernels are compiled for (register budget 65536 / (256 * n)); measured on
 // configs 3 / 5 (ms per 1024 scenes): (4, 4) 0.352 / 2.325, (5, 4) 0.345 / 2.297, (4, 5) 0.362 / 2.400, (5, 5) 0.350 / 2.384,
 // (6, 6) 0.375 / 2.530
@@ -46,9 +49,15 @@ constexpr int B_THREADS = 256;
 #define PBR_B_TRI_OCC 5
 #endif
 #ifndef PBR_B_RASTER_OCC
-#define PBR_B_RASTER_OCC 4
+#define PBR_B_RASTER_OCC 32
 #endif
-constexpr int B_WPB = 8;                            // block-warps per CTA of the raster kernel
+#ifndef PBR_B_WPB
+#define PBR_B_WPB 1
+#endif
+// (the raster warps are independent of each other: with eight per CTA a CTA's slot stays taken until its slowest warp is
+// done -- measured on configs 3 / 5, ms per 1024 scenes: 8 warps 0.340 / 2.278, 4: 0.328 / 2.073, 2: 0.327 / 2.087,
+// 1 (32 CTAs per SM): 0.318 / 2.025)
+constexpr int B_WPB = PBR_B_WPB;                    // block-warps per CTA of the raster kernel
 constexpr int B_GATHER = 8;                         // records staged per round (8 x 64 B = one 16-byte load per lane)
 
 // ------------------------------------------------------------------------------------------------
