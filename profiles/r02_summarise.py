@@ -73,8 +73,8 @@ out = ["# Round 2, final: the large-scene path (raster_binned.cuh) on BASELINE c
        "# config 5 (mixed-mesh x 64 instances, 256^2; 1024 / 512 scenes per capture) -- ncu --set full, one launch per kernel", ""]
 out += ["## device time per frame, block-list path vs the band-based path it replaces (PBR_B200_LARGE=staged), same box"]
 out += [l for l in open(os.path.join(G, "r02z_cfg_times.log")).read().splitlines() if l.startswith("config")]
-out += ["   (lines 1-2: block lists, lines 3-4: band-based; the ncu sections below were captured with eight block-warps per CTA of",
-        "   raster_binned_kernel -- 0.342 / 2.282 ms -- the final build launches one warp per CTA, 32 CTAs per SM)", ""]
+out += ["   (lines 1-2: block lists, lines 3-4: band-based; raster_binned_kernel with one block-warp per CTA, 32 CTAs per SM -- with",
+        "   eight warps per CTA the same build measured 0.342 / 2.282 ms; re-captured by profiles/r02_capture_large.sh)", ""]
 for cfg in (3, 5):
     out += [f"## config {cfg}: launch shares (ncu --metrics gpu__time_duration.sum, python profiles/staged_workloads.py {cfg} 1024)"]
     out += shares(os.path.join(G, f"r02z_cfg{cfg}_launches.csv")) + [""]
